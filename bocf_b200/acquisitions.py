@@ -1,0 +1,267 @@
+"""Acquisition classes with the reference's plugin surface, backed by the CUDA library.
+
+AcquisitionBase  GPyOpt/acquisitions/base.py:6-74
+uEI_noiseless    uEI_noiseless.py:9-175   (EI-CF)
+uPI              uPI.py                   (no gradient)
+maEI / maPI      maEI.py / maPI.py        (analytic, linear scalarisation)
+EI / PI          EI.py / PI.py            (single-output, single hyper-sample)
+
+Same constructor arguments, method names, shapes and sign conventions; ``_compute_acq`` /
+``_compute_acq_withGradients`` take numpy (N,d) and return numpy ((N,1), (N,d)), or take CUDA torch
+tensors and return CUDA torch tensors.  The reference's pathos pool (uEI_noiseless.py:85-97) is gone:
+all candidates of a call are evaluated by one fused device sweep.
+
+Reference behaviours kept on purpose: f* is computed once per call with
+whichever hyper-sample is currently selected and the model is left on the last hyper-sample (q2);
+the gradient call draws ONE fresh theta when the parameter distribution is sampled (q4); the value
+uses max(.,0) while the gradient indicator is a strict > (q10); uPI/maPI add 1e-6 to f* (q11).
+One deviation: with ``fixed_hyps=True`` the reference averages 10 identical passes (q6); here the
+identical passes are evaluated once.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _host(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(ctypes.c_void_p)
+
+
+class AcquisitionBase(object):
+    """GPyOpt/acquisitions/base.py:6-74."""
+    analytical_gradient_prediction = False
+
+    def __init__(self, model, space, optimizer, cost_withGradients=None):
+        self.model = model
+        self.space = space
+        self.optimizer = optimizer
+        self.analytical_gradient_acq = self.analytical_gradient_prediction and self.model.analytical_gradient_prediction
+        self.cost_withGradients = cost_withGradients
+
+    def acquisition_function(self, x):
+        return -self._compute_acq(x)
+
+    def acquisition_function_withGradients(self, x):
+        f_acqu, df_acqu = self._compute_acq_withGradients(x)
+        return -f_acqu, -df_acqu
+
+    def optimize(self, duplicate_manager=None, x_baseline=None):
+        if not self.analytical_gradient_acq:
+            out = self.optimizer.optimize(f=self.acquisition_function, duplicate_manager=duplicate_manager,
+                                          x_baseline=x_baseline)
+        else:
+            out = self.optimizer.optimize(f=self.acquisition_function, f_df=self.acquisition_function_withGradients,
+                                          duplicate_manager=duplicate_manager, x_baseline=x_baseline)
+        return out
+
+    def _compute_acq(self, x):
+        raise NotImplementedError('')
+
+    def _compute_acq_withGradients(self, x):
+        raise NotImplementedError('')
+
+    # ---- shared device plumbing -----------------------------------------------------------------------
+    def _n_hyps_effective(self):
+        H_loaded = self.model.n_hyper_samples_loaded()
+        return 1 if (self.model.fixed_hyps or H_loaded == 1) else min(self.n_hyps_samples, H_loaded)
+
+    def _run(self, variant, X, theta, weight, fstar, grad, Zt=None, S=0, form=0):
+        model = self.model
+        lib = model._lib
+        Xd, is_t = model._dev_in(X)
+        N, d = Xd.shape
+        theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        L = theta.shape[0]
+        th_h, th_p = _host(theta)
+        w_h, w_p = _host(weight)
+        f_h, f_p = _host(fstar)
+        H_use = f_h.shape[0]
+        with torch.cuda.device(model.device):
+            acq = torch.empty((N,), dtype=torch.float64, device=model.device)
+            dacq = torch.empty((N, d), dtype=torch.float64, device=model.device) if grad else None
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.bocf_acq_eval(model._handle, _lib.VARIANTS[variant], _lib.COMPOSITES[self.utility.composite],
+                                         _ptr(Xd), N, _ptr(Zt), S, th_p, L, theta.shape[1], w_p, f_p, H_use, form,
+                                         _ptr(acq), _ptr(dacq), st))
+        acq = acq.reshape(N, 1)
+        if not is_t:
+            acq = acq.cpu().numpy()
+            dacq = None if dacq is None else dacq.cpu().numpy()
+        return (acq, dacq) if grad else acq
+
+
+class uEI_noiseless(AcquisitionBase):
+    """EI-CF (uEI_noiseless.py:9-175)."""
+    analytical_gradient_prediction = True
+    _variant = "ei_cf"
+
+    def __init__(self, model, space, optimizer=None, cost_withGradients=None, utility=None):
+        self.optimizer = optimizer
+        self.utility = utility
+        super(uEI_noiseless, self).__init__(model, space, optimizer, cost_withGradients=cost_withGradients)
+        self.n_attributes = self.model.output_dim
+        self.W_samples = np.random.normal(size=(25, self.n_attributes))        # uEI_noiseless.py:31
+        self.n_hyps_samples = min(10, self.model.number_of_hyps_samples())     # :32
+        self.use_full_support = self.utility.parameter_dist.use_full_support   # :33
+        if self.use_full_support:
+            self.utility_params_samples = self.utility.parameter_dist.support
+            self.utility_prob_dist = np.atleast_1d(self.utility.parameter_dist.prob_dist)
+        else:
+            self.utility_params_samples = self.utility.parameter_dist.sample(10)
+        self._Zt_cache = (None, None)
+
+    def _Zt(self):
+        """Transposed base samples (m, S) on the device; refreshed when W_samples is replaced."""
+        key, Zt = self._Zt_cache
+        W = self.W_samples
+        if key is None or key[0] is not W or key[1] != W.shape:
+            W = np.ascontiguousarray(np.asarray(W, dtype=np.float64))
+            Zt = torch.from_numpy(np.ascontiguousarray(W.T)).to(self.model.device)
+            self._Zt_cache = ((self.W_samples, W.shape), Zt)
+        return Zt
+
+    def _fstar(self, theta):
+        """max_n U(theta_l, mu(X_n)) with the CURRENT hyper-sample (uEI_noiseless.py:66,76; quirk q2), (H_use, L)."""
+        model = self.model
+        fX = model._posterior_mean_at_evaluated_points_dev()                  # (m, n) on device
+        theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        L, p = theta.shape
+        th_h, th_p = _host(theta)
+        n = fX.shape[1]
+        with torch.cuda.device(model.device):
+            U = torch.empty((L, n), dtype=torch.float64, device=model.device)
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(model._lib.bocf_utility_eval(_lib.COMPOSITES[self.utility.composite], model.output_dim,
+                                                    _ptr(fX.contiguous()), n, th_p, L, p, _ptr(U), st))
+            fstar = U.max(dim=1).values.cpu().numpy()
+        H_use = self._n_hyps_effective()
+        return np.tile(fstar[None, :], (H_use, 1))
+
+    def _weights(self, L):
+        if self.use_full_support:
+            return np.asarray(self.utility_prob_dist, dtype=np.float64).reshape(-1)
+        return np.full(L, 1.0 / L)
+
+    def _finish(self):
+        # the reference leaves the model on its last hyper-sample after the h loop
+        self.model.set_hyperparameters(self._n_hyps_effective() - 1)
+
+    def _compute_acq(self, X, parallel=True):
+        # uEI_noiseless.py:40-61 (+ :63-83 / :85-116)
+        theta = np.atleast_2d(self.utility_params_samples)
+        fstar = self._fstar(theta)
+        Zt = self._Zt()
+        out = self._run(self._variant, X, theta, self._weights(len(theta)), fstar, False, Zt, Zt.shape[1])
+        self._finish()
+        return out
+
+    def _compute_acq_withGradients(self, X):
+        # uEI_noiseless.py:118-170
+        if self.use_full_support:
+            theta = self.utility.parameter_dist.support
+        else:
+            theta = self.utility.parameter_dist.sample(1)                     # :126 (quirk q4)
+        theta = np.atleast_2d(theta)
+        fstar = self._fstar(theta)
+        Zt = self._Zt()
+        out = self._run(self._variant, X, theta, self._weights(len(theta)), fstar, True, Zt, Zt.shape[1])
+        self._finish()
+        return out
+
+    def update_Z_samples(self, n_samples=None):
+        # uEI_noiseless.py:172-174
+        self.W_samples = np.random.normal(size=self.W_samples.shape)
+
+
+class uPI(uEI_noiseless):
+    """uPI.py: MC probability of improvement of the composite; value only (uPI.py:19)."""
+    analytical_gradient_prediction = False
+    _variant = "pi_cf"
+
+    def __init__(self, *a, **kw):
+        super(uPI, self).__init__(*a, **kw)
+        self.jitter = 1e-6                 # uPI.py:40; added to f* inside the kernel
+
+    def _compute_acq_withGradients(self, X):
+        raise NotImplementedError("uPI has no analytical gradient (uPI.py:19)")
+
+
+class maEI(AcquisitionBase):
+    """maEI.py: analytic EI of theta^T y, averaged over theta and hyper-samples."""
+    analytical_gradient_prediction = True
+    _variant = "ma_ei"
+    _n_theta_value = 3                     # maEI.py:46
+    _n_theta_grad = 3                      # maEI.py:65
+
+    def __init__(self, model, space, optimizer=None, cost_withGradients=None, utility=None):
+        self.optimizer = optimizer
+        self.utility = utility
+        super(maEI, self).__init__(model, space, optimizer, cost_withGradients=cost_withGradients)
+        self.use_full_support = self.utility.parameter_dist.use_full_support
+        self.n_hyps_samples = min(10, self.model.number_of_hyps_samples())
+
+    def _theta(self, k):
+        if self.use_full_support:
+            self.utility_params_samples = self.utility.parameter_dist.support
+            self.utility_param_dist = np.atleast_1d(self.utility.parameter_dist.prob_dist)
+            w = np.asarray(self.utility_param_dist, dtype=np.float64).reshape(-1)
+        else:
+            self.utility_params_samples = self.utility.parameter_dist.sample(k)
+            w = np.full(len(self.utility_params_samples), 1.0 / len(self.utility_params_samples))
+        return np.atleast_2d(np.asarray(self.utility_params_samples, dtype=np.float64)), w
+
+    def _best(self, theta):
+        """best_l = max_n theta_l^T mu_h(X_n), recomputed per hyper-sample (maEI.py:88,129-136): (H_use, L)."""
+        model = self.model
+        H_use = self._n_hyps_effective()
+        th = torch.from_numpy(theta).to(model.device)
+        best = np.empty((H_use, theta.shape[0]))
+        for h in range(H_use):
+            model.set_hyperparameters(h)
+            mu = model._posterior_mean_at_evaluated_points_dev()             # (m, n)
+            best[h] = (th @ mu).max(dim=1).values.cpu().numpy()
+        return best
+
+    def _compute_acq(self, X):
+        theta, w = self._theta(self._n_theta_value)
+        out = self._run(self._variant, X, theta, w, self._best(theta), False, form=0)
+        return out
+
+    def _compute_acq_withGradients(self, X):
+        theta, w = self._theta(self._n_theta_grad)
+        return self._run(self._variant, X, theta, w, self._best(theta), True, form=1)
+
+
+class maPI(maEI):
+    """maPI.py: analytic PI of theta^T y (jitter 1e-6 on the incumbent, maPI.py:35,151)."""
+    _variant = "ma_pi"
+    _n_theta_value = 10                    # maPI.py:45
+    _n_theta_grad = 3                      # maPI.py:63
+
+    def __init__(self, *a, **kw):
+        super(maPI, self).__init__(*a, **kw)
+        self.jitter = 1e-6
+
+
+class EI(maEI):
+    """EI.py: single-output twin of maEI; n_hyps_samples = 1 (EI.py:36)."""
+
+    def __init__(self, *a, **kw):
+        super(EI, self).__init__(*a, **kw)
+        self.n_hyps_samples = 1
+
+
+class PI(maPI):
+    """PI.py: single-output twin of maPI; n_hyps_samples = 1."""
+
+    def __init__(self, *a, **kw):
+        super(PI, self).__init__(*a, **kw)
+        self.n_hyps_samples = 1

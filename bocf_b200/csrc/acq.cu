@@ -1,0 +1,452 @@
+// acq.cu -- acquisition kernels (north-star subsystem 3, SURVEY K3 / K3' / C1-local).
+//
+// mc_acq_kernel : EI-CF / PI-CF.  One warp per candidate; lanes split the S base samples (coalesced
+//   reads of the transposed Z), h = mu + sigma*Z per output, separable composite U = sum_j phi_j(h_j),
+//   improvement max(U - f*, 0) (or the PI indicator), warp-shuffle reduction over samples, and the
+//   pathwise gradient  sum_s 1[U>f*] dU(h)^T (dmu + (Z/(2 sigma)) * dvar)  folded into per-output
+//   sums A_j = sum_s 1 dphi_j, B_j = sum_s 1 dphi_j Z_sj  (uEI_noiseless.py:71-80,148-166; uPI.py:74-83).
+// ma_acq_kernel : analytic EI / PI of theta^T y (maEI.py:81-126, maPI.py, EI.py, PI.py).
+// topk kernels  : local top-k of the acquisition (anchor_points_generator.py:59-64), deterministic ties.
+#include <math_constants.h>
+
+#include "model.h"
+#include "common.cuh"
+
+namespace bocf {
+
+// ---------------------------------------------------------------------------------------------------
+// separable composites: U(theta, y) = sum_j phi_j(y_j)
+struct CompCtx {
+  double th;     // theta entry relevant for output j (theta_j, or the scalar a for ROSEN)
+  double c;      // EXP_COS coefficient c_j
+  int lower;     // ROSEN: 1 if j < m/2, 0 if m/2 <= j < 2(m/2), -1 if unused
+};
+
+template <int COMP>
+__device__ __forceinline__ CompCtx comp_ctx(const double* __restrict__ theta_l, int j, int m) {
+  CompCtx c;
+  c.th = 0.0;
+  c.c = 0.0;
+  c.lower = 0;
+  if (COMP == BOCF_U_SUMSQ_TARGET || COMP == BOCF_U_LINEAR) c.th = theta_l[j];
+  if (COMP == BOCF_U_EXP_COS) {
+    const double cc[5] = {1., 2., 5., 2., 3.};
+    c.c = cc[j % 5];
+  }
+  if (COMP == BOCF_U_ROSEN_COMPOSITE) {
+    c.th = theta_l[0];
+    const int hh = m / 2;
+    c.lower = (j < hh) ? 1 : ((j < 2 * hh) ? 0 : -1);
+  }
+  return c;
+}
+
+template <int COMP>
+__device__ __forceinline__ double comp_phi(const CompCtx& c, double y) {
+  if (COMP == BOCF_U_SUMSQ_TARGET) {
+    const double a = y - c.th;
+    return -(a * a);
+  } else if (COMP == BOCF_U_NEG_SUM_EXP) {
+    return -exp(y);
+  } else if (COMP == BOCF_U_EXP_COS) {
+    return -(c.c * (exp(-y / CUDART_PI) * cos(CUDART_PI * y)));
+  } else if (COMP == BOCF_U_ROSEN_COMPOSITE) {
+    if (c.lower == 1) {
+      const double a = c.th - y;
+      return -(a * a);
+    }
+    if (c.lower == 0) return -(100.0 * (y * y));
+    return 0.0;
+  } else {
+    return c.th * y;
+  }
+}
+
+template <int COMP>
+__device__ __forceinline__ double comp_dphi(const CompCtx& c, double y) {
+  if (COMP == BOCF_U_SUMSQ_TARGET) {
+    return -2.0 * (y - c.th);
+  } else if (COMP == BOCF_U_NEG_SUM_EXP) {
+    return -exp(y);
+  } else if (COMP == BOCF_U_EXP_COS) {
+    const double e = exp(-y / CUDART_PI);
+    const double aux = -CUDART_PI * (e * sin(CUDART_PI * y)) - (e * cos(CUDART_PI * y)) / CUDART_PI;
+    return -(c.c * aux);
+  } else if (COMP == BOCF_U_ROSEN_COMPOSITE) {
+    if (c.lower == 1) return 2.0 * (c.th - y);
+    if (c.lower == 0) return -200.0 * y;
+    return 0.0;
+  } else {
+    return c.th;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+constexpr int MC_WARPS = 8;
+
+// MODE: 0 = EI value only, 1 = EI value + gradient, 2 = PI value
+template <int COMP, int MODE>
+__global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
+    const double* __restrict__ mean, const double* __restrict__ var, const double* __restrict__ dmean,
+    const double* __restrict__ dvar, int64_t Nc, int64_t Nvalid, int m, int d, const double* __restrict__ Zt, int S,
+    const double* __restrict__ theta, int L, int p, const double* __restrict__ weight,
+    const double* __restrict__ fstar, double scale, int accumulate, double* __restrict__ acq,
+    double* __restrict__ dacq) {
+  __shared__ double s_mu[MC_WARPS][MAXM];
+  __shared__ double s_sig[MC_WARPS][MAXM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * MC_WARPS + warp;
+  if (i >= Nvalid) return;
+  for (int j = lane; j < m; j += 32) {
+    s_mu[warp][j] = mean[(int64_t)j * Nc + i];
+    s_sig[warp][j] = sqrt(var[(int64_t)j * Nc + i]);       // uEI_noiseless.py:74,151
+  }
+  __syncwarp();
+
+  double val_total = 0.0;   // sum_l w_l sum_s improvement
+  double grad_q = 0.0;      // lane q < d
+  for (int l = 0; l < L; ++l) {
+    const double* th = theta + (int64_t)l * p;
+    const double wl = weight[l];
+    const double fs = (MODE == 2) ? fstar[l] + 1e-6 : fstar[l];       // uPI.py:83 jitter
+    double val_l = 0.0;
+    for (int sb = 0; sb < S; sb += 1024) {
+      unsigned mask = 0u;
+#pragma unroll 1
+      for (int k = 0; k < 32; ++k) {
+        const int s = sb + k * 32 + lane;
+        if (s < S) {
+          double U = 0.0;
+          for (int j = 0; j < m; ++j) {
+            const CompCtx c = comp_ctx<COMP>(th, j, m);
+            const double a = s_mu[warp][j] + s_sig[warp][j] * Zt[(int64_t)j * S + s];
+            U += comp_phi<COMP>(c, a);
+          }
+          if (MODE == 2) {
+            val_l += ((U - fs) > 0.0) ? 1.0 : 0.0;
+          } else {
+            val_l += fmax(U - fs, 0.0);                                   // uEI_noiseless.py:80,161
+            if (U > fs) mask |= (1u << k);                                // :162 strict >
+          }
+        }
+      }
+      if (MODE == 1) {
+        if (__any_sync(0xffffffffu, mask != 0u)) {
+          for (int j = 0; j < m; ++j) {
+            const CompCtx c = comp_ctx<COMP>(th, j, m);
+            const double muj = s_mu[warp][j], sgj = s_sig[warp][j];
+            double Aj = 0.0, Bj = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < 32; ++k) {
+              const bool on = (mask >> k) & 1u;
+              if (__ballot_sync(0xffffffffu, on) == 0u) continue;
+              if (on) {
+                const int s = sb + k * 32 + lane;
+                const double z = Zt[(int64_t)j * S + s];
+                const double dp = comp_dphi<COMP>(c, muj + sgj * z);
+                Aj += dp;
+                Bj += dp * z;
+              }
+            }
+            Aj = warp_sum(Aj);
+            Bj = warp_sum(Bj);
+            if (lane < d) {
+              const int64_t o = ((int64_t)j * Nc + i) * d + lane;
+              grad_q += wl * (Aj * dmean[o] + Bj * (0.5 / sgj) * dvar[o]);   // :163-166
+            }
+          }
+        }
+      }
+    }
+    val_total += wl * warp_sum(val_l);
+  }
+  if (lane == 0) {
+    const double v = val_total * scale;
+    acq[i] = accumulate ? acq[i] + v : v;
+  }
+  if (MODE == 1 && lane < d) {
+    const double gq = grad_q * scale;
+    dacq[i * d + lane] = accumulate ? dacq[i * d + lane] + gq : gq;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// analytic EI / PI of the linear scalarisation.  One thread per candidate.
+// PI: 0 = maEI, 1 = maPI.   GRAD: with gradient.  FORM (EI only): 1 = (mu-best)Phi + sigma phi (maEI.py:117-119,
+// norm.cdf/pdf, sigma not clipped), 0 = sigma (u Phi + phi) with sigma clipped inside _get_quantiles (:95-96,147-163).
+template <int PI, int GRAD>
+__global__ void ma_acq_kernel(const double* __restrict__ mean, const double* __restrict__ var,
+                              const double* __restrict__ dmean, const double* __restrict__ dvar, int64_t Nc,
+                              int64_t Nvalid, int m, int d, const double* __restrict__ theta, int L, int p,
+                              const double* __restrict__ weight, const double* __restrict__ best, int form,
+                              double scale, int accumulate, double* __restrict__ acq, double* __restrict__ dacq) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nvalid) return;
+  double val = 0.0;
+  double g[MAXD];
+#pragma unroll
+  for (int q = 0; q < MAXD; ++q) g[q] = 0.0;
+  for (int l = 0; l < L; ++l) {
+    const double* th = theta + (int64_t)l * p;
+    double mu = 0.0, s2 = 0.0;
+    for (int j = 0; j < m; ++j) {
+      const double t = th[j];
+      mu += t * mean[(int64_t)j * Nc + i];
+      s2 += (t * t) * var[(int64_t)j * Nc + i];
+    }
+    const double sigma = sqrt(s2);
+    const double b = best[l] + (PI ? 1e-6 : 0.0);                            // maPI.py:151
+    double phi, Phi, u;
+    if (!PI && form == 1) {
+      u = (mu - b) / sigma;                                                  // maEI.py:117-118 (scipy norm)
+    } else {
+      const double sc = (sigma < 1e-10) ? 1e-10 : sigma;                     // maEI.py:155-160
+      u = (mu - b) / sc;
+    }
+    phi = exp(-0.5 * (u * u)) / sqrt(2.0 * CUDART_PI);
+    Phi = 0.5 * erfc(-u / sqrt(2.0));
+    double v;
+    if (PI) v = Phi;                                                         // maPI.py:92,113
+    else if (form == 1) v = (mu - b) * Phi + sigma * phi;                    // maEI.py:119
+    else v = sigma * (u * Phi + phi);                                        // maEI.py:96
+    const double wl = weight[l];
+    val += wl * v;
+    if (GRAD) {
+#pragma unroll
+      for (int q = 0; q < MAXD; ++q) {
+        if (q < d) {
+          double dmu = 0.0, dsg = 0.0;
+          for (int j = 0; j < m; ++j) {
+            const double t = th[j];
+            const int64_t o = ((int64_t)j * Nc + i) * d + q;
+            dmu += t * dmean[o];
+            dsg += (t * t) * dvar[o];
+          }
+          dsg = 0.5 * dsg / sigma;                                           // maEI.py:121
+          if (PI) g[q] += wl * ((phi / sigma) * (dmu - u * dsg));            // maPI.py:116
+          else g[q] += wl * (dmu * Phi + phi * dsg);                         // maEI.py:122
+        }
+      }
+    }
+  }
+  const double v = val * scale;
+  acq[i] = accumulate ? acq[i] + v : v;
+  if (GRAD) {
+#pragma unroll
+    for (int q = 0; q < MAXD; ++q)
+      if (q < d) {
+        const double gq = g[q] * scale;
+        dacq[i * d + q] = accumulate ? dacq[i * d + q] + gq : gq;
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int COMP>
+__global__ void utility_eval_kernel(int m, const double* __restrict__ Y, int64_t N, const double* __restrict__ theta,
+                                    int L, int p, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = blockIdx.y;
+  if (i >= N) return;
+  const double* th = theta + (int64_t)l * p;
+  double U = 0.0;
+  for (int j = 0; j < m; ++j) {
+    const CompCtx c = comp_ctx<COMP>(th, j, m);
+    U += comp_phi<COMP>(c, Y[(int64_t)j * N + i]);
+  }
+  out[(int64_t)l * N + i] = U;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// top-k (largest value, ties -> smaller index).  key order: a before b  <=>  va > vb || (va == vb && ia < ib)
+__device__ __forceinline__ bool key_before(double va, int64_t ia, double vb, int64_t ib) {
+  return (va > vb) || (va == vb && ia < ib);
+}
+
+constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_MAXK = 64;
+
+// Each block selects the k best of its segment [seg0, seg1) by k rounds of arg-max under the previous pick.
+// vals/idx describe the candidate pool: value = vals[t], index = idx ? idx[t] : t.
+__global__ void __launch_bounds__(TOPK_THREADS) topk_select_kernel(const double* __restrict__ vals,
+                                                                   const int64_t* __restrict__ idx, int64_t N,
+                                                                   int64_t seg, int k, double* __restrict__ out_val,
+                                                                   int64_t* __restrict__ out_idx) {
+  __shared__ double sv[TOPK_THREADS / 32];
+  __shared__ int64_t si[TOPK_THREADS / 32];
+  __shared__ double pv;
+  __shared__ int64_t pi;
+  const int64_t seg0 = (int64_t)blockIdx.x * seg;
+  const int64_t seg1 = min(N, seg0 + seg);
+  double prev_v = CUDART_INF;
+  int64_t prev_i = -1;
+  for (int r = 0; r < k; ++r) {
+    double bv = -CUDART_INF;
+    int64_t bi = INT64_MAX;
+    for (int64_t t = seg0 + threadIdx.x; t < seg1; t += TOPK_THREADS) {
+      double v = vals[t];
+      if (!(v == v)) v = -CUDART_INF;                       // NaN sorts last
+      const int64_t id = idx ? idx[t] : t;
+      if (id < 0) continue;                                 // empty slot
+      // strictly after the previous pick, and better than the running best
+      if (key_before(prev_v, prev_i, v, id) && key_before(v, id, bv, bi)) {
+        bv = v;
+        bi = id;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (key_before(ov, oi, bv, bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if ((threadIdx.x & 31) == 0) {
+      sv[threadIdx.x >> 5] = bv;
+      si[threadIdx.x >> 5] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double fv = sv[0];
+      int64_t fi = si[0];
+      for (int w = 1; w < TOPK_THREADS / 32; ++w)
+        if (key_before(sv[w], si[w], fv, fi)) {
+          fv = sv[w];
+          fi = si[w];
+        }
+      pv = fv;
+      pi = fi;
+      out_val[(int64_t)blockIdx.x * k + r] = fv;
+      out_idx[(int64_t)blockIdx.x * k + r] = (fi == INT64_MAX) ? -1 : fi;
+    }
+    __syncthreads();
+    prev_v = pv;
+    prev_i = pi;
+    if (prev_i == INT64_MAX) {   // pool exhausted: fill the rest with empties
+      for (int rr = r + 1 + threadIdx.x; rr < k; rr += TOPK_THREADS) {
+        out_val[(int64_t)blockIdx.x * k + rr] = -CUDART_INF;
+        out_idx[(int64_t)blockIdx.x * k + rr] = -1;
+      }
+      break;
+    }
+    __syncthreads();
+  }
+}
+
+// record = (value, global index as double, x_0 .. x_{d-1})
+__global__ void topk_gather_kernel(const double* __restrict__ val, const int64_t* __restrict__ idx,
+                                   const double* __restrict__ Xc, int d, int k, int64_t index_offset,
+                                   double* __restrict__ out_rec) {
+  const int r = blockIdx.x;
+  if (r >= k) return;
+  const int64_t id = idx[r];
+  double* rec = out_rec + (int64_t)r * (2 + d);
+  if (threadIdx.x == 0) {
+    rec[0] = (id >= 0) ? val[r] : -CUDART_INF;
+    rec[1] = (id >= 0) ? (double)(id + index_offset) : -1.0;
+  }
+  for (int q = threadIdx.x; q < d; q += blockDim.x) rec[2 + q] = (id >= 0) ? Xc[id * d + q] : 0.0;
+}
+
+// ===================================================================================================
+template <int COMP>
+static int launch_mc_t(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvalid, double* acq, double* dacq,
+                       cudaStream_t st) {
+  const unsigned grid = (unsigned)ceil_div(Nvalid, MC_WARPS);
+  const int mode = (P.variant == BOCF_ACQ_PI_CF) ? 2 : (dacq ? 1 : 0);
+#define BOCF_MC_ARGS                                                                                              \
+  cb.mean, cb.var, cb.dmean, cb.dvar, cb.Nc, Nvalid, P.m, P.d, P.Zt, P.S, P.theta, P.L, P.p, P.weight, P.fstar, \
+      P.scale, P.accumulate, acq, dacq
+  if (mode == 0) mc_acq_kernel<COMP, 0><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
+  else if (mode == 1) mc_acq_kernel<COMP, 1><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
+  else mc_acq_kernel<COMP, 2><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
+#undef BOCF_MC_ARGS
+  BOCF_LAUNCH_OK("mc_acq_kernel");
+  return 0;
+}
+
+int launch_acq_chunk(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvalid, double* acq, double* dacq,
+                     cudaStream_t st) {
+  if (Nvalid <= 0) return 0;
+  if (P.variant == BOCF_ACQ_EI_CF || P.variant == BOCF_ACQ_PI_CF) {
+    if (P.m > MAXM) {
+      set_error("mc acquisition: m exceeds MAXM");
+      return -5;
+    }
+    switch (P.composite) {
+      case BOCF_U_SUMSQ_TARGET: return launch_mc_t<BOCF_U_SUMSQ_TARGET>(P, cb, Nvalid, acq, dacq, st);
+      case BOCF_U_NEG_SUM_EXP: return launch_mc_t<BOCF_U_NEG_SUM_EXP>(P, cb, Nvalid, acq, dacq, st);
+      case BOCF_U_EXP_COS: return launch_mc_t<BOCF_U_EXP_COS>(P, cb, Nvalid, acq, dacq, st);
+      case BOCF_U_ROSEN_COMPOSITE: return launch_mc_t<BOCF_U_ROSEN_COMPOSITE>(P, cb, Nvalid, acq, dacq, st);
+      case BOCF_U_LINEAR: return launch_mc_t<BOCF_U_LINEAR>(P, cb, Nvalid, acq, dacq, st);
+      default: set_error("unknown composite"); return -1;
+    }
+  }
+  const unsigned grid = (unsigned)ceil_div(Nvalid, 128);
+  const int pi = (P.variant == BOCF_ACQ_MA_PI) ? 1 : 0;
+#define BOCF_MA_ARGS                                                                                         \
+  cb.mean, cb.var, cb.dmean, cb.dvar, cb.Nc, Nvalid, P.m, P.d, P.theta, P.L, P.p, P.weight, P.fstar,        \
+      P.with_grad_formula, P.scale, P.accumulate, acq, dacq
+  if (pi) {
+    if (dacq) ma_acq_kernel<1, 1><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
+    else ma_acq_kernel<1, 0><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
+  } else {
+    if (dacq) ma_acq_kernel<0, 1><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
+    else ma_acq_kernel<0, 0><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
+  }
+#undef BOCF_MA_ARGS
+  BOCF_LAUNCH_OK("ma_acq_kernel");
+  return 0;
+}
+
+int launch_utility_eval(int composite, int m, const double* Y, int64_t N, const double* theta, int L, int p,
+                        double* out, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(N, 256), (unsigned)L);
+  switch (composite) {
+    case BOCF_U_SUMSQ_TARGET: utility_eval_kernel<BOCF_U_SUMSQ_TARGET><<<grid, 256, 0, st>>>(m, Y, N, theta, L, p, out); break;
+    case BOCF_U_NEG_SUM_EXP: utility_eval_kernel<BOCF_U_NEG_SUM_EXP><<<grid, 256, 0, st>>>(m, Y, N, theta, L, p, out); break;
+    case BOCF_U_EXP_COS: utility_eval_kernel<BOCF_U_EXP_COS><<<grid, 256, 0, st>>>(m, Y, N, theta, L, p, out); break;
+    case BOCF_U_ROSEN_COMPOSITE: utility_eval_kernel<BOCF_U_ROSEN_COMPOSITE><<<grid, 256, 0, st>>>(m, Y, N, theta, L, p, out); break;
+    case BOCF_U_LINEAR: utility_eval_kernel<BOCF_U_LINEAR><<<grid, 256, 0, st>>>(m, Y, N, theta, L, p, out); break;
+    default: set_error("unknown composite"); return -1;
+  }
+  BOCF_LAUNCH_OK("utility_eval_kernel");
+  return 0;
+}
+
+static int64_t topk_blocks(int64_t N) {
+  int64_t b = ceil_div(N, 8192);
+  if (b > 1024) b = 1024;
+  if (b < 1) b = 1;
+  return b;
+}
+
+uint64_t topk_workspace_bytes(int64_t N, int k) {
+  const int64_t B = topk_blocks(N);
+  return (uint64_t)((B + 1) * k) * (sizeof(double) + sizeof(int64_t)) + 256;
+}
+
+int launch_topk(const double* acq, const double* Xc, int64_t N, int d, int k, int64_t index_offset, double* out_rec,
+                void* workspace, cudaStream_t st) {
+  if (k < 1 || k > TOPK_MAXK) {
+    set_error("topk: k out of range");
+    return -1;
+  }
+  const int64_t B = topk_blocks(N);
+  const int64_t seg = ceil_div(N, B);
+  double* v1 = reinterpret_cast<double*>(workspace);
+  double* v2 = v1 + B * k;
+  int64_t* i1 = reinterpret_cast<int64_t*>(v2 + k);
+  int64_t* i2 = i1 + B * k;
+  topk_select_kernel<<<(unsigned)B, TOPK_THREADS, 0, st>>>(acq, nullptr, N, seg, k, v1, i1);
+  BOCF_LAUNCH_OK("topk_select_kernel");
+  topk_select_kernel<<<1, TOPK_THREADS, 0, st>>>(v1, i1, B * k, B * k, k, v2, i2);
+  BOCF_LAUNCH_OK("topk_select_kernel");
+  topk_gather_kernel<<<k, 32, 0, st>>>(v2, i2, Xc, d, k, index_offset, out_rec);
+  BOCF_LAUNCH_OK("topk_gather_kernel");
+  return 0;
+}
+
+}  // namespace bocf

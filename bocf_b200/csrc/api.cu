@@ -1,0 +1,477 @@
+// api.cu -- the C ABI of libbocf_b200 (include/bocf_b200.h): handle management, the jitchol retry
+// loop, candidate chunking and the fused sweep  posterior -> acquisition  over all hyper-samples.
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "model.h"
+
+namespace bocf {
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) return 0;
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  return 0;
+}
+template <typename T>
+static void dev_free(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+static void free_data(bocf_model* M) {
+  dev_free(M->X);
+  dev_free(M->Y);
+  dev_free(M->yc);
+  dev_free(M->ybar);
+}
+static void free_factor(bocf_model* M) {
+  dev_free(M->Xs);
+  dev_free(M->xsq);
+  dev_free(M->Lmat);
+  dev_free(M->Linv);
+  dev_free(M->Dinv);
+  dev_free(M->alpha);
+  dev_free(M->tvec);
+  dev_free(M->info);
+  M->factorized = false;
+}
+
+static int ensure_scratch(bocf_model* M, uint64_t bytes) {
+  if (M->scratch_bytes >= bytes) return 0;
+  if (M->scratch) cudaFree(M->scratch);
+  M->scratch = nullptr;
+  M->scratch_bytes = 0;
+  BOCF_CUDA_OK(cudaMalloc(&M->scratch, bytes));
+  M->scratch_bytes = bytes;
+  return 0;
+}
+
+// Choose the candidate chunk (multiple of 128) so the per-chunk scratch fits the handle's limit.
+static int64_t pick_chunk(const bocf_model* M, int64_t N, bool grad, uint64_t extra_per_cand) {
+  const uint64_t per = chunk_bytes_per_candidate(M, grad) + extra_per_cand;
+  int64_t nc = (int64_t)(M->scratch_limit / per);
+  nc = nc / TILE * TILE;
+  if (nc < TILE) nc = TILE;
+  const int64_t need = round_up(N, TILE);
+  if (nc > need) nc = need;
+  if (nc > (1 << 17)) nc = 1 << 17;
+  return nc;
+}
+
+static int check_ready(const bocf_model* M) {
+  if (!M) {
+    set_error("null model handle");
+    return BOCF_ERR_INVALID;
+  }
+  if (!M->factorized) {
+    set_error("model not factorized: call bocf_model_set_data, bocf_model_set_hypers, bocf_model_factorize first");
+    return BOCF_ERR_INVALID;
+  }
+  return 0;
+}
+}  // namespace bocf
+
+using namespace bocf;
+
+extern "C" {
+
+const char* bocf_last_error(void) { return g_err.c_str(); }
+const char* bocf_version(void) { return "bocf_b200 0.1 sm_100a fp64-dmma"; }
+uint64_t bocf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int bocf_model_create(bocf_model** out, int m, int d, int kernel, int device) {
+  if (!out || m < 1 || d < 1 || d > MAXD || kernel < 0 || kernel > BOCF_KERN_MATERN32) {
+    set_error("bocf_model_create: invalid arguments (need m >= 1, 1 <= d <= 16, known kernel)");
+    return BOCF_ERR_INVALID;
+  }
+  int ndev = 0;
+  BOCF_CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) {
+    set_error("bocf_model_create: no such CUDA device");
+    return BOCF_ERR_INVALID;
+  }
+  bocf_model* M = new (std::nothrow) bocf_model();
+  if (!M) {
+    set_error("out of host memory");
+    return BOCF_ERR_INVALID;
+  }
+  M->m = m;
+  M->d = d;
+  M->kernel = kernel;
+  M->device = device;
+  *out = M;
+  return 0;
+}
+
+int bocf_model_destroy(bocf_model* M) {
+  if (!M) return 0;
+  DeviceGuard dg(M->device);
+  free_data(M);
+  free_factor(M);
+  dev_free(M->hyp);
+  if (M->scratch) cudaFree(M->scratch);
+  delete M;
+  return 0;
+}
+
+int bocf_model_n(const bocf_model* M) { return M ? M->n : -1; }
+int bocf_model_H(const bocf_model* M) { return M ? M->H : -1; }
+
+int bocf_model_set_scratch_limit(bocf_model* M, uint64_t bytes) {
+  if (!M || bytes < (64ull << 20)) {
+    set_error("scratch limit must be at least 64 MiB");
+    return BOCF_ERR_INVALID;
+  }
+  M->scratch_limit = bytes;
+  return 0;
+}
+
+int bocf_model_set_data(bocf_model* M, int n, const double* X, const double* Y, void* stream) {
+  if (!M || n < 1 || !X || !Y) {
+    set_error("bocf_model_set_data: invalid arguments");
+    return BOCF_ERR_INVALID;
+  }
+  DeviceGuard dg(M->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n != M->n) {
+    free_data(M);
+    free_factor(M);
+    M->n = n;
+    M->n_pad = (int)round_up(n, TILE);
+    M->n16 = (int)round_up(n, 16);
+    M->nb = M->n_pad / TILE;
+    if (int rc = dev_alloc(&M->X, (size_t)n * M->d)) return rc;
+    if (int rc = dev_alloc(&M->Y, (size_t)n * M->m)) return rc;
+    if (int rc = dev_alloc(&M->yc, (size_t)M->n_pad * M->m)) return rc;
+    if (int rc = dev_alloc(&M->ybar, (size_t)M->m)) return rc;
+  }
+  BOCF_CUDA_OK(cudaMemcpyAsync(M->X, X, sizeof(double) * n * M->d, cudaMemcpyDeviceToDevice, st));
+  BOCF_CUDA_OK(cudaMemcpyAsync(M->Y, Y, sizeof(double) * n * M->m, cudaMemcpyDeviceToDevice, st));
+  M->has_data = true;
+  M->factorized = false;
+  return 0;
+}
+
+int bocf_model_set_hypers(bocf_model* M, int H, const double* variance, const double* lengthscale,
+                          const double* noise) {
+  if (!M || H < 1 || !variance || !lengthscale || !noise) {
+    set_error("bocf_model_set_hypers: invalid arguments");
+    return BOCF_ERR_INVALID;
+  }
+  DeviceGuard dg(M->device);
+  const int Hm = H * M->m;
+  std::vector<OutHyp> hv(Hm);
+  for (int hj = 0; hj < Hm; ++hj) {
+    OutHyp& o = hv[hj];
+    std::memset(&o, 0, sizeof(o));
+    o.variance = variance[hj];
+    o.noise = noise[hj];
+    for (int q = 0; q < MAXD; ++q) o.ls[q] = 1.0;
+    for (int q = 0; q < M->d; ++q) o.ls[q] = lengthscale[(size_t)hj * M->d + q];
+    if (!(o.variance > 0.0) || !(o.noise >= 0.0)) {
+      set_error("bocf_model_set_hypers: variance must be > 0 and noise >= 0");
+      return BOCF_ERR_INVALID;
+    }
+    for (int q = 0; q < M->d; ++q)
+      if (!(o.ls[q] > 0.0)) {
+        set_error("bocf_model_set_hypers: lengthscales must be > 0");
+        return BOCF_ERR_INVALID;
+      }
+  }
+  if (H != M->H) {
+    free_factor(M);
+    dev_free(M->hyp);
+    M->H = H;
+    if (int rc = dev_alloc(&M->hyp, (size_t)Hm)) return rc;
+  }
+  M->hyp_host = hv;
+  M->has_hyp = true;
+  M->factorized = false;
+  return 0;
+}
+
+int bocf_model_factorize(bocf_model* M, double* jitter_out, void* stream) {
+  if (!M || !M->has_data || !M->has_hyp) {
+    set_error("bocf_model_factorize: set data and hyper-parameters first");
+    return BOCF_ERR_INVALID;
+  }
+  DeviceGuard dg(M->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Hm = M->H * M->m;
+  const size_t nn = (size_t)M->n_pad * M->n_pad;
+  if (!M->Lmat) {
+    if (int rc = dev_alloc(&M->Xs, (size_t)Hm * M->n_pad * M->d)) return rc;
+    if (int rc = dev_alloc(&M->xsq, (size_t)Hm * M->n_pad)) return rc;
+    if (int rc = dev_alloc(&M->Lmat, (size_t)Hm * nn)) return rc;
+    if (int rc = dev_alloc(&M->Linv, (size_t)Hm * nn)) return rc;
+    if (int rc = dev_alloc(&M->Dinv, (size_t)Hm * M->nb * TILE * TILE)) return rc;
+    if (int rc = dev_alloc(&M->alpha, (size_t)Hm * M->n_pad)) return rc;
+    if (int rc = dev_alloc(&M->tvec, (size_t)Hm * M->n_pad)) return rc;
+    if (int rc = dev_alloc(&M->info, (size_t)Hm)) return rc;
+  }
+  for (auto& o : M->hyp_host) o.jitter = 0.0;
+  std::vector<int> info(Hm, 0);
+  std::vector<int> tries(Hm, 0);
+  // jitchol (GPy/util/linalg.py:52-83): plain dpotrf first; on failure jitter = mean(diag) * 1e-6, then up to
+  // maxtries = 5 attempts, jitter *= 10 after each failure.
+  for (int attempt = 0; attempt <= 5; ++attempt) {
+    BOCF_CUDA_OK(cudaMemcpyAsync(M->hyp, M->hyp_host.data(), sizeof(OutHyp) * Hm, cudaMemcpyHostToDevice, st));
+    if (int rc = launch_prepare(M, st)) return rc;
+    if (int rc = launch_gram(M, st)) return rc;
+    if (int rc = launch_cholesky(M, st)) return rc;
+    BOCF_CUDA_OK(cudaMemcpyAsync(info.data(), M->info, sizeof(int) * Hm, cudaMemcpyDeviceToHost, st));
+    BOCF_CUDA_OK(cudaStreamSynchronize(st));
+    bool any_fail = false;
+    for (int hj = 0; hj < Hm; ++hj) {
+      if (info[hj] == 0) continue;
+      any_fail = true;
+      OutHyp& o = M->hyp_host[hj];
+      const double diag_mean = o.variance + o.noise + 1e-8;     // every diagonal entry of Ky is equal
+      if (diag_mean <= 0.0) {
+        set_error("not pd: non-positive diagonal elements");
+        return BOCF_ERR_NONPOS_DIAG;
+      }
+      o.jitter = (tries[hj] == 0) ? diag_mean * 1e-6 : o.jitter * 10.0;
+      tries[hj] += 1;
+      if (tries[hj] > 5 || !std::isfinite(o.jitter)) {
+        set_error("not positive definite, even with jitter.");
+        return BOCF_ERR_NOT_PD;
+      }
+    }
+    if (!any_fail) break;
+  }
+  if (int rc = launch_inverse_and_alpha(M, st)) return rc;
+  BOCF_CUDA_OK(cudaStreamSynchronize(st));
+  if (jitter_out)
+    for (int hj = 0; hj < Hm; ++hj) jitter_out[hj] = M->hyp_host[hj].jitter;
+  M->factorized = true;
+  return 0;
+}
+
+int bocf_model_get_factor(bocf_model* M, int h, int j, double* L, double* Linv, double* alpha, void* stream) {
+  if (int rc = check_ready(M)) return rc;
+  if (h < 0 || h >= M->H || j < 0 || j >= M->m) {
+    set_error("bocf_model_get_factor: index out of range");
+    return BOCF_ERR_INVALID;
+  }
+  DeviceGuard dg(M->device);
+  return launch_copy_factor(M, h * M->m + j, L, Linv, alpha, static_cast<cudaStream_t>(stream));
+}
+
+// gather chunk-local (m x Nc [x d]) results into the caller's (m x N [x d]) arrays
+static int scatter_out(const double* src, int64_t Nc, double* dst, int64_t N, int64_t off, int64_t cnt, int m,
+                       int inner, cudaStream_t st) {
+  if (!dst) return 0;
+  BOCF_CUDA_OK(cudaMemcpy2DAsync(dst + off * inner, sizeof(double) * N * inner, src, sizeof(double) * Nc * inner,
+                                 sizeof(double) * cnt * inner, m, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int bocf_posterior(bocf_model* M, int h, const double* Xc, int64_t N, int noiseless, double* mean, double* var,
+                   double* dmean, double* dvar, void* stream) {
+  if (int rc = check_ready(M)) return rc;
+  if (h < 0 || h >= M->H || !Xc || N < 0) {
+    set_error("bocf_posterior: invalid arguments");
+    return BOCF_ERR_INVALID;
+  }
+  if (N == 0) return 0;
+  DeviceGuard dg(M->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool grad = (dvar != nullptr) || (dmean != nullptr);
+  const int64_t Nc = pick_chunk(M, N, grad, 0);
+  if (int rc = ensure_scratch(M, chunk_bytes_per_candidate(M, grad) * Nc + (1 << 16))) return rc;
+  ChunkBuffers cb;
+  carve_chunk(M, M->scratch, Nc, grad, &cb);
+  for (int64_t off = 0; off < N; off += Nc) {
+    const int64_t cnt = (N - off < Nc) ? N - off : Nc;
+    if (int rc = launch_posterior_chunk(M, h, Xc + off * M->d, cnt, grad, noiseless != 0, cb, st, var != nullptr,
+                                        dvar != nullptr))
+      return rc;
+    if (int rc = scatter_out(cb.mean, Nc, mean, N, off, cnt, M->m, 1, st)) return rc;
+    if (var)
+      if (int rc = scatter_out(cb.var, Nc, var, N, off, cnt, M->m, 1, st)) return rc;
+    if (dmean)
+      if (int rc = scatter_out(cb.dmean, Nc, dmean, N, off, cnt, M->m, M->d, st)) return rc;
+    if (dvar)
+      if (int rc = scatter_out(cb.dvar, Nc, dvar, N, off, cnt, M->m, M->d, st)) return rc;
+  }
+  return 0;
+}
+
+int bocf_acq_eval(bocf_model* M, int variant, int composite, const double* Xc, int64_t N, const double* Zt, int S,
+                  const double* theta, int L, int p, const double* weight, const double* fstar, int H_use,
+                  int with_grad_formula, double* acq, double* dacq, void* stream) {
+  if (int rc = check_ready(M)) return rc;
+  const bool mc = (variant == BOCF_ACQ_EI_CF || variant == BOCF_ACQ_PI_CF);
+  if (!Xc || N < 0 || !acq || L < 1 || !weight || !fstar || H_use < 1 || H_use > M->H || variant < 0 ||
+      variant > BOCF_ACQ_MA_PI || (mc && (!Zt || S < 1)) || (p > 0 && !theta)) {
+    set_error("bocf_acq_eval: invalid arguments");
+    return BOCF_ERR_INVALID;
+  }
+  if (variant == BOCF_ACQ_PI_CF && dacq) {
+    set_error("uPI has no analytical gradient (uPI.py:19 analytical_gradient_prediction = False)");
+    return BOCF_ERR_UNSUPPORTED;
+  }
+  if (!mc && p != M->m) {
+    set_error("maEI/maPI need theta of length m (linear scalarisation)");
+    return BOCF_ERR_INVALID;
+  }
+  if (mc) {
+    const int need_p = (composite == BOCF_U_SUMSQ_TARGET || composite == BOCF_U_LINEAR) ? M->m
+                       : (composite == BOCF_U_ROSEN_COMPOSITE ? 1 : 0);
+    if (p < need_p) {
+      set_error("bocf_acq_eval: theta has too few entries for this composite");
+      return BOCF_ERR_INVALID;
+    }
+  }
+  if (N == 0) return 0;
+  DeviceGuard dg(M->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool grad = (dacq != nullptr);
+
+  // small host-side parameters -> tail of the scratch buffer
+  const size_t n_theta = (size_t)L * (p > 0 ? p : 1);
+  const size_t par_doubles = n_theta + (size_t)L + (size_t)H_use * L;
+  const int64_t Nc = pick_chunk(M, N, grad, 0);
+  const uint64_t chunk_bytes = chunk_bytes_per_candidate(M, grad) * Nc + (1 << 16);
+  if (int rc = ensure_scratch(M, chunk_bytes + par_doubles * sizeof(double) + 256)) return rc;
+  ChunkBuffers cb;
+  carve_chunk(M, M->scratch, Nc, grad, &cb);
+  double* par = reinterpret_cast<double*>(reinterpret_cast<char*>(M->scratch) + (chunk_bytes / 256 + 1) * 256);
+  std::vector<double> hostpar(par_doubles, 0.0);
+  if (p > 0) std::memcpy(hostpar.data(), theta, sizeof(double) * L * p);
+  std::memcpy(hostpar.data() + n_theta, weight, sizeof(double) * L);
+  std::memcpy(hostpar.data() + n_theta + L, fstar, sizeof(double) * H_use * L);
+  BOCF_CUDA_OK(cudaMemcpyAsync(par, hostpar.data(), sizeof(double) * par_doubles, cudaMemcpyHostToDevice, st));
+  BOCF_CUDA_OK(cudaStreamSynchronize(st));   // hostpar is pageable and goes out of scope
+
+  AcqParams P;
+  P.variant = variant;
+  P.composite = composite;
+  P.m = M->m;
+  P.d = M->d;
+  P.S = S;
+  P.L = L;
+  P.p = p;
+  P.with_grad_formula = with_grad_formula;
+  P.Zt = Zt;
+  P.theta = par;
+  P.weight = par + n_theta;
+  P.scale = mc ? 1.0 / ((double)H_use * (double)S) : 1.0 / (double)H_use;
+
+  for (int64_t off = 0; off < N; off += Nc) {
+    const int64_t cnt = (N - off < Nc) ? N - off : Nc;
+    for (int h = 0; h < H_use; ++h) {
+      if (int rc = launch_posterior_chunk(M, h, Xc + off * M->d, cnt, grad, false, cb, st)) return rc;
+      P.fstar = par + n_theta + L + (size_t)h * L;
+      P.accumulate = (h > 0) ? 1 : 0;
+      if (int rc = launch_acq_chunk(P, cb, cnt, acq + off, grad ? dacq + off * M->d : nullptr, st)) return rc;
+    }
+  }
+  return 0;
+}
+
+int bocf_acq_eval_host(bocf_model* M, int variant, int composite, const double* Xc_host, int64_t N,
+                       const double* Zt_dev, int S, const double* theta, int L, int p, const double* weight,
+                       const double* fstar, int H_use, int with_grad_formula, double* acq_host, double* dacq_host,
+                       void* stream) {
+  if (int rc = check_ready(M)) return rc;
+  if (!Xc_host || !acq_host || N < 0) {
+    set_error("bocf_acq_eval_host: invalid arguments");
+    return BOCF_ERR_INVALID;
+  }
+  if (N == 0) return 0;
+  DeviceGuard dg(M->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double *dX = nullptr, *dA = nullptr, *dG = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = dev_alloc(&dX, (size_t)N * M->d))) break;
+    if ((rc = dev_alloc(&dA, (size_t)N))) break;
+    if (dacq_host && (rc = dev_alloc(&dG, (size_t)N * M->d))) break;
+    if (cudaMemcpyAsync(dX, Xc_host, sizeof(double) * N * M->d, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      set_error("H2D copy of candidates failed");
+      rc = BOCF_ERR_CUDA;
+      break;
+    }
+    if ((rc = bocf_acq_eval(M, variant, composite, dX, N, Zt_dev, S, theta, L, p, weight, fstar, H_use,
+                            with_grad_formula, dA, dG, stream)))
+      break;
+    if (cudaMemcpyAsync(acq_host, dA, sizeof(double) * N, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        (dG && cudaMemcpyAsync(dacq_host, dG, sizeof(double) * N * M->d, cudaMemcpyDeviceToHost, st) != cudaSuccess) ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      set_error("D2H copy of results failed");
+      rc = BOCF_ERR_CUDA;
+      break;
+    }
+  } while (0);
+  dev_free(dX);
+  dev_free(dA);
+  dev_free(dG);
+  return rc;
+}
+
+int bocf_utility_eval(int composite, int m, const double* Y, int64_t N, const double* theta, int L, int p,
+                      double* out, void* stream) {
+  if (!Y || !out || N < 0 || L < 1 || m < 1 || (p > 0 && !theta)) {
+    set_error("bocf_utility_eval: invalid arguments");
+    return BOCF_ERR_INVALID;
+  }
+  if (N == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* dth = nullptr;
+  const size_t n_theta = (size_t)L * (p > 0 ? p : 1);
+  if (int rc = dev_alloc(&dth, n_theta)) return rc;
+  int rc = 0;
+  if (p > 0 && cudaMemcpyAsync(dth, theta, sizeof(double) * L * p, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    set_error("H2D copy of theta failed");
+    rc = BOCF_ERR_CUDA;
+  }
+  if (!rc) rc = launch_utility_eval(composite, m, Y, N, dth, L, p, out, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess && !rc) {
+    set_error("bocf_utility_eval: stream sync failed");
+    rc = BOCF_ERR_CUDA;
+  }
+  dev_free(dth);
+  return rc;
+}
+
+int bocf_topk(const double* acq, const double* Xc, int64_t N, int d, int k, int64_t index_offset, double* out_rec,
+              void* stream) {
+  if (!acq || !Xc || !out_rec || N < 1 || d < 1 || k < 1) {
+    set_error("bocf_topk: invalid arguments");
+    return BOCF_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* ws = nullptr;
+  BOCF_CUDA_OK(cudaMallocAsync(&ws, topk_workspace_bytes(N, k), st));
+  int rc = launch_topk(acq, Xc, N, d, k, index_offset, out_rec, ws, st);
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
+}  // extern "C"

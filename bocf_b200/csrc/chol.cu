@@ -1,0 +1,399 @@
+// chol.cu -- per-iteration model factorisation on device, fp64 (north-star subsystem 4).
+//
+// For every (hyper-sample h, output j):   Ky = K(X,X) + (sigma_n^2 + 1e-8 [+ jitter]) I
+//   L = chol(Ky) (lower)          exact_gaussian_inference.py:43-49 -> linalg.py:52-83 (jitchol)
+//   Linv = L^-1                   used by the candidate sweep instead of LAPACK dtrtrs (posterior.py:312)
+//   alpha = Ky^-1 (y - ybar)      exact_gaussian_inference.py:51 (dpotrs)
+// Blocked right-looking Cholesky with 128 x 128 blocks: the diagonal block is factorised and
+// inverted by one CTA in shared memory, the panel solve and the trailing SYRK run on the DMMA
+// tile engine (gemm_f64.cuh) batched over all H*m matrices.  L^-1 is then built block-row by
+// block-row with the same engine.
+#include "gemm_f64.cuh"
+#include "kernfn.cuh"
+#include "model.h"
+
+namespace bocf {
+
+// ---------------------------------------------------------------------------------------------------
+// ybar / centred observations (GPy/util/normalizer.py:57-66: mean only, std == 1)
+__global__ void ybar_kernel(const double* __restrict__ Y, int n, int n_pad, int m, int H, double* __restrict__ ybar,
+                            double* __restrict__ yc, OutHyp* __restrict__ hyp) {
+  __shared__ double red[32];
+  __shared__ double mean_s;
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (int b = threadIdx.x; b < n; b += blockDim.x) s += Y[(int64_t)j * n + b];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    mean_s = tot / (double)n;
+    ybar[j] = mean_s;
+    for (int h = 0; h < H; ++h) hyp[h * m + j].ybar = mean_s;
+  }
+  __syncthreads();
+  const double mu = mean_s;
+  for (int b = threadIdx.x; b < n_pad; b += blockDim.x)
+    yc[(int64_t)j * n_pad + b] = (b < n) ? (Y[(int64_t)j * n + b] - mu) / 1.0 : 0.0;
+}
+
+// Xs = X / lengthscale (stationary.py:161-164, se.py:86-89), xsq = sum_q Xs^2 (stationary.py:141-142)
+__global__ void scale_inputs_kernel(const double* __restrict__ X, int n, int n_pad, int d,
+                                    const OutHyp* __restrict__ hyp, double* __restrict__ Xs,
+                                    double* __restrict__ xsq) {
+  const int hj = blockIdx.y;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_pad) return;
+  const OutHyp& hp = hyp[hj];
+  double s = 0.0;
+  for (int q = 0; q < d; ++q) {
+    double v = (b < n) ? X[(int64_t)b * d + q] / hp.ls[q] : 0.0;
+    Xs[((int64_t)hj * n_pad + b) * d + q] = v;
+    s += v * v;
+  }
+  xsq[(int64_t)hj * n_pad + b] = s;
+}
+
+// Training Gram matrix + diagonal term (exact_gaussian_inference.py:43-47).
+// Stationary kinds: r^2 = -2 Xs Xs^T + (xsq_a + xsq_b), diagonal forced to 0, clipped (stationary.py:134-139).
+// SE: exact squared differences, diagonal = variance (se.py:56-58).
+template <int KIND>
+__global__ void gram_kernel(const double* __restrict__ Xs, const double* __restrict__ xsq,
+                            const OutHyp* __restrict__ hyp, int n, int n_pad, int d, double* __restrict__ A) {
+  const int hj = blockIdx.z;
+  const int a = blockIdx.y * 16 + threadIdx.y;
+  const int b = blockIdx.x * 16 + threadIdx.x;
+  __shared__ double sa[16][MAXD + 1], sb[16][MAXD + 1];
+  const double* Xh = Xs + (int64_t)hj * n_pad * d;
+  for (int q = threadIdx.x; q < d; q += 16) sa[threadIdx.y][q] = Xh[(int64_t)a * d + q];
+  for (int q = threadIdx.y; q < d; q += 16) sb[threadIdx.x][q] = Xh[(int64_t)b * d + q];
+  __syncthreads();
+  const OutHyp& hp = hyp[hj];
+  double val = 0.0;
+  if (a < n && b < n) {
+    double r2;
+    if (KIND == BOCF_KERN_SE) {
+      r2 = 0.0;
+      for (int q = 0; q < d; ++q) {
+        double df = sa[threadIdx.y][q] - sb[threadIdx.x][q];
+        r2 += df * df;
+      }
+      if (a == b) r2 = 0.0;
+    } else {
+      double dot = 0.0;
+      for (int q = 0; q < d; ++q) dot += sa[threadIdx.y][q] * sb[threadIdx.x][q];
+      r2 = -2.0 * dot + (xsq[(int64_t)hj * n_pad + a] + xsq[(int64_t)hj * n_pad + b]);
+      if (a == b) r2 = 0.0;
+      r2 = fmax(r2, 0.0);
+    }
+    double k, gdummy;
+    kern_eval<KIND, false>(r2, hp.variance, k, gdummy);
+    if (a == b) k += hp.noise + 1e-8 + hp.jitter;
+    val = k;
+  }
+  A[((int64_t)hj * n_pad + a) * n_pad + b] = val;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Diagonal block: unblocked Cholesky + in-place triangular inverse in shared memory (one CTA / matrix).
+constexpr int DLD = TILE + 1;
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lmat, double* __restrict__ Dinv,
+                                                         int* __restrict__ info, int n, int n_pad, int nb, int kb) {
+  extern __shared__ double T[];   // TILE x DLD
+  const int hj = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int k0 = kb * TILE;
+  const int nrem = min(TILE, n - k0);
+  double* Ablk = Lmat + (int64_t)hj * n_pad * n_pad + (int64_t)k0 * n_pad + k0;
+  for (int idx = tid; idx < TILE * TILE; idx += 256) {
+    int r = idx >> 7, c = idx & 127;
+    double v = (r < nrem && c < nrem) ? Ablk[(int64_t)r * n_pad + c] : (r == c ? 1.0 : 0.0);
+    T[r * DLD + c] = v;
+  }
+  __syncthreads();
+  for (int c = 0; c < TILE; ++c) {
+    double piv = T[c * DLD + c];
+    if (!(piv > 0.0)) {                       // dpotrf info != 0  -> jitchol retry on the host side
+      if (tid == 0 && info[hj] == 0) info[hj] = k0 + c + 1;
+      piv = 1.0;
+    }
+    const double s = sqrt(piv);
+    __syncthreads();
+    if (tid == 0) T[c * DLD + c] = s;
+    for (int r = c + 1 + tid; r < TILE; r += 256) T[r * DLD + c] /= s;
+    __syncthreads();
+    const int w = TILE - 1 - c;
+    for (int idx = tid; idx < w * w; idx += 256) {
+      int rr = idx / w, cc = idx - rr * w;
+      if (cc <= rr) {
+        int r = c + 1 + rr, c2 = c + 1 + cc;
+        T[r * DLD + c2] -= T[r * DLD + c] * T[c2 * DLD + c];
+      }
+    }
+    __syncthreads();
+  }
+  // write the factor back (lower triangle of the valid part; strict upper and padding -> 0)
+  for (int idx = tid; idx < TILE * TILE; idx += 256) {
+    int r = idx >> 7, c = idx & 127;
+    Ablk[(int64_t)r * n_pad + c] = (r < nrem && c <= r) ? T[r * DLD + c] : 0.0;
+  }
+  __syncthreads();
+  // in-place inverse of the lower-triangular block, last column first (dtrti2, lower, non-unit)
+  for (int j = TILE - 1; j >= 0; --j) {
+    const double ajj = 1.0 / T[j * DLD + j];
+    double acc = 0.0;
+    const int r = j + 1 + tid;
+    if (r < TILE) {
+      for (int t = j + 1; t <= r; ++t) acc += T[r * DLD + t] * T[t * DLD + j];
+    }
+    __syncthreads();
+    if (r < TILE) T[r * DLD + j] = -acc * ajj;
+    if (tid == 0) T[j * DLD + j] = ajj;
+    __syncthreads();
+  }
+  double* Dblk = Dinv + ((int64_t)hj * nb + kb) * TILE * TILE;
+  for (int idx = tid; idx < TILE * TILE; idx += 256) {
+    int r = idx >> 7, c = idx & 127;
+    Dblk[idx] = (r < nrem && c <= r) ? T[r * DLD + c] : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Panel solve: A[I][K] <- A[I][K] . L_KK^-T  (= A . Dinv^T), I > K.   grid (nb-1-K, H*m)
+__global__ void __launch_bounds__(gemm::THREADS, 1) trsm_panel_kernel(double* __restrict__ Lmat,
+                                                                      const double* __restrict__ Dinv, int n_pad,
+                                                                      int nb, int kb) {
+  extern __shared__ __align__(16) double smem[];
+  const int hj = blockIdx.y;
+  const int I = kb + 1 + blockIdx.x;
+  double* Ablk = Lmat + (int64_t)hj * n_pad * n_pad + (int64_t)I * TILE * n_pad + (int64_t)kb * TILE;
+  const double* D = Dinv + ((int64_t)hj * nb + kb) * TILE * TILE;
+  double acc[8][4][2];
+  gemm::zero_acc(acc);
+  // A(m,k) = Ablk[m*n_pad + k] (m-major) ; B(k,n) = Dinv[n][k] (n-major)
+  gemm::mainloop<false, false>(acc, Ablk, n_pad, D, TILE, 0, TILE, smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int mbase = (warp >> 2) * 64, nbase = (warp & 3) * 32;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = mbase + 8 * i + g, c = nbase + 8 * j + 2 * t;
+      *reinterpret_cast<double2*>(Ablk + (int64_t)r * n_pad + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+}
+
+// Trailing update: A[I][J] -= P_I . P_J^T for K < J <= I.   grid (#pairs, H*m)
+__global__ void __launch_bounds__(gemm::THREADS, 1) syrk_update_kernel(double* __restrict__ Lmat, int n_pad, int nb,
+                                                                       int kb) {
+  extern __shared__ __align__(16) double smem[];
+  const int hj = blockIdx.y;
+  // decode the lower-triangular pair index
+  int p = blockIdx.x;
+  int rr = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+  while ((rr + 1) * (rr + 2) / 2 <= p) ++rr;
+  while (rr * (rr + 1) / 2 > p) --rr;
+  const int cc = p - rr * (rr + 1) / 2;
+  const int I = kb + 1 + rr, J = kb + 1 + cc;
+  double* base = Lmat + (int64_t)hj * n_pad * n_pad;
+  const double* PI = base + (int64_t)I * TILE * n_pad + (int64_t)kb * TILE;
+  const double* PJ = base + (int64_t)J * TILE * n_pad + (int64_t)kb * TILE;
+  double* C = base + (int64_t)I * TILE * n_pad + (int64_t)J * TILE;
+  double acc[8][4][2];
+  gemm::zero_acc(acc);
+  gemm::mainloop<false, false>(acc, PI, n_pad, PJ, n_pad, 0, TILE, smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int mbase = (warp >> 2) * 64, nbase = (warp & 3) * 32;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = mbase + 8 * i + g, c = nbase + 8 * j + 2 * t;
+      double2* ptr = reinterpret_cast<double2*>(C + (int64_t)r * n_pad + c);
+      double2 old = *ptr;
+      old.x -= acc[i][j][0];
+      old.y -= acc[i][j][1];
+      *ptr = old;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Blocked inverse of L.  Diagonal blocks come from Dinv; block row I is built from rows < I:
+//   S[I][J]    = sum_{T=J}^{I-1} L[I][T] . Linv[T][J]          (step 1, stored in place of Linv[I][J])
+//   Linv[I][J] = -Dinv_I . S[I][J]                              (step 2)
+__global__ void linv_init_kernel(double* __restrict__ Linv, const double* __restrict__ Dinv, int n_pad, int nb) {
+  const int hj = blockIdx.y, kb = blockIdx.x;
+  const double* D = Dinv + ((int64_t)hj * nb + kb) * TILE * TILE;
+  double* dst = Linv + (int64_t)hj * n_pad * n_pad + (int64_t)kb * TILE * n_pad + (int64_t)kb * TILE;
+  for (int idx = threadIdx.x; idx < TILE * TILE; idx += blockDim.x) {
+    int r = idx >> 7, c = idx & 127;
+    dst[(int64_t)r * n_pad + c] = D[idx];
+  }
+}
+
+template <int STEP>
+__global__ void __launch_bounds__(gemm::THREADS, 1) linv_row_kernel(const double* __restrict__ Lmat,
+                                                                    double* __restrict__ Linv,
+                                                                    const double* __restrict__ Dinv, int n_pad, int nb,
+                                                                    int I) {
+  extern __shared__ __align__(16) double smem[];
+  const int hj = blockIdx.y, J = blockIdx.x;   // J < I
+  const double* Lb = Lmat + (int64_t)hj * n_pad * n_pad;
+  double* Li = Linv + (int64_t)hj * n_pad * n_pad;
+  double* C = Li + (int64_t)I * TILE * n_pad + (int64_t)J * TILE;
+  double acc[8][4][2];
+  gemm::zero_acc(acc);
+  if (STEP == 1) {
+    // A(m,k) = L[I*128+m][k] (m-major) ; B(k,n) = Linv[k][J*128+n] (k-major) ; k in [J*128, I*128)
+    gemm::mainloop<false, true>(acc, Lb + (int64_t)I * TILE * n_pad, n_pad, Li + (int64_t)J * TILE, n_pad, J * TILE,
+                                I * TILE, smem);
+  } else {
+    // A = Dinv_I (m-major, ld 128) ; B(k,n) = S[k][n] at C[k*n_pad + n] (k-major)
+    const double* D = Dinv + ((int64_t)hj * nb + I) * TILE * TILE;
+    gemm::mainloop<false, true>(acc, D, TILE, C, n_pad, 0, TILE, smem);
+  }
+  const double sgn = (STEP == 1) ? 1.0 : -1.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int mbase = (warp >> 2) * 64, nbase = (warp & 3) * 32;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = mbase + 8 * i + g, c = nbase + 8 * j + 2 * t;
+      *reinterpret_cast<double2*>(C + (int64_t)r * n_pad + c) =
+          make_double2(sgn * acc[i][j][0], sgn * acc[i][j][1]);
+    }
+}
+
+// t = Linv . yc   (warp per row)
+__global__ void linv_matvec_kernel(const double* __restrict__ Linv, const double* __restrict__ yc, int m, int n_pad,
+                                   double* __restrict__ tvec) {
+  const int hj = blockIdx.y, j = hj % m;
+  const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (a >= n_pad) return;
+  const int lane = threadIdx.x & 31;
+  const double* row = Linv + (int64_t)hj * n_pad * n_pad + (int64_t)a * n_pad;
+  const double* y = yc + (int64_t)j * n_pad;
+  double s = 0.0;
+  for (int b = lane; b <= a; b += 32) s += row[b] * y[b];
+  s = warp_sum(s);
+  if (lane == 0) tvec[(int64_t)hj * n_pad + a] = s;
+}
+
+// alpha = Linv^T . t   (thread per column, coalesced over b)
+__global__ void linv_t_matvec_kernel(const double* __restrict__ Linv, const double* __restrict__ tvec, int n_pad,
+                                     double* __restrict__ alpha) {
+  const int hj = blockIdx.y;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_pad) return;
+  const double* Li = Linv + (int64_t)hj * n_pad * n_pad;
+  const double* tv = tvec + (int64_t)hj * n_pad;
+  double s = 0.0;
+  for (int a = b; a < n_pad; ++a) s += Li[(int64_t)a * n_pad + b] * tv[a];
+  alpha[(int64_t)hj * n_pad + b] = s;
+}
+
+__global__ void copy_factor_kernel(const double* __restrict__ src, int n, int n_pad, int lower_only,
+                                   double* __restrict__ dst) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * n) return;
+  int r = (int)(idx / n), c = (int)(idx % n);
+  double v = src[(int64_t)r * n_pad + c];
+  if (lower_only && c > r) v = 0.0;
+  dst[idx] = v;
+}
+
+// ===================================================================================================
+int launch_prepare(bocf_model* M, cudaStream_t st) {
+  const int Hm = M->H * M->m;
+  ybar_kernel<<<M->m, 256, 0, st>>>(M->Y, M->n, M->n_pad, M->m, M->H, M->ybar, M->yc, M->hyp);
+  BOCF_LAUNCH_OK("ybar_kernel");
+  dim3 grid((unsigned)ceil_div(M->n_pad, 128), (unsigned)Hm);
+  scale_inputs_kernel<<<grid, 128, 0, st>>>(M->X, M->n, M->n_pad, M->d, M->hyp, M->Xs, M->xsq);
+  BOCF_LAUNCH_OK("scale_inputs_kernel");
+  return 0;
+}
+
+int launch_gram(bocf_model* M, cudaStream_t st) {
+  const int Hm = M->H * M->m;
+  dim3 grid((unsigned)(M->n_pad / 16), (unsigned)(M->n_pad / 16), (unsigned)Hm), block(16, 16);
+  switch (M->kernel) {
+    case BOCF_KERN_SE: gram_kernel<BOCF_KERN_SE><<<grid, block, 0, st>>>(M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, M->Lmat); break;
+    case BOCF_KERN_RBF: gram_kernel<BOCF_KERN_RBF><<<grid, block, 0, st>>>(M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, M->Lmat); break;
+    case BOCF_KERN_MATERN52: gram_kernel<BOCF_KERN_MATERN52><<<grid, block, 0, st>>>(M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, M->Lmat); break;
+    case BOCF_KERN_MATERN32: gram_kernel<BOCF_KERN_MATERN32><<<grid, block, 0, st>>>(M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, M->Lmat); break;
+    default: set_error("unknown kernel kind"); return -1;
+  }
+  BOCF_LAUNCH_OK("gram_kernel");
+  return 0;
+}
+
+static int set_smem_attrs() {
+  static bool done = false;
+  if (done) return 0;
+  BOCF_CUDA_OK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    TILE * DLD * (int)sizeof(double)));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(linv_row_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(linv_row_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+  done = true;
+  return 0;
+}
+
+int launch_cholesky(bocf_model* M, cudaStream_t st) {
+  if (int rc = set_smem_attrs()) return rc;
+  const int Hm = M->H * M->m, nb = M->nb;
+  BOCF_CUDA_OK(cudaMemsetAsync(M->info, 0, sizeof(int) * Hm, st));
+  for (int kb = 0; kb < nb; ++kb) {
+    potrf_diag_kernel<<<Hm, 256, TILE * DLD * sizeof(double), st>>>(M->Lmat, M->Dinv, M->info, M->n, M->n_pad, nb, kb);
+    BOCF_LAUNCH_OK("potrf_diag_kernel");
+    const int rem = nb - 1 - kb;
+    if (rem > 0) {
+      trsm_panel_kernel<<<dim3(rem, Hm), gemm::THREADS, gemm::SMEM_BYTES, st>>>(M->Lmat, M->Dinv, M->n_pad, nb, kb);
+      BOCF_LAUNCH_OK("trsm_panel_kernel");
+      syrk_update_kernel<<<dim3(rem * (rem + 1) / 2, Hm), gemm::THREADS, gemm::SMEM_BYTES, st>>>(M->Lmat, M->n_pad, nb, kb);
+      BOCF_LAUNCH_OK("syrk_update_kernel");
+    }
+  }
+  return 0;
+}
+
+int launch_inverse_and_alpha(bocf_model* M, cudaStream_t st) {
+  if (int rc = set_smem_attrs()) return rc;
+  const int Hm = M->H * M->m, nb = M->nb;
+  BOCF_CUDA_OK(cudaMemsetAsync(M->Linv, 0, sizeof(double) * (size_t)Hm * M->n_pad * M->n_pad, st));
+  linv_init_kernel<<<dim3(nb, Hm), 256, 0, st>>>(M->Linv, M->Dinv, M->n_pad, nb);
+  BOCF_LAUNCH_OK("linv_init_kernel");
+  for (int I = 1; I < nb; ++I) {
+    linv_row_kernel<1><<<dim3(I, Hm), gemm::THREADS, gemm::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
+    BOCF_LAUNCH_OK("linv_row_kernel<1>");
+    linv_row_kernel<2><<<dim3(I, Hm), gemm::THREADS, gemm::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
+    BOCF_LAUNCH_OK("linv_row_kernel<2>");
+  }
+  linv_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 8), Hm), 256, 0, st>>>(M->Linv, M->yc, M->m, M->n_pad, M->tvec);
+  BOCF_LAUNCH_OK("linv_matvec_kernel");
+  linv_t_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 128), Hm), 128, 0, st>>>(M->Linv, M->tvec, M->n_pad, M->alpha);
+  BOCF_LAUNCH_OK("linv_t_matvec_kernel");
+  return 0;
+}
+
+int launch_copy_factor(bocf_model* M, int hj, double* L, double* Linv, double* alpha, cudaStream_t st) {
+  const int64_t nn = (int64_t)M->n * M->n;
+  const unsigned blocks = (unsigned)ceil_div(nn, 256);
+  if (L) {
+    copy_factor_kernel<<<blocks, 256, 0, st>>>(M->Lmat + (int64_t)hj * M->n_pad * M->n_pad, M->n, M->n_pad, 1, L);
+    BOCF_LAUNCH_OK("copy_factor_kernel");
+  }
+  if (Linv) {
+    copy_factor_kernel<<<blocks, 256, 0, st>>>(M->Linv + (int64_t)hj * M->n_pad * M->n_pad, M->n, M->n_pad, 1, Linv);
+    BOCF_LAUNCH_OK("copy_factor_kernel");
+  }
+  if (alpha)
+    BOCF_CUDA_OK(cudaMemcpyAsync(alpha, M->alpha + (int64_t)hj * M->n_pad, sizeof(double) * M->n, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+}  // namespace bocf

@@ -1,0 +1,98 @@
+// model.h -- internal handle layout and kernel-launcher prototypes (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+
+#include "../../include/bocf_b200.h"
+
+namespace bocf {
+
+constexpr int MAXD = 16;      // max input dimension (register / shared tiles are sized by this)
+constexpr int MAXM = 64;      // max outputs handled by the MC kernel's per-warp staging
+constexpr int TILE = 128;     // GEMM tile edge == Cholesky block size
+
+// Per (hyper-sample, output) constants, resident in device memory.
+struct OutHyp {
+  double variance;            // sigma_f^2
+  double noise;               // sigma_n^2 (Gaussian likelihood variance)
+  double ybar;                // training mean of output j (Standardize, std == 1)
+  double jitter;              // extra diagonal jitter added by the jitchol retry loop
+  double ls[MAXD];            // lengthscale per input dimension
+};
+
+}  // namespace bocf
+
+struct bocf_model {
+  int m = 0, d = 0, kernel = 0, device = 0;
+  int n = 0, n_pad = 0, n16 = 0, nb = 0, H = 0;
+  bool has_data = false, has_hyp = false, factorized = false;
+
+  double* X = nullptr;        // n x d
+  double* Y = nullptr;        // m x n
+  double* yc = nullptr;       // m x n_pad   centred observations (zero padded)
+  double* ybar = nullptr;     // m
+  bocf::OutHyp* hyp = nullptr;            // H*m
+  std::vector<bocf::OutHyp> hyp_host;
+  double* Xs = nullptr;       // H*m x n_pad x d   training inputs / lengthscale (zero padded rows)
+  double* xsq = nullptr;      // H*m x n_pad
+  double* Lmat = nullptr;     // H*m x n_pad x n_pad   Gram, then its lower Cholesky factor
+  double* Linv = nullptr;     // H*m x n_pad x n_pad   L^-1 (lower, zero padded)
+  double* Dinv = nullptr;     // H*m x nb x 128 x 128  inverses of L's diagonal blocks
+  double* alpha = nullptr;    // H*m x n_pad
+  double* tvec = nullptr;     // H*m x n_pad           L^-1 (y - ybar)
+  int* info = nullptr;        // H*m                   first failing pivot (1-based) or 0
+
+  void* scratch = nullptr;
+  uint64_t scratch_bytes = 0;
+  uint64_t scratch_limit = 4ull << 30;
+};
+
+namespace bocf {
+
+// ---- chol.cu ------------------------------------------------------------------------------------
+int launch_prepare(bocf_model* M, cudaStream_t st);                       // ybar, yc, Xs, xsq
+int launch_gram(bocf_model* M, cudaStream_t st);                          // K + (noise+1e-8+jitter) I
+int launch_cholesky(bocf_model* M, cudaStream_t st);                      // blocked potrf, info flags
+int launch_inverse_and_alpha(bocf_model* M, cudaStream_t st);             // Linv, alpha
+int launch_copy_factor(bocf_model* M, int hj, double* L, double* Linv, double* alpha, cudaStream_t st);
+
+// ---- posterior.cu -------------------------------------------------------------------------------
+struct ChunkBuffers {          // scratch views for one candidate chunk (Nc rows, multiple of 128)
+  int64_t Nc;
+  double* KsT;                 // m x n16 x Nc      cross-covariance, transposed (row b, col i)
+  double* GsT;                 // m x n16 x Nc      dK/dr * 1/r (gradient weights), transposed
+  double* V;                   // m x Nc x n_pad    L^-1 k*
+  double* part_var;            // m x nb x Nc       per column-tile partial sums of v^2
+  double* part_dvar;           // m x nb x Nc x d   per column-tile partial variance gradients
+  double* mean;                // m x Nc
+  double* var;                 // m x Nc
+  double* dmean;               // m x Nc x d
+  double* dvar;                // m x Nc x d
+};
+uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad);
+void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* out);
+// Posterior of hyper-sample h for candidates Xc[0..Nvalid) into the chunk buffers.
+// grad: also K*-side gradient quantities (dmean, G*); need_var / need_dvar select the two contractions.
+int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, bool noiseless,
+                           const ChunkBuffers& cb, cudaStream_t st, bool need_var = true, bool need_dvar = true);
+
+// ---- acq.cu -------------------------------------------------------------------------------------
+struct AcqParams {
+  int variant, composite, m, d, S, L, p, with_grad_formula;
+  const double* Zt;            // [dev] m x S
+  const double* theta;         // [dev] L x p
+  const double* weight;        // [dev] L
+  const double* fstar;         // [dev] L    (already for this hyper-sample)
+  double scale;                // 1 / (H * S)  or 1 / H
+  int accumulate;              // 0: overwrite outputs, 1: add
+};
+int launch_acq_chunk(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvalid, double* acq, double* dacq,
+                     cudaStream_t st);
+int launch_utility_eval(int composite, int m, const double* Y, int64_t N, const double* theta, int L, int p,
+                        double* out, cudaStream_t st);
+int launch_topk(const double* acq, const double* Xc, int64_t N, int d, int k, int64_t index_offset,
+                double* out_rec, void* workspace, cudaStream_t st);
+uint64_t topk_workspace_bytes(int64_t N, int k);
+
+}  // namespace bocf

@@ -1,0 +1,378 @@
+// posterior.cu -- batched multi-output GP posterior at a chunk of candidates (north-star subsystems 1+2).
+//
+// For hyper-sample h and every output j, at Nc candidates:
+//   kstar_kernel      K*  = K(x*, X)         stationary.py:104-166 / se.py:44-73      (CUDA cores + MUFU)
+//                     mu  = K* alpha + ybar  posterior.py:299-305, gp.py:398-399
+//                     dmu = gradients_X(alpha^T, x*, X)   gp.py:446, stationary.py:332-342, stationary_utils.c
+//                     G*  = dK/dr / r        (weights for the variance gradient)
+//   var_gemm_kernel   V   = K* Linv^T  (= L^-1 K(X,x*), the reference's dtrtrs route, posterior.py:312)
+//                     var = k** - sum V^2 (+ noise), clipped 1e-10    posterior.py:313, gaussian.py:110, gpmodel.py:174
+//   dvar_gemm_kernel  Wt  = V Linv     (= K* W^-1, gp.py:474)
+//                     dvar = gradients_X(-2 Wt, x*, X)               gp.py:475
+// The two contractions run on the fp64 tensor-core tile engine (DMMA.8x8x4) and skip the zero
+// blocks of the triangular factor; K*, G* and V live in a per-chunk HBM scratch, everything else
+// (n x n factor, training inputs) is L2-resident and shared by all candidate tiles of one output.
+#include "gemm_f64.cuh"
+#include "kernfn.cuh"
+#include "model.h"
+
+namespace bocf {
+
+// ===================================================================================================
+// K*, mean, mean-gradient.  One thread per candidate, training points staged through shared memory.
+template <int KIND, int DP, bool GRAD>
+__global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ Xc, int64_t Nvalid, int64_t Nc, int d,
+                                                    int n, int n16, int n_pad, int m, int h,
+                                                    const OutHyp* __restrict__ hyp, const double* __restrict__ XsAll,
+                                                    const double* __restrict__ xsqAll,
+                                                    const double* __restrict__ alphaAll, double* __restrict__ KsT,
+                                                    double* __restrict__ GsT, double* __restrict__ mean,
+                                                    double* __restrict__ dmean) {
+  __shared__ double sX[128][DP];
+  __shared__ double sxsq[128];
+  __shared__ double salpha[128];
+  const int tid = threadIdx.x;
+  const int j = blockIdx.y;
+  const int hj = h * m + j;
+  const int64_t i = (int64_t)blockIdx.x * 128 + tid;
+  const OutHyp& hp = hyp[hj];
+  const double variance = hp.variance;
+
+  double xs[DP];
+  double xsq_i = 0.0;
+#pragma unroll
+  for (int q = 0; q < DP; ++q) {
+    double v = 0.0;
+    if (q < d && i < Nvalid) v = Xc[i * d + q] / hp.ls[q];
+    xs[q] = v;
+    xsq_i += v * v;
+  }
+  double mu = 0.0;
+  double gm[DP];
+#pragma unroll
+  for (int q = 0; q < DP; ++q) gm[q] = 0.0;
+
+  const double* Xs = XsAll + (int64_t)hj * n_pad * d;
+  const double* xsq = xsqAll + (int64_t)hj * n_pad;
+  const double* alpha = alphaAll + (int64_t)hj * n_pad;
+  double* Kout = KsT + (int64_t)j * n16 * Nc;
+  double* Gout = GRAD ? GsT + (int64_t)j * n16 * Nc : nullptr;
+
+  for (int b0 = 0; b0 < n16; b0 += 128) {
+    __syncthreads();
+    for (int idx = tid; idx < 128 * DP; idx += 128) {
+      int bb = idx / DP, q = idx - bb * DP;
+      int b = b0 + bb;
+      sX[bb][q] = (q < d && b < n) ? Xs[(int64_t)b * d + q] : 0.0;
+    }
+    {
+      int b = b0 + tid;
+      sxsq[tid] = (b < n) ? xsq[b] : 0.0;
+      salpha[tid] = (b < n) ? alpha[b] : 0.0;
+    }
+    __syncthreads();
+    const int bmax = min(128, n16 - b0);
+    for (int bb = 0; bb < bmax; ++bb) {
+      const int b = b0 + bb;
+      double kv = 0.0, gv = 0.0;
+      if (b < n) {
+        double r2;
+        if (KIND == BOCF_KERN_SE) {
+          r2 = 0.0;
+#pragma unroll
+          for (int q = 0; q < DP; ++q) {
+            double df = xs[q] - sX[bb][q];
+            r2 += df * df;
+          }
+        } else {
+          double dot = 0.0;
+#pragma unroll
+          for (int q = 0; q < DP; ++q) dot += xs[q] * sX[bb][q];
+          r2 = -2.0 * dot + (xsq_i + sxsq[bb]);
+          r2 = fmax(r2, 0.0);
+        }
+        kern_eval<KIND, GRAD>(r2, variance, kv, gv);
+        const double a = salpha[bb];
+        mu += kv * a;
+        if (GRAD) {
+          const double w = gv * a;
+#pragma unroll
+          for (int q = 0; q < DP; ++q) gm[q] += w * (xs[q] - sX[bb][q]);
+        }
+      }
+      Kout[(int64_t)b * Nc + i] = kv;
+      if (GRAD) Gout[(int64_t)b * Nc + i] = gv;
+    }
+  }
+  mean[(int64_t)j * Nc + i] = mu + hp.ybar;
+  if (GRAD) {
+#pragma unroll
+    for (int q = 0; q < DP; ++q)
+      if (q < d) dmean[((int64_t)j * Nc + i) * d + q] = gm[q] / hp.ls[q];
+  }
+}
+
+// ===================================================================================================
+// V = K* Linv^T on the lower triangle; per column-tile partial sums of V^2.
+// grid.x = m * a_tiles * i_tiles, heaviest column tiles (largest K extent) first.
+__global__ void __launch_bounds__(gemm::THREADS, 1) var_gemm_kernel(const double* __restrict__ KsT,
+                                                                    const double* __restrict__ LinvAll,
+                                                                    double* __restrict__ V,
+                                                                    double* __restrict__ part_var, int64_t Nc, int n16,
+                                                                    int n_pad, int nb, int m, int h, int store_v) {
+  extern __shared__ __align__(16) double smem[];
+  const int i_tiles = (int)(Nc / TILE);
+  int bid = blockIdx.x;
+  const int it = bid % i_tiles;
+  bid /= i_tiles;
+  const int at = nb - 1 - (bid % nb);
+  const int j = bid / nb;
+  const int hj = h * m + j;
+
+  const double* A = KsT + (int64_t)j * n16 * Nc + (int64_t)it * TILE;                 // A(m,k) = KsT[k*Nc + m]
+  const double* B = LinvAll + (int64_t)hj * n_pad * n_pad + (int64_t)at * TILE * n_pad; // B(k,n) = Linv[n*n_pad + k]
+  const int k_end = min(n16, (at + 1) * TILE);
+
+  double acc[8][4][2];
+  gemm::zero_acc(acc);
+  gemm::mainloop<true, false>(acc, A, Nc, B, n_pad, 0, k_end, smem);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int mbase = wm * 64, nbase = wn * 32;
+  double* red = smem;   // [4][128]
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn) s += acc[i][jn][0] * acc[i][jn][0] + acc[i][jn][1] * acc[i][jn][1];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (t == 0) red[wn * TILE + mbase + 8 * i + g] = s;
+  }
+  if (store_v) {
+    double* Vt = V + ((int64_t)j * Nc + (int64_t)it * TILE) * n_pad + (int64_t)at * TILE;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+        int r = mbase + 8 * i + g, c = nbase + 8 * jn + 2 * t;
+        *reinterpret_cast<double2*>(Vt + (int64_t)r * n_pad + c) = make_double2(acc[i][jn][0], acc[i][jn][1]);
+      }
+  }
+  __syncthreads();
+  if (threadIdx.x < TILE) {
+    const int r = threadIdx.x;
+    double s = (red[r] + red[TILE + r]) + (red[2 * TILE + r] + red[3 * TILE + r]);
+    part_var[((int64_t)j * nb + at) * Nc + (int64_t)it * TILE + r] = s;
+  }
+}
+
+// ===================================================================================================
+// Wt = V Linv on the lower triangle; epilogue contracts  Wt * G* * (xs_i - Xs_b)  over the tile's
+// columns into per column-tile partial variance gradients.   grid.x = m * b_tiles * i_tiles.
+__global__ void __launch_bounds__(gemm::THREADS, 1) dvar_gemm_kernel(
+    const double* __restrict__ V, const double* __restrict__ LinvAll, const double* __restrict__ GsT,
+    const double* __restrict__ Xc, int64_t Nvalid, const double* __restrict__ XsAll, const OutHyp* __restrict__ hyp,
+    double* __restrict__ part_dvar, int64_t Nc, int n, int n16, int n_pad, int nb, int m, int d, int h) {
+  extern __shared__ __align__(16) double smem[];
+  const int i_tiles = (int)(Nc / TILE);
+  int bid = blockIdx.x;
+  const int it = bid % i_tiles;
+  bid /= i_tiles;
+  const int bt = bid % nb;          // ascending: largest K extent first
+  const int j = bid / nb;
+  const int hj = h * m + j;
+
+  const double* A = V + ((int64_t)j * Nc + (int64_t)it * TILE) * n_pad;                 // A(m,k) = V[m*n_pad + k]
+  const double* B = LinvAll + (int64_t)hj * n_pad * n_pad + (int64_t)bt * TILE;           // B(k,n) = Linv[k*n_pad + n]
+  double acc[8][4][2];
+  gemm::zero_acc(acc);
+  gemm::mainloop<false, true>(acc, A, n_pad, B, n_pad, bt * TILE, n16, smem);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int mbase = wm * 64, nbase = wn * 32;
+  const OutHyp& hp = hyp[hj];
+
+  // stage scaled candidate / training coordinates for this tile:  sxi[q][row], sxb[q][col]
+  double* sxi = smem;                       // d x 128
+  double* sxb = smem + d * TILE;            // d x 128
+  double* red = smem + 2 * d * TILE;        // 4 x 128 x d   (6*d KiB <= 96 KiB for d <= MAXD)
+  for (int idx = tid; idx < d * TILE; idx += gemm::THREADS) {
+    int r = idx / d, q = idx - r * d;
+    int64_t i = (int64_t)it * TILE + r;
+    sxi[q * TILE + r] = (i < Nvalid) ? Xc[i * d + q] / hp.ls[q] : 0.0;
+    int b = bt * TILE + r;
+    sxb[q * TILE + r] = XsAll[((int64_t)hj * n_pad + b) * d + q];
+  }
+  // wg = Wt * G*
+  const double* Gj = GsT + (int64_t)j * n16 * Nc + (int64_t)it * TILE;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = mbase + 8 * i + g;
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int b = bt * TILE + nbase + 8 * jn + 2 * t + e;
+        const double gv = (b < n) ? Gj[(int64_t)b * Nc + r] : 0.0;
+        acc[i][jn][e] *= gv;
+      }
+  }
+  __syncthreads();
+  for (int q = 0; q < d; ++q) {
+    double xb[4][2];
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn) {
+      xb[jn][0] = sxb[q * TILE + nbase + 8 * jn + 2 * t];
+      xb[jn][1] = sxb[q * TILE + nbase + 8 * jn + 2 * t + 1];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = mbase + 8 * i + g;
+      const double xi = sxi[q * TILE + r];
+      double s = 0.0;
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+        s += acc[i][jn][0] * (xi - xb[jn][0]);
+        s += acc[i][jn][1] * (xi - xb[jn][1]);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (t == 0) red[(wn * TILE + r) * d + q] = s;
+    }
+  }
+  __syncthreads();
+  double* out = part_dvar + (((int64_t)j * nb + bt) * Nc + (int64_t)it * TILE) * d;
+  for (int idx = tid; idx < TILE * d; idx += gemm::THREADS) {
+    double s = (red[idx] + red[TILE * d + idx]) + (red[2 * TILE * d + idx] + red[3 * TILE * d + idx]);
+    out[idx] = s;
+  }
+}
+
+// ===================================================================================================
+// var = clip(k** - sum_tiles part_var (+ noise), 1e-10);  dvar = (-2 / l_q) sum_tiles part_dvar
+__global__ void finalize_kernel(const double* __restrict__ part_var, const double* __restrict__ part_dvar,
+                                const OutHyp* __restrict__ hyp, int64_t Nc, int nb, int m, int d, int h, int grad,
+                                int noiseless, double* __restrict__ var, double* __restrict__ dvar) {
+  const int j = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nc) return;
+  const OutHyp& hp = hyp[h * m + j];
+  double s = 0.0;
+  for (int tI = 0; tI < nb; ++tI) s += part_var[((int64_t)j * nb + tI) * Nc + i];
+  double v = hp.variance - s;
+  if (!noiseless) v = hp.noise + v;
+  var[(int64_t)j * Nc + i] = fmax(v, 1e-10);
+  if (grad) {
+    for (int q = 0; q < d; ++q) {
+      double gsum = 0.0;
+      for (int tI = 0; tI < nb; ++tI) gsum += part_dvar[(((int64_t)j * nb + tI) * Nc + i) * d + q];
+      dvar[((int64_t)j * Nc + i) * d + q] = -2.0 * gsum / hp.ls[q];
+    }
+  }
+}
+
+// ===================================================================================================
+uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
+  uint64_t per = 0;
+  per += (uint64_t)M->m * M->n16;                       // KsT
+  per += (uint64_t)M->m * M->nb;                        // part_var
+  per += 2ull * M->m;                                   // mean, var
+  if (grad) {
+    per += (uint64_t)M->m * M->n16;                     // GsT
+    per += (uint64_t)M->m * M->n_pad;                   // V
+    per += (uint64_t)M->m * M->nb * M->d;               // part_dvar
+    per += 2ull * M->m * M->d;                          // dmean, dvar
+  }
+  return per * sizeof(double);
+}
+
+void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* cb) {
+  double* p = reinterpret_cast<double*>(base);
+  auto take = [&](uint64_t count) {
+    double* r = p;
+    p += round_up((int64_t)count, 32);
+    return r;
+  };
+  cb->Nc = Nc;
+  cb->KsT = take((uint64_t)M->m * M->n16 * Nc);
+  cb->part_var = take((uint64_t)M->m * M->nb * Nc);
+  cb->mean = take((uint64_t)M->m * Nc);
+  cb->var = take((uint64_t)M->m * Nc);
+  if (grad) {
+    cb->GsT = take((uint64_t)M->m * M->n16 * Nc);
+    cb->V = take((uint64_t)M->m * Nc * M->n_pad);
+    cb->part_dvar = take((uint64_t)M->m * M->nb * Nc * M->d);
+    cb->dmean = take((uint64_t)M->m * Nc * M->d);
+    cb->dvar = take((uint64_t)M->m * Nc * M->d);
+  } else {
+    cb->GsT = cb->V = cb->part_dvar = cb->dmean = cb->dvar = nullptr;
+  }
+}
+
+template <int KIND, int DP>
+static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, const ChunkBuffers& cb,
+                          cudaStream_t st) {
+  dim3 grid((unsigned)(cb.Nc / 128), (unsigned)M->m);
+  if (grad)
+    kstar_kernel<KIND, DP, true><<<grid, 128, 0, st>>>(Xc, Nvalid, cb.Nc, M->d, M->n, M->n16, M->n_pad, M->m, h, M->hyp,
+                                                       M->Xs, M->xsq, M->alpha, cb.KsT, cb.GsT, cb.mean, cb.dmean);
+  else
+    kstar_kernel<KIND, DP, false><<<grid, 128, 0, st>>>(Xc, Nvalid, cb.Nc, M->d, M->n, M->n16, M->n_pad, M->m, h,
+                                                        M->hyp, M->Xs, M->xsq, M->alpha, cb.KsT, nullptr, cb.mean,
+                                                        nullptr);
+  BOCF_LAUNCH_OK("kstar_kernel");
+  return 0;
+}
+
+template <int KIND>
+static int launch_kstar_k(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, const ChunkBuffers& cb,
+                          cudaStream_t st) {
+  const int d = M->d;
+  if (d <= 4) return launch_kstar_t<KIND, 4>(M, h, Xc, Nvalid, grad, cb, st);
+  if (d <= 8) return launch_kstar_t<KIND, 8>(M, h, Xc, Nvalid, grad, cb, st);
+  if (d <= 12) return launch_kstar_t<KIND, 12>(M, h, Xc, Nvalid, grad, cb, st);
+  return launch_kstar_t<KIND, MAXD>(M, h, Xc, Nvalid, grad, cb, st);
+}
+
+int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, bool noiseless,
+                           const ChunkBuffers& cb, cudaStream_t st, bool need_var, bool need_dvar) {
+  static bool attrs = false;
+  if (!attrs) {
+    BOCF_CUDA_OK(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+    BOCF_CUDA_OK(cudaFuncSetAttribute(dvar_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+    attrs = true;
+  }
+  need_dvar = need_dvar && grad;
+  need_var = need_var || need_dvar;
+  int rc;
+  switch (M->kernel) {
+    case BOCF_KERN_SE: rc = launch_kstar_k<BOCF_KERN_SE>(M, h, Xc, Nvalid, grad, cb, st); break;
+    case BOCF_KERN_RBF: rc = launch_kstar_k<BOCF_KERN_RBF>(M, h, Xc, Nvalid, grad, cb, st); break;
+    case BOCF_KERN_MATERN52: rc = launch_kstar_k<BOCF_KERN_MATERN52>(M, h, Xc, Nvalid, grad, cb, st); break;
+    case BOCF_KERN_MATERN32: rc = launch_kstar_k<BOCF_KERN_MATERN32>(M, h, Xc, Nvalid, grad, cb, st); break;
+    default: set_error("unknown kernel kind"); return -1;
+  }
+  if (rc) return rc;
+  if (!need_var) return 0;      // mean (and mean gradient) only: no contraction against the factor
+  const unsigned tiles = (unsigned)((cb.Nc / TILE) * M->nb * M->m);
+  var_gemm_kernel<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(cb.KsT, M->Linv, cb.V, cb.part_var, cb.Nc, M->n16,
+                                                                  M->n_pad, M->nb, M->m, h, need_dvar ? 1 : 0);
+  BOCF_LAUNCH_OK("var_gemm_kernel");
+  if (need_dvar) {
+    dvar_gemm_kernel<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(cb.V, M->Linv, cb.GsT, Xc, Nvalid, M->Xs, M->hyp,
+                                                                    cb.part_dvar, cb.Nc, M->n, M->n16, M->n_pad, M->nb,
+                                                                    M->m, M->d, h);
+    BOCF_LAUNCH_OK("dvar_gemm_kernel");
+  }
+  dim3 fgrid((unsigned)ceil_div(cb.Nc, 256), (unsigned)M->m);
+  finalize_kernel<<<fgrid, 256, 0, st>>>(cb.part_var, cb.part_dvar, M->hyp, cb.Nc, M->nb, M->m, M->d, h,
+                                         need_dvar ? 1 : 0, noiseless ? 1 : 0, cb.var, cb.dvar);
+  BOCF_LAUNCH_OK("finalize_kernel");
+  return 0;
+}
+
+}  // namespace bocf

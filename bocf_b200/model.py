@@ -1,0 +1,241 @@
+"""multi_outputGP with the reference's interface (multi_outputGP.py:9-348), backed by the CUDA library.
+
+m independent single-output exact GPs.  The prediction methods keep the reference's names, argument
+meaning and output shapes ((m,N) / (m,N,d) float64); numpy in -> numpy out, CUDA torch tensors in ->
+CUDA torch tensors out (no host round trip).  All arithmetic runs in libbocf_b200 (fp64, sm_100a);
+there is no CPU fallback.
+
+Hyper-parameter fitting (ML-II + HMC, GPyOpt/models/gpmodel.py:102-128) is out of scope for this
+path: hyper-samples are supplied with ``set_hyperparameter_samples`` (or default to
+the kernels' initial values, exactly what ``fixed_hyps=True`` does in the reference).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import kern as _kern
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class multi_outputGP(object):
+    analytical_gradient_prediction = True
+
+    def __init__(self, output_dim, kernel=None, noise_var=None, exact_feval=None, n_samples=10, ARD=None,
+                 fixed_hyps=False, device=None):
+        self.output_dim = int(output_dim)
+        self.kernel = [None] * output_dim if kernel is None else list(kernel)
+        self.noise_var = [None] * output_dim if noise_var is None else list(noise_var)
+        self.exact_feval = [False] * output_dim if exact_feval is None else list(exact_feval)
+        self.n_samples = n_samples
+        self.ARD = [True] * output_dim if ARD is None else list(ARD)
+        self.fixed_hyps = fixed_hyps
+        if device is None:
+            device = "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cuda:0"
+        self.device = torch.device(device)
+        self._lib = _lib.load_library()
+        self._handle = None
+        self._handle_sig = None
+        self._explicit_hyp = False
+        self._hyp = None            # (kind, variance (H,m), lengthscale (H,m,d), noise (H,m))
+        self._current_h = 0
+        self.X = None
+        self.Y = None
+        self.input_dim = None
+        self.jitter_added = None
+
+    # ---- hyper-parameters ---------------------------------------------------------------------------
+    def set_hyperparameter_samples(self, variance, lengthscale, noise, kind=None):
+        """Load H hyper-samples: variance (H,m), lengthscale (H,m,d), noise (H,m).
+
+        Stands in for the per-sample GPRegression instances GPModel.updateModel fills from HMC
+        (gpmodel.py:121-126).  ``kind`` in {'se','rbf','matern52','matern32'}.
+        """
+        variance = np.ascontiguousarray(variance, dtype=np.float64)
+        lengthscale = np.ascontiguousarray(lengthscale, dtype=np.float64)
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        H, m = variance.shape
+        assert m == self.output_dim and lengthscale.shape[:2] == (H, m) and noise.shape == (H, m)
+        if kind is None:
+            kind = self._kernel_kind()
+        self._hyp = (kind, variance, lengthscale, noise)
+        self._explicit_hyp = True
+        if self.X is not None:
+            self._upload_and_factorize()
+
+    def _kernel_kind(self):
+        kinds = set(k.kind for k in self.kernel if k is not None)
+        if len(kinds) > 1:
+            raise NotImplementedError("all outputs must share one kernel family (one enum per device model)")
+        return kinds.pop() if kinds else "se"
+
+    def _default_hypers(self, d, Y_all):
+        """Initial hyper-parameters of the reference's model constructors, as one hyper-sample (H = 1)."""
+        m = self.output_dim
+        var = np.empty((1, m))
+        ls = np.empty((1, m, d))
+        noise = np.empty((1, m))
+        for j in range(m):
+            k = self.kernel[j]
+            if k is None:
+                if self.fixed_hyps:     # gpmodel_fixed_hyps.py:49-50
+                    k = _kern.SE(d, variance=2., lengthscale=0.3)
+                else:                   # gpmodel.py:57-58
+                    k = _kern.SE(d, variance=1., ARD=self.ARD[j])
+            var[0, j] = k.variance[0]
+            ls[0, j, :] = k.lengthscale_vector()
+            if self.fixed_hyps:         # gpmodel_fixed_hyps.py:56
+                noise[0, j] = 1e-10 if self.noise_var[j] is None else self.noise_var[j]
+            elif self.exact_feval[j]:   # gpmodel.py:72-73
+                noise[0, j] = 1e-6
+            else:                       # gpmodel.py:64
+                noise[0, j] = np.var(Y_all[j]) * 0.01 if self.noise_var[j] is None else self.noise_var[j]
+        return (self._kernel_kind(), var, ls, noise)
+
+    # ---- data -----------------------------------------------------------------------------------------
+    def updateModel(self, X_all, Y_all):
+        """multi_outputGP.py:97-102.  X_all (n,d); Y_all list of m arrays (n,1)."""
+        X = np.ascontiguousarray(X_all, dtype=np.float64)
+        Y = np.ascontiguousarray(np.stack([np.asarray(y, dtype=np.float64).reshape(-1) for y in Y_all], axis=0))
+        assert Y.shape == (self.output_dim, X.shape[0])
+        self.X = X
+        self.Y = Y
+        self.input_dim = X.shape[1]
+        if self._hyp is None or not getattr(self, "_explicit_hyp", False):
+            self._hyp = self._default_hypers(self.input_dim, Y_all)
+        self._upload_and_factorize()
+
+    def _upload_and_factorize(self):
+        kind, variance, lengthscale, noise = self._hyp
+        lib = self._lib
+        d = self.input_dim
+        if lengthscale.shape[2] != d:
+            assert lengthscale.shape[2] == 1
+            lengthscale = np.ascontiguousarray(np.broadcast_to(lengthscale, lengthscale.shape[:2] + (d,)))
+        if self._handle is None or self._handle_sig != (kind, d):
+            self._destroy()
+            h = ctypes.c_void_p()
+            _lib.check(lib.bocf_model_create(ctypes.byref(h), self.output_dim, d, _lib.KERNELS[kind],
+                                             self.device.index or 0))
+            self._handle = h
+            self._handle_sig = (kind, d)
+        with torch.cuda.device(self.device):
+            Xd = torch.from_numpy(self.X).to(self.device)
+            Yd = torch.from_numpy(self.Y).to(self.device)
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.bocf_model_set_data(self._handle, self.X.shape[0], _ptr(Xd), _ptr(Yd), st))
+            _lib.check(lib.bocf_model_set_hypers(self._handle, variance.shape[0],
+                                                 variance.ctypes.data_as(ctypes.c_void_p),
+                                                 lengthscale.ctypes.data_as(ctypes.c_void_p),
+                                                 noise.ctypes.data_as(ctypes.c_void_p)))
+            jit = np.zeros(variance.shape, dtype=np.float64)
+            _lib.check(lib.bocf_model_factorize(self._handle, jit.ctypes.data_as(ctypes.c_void_p), st))
+            self.jitter_added = jit
+        self._X_dev = Xd
+        self._current_h = 0
+
+    def _destroy(self):
+        if getattr(self, "_handle", None) is not None:
+            self._lib.bocf_model_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    # ---- bookkeeping (multi_outputGP.py:109-135) ----------------------------------------------------
+    def number_of_hyps_samples(self):
+        return self.n_samples
+
+    def n_hyper_samples_loaded(self):
+        return 1 if self._hyp is None else int(self._hyp[1].shape[0])
+
+    def set_hyperparameters(self, n):
+        # GPModel.set_hyperparameters selects instance n (gpmodel.py:136-137);
+        # GPModelFixedHyps.set_hyperparameters is a no-op (gpmodel_fixed_hyps.py:76-77)
+        H = self.n_hyper_samples_loaded()
+        self._current_h = 0 if (self.fixed_hyps or H == 1) else int(n)
+        if self._current_h >= H:
+            raise IndexError("hyper-sample %d not loaded (H = %d)" % (n, H))
+
+    def get_evaluated_points(self):
+        return np.copy(self.X)
+
+    # ---- prediction ---------------------------------------------------------------------------------
+    def _dev_in(self, X):
+        if isinstance(X, torch.Tensor):
+            Xd = X.to(device=self.device, dtype=torch.float64)
+            if Xd.dim() == 1:
+                Xd = Xd[None, :]
+            return Xd.contiguous(), True
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        return torch.from_numpy(np.ascontiguousarray(X)).to(self.device), False
+
+    def _posterior(self, X, want_mean=True, want_var=False, want_dmean=False, want_dvar=False, noiseless=False):
+        if self._handle is None:
+            raise RuntimeError("model has no data: call updateModel first")
+        Xd, is_t = self._dev_in(X)
+        N, d = Xd.shape
+        assert d == self.input_dim
+        m = self.output_dim
+        with torch.cuda.device(self.device):
+            mean = torch.empty((m, N), dtype=torch.float64, device=self.device)
+            var = torch.empty((m, N), dtype=torch.float64, device=self.device) if want_var else None
+            dmean = torch.empty((m, N, d), dtype=torch.float64, device=self.device) if want_dmean else None
+            dvar = torch.empty((m, N, d), dtype=torch.float64, device=self.device) if want_dvar else None
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(self._lib.bocf_posterior(self._handle, self._current_h, _ptr(Xd), N, 1 if noiseless else 0,
+                                                _ptr(mean), _ptr(var), _ptr(dmean), _ptr(dvar), st))
+        outs = (mean if want_mean else None, var, dmean, dvar)
+        if is_t:
+            return outs
+        return tuple(None if o is None else o.cpu().numpy() for o in outs)
+
+    def predict(self, X, full_cov=False):
+        """multi_outputGP.py:138-149: (mean (m,N), variance incl. noise, clipped at 1e-10 (gpmodel.py:147))."""
+        mean, var, _, _ = self._posterior(X, want_var=True)
+        return mean, var
+
+    def predict_noiseless(self, X, full_cov=False):
+        mean, var, _, _ = self._posterior(X, want_var=True, noiseless=True)
+        return mean, var
+
+    def posterior_mean(self, X):
+        return self._posterior(X)[0]
+
+    def posterior_mean_at_evaluated_points(self):
+        """multi_outputGP.py:176-180; stays on the device when called by the acquisitions."""
+        return self._posterior(self.X)[0]
+
+    def _posterior_mean_at_evaluated_points_dev(self):
+        return self._posterior(self._X_dev)[0]
+
+    def posterior_variance(self, X):
+        return self._posterior(X, want_var=True)[1]
+
+    def posterior_variance_noiseless(self, X):
+        return self._posterior(X, want_var=True, noiseless=True)[1]
+
+    def posterior_mean_gradient(self, X):
+        return self._posterior(X, want_dmean=True)[2]
+
+    def posterior_variance_gradient(self, X):
+        return self._posterior(X, want_dvar=True)[3]
+
+    # ---- inspection (tests) ---------------------------------------------------------------------------
+    def get_factor(self, h, j):
+        """(L, Linv, alpha) of output j under hyper-sample h as numpy arrays."""
+        n = self.X.shape[0]
+        with torch.cuda.device(self.device):
+            L = torch.empty((n, n), dtype=torch.float64, device=self.device)
+            Li = torch.empty((n, n), dtype=torch.float64, device=self.device)
+            al = torch.empty((n,), dtype=torch.float64, device=self.device)
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(self._lib.bocf_model_get_factor(self._handle, h, j, _ptr(L), _ptr(Li), _ptr(al), st))
+        return L.cpu().numpy(), Li.cpu().numpy(), al.cpu().numpy()

@@ -1,0 +1,151 @@
+/*
+ * bocf_b200.h -- C ABI of the B200-native EI-CF hot path (libbocf_b200.so).
+ *
+ * The reference (RaulAstudillo06/BOCF) has NO FFI boundary on this path: it is numpy/scipy
+ * plus one C/OpenMP routine (GPy/kern/src/stationary_utils.c:_grad_X).  The entry points below
+ * are what a binding of the reference's Python plugin surface calls instead of the numpy code;
+ * each one cites the reference interface it replaces (paths relative to the reference checkout).
+ * INTEGRATION.md shows the ctypes stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - plain C, no torch types.  All matrices are row-major IEEE fp64.
+ *  - pointers marked [dev] are device pointers on the model's device, owned by the caller;
+ *    pointers marked [host] are host pointers.  The library owns only the handle's buffers.
+ *  - every call is stream-ordered on `stream` (a cudaStream_t passed as void*; NULL = default).
+ *  - return value: 0 on success, negative bocf_status otherwise; never throws across the ABI.
+ *    bocf_last_error() returns a thread-local human-readable message for the last failure.
+ *  - one handle per device; a handle is not thread-safe (the reference is single-threaded).
+ */
+#ifndef BOCF_B200_H_
+#define BOCF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bocf_model bocf_model;
+
+enum bocf_status {
+  BOCF_OK = 0,
+  BOCF_ERR_INVALID = -1,      /* bad argument / call order                                    */
+  BOCF_ERR_CUDA = -2,         /* CUDA runtime error (message in bocf_last_error)              */
+  BOCF_ERR_NOT_PD = -3,       /* "not positive definite, even with jitter." GPy/util/linalg.py:71 */
+  BOCF_ERR_NONPOS_DIAG = -4,  /* "not pd: non-positive diagonal elements"  GPy/util/linalg.py:60  */
+  BOCF_ERR_UNSUPPORTED = -5
+};
+
+/* Covariance kernels on the path. */
+enum bocf_kernel {
+  BOCF_KERN_SE = 0,        /* GPy/kern/src/se.py:44-101,135-148 (exact-difference sq. distance) */
+  BOCF_KERN_RBF = 1,       /* GPy/kern/src/rbf.py:42-46 on GPy/kern/src/stationary.py:104-166   */
+  BOCF_KERN_MATERN52 = 2,  /* GPy/kern/src/stationary.py:529-533                                */
+  BOCF_KERN_MATERN32 = 3   /* GPy/kern/src/stationary.py:440-444                                */
+};
+
+/* Composite utilities U(theta, y) found in the reference's scripts. */
+enum bocf_composite {
+  BOCF_U_SUMSQ_TARGET = 0,     /* -sum_j (y_j-theta_j)^2          test_1a.py:89-96   p = m */
+  BOCF_U_NEG_SUM_EXP = 1,      /* -sum_j exp(y_j)                 test_2a.py:60-65   p = 0 */
+  BOCF_U_EXP_COS = 2,          /* -sum_j c_j e^{-y_j/pi}cos(pi y_j) test_3a.py:53-67 p = 0 */
+  BOCF_U_ROSEN_COMPOSITE = 3,  /* -sum_{j<m/2} (theta-y_j)^2+100 y_{j+m/2}^2  test_5a.py:48-59 p = 1 */
+  BOCF_U_LINEAR = 4            /* theta . y                       test_1b.py:89-93   p = m */
+};
+
+/* Acquisition variants. */
+enum bocf_acq_variant {
+  BOCF_ACQ_EI_CF = 0,  /* uEI_noiseless.py:63-83,138-170  MC composite EI (+ pathwise gradient) */
+  BOCF_ACQ_PI_CF = 1,  /* uPI.py:66-86                     MC composite PI, value only           */
+  BOCF_ACQ_MA_EI = 2,  /* maEI.py:81-126 / EI.py:79-123    analytic EI of theta^T y              */
+  BOCF_ACQ_MA_PI = 3   /* maPI.py:80-120 / PI.py           analytic PI of theta^T y              */
+};
+
+const char* bocf_last_error(void);
+/* Library / build identification ("bocf_b200 <ver> sm_100a"). */
+const char* bocf_version(void);
+
+/* ---- model: replaces multi_outputGP (multi_outputGP.py:9-348) + GPModel/GPModelFixedHyps prediction
+ *      state (GPyOpt/models/gpmodel.py:136-175,259-271) -------------------------------------------- */
+
+/* m independent outputs over d inputs, all with the same kernel family. */
+int bocf_model_create(bocf_model** out, int m, int d, int kernel, int device);
+int bocf_model_destroy(bocf_model* mdl);
+
+/* Training data.  X [dev] n x d, Y [dev] m x n (row j = observations of output j).
+ * Replaces GP.set_XY (GPy/core/gp.py:191-227) incl. the fork's mean-only normaliser
+ * (GPy/util/normalizer.py:57-66). */
+int bocf_model_set_data(bocf_model* mdl, int n, const double* X, const double* Y, void* stream);
+
+/* H hyper-parameter samples.  variance [host] H x m, lengthscale [host] H x m x d, noise [host] H x m.
+ * Replaces the per-sample GPRegression instances of GPModel (gpmodel.py:80-100,121-126). */
+int bocf_model_set_hypers(bocf_model* mdl, int H, const double* variance, const double* lengthscale,
+                          const double* noise);
+
+/* Gram + Cholesky + L^-1 + alpha for every (h, j), fp64 on device.  Replaces
+ * ExactGaussianInference.inference (exact_gaussian_inference.py:43-51), pdinv/jitchol/dpotrs
+ * (GPy/util/linalg.py:52-83,112-121,189-210).  jitter_out [host, may be NULL] H x m receives the
+ * jitter jitchol had to add (0 if none).  Synchronises the stream (needs the device info flag). */
+int bocf_model_factorize(bocf_model* mdl, double* jitter_out, void* stream);
+
+/* Copy one factor out for inspection (tests): L, Linv n x n row-major, alpha n, [dev] or NULL. */
+int bocf_model_get_factor(bocf_model* mdl, int h, int j, double* L, double* Linv, double* alpha,
+                          void* stream);
+int bocf_model_n(const bocf_model* mdl);
+int bocf_model_H(const bocf_model* mdl);
+
+/* Upper bound, in bytes, of the handle's internal scratch (default 4 GiB). */
+int bocf_model_set_scratch_limit(bocf_model* mdl, uint64_t bytes);
+
+/* Posterior of hyper-sample h at N candidates Xc [dev] N x d.  Outputs [dev], any may be NULL:
+ *   mean  m x N      GP.posterior_mean            gp.py:380-400 -> posterior.py:299-305
+ *   var   m x N      GP.posterior_variance (+noise) gp.py:403-418 -> posterior.py:308-320, clipped at
+ *                    1e-10 as GPModel.posterior_variance does (gpmodel.py:174); noiseless=1 omits the
+ *                    likelihood variance (gp.py:421-435, gpmodel.py:183)
+ *   dmean m x N x d  GP.posterior_mean_gradient     gp.py:438-461 (Stationary.gradients_X / _grad_X)
+ *   dvar  m x N x d  GP.posterior_variance_gradient gp.py:464-490 (not clipped, no noise term)
+ * Stacking order is multi_outputGP's (multi_outputGP.py:165-191,284-306). */
+int bocf_posterior(bocf_model* mdl, int h, const double* Xc, int64_t N, int noiseless, double* mean,
+                   double* var, double* dmean, double* dvar, void* stream);
+
+/* ---- acquisition: replaces _compute_acq / _compute_acq_withGradients ------------------------------
+ * Xc   [dev] N x d candidates
+ * Zt   [dev] m x S base samples, TRANSPOSED W_samples (uEI_noiseless.py:31), MC variants only
+ * theta [host] L x p utility parameters; weight [host] L (prob_dist for full support, 1/L otherwise)
+ * fstar [host] H x L: EI_CF/PI_CF: max_n U(theta_l, mu(X_n)) (uEI_noiseless.py:76; the reference
+ *        evaluates it once with whichever hyper-sample is current, quirk q2 -- the caller decides);
+ *        MA_EI/MA_PI: best_l per hyper-sample (maEI.py:129-136).  PI jitter 1e-6 is added inside.
+ * H_use: number of hyper-samples averaged (min(10, n_samples), uEI_noiseless.py:32)
+ * with_grad_formula: MA_EI only -- 1 uses the (mu-best)Phi+sigma*phi form of maEI.py:117-119, 0 the
+ *        sigma(u Phi+phi) form of maEI.py:95-96; ignored elsewhere.
+ * acq  [dev] N     ;  dacq [dev] N x d or NULL (value only). */
+int bocf_acq_eval(bocf_model* mdl, int variant, int composite, const double* Xc, int64_t N,
+                  const double* Zt, int S, const double* theta, int L, int p, const double* weight,
+                  const double* fstar, int H_use, int with_grad_formula, double* acq, double* dacq,
+                  void* stream);
+
+/* Same call with HOST candidate / result buffers (pinned or pageable): copies Xc in, runs the sweep,
+ * copies acq/dacq out, and synchronises.  This is the end-to-end entry bench.py times as `e2e`. */
+int bocf_acq_eval_host(bocf_model* mdl, int variant, int composite, const double* Xc_host, int64_t N,
+                       const double* Zt_dev, int S, const double* theta, int L, int p,
+                       const double* weight, const double* fstar, int H_use, int with_grad_formula,
+                       double* acq_host, double* dacq_host, void* stream);
+
+/* U(theta_l, Y[:, i]) for a batch: Y [dev] m x N -> out [dev] L x N.  Used for f* (uEI_noiseless.py:76). */
+int bocf_utility_eval(int composite, int m, const double* Y, int64_t N, const double* theta, int L,
+                      int p, double* out, void* stream);
+
+/* Local top-k of the LARGEST acq values (anchor selection, anchor_points_generator.py:59-64 with
+ * f = -acq).  Ties break on the smaller candidate index.  out_val [dev] k, out_idx [dev] k (int64,
+ * index + index_offset), out_x [dev] k x d (gathered rows of Xc) -- laid out contiguously as one
+ * k x (2 + d) fp64 record buffer `out_rec` (value, index-as-double, x...) ready for ncclAllGather. */
+int bocf_topk(const double* acq, const double* Xc, int64_t N, int d, int k, int64_t index_offset,
+              double* out_rec, void* stream);
+
+/* Counters for bench.py's gpu_launches claim: number of kernels this library has launched. */
+uint64_t bocf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOCF_B200_H_ */

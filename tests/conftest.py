@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def built_library():
+    """Build (or reuse) libbocf_b200.so; nvcc cross-compiles sm_100a without a GPU."""
+    import __graft_entry__ as ge
+    return ge.build_library()
+
+
+@pytest.fixture(scope="session")
+def cuda_device(built_library):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return "cuda:0"
