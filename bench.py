@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- EI-CF acquisition evaluations/sec WITH gradients (BASELINE.json metric) on N B200s.
+
+One step = one pass of the hot path over one batch of synthetic candidates on every rank:
+GP posterior (mean, variance, both gradients) of all m outputs -> fused MC composite EI and its
+pathwise gradient over all S base samples -> local top-16 (+ NCCL all-gather of the top-k records
+when N > 1, the path's only exchange).  Workload: BASELINE.json configs[2] (m=16, d=10, n=1000,
+Matern-5/2 ARD, 1024 MC samples, sum-of-squares composite), 1M candidates per GPU per step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (one JSON line on rank 0)
+    python bench.py --impl reference ...                          the reference's CPU algorithm (oracle port)
+
+`value`  : device-resident inputs, CUDA-event timed, max over ranks.
+`e2e`    : the same sweep through the public plugin call acquisition_function_withGradients(numpy) with
+           pinned HOST candidates in and HOST results out (H2D/D2H inside the timed region).
+`roofline`: dominant kernel's algorithmic fp64 flops / its CUDA-event time, against an fp64 DGEMM peak
+           measured in this run (MEASURED_PEAKS.json carries no fp64 figure).
+`cpu_baseline`: the oracle port (reference loop structure) timed on this box's host cores, N=1 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[2]: the configuration the metric is quoted on
+    "cfg3": dict(m=16, d=10, n=1000, kind="matern52", composite="sumsq_target", S=1024, H=1, L=1, N=1000000),
+    # BASELINE.json configs[1]
+    "cfg2": dict(m=4, d=6, n=200, kind="rbf", composite="sumsq_target", S=256, H=1, L=1, N=100000),
+}
+K_TOP = 16
+
+
+def f_grad(c):
+    """Algorithmic flops per evaluation with gradients, SURVEY.md 8(d)."""
+    m, n, d, S, H, L = c["m"], c["n"], c["d"], c["S"], c["H"], c["L"]
+    return H * (m * (2 * n * n + n * (7 * d + 14)) + L * S * (12 * m + 2) + 4 * m * d)
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- reference arm (CPU) -----------------------------------------------------------------------------------
+def cpu_literal_rate(P, budget_s, chunk=32):
+    """evals/s of the oracle port with the reference's loop structure (uEI_noiseless.py:138-170), gradients on."""
+    from tests.helpers import oracle_model, oracle_acq
+    om = oracle_model(P)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        lo = done % max(1, P.N - chunk)
+        oracle_acq(P, grad=True, vectorised=False, Xc=P.Xc[lo:lo + chunk], model=om)
+        done += chunk
+        el = time.perf_counter() - t0
+        if el > budget_s:
+            break
+    return done / el, done, el
+
+
+def cpu_vectorised_rate(P, budget_s, chunk=2048):
+    from tests.helpers import oracle_model, oracle_acq
+    om = oracle_model(P)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        lo = done % max(1, P.N - chunk)
+        oracle_acq(P, grad=True, vectorised=True, Xc=P.Xc[lo:lo + chunk], model=om)
+        done += chunk
+        el = time.perf_counter() - t0
+        if el > budget_s:
+            break
+    return done / el, done, el
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from tests.helpers import make_problem, oracle_model, oracle_acq
+    c = dict(cfg)
+    sample = args.ref_sample
+    P = make_problem(m=c["m"], d=c["d"], n=c["n"], H=c["H"], kind=c["kind"], composite=c["composite"], N=4096,
+                     S=c["S"], L=c["L"], seed=0)
+    om = oracle_model(P)
+    for w in range(args.warmup):
+        oracle_acq(P, grad=True, vectorised=False, Xc=P.Xc[:min(8, sample)], model=om)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        lo = (k * sample) % (P.N - sample)
+        oracle_acq(P, grad=True, vectorised=False, Xc=P.Xc[lo:lo + sample], model=om)
+    el = time.perf_counter() - t0
+    val = args.steps * sample / el
+    line = {
+        "impl": "reference", "metric": "EI-CF acq evals/sec with grads", "value": val, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(c, sample),
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "%d candidates x %d MC samples per step; oracle port with the reference's loop "
+                                   "structure (uEI_noiseless.py:138-170: Python loops over theta x Z x candidates, "
+                                   "per-output LAPACK/BLAS posterior on all host threads)" % (sample, c["S"])},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(c, n_per_gpu):
+    return {"workload": "BASELINE.json configs[2]: synthetic independent multi-output GP m=%d d=%d n=%d %s-ARD, "
+                        "%s composite, EI-CF with gradients, %d MC base samples, H=%d, L=%d"
+                        % (c["m"], c["d"], c["n"], c["kind"], c["composite"], c["S"], c["H"], c["L"]),
+            "candidates_per_gpu_per_step": int(n_per_gpu), "mc_samples": c["S"], "top_k": K_TOP,
+            "l2": "256 MiB flush between steps; per-step K*/V scratch (GiBs) far exceeds the 126 MB L2"}
+
+
+# ---- our arm -----------------------------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        ge.build_library()
+    if world > 1:
+        dist.barrier()
+    import bocf_b200
+    from bocf_b200 import _lib, distributed as bd
+    from tests.helpers import make_problem, product_model, product_utility
+
+    c = dict(cfg)
+    N = args.candidates or c["N"]
+    P = make_problem(m=c["m"], d=c["d"], n=c["n"], H=c["H"], kind=c["kind"], composite=c["composite"], N=4096,
+                     S=c["S"], L=c["L"], seed=0)
+    t_setup = time.perf_counter()
+    model = product_model(P, str(dev))
+    torch.cuda.synchronize()
+    t_factor = time.perf_counter() - t_setup
+    acq = bocf_b200.uEI_noiseless(model, None, utility=product_utility(P))
+    acq.W_samples = P.Z
+    # this rank's shard of the global candidate set (weak scaling: N per rank), seeded per rank
+    Xh = torch.from_numpy(np.random.default_rng(7 + 1000 * rank).uniform(size=(N, c["d"]))).pin_memory()
+    Xd = Xh.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        model.set_hyperparameters(0)
+        a, g = acq._compute_acq_withGradients(Xd)
+        rec = bd.local_topk(a, Xd, K_TOP, index_offset=rank * N)
+        return bd.allgather_topk(rec, K_TOP) if world > 1 else rec
+
+    def step_host():
+        model.set_hyperparameters(0)
+        f, df = acq.acquisition_function_withGradients(Xh.numpy())
+        return f, df
+
+    def timed(fn, steps, profile=False):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if profile:
+            _lib.profile_enable(True)
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+            flush.zero_()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - l0
+        prof = _lib.profile_report() if profile else None
+        if profile:
+            _lib.profile_enable(False)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), launches, prof
+
+    for _ in range(args.warmup):
+        step_device()
+        flush.zero_()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, _, launches, prof = timed(step_device, args.steps, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    step_host()                                                     # warm the host path (pinned staging, allocator)
+    _, ms_e2e, _, _ = timed(step_host, args.steps)
+
+    # fp64 peak: cuBLAS DGEMM 8192^3, best of 5, measured here because MEASURED_PEAKS.json has no fp64 entry
+    peak_tf = None
+    if rank == 0:
+        A = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        B = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        torch.matmul(A, B)
+        best = 1e30
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(A, B)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        peak_tf = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del A, B
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    evals = args.steps * N * world
+    value = evals / (ms_dev * 1e-3)
+    e2e_value = evals / (ms_e2e * 1e-3)
+    F = f_grad(c)
+    # dominant kernel and its algorithmic flops: each of the two triangular contractions does n^2 flop per
+    # (candidate, output) -- the 2 n^2 term of F_grad split evenly (DESIGN.md "kernels")
+    gemm_names = ["dvar_gemm_kernel", "var_gemm_kernel"]
+    dom = max(gemm_names, key=lambda k: prof.get(k, (0, 0.0))[1])
+    cnt, tot_ms = prof[dom]
+    cand_per_launch = args.steps * N / cnt
+    flops_per_launch = c["m"] * float(c["n"]) ** 2 * cand_per_launch
+    achieved_tf = flops_per_launch / (tot_ms / cnt * 1e-3) / 1e12
+    total_kernel_ms = sum(v[1] for v in prof.values())
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None,
+                "peak_source": "fp64 cuBLAS DGEMM 8192^3 best-of-5 measured in this run (MEASURED_PEAKS.json has no "
+                               "fp64 entry; fp64 contractions run on DMMA.8x8x4, there is no fp64 tcgen05 kind)",
+                "launches": cnt, "avg_launch_ms": tot_ms / cnt,
+                "kernel_share_of_step": tot_ms / total_kernel_ms,
+                "step_achieved": F * value / world / 1e12, "step_frac": F * value / world / 1e12 / peak_tf,
+                "kernel_ms": {k: v[1] for k, v in prof.items()}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate_l, done_l, el_l = cpu_literal_rate(P, args.cpu_budget)
+        rate_v, done_v, el_v = cpu_vectorised_rate(P, args.cpu_budget / 2)
+        cpu = {"value": rate_l, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "%d candidates x %d MC samples in %.1f s; oracle port with the reference's loop structure "
+                         "(Python loops over theta x Z x candidates; LAPACK/BLAS posterior on all host threads)"
+                         % (done_l, c["S"], el_l),
+               "vectorised_numpy_value": rate_v,
+               "vectorised_sample": "%d candidates in %.1f s, chunks of 2048" % (done_v, el_v)}
+
+    line = {
+        "metric": "EI-CF acq evals/sec with grads", "value": value, "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(c, N), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(N * c["d"] * 8),
+                "d2h_bytes_per_step": int(N * 8 + N * c["d"] * 8), "ms_per_step": ms_e2e / args.steps,
+                "api": "uEI_noiseless.acquisition_function_withGradients(numpy (N,d)) -> numpy (N,1),(N,d)"},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "cand_x_samples_per_s": value * c["S"], "factorize_s": t_factor,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU per step (default: the config's)")
+    ap.add_argument("--ref-sample", type=int, default=96, help="candidates per step of the reference arm")
+    ap.add_argument("--cpu-budget", type=float, default=16.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+    return run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

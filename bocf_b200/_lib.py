@@ -19,7 +19,7 @@ EXPORTS = [
     "bocf_model_create", "bocf_model_destroy", "bocf_model_set_data", "bocf_model_set_hypers",
     "bocf_model_factorize", "bocf_model_get_factor", "bocf_model_n", "bocf_model_H",
     "bocf_model_set_scratch_limit", "bocf_posterior", "bocf_acq_eval", "bocf_acq_eval_host",
-    "bocf_utility_eval", "bocf_topk",
+    "bocf_utility_eval", "bocf_topk", "bocf_profile_enable", "bocf_profile_report",
 ]
 
 
@@ -63,6 +63,8 @@ def load_library():
     lib.bocf_acq_eval_host.argtypes = lib.bocf_acq_eval.argtypes
     lib.bocf_utility_eval.argtypes = [i32, i32, c_dp, i64, c_dp, i32, i32, c_dp, c_vp]
     lib.bocf_topk.argtypes = [c_dp, c_dp, i64, i32, i32, i64, c_dp, c_vp]
+    lib.bocf_profile_enable.argtypes = [i32]
+    lib.bocf_profile_report.argtypes = [ctypes.c_char_p, i32]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("bocf_last_error", "bocf_version", "bocf_launch_count"):
@@ -78,6 +80,22 @@ def check(rc):
     if rc == -3:
         raise NotPositiveDefiniteError(rc, msg)
     raise BocfError(rc, msg)
+
+
+def profile_enable(on=True):
+    load_library().bocf_profile_enable(1 if on else 0)
+
+
+def profile_report():
+    """{kernel class: (launches, total device ms)} since profile_enable(True); synchronises the device."""
+    lib = load_library()
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.bocf_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def launch_count():

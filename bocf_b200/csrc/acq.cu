@@ -359,9 +359,12 @@ static int launch_mc_t(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvali
 #define BOCF_MC_ARGS                                                                                              \
   cb.mean, cb.var, cb.dmean, cb.dvar, cb.Nc, Nvalid, P.m, P.d, P.Zt, P.S, P.theta, P.L, P.p, P.weight, P.fstar, \
       P.scale, P.accumulate, acq, dacq
+  {
+  ProfScope ps("mc_acq_kernel", st);
   if (mode == 0) mc_acq_kernel<COMP, 0><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
   else if (mode == 1) mc_acq_kernel<COMP, 1><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
   else mc_acq_kernel<COMP, 2><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
+  }
 #undef BOCF_MC_ARGS
   BOCF_LAUNCH_OK("mc_acq_kernel");
   return 0;

@@ -16,6 +16,29 @@ static std::atomic<uint64_t> g_launches{0};
 void set_error(const std::string& msg) { g_err = msg; }
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- per-kernel event timing ---------------------------------------------------------------------------------
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec*> g_prof;
+ProfScope::ProfScope(const char* name, cudaStream_t stream) : st(stream) {
+  if (!g_prof_on) return;
+  ProfRec* r = new ProfRec();
+  r->name = name;
+  cudaEventCreate(&r->a);
+  cudaEventCreate(&r->b);
+  cudaEventRecord(r->a, st);
+  rec = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec) return;
+  ProfRec* r = static_cast<ProfRec*>(rec);
+  cudaEventRecord(r->b, st);
+  g_prof.push_back(r);
+}
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
@@ -102,6 +125,48 @@ extern "C" {
 const char* bocf_last_error(void) { return g_err.c_str(); }
 const char* bocf_version(void) { return "bocf_b200 0.1 sm_100a fp64-dmma"; }
 uint64_t bocf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int bocf_profile_enable(int on) {
+  for (ProfRec* r : g_prof) {
+    cudaEventDestroy(r->a);
+    cudaEventDestroy(r->b);
+    delete r;
+  }
+  g_prof.clear();
+  g_prof_on = (on != 0);
+  return 0;
+}
+
+// Writes one line per kernel class "name count total_ms\n" into buf; returns bytes written (or needed size).
+int bocf_profile_report(char* buf, int buf_bytes) {
+  cudaDeviceSynchronize();
+  std::vector<std::string> names;
+  std::vector<uint64_t> counts;
+  std::vector<double> totals;
+  for (ProfRec* r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r->a, r->b) != cudaSuccess) continue;
+    size_t k = 0;
+    for (; k < names.size(); ++k)
+      if (names[k] == r->name) break;
+    if (k == names.size()) {
+      names.push_back(r->name);
+      counts.push_back(0);
+      totals.push_back(0.0);
+    }
+    counts[k] += 1;
+    totals[k] += ms;
+  }
+  std::string out;
+  for (size_t k = 0; k < names.size(); ++k)
+    out += names[k] + " " + std::to_string(counts[k]) + " " + std::to_string(totals[k]) + "\n";
+  if (buf && buf_bytes > 0) {
+    size_t ncopy = out.size() < (size_t)buf_bytes - 1 ? out.size() : (size_t)buf_bytes - 1;
+    std::memcpy(buf, out.data(), ncopy);
+    buf[ncopy] = 0;
+  }
+  return (int)out.size() + 1;
+}
 
 int bocf_model_create(bocf_model** out, int m, int d, int kernel, int device) {
   if (!out || m < 1 || d < 1 || d > MAXD || kernel < 0 || kernel > BOCF_KERN_MATERN32) {

@@ -29,6 +29,14 @@ void count_launch(uint64_t n = 1);
     }                                                                                        \
   } while (0)
 
+// Optional per-kernel timing (bocf_profile_enable): CUDA events recorded on the launch stream around a kernel.
+struct ProfScope {
+  void* rec = nullptr;
+  cudaStream_t st;
+  ProfScope(const char* name, cudaStream_t stream);
+  ~ProfScope();
+};
+
 inline int64_t round_up(int64_t x, int64_t q) { return (x + q - 1) / q * q; }
 inline int64_t ceil_div(int64_t x, int64_t q) { return (x + q - 1) / q; }
 

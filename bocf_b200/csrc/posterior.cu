@@ -349,28 +349,38 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
   need_dvar = need_dvar && grad;
   need_var = need_var || need_dvar;
   int rc;
-  switch (M->kernel) {
-    case BOCF_KERN_SE: rc = launch_kstar_k<BOCF_KERN_SE>(M, h, Xc, Nvalid, grad, cb, st); break;
-    case BOCF_KERN_RBF: rc = launch_kstar_k<BOCF_KERN_RBF>(M, h, Xc, Nvalid, grad, cb, st); break;
-    case BOCF_KERN_MATERN52: rc = launch_kstar_k<BOCF_KERN_MATERN52>(M, h, Xc, Nvalid, grad, cb, st); break;
-    case BOCF_KERN_MATERN32: rc = launch_kstar_k<BOCF_KERN_MATERN32>(M, h, Xc, Nvalid, grad, cb, st); break;
-    default: set_error("unknown kernel kind"); return -1;
+  {
+    ProfScope ps("kstar_kernel", st);
+    switch (M->kernel) {
+      case BOCF_KERN_SE: rc = launch_kstar_k<BOCF_KERN_SE>(M, h, Xc, Nvalid, grad, cb, st); break;
+      case BOCF_KERN_RBF: rc = launch_kstar_k<BOCF_KERN_RBF>(M, h, Xc, Nvalid, grad, cb, st); break;
+      case BOCF_KERN_MATERN52: rc = launch_kstar_k<BOCF_KERN_MATERN52>(M, h, Xc, Nvalid, grad, cb, st); break;
+      case BOCF_KERN_MATERN32: rc = launch_kstar_k<BOCF_KERN_MATERN32>(M, h, Xc, Nvalid, grad, cb, st); break;
+      default: set_error("unknown kernel kind"); return -1;
+    }
   }
   if (rc) return rc;
   if (!need_var) return 0;      // mean (and mean gradient) only: no contraction against the factor
   const unsigned tiles = (unsigned)((cb.Nc / TILE) * M->nb * M->m);
-  var_gemm_kernel<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(cb.KsT, M->Linv, cb.V, cb.part_var, cb.Nc, M->n16,
-                                                                  M->n_pad, M->nb, M->m, h, need_dvar ? 1 : 0);
+  {
+    ProfScope ps("var_gemm_kernel", st);
+    var_gemm_kernel<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(cb.KsT, M->Linv, cb.V, cb.part_var, cb.Nc, M->n16,
+                                                                    M->n_pad, M->nb, M->m, h, need_dvar ? 1 : 0);
+  }
   BOCF_LAUNCH_OK("var_gemm_kernel");
   if (need_dvar) {
+    ProfScope ps("dvar_gemm_kernel", st);
     dvar_gemm_kernel<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(cb.V, M->Linv, cb.GsT, Xc, Nvalid, M->Xs, M->hyp,
                                                                     cb.part_dvar, cb.Nc, M->n, M->n16, M->n_pad, M->nb,
                                                                     M->m, M->d, h);
-    BOCF_LAUNCH_OK("dvar_gemm_kernel");
   }
+  if (need_dvar) BOCF_LAUNCH_OK("dvar_gemm_kernel");
   dim3 fgrid((unsigned)ceil_div(cb.Nc, 256), (unsigned)M->m);
-  finalize_kernel<<<fgrid, 256, 0, st>>>(cb.part_var, cb.part_dvar, M->hyp, cb.Nc, M->nb, M->m, M->d, h,
-                                         need_dvar ? 1 : 0, noiseless ? 1 : 0, cb.var, cb.dvar);
+  {
+    ProfScope ps("finalize_kernel", st);
+    finalize_kernel<<<fgrid, 256, 0, st>>>(cb.part_var, cb.part_dvar, M->hyp, cb.Nc, M->nb, M->m, M->d, h,
+                                           need_dvar ? 1 : 0, noiseless ? 1 : 0, cb.var, cb.dvar);
+  }
   BOCF_LAUNCH_OK("finalize_kernel");
   return 0;
 }

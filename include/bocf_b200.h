@@ -142,6 +142,11 @@ int bocf_utility_eval(int composite, int m, const double* Y, int64_t N, const do
 int bocf_topk(const double* acq, const double* Xc, int64_t N, int d, int k, int64_t index_offset,
               double* out_rec, void* stream);
 
+/* Per-kernel device timing for bench.py's live roofline: when enabled, every kernel launch is bracketed by CUDA
+ * events on its stream.  bocf_profile_report synchronises the device and writes "name count total_ms" lines. */
+int bocf_profile_enable(int on);
+int bocf_profile_report(char* buf, int buf_bytes);
+
 /* Counters for bench.py's gpu_launches claim: number of kernels this library has launched. */
 uint64_t bocf_launch_count(void);
 

@@ -194,7 +194,12 @@ class uEI_noiseless(AcquisitionBase):
                     act = valx > fstar
                     if not np.any(act):
                         continue
-                    dU = np.stack([self.utility.eval_gradient(theta, a[:, i]) for i in np.nonzero(act)[0]], axis=1)
+                    name = getattr(self.utility, 'composite_name', None)
+                    if name is not None:
+                        from .utility import eval_gradient_batch
+                        dU = eval_gradient_batch(name, theta, a[:, act])
+                    else:
+                        dU = np.stack([self.utility.eval_gradient(theta, a[:, i]) for i in np.nonzero(act)[0]], axis=1)
                     b = (0.5 * W[:, None] / sigmaX[:, act])[:, :, None] * dvar_dX[:, act, :] + dmuX_dX[:, act, :]
                     marginal_dacq_dX[act, :, l] += np.einsum('ji,jiq->iq', dU, b)
         marginal_acqX /= (self.n_hyps_samples * n_w)

@@ -133,4 +133,30 @@ COMPOSITES = {
 
 def make_utility(name, parameter_dist):
     U, dU, linear = COMPOSITES[name]
-    return Utility(func=U, dfunc=dU, parameter_dist=parameter_dist, linear=linear)
+    ut = Utility(func=U, dfunc=dU, parameter_dist=parameter_dist, linear=linear)
+    ut.composite_name = name
+    return ut
+
+
+def eval_gradient_batch(name, parameter, a):
+    """grad_y U(theta, a[:, k]) for every column k of a (m, K): the same expressions as the *_dU functions
+    above with the attribute axis kept explicit (used only by the vectorised twin of the reference loops)."""
+    m = a.shape[0]
+    if name == 'sumsq_target':
+        return -2 * (a - np.asarray(parameter, dtype=float).reshape(-1)[:, None])
+    if name == 'neg_sum_exp':
+        return -np.exp(a)
+    if name == 'exp_cos':
+        aux = -np.pi * np.multiply(np.exp(-a / np.pi), np.sin(np.pi * a)) \
+            - np.multiply(np.exp(-a / np.pi), np.cos(np.pi * a)) / np.pi
+        return -exp_cos_c(m)[:, None] * aux
+    if name == 'rosen_composite':
+        h = m // 2
+        th = np.asarray(parameter, dtype=float).reshape(-1)[0]
+        g = np.zeros_like(a)
+        g[:h] = 2 * (th - a[:h])
+        g[h:2 * h] = -200 * a[h:2 * h]
+        return g
+    if name == 'linear':
+        return np.broadcast_to(np.asarray(parameter, dtype=float).reshape(-1)[:, None], a.shape)
+    raise ValueError(name)

@@ -9,6 +9,34 @@ class Problem(object):
     pass
 
 
+def _gen_kernel(kind, variance, ls, X):
+    """Plain-numpy covariance used ONLY to draw synthetic observations (independent of oracle/ and of the product)."""
+    Xs = X / ls
+    r2 = np.maximum(((Xs[:, None, :] - Xs[None, :, :]) ** 2).sum(-1), 0.0)
+    r = np.sqrt(r2)
+    if kind in ("se", "rbf"):
+        return variance * np.exp(-0.5 * r2)
+    if kind == "matern52":
+        return variance * (1 + np.sqrt(5.) * r + 5. / 3 * r2) * np.exp(-np.sqrt(5.) * r)
+    return variance * (1 + np.sqrt(3.) * r) * np.exp(-np.sqrt(3.) * r)
+
+
+def _gen_score(composite, theta, Y):
+    """Utility of the observations (m, n) under theta; only ranks training points for candidate placement."""
+    m = Y.shape[0]
+    if composite == "sumsq_target":
+        return -((Y - theta[:, None]) ** 2).sum(0)
+    if composite == "neg_sum_exp":
+        return -np.exp(Y).sum(0)
+    if composite == "exp_cos":
+        c = np.array([1., 2., 5., 2., 3.])[np.arange(m) % 5]
+        return -(c[:, None] * np.exp(-Y / np.pi) * np.cos(np.pi * Y)).sum(0)
+    if composite == "rosen_composite":
+        h = m // 2
+        return -((theta[0] - Y[:h]) ** 2 + 100 * Y[h:2 * h] ** 2).sum(0)
+    return theta @ Y
+
+
 def make_problem(m=4, d=6, n=200, H=1, kind="rbf", composite="sumsq_target", N=1024, S=256, L=1, seed=0,
                  noise=1e-2, prior_draw=True, focus=0.75, focus_scale=0.08):
     """Synthetic inputs of SURVEY.md 8(d): X ~ U[0,1]^{n x d}, Y_j a prior-GP draw + noise, lengthscales
@@ -24,8 +52,7 @@ def make_problem(m=4, d=6, n=200, H=1, kind="rbf", composite="sumsq_target", N=1
     for j in range(m):
         r = np.random.default_rng(1000 + j + 17 * seed)
         if prior_draw and n <= 2500:
-            from oracle.kern import Kern
-            K = Kern(kind, d, P.variance[0, j], P.lengthscale[0, j], ARD=True).K(P.X)
+            K = _gen_kernel(kind, P.variance[0, j], P.lengthscale[0, j], P.X)
             K[np.diag_indices_from(K)] += 1e-8
             Lc = np.linalg.cholesky(K)
             y = Lc @ r.standard_normal(n) + np.sqrt(noise) * r.standard_normal(n)
@@ -51,9 +78,8 @@ def make_problem(m=4, d=6, n=200, H=1, kind="rbf", composite="sumsq_target", N=1
     if focus > 0:
         # uniformly random candidates almost never improve on the incumbent; move a fraction of them next to the
         # best observed points so the parity checks see plenty of non-zero EI values and gradients
-        from oracle.utility import COMPOSITES
         Ymat = np.concatenate(P.Y, axis=1).T                       # (m, n)
-        score = np.asarray(COMPOSITES[composite][0](P.theta[0], Ymat)).reshape(-1)
+        score = _gen_score(composite, P.theta[0], Ymat)
         top = np.argsort(-score)[:8]
         k = int(focus * N)
         cr = np.random.default_rng(31 + seed)
