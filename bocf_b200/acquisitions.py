@@ -128,8 +128,8 @@ class uEI_noiseless(AcquisitionBase):
             self._Zt_cache = ((self.W_samples, W.shape), Zt)
         return Zt
 
-    def _fstar(self, theta):
-        """max_n U(theta_l, mu(X_n)) with the CURRENT hyper-sample (uEI_noiseless.py:66,76; quirk q2), (H_use, L)."""
+    def _fstar_current(self, theta):
+        """max_n U(theta_l, mu(X_n)) under the CURRENTLY selected hyper-sample: (L,)."""
         model = self.model
         fX = model._posterior_mean_at_evaluated_points_dev()                  # (m, n) on device
         theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
@@ -141,9 +141,23 @@ class uEI_noiseless(AcquisitionBase):
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             _lib.check(model._lib.bocf_utility_eval(_lib.COMPOSITES[self.utility.composite], model.output_dim,
                                                     _ptr(fX.contiguous()), n, th_p, L, p, _ptr(U), st))
-            fstar = U.max(dim=1).values.cpu().numpy()
+            return U.max(dim=1).values.cpu().numpy()
+
+    def _fstar(self, theta, per_hyper_sample=False):
+        """Incumbent f*_l as an (H_use, L) table.
+
+        per_hyper_sample=False: evaluated ONCE, before the h loop, with whichever hyper-sample is current
+        (uEI_noiseless.py:66,76 and :141,155 -- the sequential value path and the gradient path, quirk q2).
+        per_hyper_sample=True: re-evaluated inside every pass h, as the pool helper does
+        (uEI_noiseless.py:99-109, the branch _compute_acq takes for more than one candidate)."""
         H_use = self._n_hyps_effective()
-        return np.tile(fstar[None, :], (H_use, 1))
+        if not per_hyper_sample:
+            return np.tile(self._fstar_current(theta)[None, :], (H_use, 1))
+        rows = []
+        for h in range(H_use):
+            self.model.set_hyperparameters(h)
+            rows.append(self._fstar_current(theta))
+        return np.stack(rows, axis=0)
 
     def _weights(self, L):
         if self.use_full_support:
@@ -157,7 +171,8 @@ class uEI_noiseless(AcquisitionBase):
     def _compute_acq(self, X, parallel=True):
         # uEI_noiseless.py:40-61 (+ :63-83 / :85-116)
         theta = np.atleast_2d(self.utility_params_samples)
-        fstar = self._fstar(theta)
+        n_cand = X.shape[0] if hasattr(X, "shape") and len(X.shape) == 2 else len(np.atleast_2d(X))
+        fstar = self._fstar(theta, per_hyper_sample=bool(parallel and n_cand > 1))     # :43-46
         Zt = self._Zt()
         out = self._run(self._variant, X, theta, self._weights(len(theta)), fstar, False, Zt, Zt.shape[1])
         self._finish()

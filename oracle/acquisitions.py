@@ -68,9 +68,16 @@ class uEI_noiseless(AcquisitionBase):
 
     # ---- value ------------------------------------------------------------------------------------
     def _compute_acq(self, X, parallel=True):
-        # uEI_noiseless.py:40-61; the pool branch (:85-116) evaluates the same sums per candidate
+        # uEI_noiseless.py:40-61.  NOTE the two branches are NOT equivalent when H > 1: the pool branch (:44,
+        # :85-116) re-evaluates f* inside the helper, i.e. with the hyper-sample of the current pass, while the
+        # sequential branch (:46, :63-83) evaluates it once before the h loop (stale hyper-sample, quirk q2).
         X = np.atleast_2d(X)
-        if self.vectorised:
+        if parallel and len(X) > 1:
+            if self.vectorised:
+                marginal_acqX = self._marginal_acq_vec(X, self.utility_params_samples, per_h_fstar=True)
+            else:
+                marginal_acqX = self._marginal_acq_parallel(X)
+        elif self.vectorised:
             marginal_acqX = self._marginal_acq_vec(X, self.utility_params_samples)
         else:
             marginal_acqX = self._marginal_acq(X, self.utility_params_samples)
@@ -99,13 +106,48 @@ class uEI_noiseless(AcquisitionBase):
         marginal_acqX /= (self.n_hyps_samples * n_w)
         return marginal_acqX
 
-    def _marginal_acq_vec(self, X, utility_params_samples):
+    def _marginal_acq_parallel(self, X):
+        # uEI_noiseless.py:85-97 with the pathos pool replaced by a serial map (the first, discarded map of
+        # :93 is skipped -- quirk q1)
+        marginal_acqX = np.zeros((X.shape[0], len(self.utility_params_samples)))
+        n_w = self.W_samples.shape[0]
+        for h in range(self.n_hyps_samples):
+            self.model.set_hyperparameters(h)
+            marginal_acqX += np.atleast_2d([self._parallel_acq_helper(x) for x in X])
+        marginal_acqX /= (self.n_hyps_samples * n_w)
+        return marginal_acqX
+
+    def _improvement(self, valx, max_valX_evaluated):
+        return max(valx - max_valX_evaluated, 0)                        # uEI_noiseless.py:114
+
+    def _parallel_acq_helper(self, x):
+        # uEI_noiseless.py:99-116
+        x = np.atleast_2d(x)
+        fX_evaluated = self.model.posterior_mean_at_evaluated_points()
+        utility_params_samples = self.utility_params_samples
+        L = len(utility_params_samples)
+        marginal_acqx = np.zeros(L)
+        mux = self.model.posterior_mean(x)[:, 0]
+        sigmax = np.sqrt(self.model.posterior_variance(x))[:, 0]
+        for l in range(L):
+            max_valX_evaluated = np.max(self.utility.eval_func(utility_params_samples[l], fX_evaluated))
+            for W in self.W_samples:
+                valx = self.utility.eval_func(utility_params_samples[l], mux + sigmax * W)
+                marginal_acqx[l] += self._improvement(valx, max_valX_evaluated)
+        return marginal_acqx
+
+    def _improvement_vec(self, valx, fstar):
+        return np.maximum(valx - fstar, 0)
+
+    def _marginal_acq_vec(self, X, utility_params_samples, per_h_fstar=False):
         fX_evaluated = self.model.posterior_mean_at_evaluated_points()
         n_w = self.W_samples.shape[0]
         L = len(utility_params_samples)
         marginal_acqX = np.zeros((X.shape[0], L))
         for h in range(self.n_hyps_samples):
             self.model.set_hyperparameters(h)
+            if per_h_fstar:
+                fX_evaluated = self.model.posterior_mean_at_evaluated_points()
             muX = self.model.posterior_mean(X)
             sigmaX = np.sqrt(self.model.posterior_variance(X))
             for l in range(L):
@@ -113,7 +155,7 @@ class uEI_noiseless(AcquisitionBase):
                 for W in self.W_samples:
                     a = muX + sigmaX * W[:, None]                      # (m, N)
                     valx = self.utility.eval_func(utility_params_samples[l], a)
-                    marginal_acqX[:, l] += np.maximum(valx - fstar, 0)
+                    marginal_acqX[:, l] += self._improvement_vec(valx, fstar)
         marginal_acqX /= (self.n_hyps_samples * n_w)
         return marginal_acqX
 
@@ -238,22 +280,12 @@ class uPI(uEI_noiseless):
         marginal_acqX /= (self.n_hyps_samples * n_w)
         return marginal_acqX
 
-    def _marginal_acq_vec(self, X, utility_params_samples):
-        fX_evaluated = self.model.posterior_mean_at_evaluated_points()
-        n_w = self.W_samples.shape[0]
-        L = len(utility_params_samples)
-        marginal_acqX = np.zeros((X.shape[0], L))
-        for h in range(self.n_hyps_samples):
-            self.model.set_hyperparameters(h)
-            muX = self.model.posterior_mean(X)
-            sigmaX = np.sqrt(self.model.posterior_variance(X))
-            for l in range(L):
-                fstar = np.max(self.utility.eval_func(utility_params_samples[l], fX_evaluated))
-                for W in self.W_samples:
-                    valx = self.utility.eval_func(utility_params_samples[l], muX + sigmaX * W[:, None])
-                    marginal_acqX[:, l] += np.where((valx - (fstar + self.jitter)) > 0., 1., 0.)
-        marginal_acqX /= (self.n_hyps_samples * n_w)
-        return marginal_acqX
+    def _improvement(self, valx, max_valX_evaluated):
+        # uPI.py:114 (pool helper) == :83
+        return np.where((valx - (max_valX_evaluated + self.jitter)) > 0., 1., 0.)
+
+    def _improvement_vec(self, valx, fstar):
+        return np.where((valx - (fstar + self.jitter)) > 0., 1., 0.)
 
     def _compute_acq_withGradients(self, X):
         raise NotImplementedError('uPI has no analytical gradient (uPI.py:19)')

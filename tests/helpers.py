@@ -102,7 +102,7 @@ def oracle_utility(P, full_support=True):
     return make_utility(P.composite, pd)
 
 
-def oracle_acq(P, grad=True, variant="uEI_noiseless", vectorised=True, Xc=None, model=None):
+def oracle_acq(P, grad=True, variant="uEI_noiseless", vectorised=True, Xc=None, model=None, parallel=True):
     from oracle import acquisitions as A
     mod = oracle_model(P) if model is None else model
     U = oracle_utility(P)
@@ -115,6 +115,8 @@ def oracle_acq(P, grad=True, variant="uEI_noiseless", vectorised=True, Xc=None, 
     if grad:
         a, g = acq._compute_acq_withGradients(Xc)
         return a[:, 0], g
+    if variant in ("uEI_noiseless", "uPI"):
+        return acq._compute_acq(Xc, parallel=parallel)[:, 0], None
     return acq._compute_acq(Xc)[:, 0], None
 
 
@@ -134,7 +136,7 @@ def product_utility(P):
     return bocf_b200.Utility(parameter_dist=pd, composite=P.composite)
 
 
-def product_acq(P, grad=True, variant="uEI_noiseless", device="cuda:0", Xc=None, model=None):
+def product_acq(P, grad=True, variant="uEI_noiseless", device="cuda:0", Xc=None, model=None, parallel=True):
     import bocf_b200
     mod = product_model(P, device) if model is None else model
     U = product_utility(P)
@@ -146,6 +148,8 @@ def product_acq(P, grad=True, variant="uEI_noiseless", device="cuda:0", Xc=None,
     if grad:
         a, g = acq._compute_acq_withGradients(Xc)
         return a[:, 0], g
+    if variant in ("uEI_noiseless", "uPI"):
+        return acq._compute_acq(Xc, parallel=parallel)[:, 0], None
     return acq._compute_acq(Xc)[:, 0], None
 
 
