@@ -8,3 +8,7 @@ from . import kern  # noqa: F401
 from .utility import Utility, ParameterDistribution  # noqa: F401
 from .model import multi_outputGP  # noqa: F401
 from .acquisitions import AcquisitionBase, uEI_noiseless, uPI, maEI, maPI, EI, PI  # noqa: F401
+from .optimization import (AcquisitionOptimizer, GeneralOptimizer, Design_space, Sequential,  # noqa: F401
+                           initial_design)
+from .cbo import CBO, MultiObjective, ExpectationUtility  # noqa: F401
+from . import cbo, optimization, distributed  # noqa: F401

@@ -150,6 +150,11 @@ class multi_outputGP(object):
             cov[j, :] = tmp2[:, 0]
         return m, cov
 
+    def predict_noiseless(self, X, full_cov=False):
+        # :151-162 -> gpmodel.py:150-159 (posterior_mean + clipped noiseless variance)
+        X = np.atleast_2d(X)
+        return self.posterior_mean(X), self.posterior_variance_noiseless(X)
+
     def posterior_mean(self, X):
         # :165-173
         m = np.empty((self.output_dim, X.shape[0]))

@@ -1,0 +1,77 @@
+"""Config 1 plumbing on the GPU: the CBO loop (cbo.py) + multistart optimiser around the CUDA path, against the
+same plumbing driven by the CPU oracle classes with the same seed."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(seed):
+    rng = np.random.default_rng(seed)
+    d, m = 2, 3
+    W = rng.standard_normal((m, d))
+
+    def f(X):
+        X = np.atleast_2d(X)
+        return np.stack([np.sin(3 * X @ W[j]) + 0.3 * j * X[:, 0] for j in range(m)], axis=0)
+    theta = f(np.array([[0.3, 0.7]])).T
+    return d, m, f, theta
+
+
+def _run(side, cuda_device, iters=2, seed=0):
+    import bocf_b200 as B
+    d, m, f, theta = _problem(3)
+    np.random.seed(seed)
+    space = B.Design_space(space=[{'name': 'var', 'type': 'continuous', 'domain': (0, 1), 'dimensionality': d}])
+    objective = B.MultiObjective(f, as_list=False, output_dim=m)
+    acq_opt = B.AcquisitionOptimizer(optimizer='lbfgs2', inner_optimizer='lbfgs2', space=space, n_starting=64, n_anchor=4)
+    X_init = B.initial_design('random', space, 2 * (d + 1))
+    var, ls, noise = np.full((1, m), 1.0), np.full((1, m, d), 0.4), np.full((1, m), 1e-4)
+    if side == "cuda":
+        model = B.multi_outputGP(m, n_samples=1, device=cuda_device)
+        model.set_hyperparameter_samples(var, ls, noise, kind="matern52")
+        pd = B.ParameterDistribution(support=theta, prob_dist=np.ones(1))
+        U = B.Utility(parameter_dist=pd, composite="sumsq_target")
+        acq = B.uEI_noiseless(model, space, optimizer=acq_opt, utility=U)
+    else:
+        from oracle.models import multi_outputGP
+        from oracle.utility import make_utility, ParameterDistribution
+        from oracle.acquisitions import uEI_noiseless
+        model = multi_outputGP.from_hyper_samples("matern52", var, ls, noise)
+        U = make_utility("sumsq_target", ParameterDistribution(support=theta, prob_dist=np.ones(1)))
+        acq = uEI_noiseless(model, space, optimizer=acq_opt, utility=U, vectorised=True)
+    expU = B.ExpectationUtility(
+        lambda th, mu, v: -np.sum(np.square((mu.T - th).T), axis=0) - np.sum(v, axis=0),
+        lambda th, mu, v: -np.concatenate((2 * (np.squeeze(mu) - th), np.ones((len(np.squeeze(v)),)))))
+    bo = B.CBO(model, space, objective, acq, B.Sequential(acq), X_init, expectation_utility=expU)
+    bo.run_optimization(max_iter=iters)
+    return bo, acq_opt
+
+
+def test_cbo_loop_matches_oracle_driven_loop(cuda_device):
+    bo_g, opt_g = _run("cuda", cuda_device)
+    bo_c, _ = _run("cpu", cuda_device)
+    assert len(bo_g.suggested_points) == 2 and bo_g.X.shape == (8, 2)
+    # same selected next point (first acquisition: identical model, identical Z, identical candidates)
+    np.testing.assert_allclose(bo_g.suggested_points[0], bo_c.suggested_points[0], atol=1e-5)
+    np.testing.assert_allclose(bo_g.historical_optimal_values[0], bo_c.historical_optimal_values[0], rtol=1e-4, atol=1e-6)
+    assert np.all(np.isfinite(bo_g.historical_optimal_values))
+    assert opt_g.last_batches > 0          # the anchors' L-BFGS evaluations were batched into shared launches
+
+
+def test_batched_multistart_equals_sequential(cuda_device):
+    """Batching the anchors' f_df calls must not change any anchor's L-BFGS-B trajectory."""
+    import bocf_b200 as B
+    from tests.helpers import make_problem, product_model, product_utility
+    P = make_problem(m=3, d=3, n=40, H=1, kind="rbf", composite="sumsq_target", N=8, S=64, seed=17)
+    model = product_model(P, cuda_device)
+    space = B.Design_space(space=[{'name': 'var', 'type': 'continuous', 'domain': (0, 1), 'dimensionality': 3}])
+    res = []
+    for batched in (True, False):
+        opt = B.AcquisitionOptimizer(space, optimizer='lbfgs2', n_starting=50, n_anchor=5, batched=batched)
+        acq = B.uEI_noiseless(model, space, optimizer=opt, utility=product_utility(P))
+        acq.W_samples = P.Z
+        np.random.seed(1)
+        res.append(acq.optimize(x_baseline=P.X[:1]))
+    np.testing.assert_allclose(res[0][0], res[1][0], atol=1e-9)
+    np.testing.assert_allclose(np.asarray(res[0][1]).reshape(-1), np.asarray(res[1][1]).reshape(-1), atol=1e-12)
