@@ -97,9 +97,9 @@ static int ensure_scratch(bocf_model* M, uint64_t bytes) {
 static int64_t pick_chunk(const bocf_model* M, int64_t N, bool grad, uint64_t extra_per_cand) {
   const uint64_t per = chunk_bytes_per_candidate(M, grad) + extra_per_cand;
   int64_t nc = (int64_t)(M->scratch_limit / per);
-  nc = nc / TILE * TILE;
-  if (nc < TILE) nc = TILE;
-  const int64_t need = round_up(N, TILE);
+  nc = nc / CAND_TILE * CAND_TILE;
+  if (nc < CAND_TILE) nc = CAND_TILE;
+  const int64_t need = round_up(N, CAND_TILE);
   if (nc > need) nc = need;
   if (nc > (1 << 17)) nc = 1 << 17;
   return nc;

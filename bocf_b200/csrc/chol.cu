@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) trsm_panel_kernel(double* __
   double acc[8][4][2];
   gemm::zero_acc(acc);
   // A(m,k) = Ablk[m*n_pad + k] (m-major) ; B(k,n) = Dinv[n][k] (n-major)
-  gemm::mainloop<false, false>(acc, Ablk, n_pad, D, TILE, 0, TILE, smem);
+  gemm::mainloop<gemm::Tile128, false, false>(acc, Ablk, n_pad, D, TILE, 0, TILE, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int mbase = (warp >> 2) * 64, nbase = (warp & 3) * 32;
 #pragma unroll
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) syrk_update_kernel(double* _
   double* C = base + (int64_t)I * TILE * n_pad + (int64_t)J * TILE;
   double acc[8][4][2];
   gemm::zero_acc(acc);
-  gemm::mainloop<false, false>(acc, PI, n_pad, PJ, n_pad, 0, TILE, smem);
+  gemm::mainloop<gemm::Tile128, false, false>(acc, PI, n_pad, PJ, n_pad, 0, TILE, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int mbase = (warp >> 2) * 64, nbase = (warp & 3) * 32;
 #pragma unroll
@@ -247,12 +247,12 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) linv_row_kernel(const double
   gemm::zero_acc(acc);
   if (STEP == 1) {
     // A(m,k) = L[I*128+m][k] (m-major) ; B(k,n) = Linv[k][J*128+n] (k-major) ; k in [J*128, I*128)
-    gemm::mainloop<false, true>(acc, Lb + (int64_t)I * TILE * n_pad, n_pad, Li + (int64_t)J * TILE, n_pad, J * TILE,
+    gemm::mainloop<gemm::Tile128, false, true>(acc, Lb + (int64_t)I * TILE * n_pad, n_pad, Li + (int64_t)J * TILE, n_pad, J * TILE,
                                 I * TILE, smem);
   } else {
     // A = Dinv_I (m-major, ld 128) ; B(k,n) = S[k][n] at C[k*n_pad + n] (k-major)
     const double* D = Dinv + ((int64_t)hj * nb + I) * TILE * TILE;
-    gemm::mainloop<false, true>(acc, D, TILE, C, n_pad, 0, TILE, smem);
+    gemm::mainloop<gemm::Tile128, false, true>(acc, D, TILE, C, n_pad, 0, TILE, smem);
   }
   const double sgn = (STEP == 1) ? 1.0 : -1.0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -335,10 +335,10 @@ static int set_smem_attrs() {
   if (done) return 0;
   BOCF_CUDA_OK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     TILE * DLD * (int)sizeof(double)));
-  BOCF_CUDA_OK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-  BOCF_CUDA_OK(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-  BOCF_CUDA_OK(cudaFuncSetAttribute(linv_row_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-  BOCF_CUDA_OK(cudaFuncSetAttribute(linv_row_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(linv_row_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(linv_row_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
   done = true;
   return 0;
 }
@@ -352,9 +352,9 @@ int launch_cholesky(bocf_model* M, cudaStream_t st) {
     BOCF_LAUNCH_OK("potrf_diag_kernel");
     const int rem = nb - 1 - kb;
     if (rem > 0) {
-      trsm_panel_kernel<<<dim3(rem, Hm), gemm::THREADS, gemm::SMEM_BYTES, st>>>(M->Lmat, M->Dinv, M->n_pad, nb, kb);
+      trsm_panel_kernel<<<dim3(rem, Hm), gemm::THREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Dinv, M->n_pad, nb, kb);
       BOCF_LAUNCH_OK("trsm_panel_kernel");
-      syrk_update_kernel<<<dim3(rem * (rem + 1) / 2, Hm), gemm::THREADS, gemm::SMEM_BYTES, st>>>(M->Lmat, M->n_pad, nb, kb);
+      syrk_update_kernel<<<dim3(rem * (rem + 1) / 2, Hm), gemm::THREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->n_pad, nb, kb);
       BOCF_LAUNCH_OK("syrk_update_kernel");
     }
   }
@@ -368,9 +368,9 @@ int launch_inverse_and_alpha(bocf_model* M, cudaStream_t st) {
   linv_init_kernel<<<dim3(nb, Hm), 256, 0, st>>>(M->Linv, M->Dinv, M->n_pad, nb);
   BOCF_LAUNCH_OK("linv_init_kernel");
   for (int I = 1; I < nb; ++I) {
-    linv_row_kernel<1><<<dim3(I, Hm), gemm::THREADS, gemm::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
+    linv_row_kernel<1><<<dim3(I, Hm), gemm::THREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
     BOCF_LAUNCH_OK("linv_row_kernel<1>");
-    linv_row_kernel<2><<<dim3(I, Hm), gemm::THREADS, gemm::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
+    linv_row_kernel<2><<<dim3(I, Hm), gemm::THREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
     BOCF_LAUNCH_OK("linv_row_kernel<2>");
   }
   linv_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 8), Hm), 256, 0, st>>>(M->Linv, M->yc, M->m, M->n_pad, M->tvec);

@@ -1,13 +1,16 @@
 // gemm_f64.cuh -- fp64 tensor-core (DMMA.8x8x4) tile engine.
 //
-// One CTA (256 threads = 8 warps as 2 (M) x 4 (N)) computes a 128 x 128 fp64 tile
+// One CTA (256 threads = 8 warps laid out WM x WN) computes a (64*WM) x (32*WN) fp64 tile
 //     acc[m][n] = sum_{k in [k_begin,k_end)} A(m,k) * B(k,n)
 // with both operands streamed global -> shared by a 3-stage cp.async ring (BK = 16) and fed to
 // mma.sync.m8n8k4.f64.  Each warp owns a 64 x 32 sub-tile = 8 x 4 MMA tiles (64 fp64 accumulators
-// per thread).  Operand layouts are template switches so the same loop serves
+// per thread).  Two tile shapes are used:
+//     Tile<2,4> = 128 x 128   Cholesky panel / trailing updates, blocked triangular inverse
+//     Tile<4,2> = 256 x  64   candidate-side contractions (narrow column tiles waste fewer MMAs on the
+//                             structurally-zero upper triangle of the factor's diagonal blocks)
+// Operand layouts are template switches so the same loop serves
 //     V  = K* . Linv^T      (A k-major, B n-major)         posterior variance (trsm-as-gemm)
 //     Wt = V  . Linv        (A m-major, B k-major)         variance-gradient weights
-//     Cholesky panel / trailing updates and the blocked triangular inverse.
 // All matrix dimensions are padded by the caller so no bounds checks are needed inside the loop;
 // k_begin / k_end are multiples of BK.  Shared-memory rows are padded by 4 doubles which makes
 // every 64-bit fragment load bank-conflict free (row stride == 4 mod 16 doubles).
@@ -17,57 +20,70 @@
 namespace bocf {
 namespace gemm {
 
-constexpr int BM = 128;
-constexpr int BN = 128;
 constexpr int BK = 16;
 constexpr int STAGES = 3;
 constexpr int THREADS = 256;
 constexpr int LD_K = BK + 4;    // operand rows hold BK doubles (k contiguous)
-constexpr int LD_X = BM + 4;    // operand rows hold 128 doubles (m / n contiguous)
-constexpr int OPER_DOUBLES = (BM * LD_K > BK * LD_X) ? BM * LD_K : BK * LD_X;   // 2560
-constexpr int STAGE_DOUBLES = 2 * OPER_DOUBLES;
-constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);          // 122880
+
+template <int WM, int WN>
+struct Tile {
+  static constexpr int NTHREADS = 32 * WM * WN;
+  static constexpr int BM = 64 * WM;
+  static constexpr int BN = 32 * WN;
+  static constexpr int LDA_X = BM + 4;     // k-major A rows hold BM doubles
+  static constexpr int LDB_X = BN + 4;     // k-major B rows hold BN doubles
+  static constexpr int A_DOUBLES = (BM * LD_K > BK * LDA_X) ? BM * LD_K : BK * LDA_X;
+  static constexpr int B_DOUBLES = (BN * LD_K > BK * LDB_X) ? BN * LD_K : BK * LDB_X;
+  static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);
+};
+using Tile128 = Tile<2, 4>;      // 128 x 128, 256 threads, 122 880 B
+using TileWide = Tile<4, 2>;     // 256 x  64, 256 threads, 153 600 B
+using TileHalf = Tile<2, 2>;     // 128 x  64, 128 threads,  92 160 B  (2 CTAs / SM)
 
 // ---- global -> shared stage loads ---------------------------------------------------------------
-// XMAJOR == false: element (x,k) at P[x*ld + k]  (k contiguous)   -> smem s[x*LD_K + k]
-// XMAJOR == true : element (x,k) at P[k*ld + x]  (x contiguous)   -> smem s[k*LD_X + x]
-template <bool KMAJOR>
+// KMAJOR == false: element (x,k) at P[x*ld + k]  (k contiguous)   -> smem s[x*LD_K + k]
+// KMAJOR == true : element (x,k) at P[k*ld + x]  (x contiguous)   -> smem s[k*LDX + x]
+template <bool KMAJOR, int ROWS, int LDX, int NTHR>
 __device__ __forceinline__ void load_operand(double* s, const double* __restrict__ P, int64_t ld, int k0,
                                              int tid) {
+  constexpr int CHUNKS = ROWS * BK / 2;           // 16-byte chunks per stage
+  static_assert(CHUNKS % NTHR == 0, "tile must split evenly over the CTA");
   if (KMAJOR) {
+    constexpr int PER_ROW = ROWS / 2;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int c = tid + THREADS * r;
-      int krow = c >> 6, xc = (c & 63) * 2;
-      cp_async16(s + krow * LD_X + xc, P + (int64_t)(k0 + krow) * ld + xc);
+    for (int r = 0; r < CHUNKS / NTHR; ++r) {
+      int c = tid + NTHR * r;
+      int krow = c / PER_ROW, xc = (c % PER_ROW) * 2;
+      cp_async16(s + krow * LDX + xc, P + (int64_t)(k0 + krow) * ld + xc);
     }
   } else {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int c = tid + THREADS * r;
+    for (int r = 0; r < CHUNKS / NTHR; ++r) {
+      int c = tid + NTHR * r;
       int row = c >> 3, kc = (c & 7) * 2;
       cp_async16(s + row * LD_K + kc, P + (int64_t)row * ld + k0 + kc);
     }
   }
 }
 
-// acc[i][j][e]: row = wm*64 + 8*i + g, col = wn*32 + 8*j + 2*t + e   (lane = 4*g + t)
-template <bool A_KMAJOR, bool B_KMAJOR>
+// acc[i][j][e]: row = wm*64 + 8*i + g, col = wn*32 + 8*j + 2*t + e   (lane = 4*g + t, warp = wm*WN + wn)
+template <class T, bool A_KMAJOR, bool B_KMAJOR>
 __device__ __forceinline__ void mainloop(double (&acc)[8][4][2], const double* __restrict__ A, int64_t lda,
                                          const double* __restrict__ B, int64_t ldb, int k_begin, int k_end,
                                          double* smem) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int mbase = (warp >> 2) * 64, nbase = (warp & 3) * 32;
+  const int mbase = (warp / (T::BN / 32)) * 64, nbase = (warp % (T::BN / 32)) * 32;
   const int KT = (k_end - k_begin) / BK;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < KT) {
-      double* st = smem + s * STAGE_DOUBLES;
-      load_operand<A_KMAJOR>(st, A, lda, k_begin + s * BK, tid);
-      load_operand<B_KMAJOR>(st + OPER_DOUBLES, B, ldb, k_begin + s * BK, tid);
+      double* st = smem + s * T::STAGE_DOUBLES;
+      load_operand<A_KMAJOR, T::BM, T::LDA_X, T::NTHREADS>(st, A, lda, k_begin + s * BK, tid);
+      load_operand<B_KMAJOR, T::BN, T::LDB_X, T::NTHREADS>(st + T::A_DOUBLES, B, ldb, k_begin + s * BK, tid);
     }
     cp_async_commit();
   }
@@ -78,23 +94,23 @@ __device__ __forceinline__ void mainloop(double (&acc)[8][4][2], const double* _
     {
       int nxt = kt + STAGES - 1;
       if (nxt < KT) {
-        double* st = smem + (nxt % STAGES) * STAGE_DOUBLES;
-        load_operand<A_KMAJOR>(st, A, lda, k_begin + nxt * BK, tid);
-        load_operand<B_KMAJOR>(st + OPER_DOUBLES, B, ldb, k_begin + nxt * BK, tid);
+        double* st = smem + (nxt % STAGES) * T::STAGE_DOUBLES;
+        load_operand<A_KMAJOR, T::BM, T::LDA_X, T::NTHREADS>(st, A, lda, k_begin + nxt * BK, tid);
+        load_operand<B_KMAJOR, T::BN, T::LDB_X, T::NTHREADS>(st + T::A_DOUBLES, B, ldb, k_begin + nxt * BK, tid);
       }
       cp_async_commit();
     }
-    const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
-    const double* sB = sA + OPER_DOUBLES;
+    const double* sA = smem + (kt % STAGES) * T::STAGE_DOUBLES;
+    const double* sB = sA + T::A_DOUBLES;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
       double a[8], b[4];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        a[i] = A_KMAJOR ? sA[(kk + t) * LD_X + mbase + 8 * i + g] : sA[(mbase + 8 * i + g) * LD_K + kk + t];
+        a[i] = A_KMAJOR ? sA[(kk + t) * T::LDA_X + mbase + 8 * i + g] : sA[(mbase + 8 * i + g) * LD_K + kk + t];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        b[j] = B_KMAJOR ? sB[(kk + t) * LD_X + nbase + 8 * j + g] : sB[(nbase + 8 * j + g) * LD_K + kk + t];
+        b[j] = B_KMAJOR ? sB[(kk + t) * T::LDB_X + nbase + 8 * j + g] : sB[(nbase + 8 * j + g) * LD_K + kk + t];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll

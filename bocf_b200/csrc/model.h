@@ -10,7 +10,8 @@ namespace bocf {
 
 constexpr int MAXD = 16;      // max input dimension (register / shared tiles are sized by this)
 constexpr int MAXM = 64;      // max outputs handled by the MC kernel's per-warp staging
-constexpr int TILE = 128;     // GEMM tile edge == Cholesky block size
+constexpr int TILE = 128;     // Cholesky block size (128 x 128 GEMM tiles)
+constexpr int CAND_TILE = 256; // candidate tile of the posterior contractions (chunks are multiples of it)
 
 // Per (hyper-sample, output) constants, resident in device memory.
 struct OutHyp {

@@ -9,14 +9,24 @@
 //                     var = k** - sum V^2 (+ noise), clipped 1e-10    posterior.py:313, gaussian.py:110, gpmodel.py:174
 //   dvar_gemm_kernel  Wt  = V Linv     (= K* W^-1, gp.py:474)
 //                     dvar = gradients_X(-2 Wt, x*, X)               gp.py:475
-// The two contractions run on the fp64 tensor-core tile engine (DMMA.8x8x4) and skip the zero
-// blocks of the triangular factor; K*, G* and V live in a per-chunk HBM scratch, everything else
+// The two contractions run on the fp64 tensor-core tile engine (DMMA.8x8x4, 256 x 64 tiles) and skip the
+// zero blocks of the triangular factor; K*, G* and V live in a per-chunk HBM scratch, everything else
 // (n x n factor, training inputs) is L2-resident and shared by all candidate tiles of one output.
 #include "gemm_f64.cuh"
 #include "kernfn.cuh"
 #include "model.h"
 
 namespace bocf {
+
+#ifdef BOCF_TILE_WIDE
+using PT = gemm::TileWide;                 // 256 candidates x 64 factor columns, 256 threads, 1 CTA / SM
+constexpr int PT_MINBLOCKS = 1;
+#else
+using PT = gemm::TileHalf;                 // 128 candidates x 64 factor columns, 128 threads, 2 CTAs / SM
+constexpr int PT_MINBLOCKS = 2;
+#endif
+constexpr int CT = PT::BM;                 // candidate tile
+constexpr int NT = PT::BN;                 // column tile
 
 // ===================================================================================================
 // K*, mean, mean-gradient.  One thread per candidate, training points staged through shared memory.
@@ -114,33 +124,33 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
 
 // ===================================================================================================
 // V = K* Linv^T on the lower triangle; per column-tile partial sums of V^2.
-// grid.x = m * a_tiles * i_tiles, heaviest column tiles (largest K extent) first.
-__global__ void __launch_bounds__(gemm::THREADS, 1) var_gemm_kernel(const double* __restrict__ KsT,
+// grid.x = m * nct * i_tiles, heaviest column tiles (largest K extent) first.
+__global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) var_gemm_kernel(const double* __restrict__ KsT,
                                                                     const double* __restrict__ LinvAll,
                                                                     double* __restrict__ V,
                                                                     double* __restrict__ part_var, int64_t Nc, int n16,
-                                                                    int n_pad, int nb, int m, int h, int store_v) {
+                                                                    int n_pad, int nct, int m, int h, int store_v) {
   extern __shared__ __align__(16) double smem[];
-  const int i_tiles = (int)(Nc / TILE);
+  const int i_tiles = (int)(Nc / CT);
   int bid = blockIdx.x;
   const int it = bid % i_tiles;
   bid /= i_tiles;
-  const int at = nb - 1 - (bid % nb);
-  const int j = bid / nb;
+  const int at = nct - 1 - (bid % nct);
+  const int j = bid / nct;
   const int hj = h * m + j;
 
-  const double* A = KsT + (int64_t)j * n16 * Nc + (int64_t)it * TILE;                 // A(m,k) = KsT[k*Nc + m]
-  const double* B = LinvAll + (int64_t)hj * n_pad * n_pad + (int64_t)at * TILE * n_pad; // B(k,n) = Linv[n*n_pad + k]
-  const int k_end = min(n16, (at + 1) * TILE);
+  const double* A = KsT + (int64_t)j * n16 * Nc + (int64_t)it * CT;                   // A(m,k) = KsT[k*Nc + m]
+  const double* B = LinvAll + (int64_t)hj * n_pad * n_pad + (int64_t)at * NT * n_pad;   // B(k,n) = Linv[n*n_pad + k]
+  const int k_end = min(n16, (at + 1) * NT);
 
   double acc[8][4][2];
   gemm::zero_acc(acc);
-  gemm::mainloop<true, false>(acc, A, Nc, B, n_pad, 0, k_end, smem);
+  gemm::mainloop<PT, true, false>(acc, A, Nc, B, n_pad, 0, k_end, smem);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;
-  const int mbase = wm * 64, nbase = wn * 32;
-  double* red = smem;   // [4][128]
+  const int wn = warp & 1;
+  const int mbase = (warp >> 1) * 64, nbase = wn * 32;
+  double* red = smem;   // [2][CT]
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     double s = 0.0;
@@ -148,10 +158,10 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) var_gemm_kernel(const double
     for (int jn = 0; jn < 4; ++jn) s += acc[i][jn][0] * acc[i][jn][0] + acc[i][jn][1] * acc[i][jn][1];
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (t == 0) red[wn * TILE + mbase + 8 * i + g] = s;
+    if (t == 0) red[wn * CT + mbase + 8 * i + g] = s;
   }
   if (store_v) {
-    double* Vt = V + ((int64_t)j * Nc + (int64_t)it * TILE) * n_pad + (int64_t)at * TILE;
+    double* Vt = V + ((int64_t)j * Nc + (int64_t)it * CT) * n_pad + (int64_t)at * NT;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -161,54 +171,56 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) var_gemm_kernel(const double
       }
   }
   __syncthreads();
-  if (threadIdx.x < TILE) {
-    const int r = threadIdx.x;
-    double s = (red[r] + red[TILE + r]) + (red[2 * TILE + r] + red[3 * TILE + r]);
-    part_var[((int64_t)j * nb + at) * Nc + (int64_t)it * TILE + r] = s;
+  {
+    const int r = threadIdx.x;     // 256 threads == CT rows
+    part_var[((int64_t)j * nct + at) * Nc + (int64_t)it * CT + r] = red[r] + red[CT + r];
   }
 }
 
 // ===================================================================================================
 // Wt = V Linv on the lower triangle; epilogue contracts  Wt * G* * (xs_i - Xs_b)  over the tile's
-// columns into per column-tile partial variance gradients.   grid.x = m * b_tiles * i_tiles.
-__global__ void __launch_bounds__(gemm::THREADS, 1) dvar_gemm_kernel(
+// columns into per column-tile partial variance gradients.   grid.x = m * nct * i_tiles.
+__global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) dvar_gemm_kernel(
     const double* __restrict__ V, const double* __restrict__ LinvAll, const double* __restrict__ GsT,
     const double* __restrict__ Xc, int64_t Nvalid, const double* __restrict__ XsAll, const OutHyp* __restrict__ hyp,
-    double* __restrict__ part_dvar, int64_t Nc, int n, int n16, int n_pad, int nb, int m, int d, int h) {
+    double* __restrict__ part_dvar, int64_t Nc, int n, int n16, int n_pad, int nct, int m, int d, int h) {
   extern __shared__ __align__(16) double smem[];
-  const int i_tiles = (int)(Nc / TILE);
+  const int i_tiles = (int)(Nc / CT);
   int bid = blockIdx.x;
   const int it = bid % i_tiles;
   bid /= i_tiles;
-  const int bt = bid % nb;          // ascending: largest K extent first
-  const int j = bid / nb;
+  const int bt = bid % nct;         // ascending: largest K extent first
+  const int j = bid / nct;
   const int hj = h * m + j;
 
-  const double* A = V + ((int64_t)j * Nc + (int64_t)it * TILE) * n_pad;                 // A(m,k) = V[m*n_pad + k]
-  const double* B = LinvAll + (int64_t)hj * n_pad * n_pad + (int64_t)bt * TILE;           // B(k,n) = Linv[k*n_pad + n]
+  const double* A = V + ((int64_t)j * Nc + (int64_t)it * CT) * n_pad;                   // A(m,k) = V[m*n_pad + k]
+  const double* B = LinvAll + (int64_t)hj * n_pad * n_pad + (int64_t)bt * NT;             // B(k,n) = Linv[k*n_pad + n]
   double acc[8][4][2];
   gemm::zero_acc(acc);
-  gemm::mainloop<false, true>(acc, A, n_pad, B, n_pad, bt * TILE, n16, smem);
+  if (bt * NT < n16) gemm::mainloop<PT, false, true>(acc, A, n_pad, B, n_pad, bt * NT, n16, smem);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;
-  const int mbase = wm * 64, nbase = wn * 32;
+  const int wn = warp & 1;
+  const int mbase = (warp >> 1) * 64, nbase = wn * 32;
   const OutHyp& hp = hyp[hj];
 
   // stage scaled candidate / training coordinates for this tile:  sxi[q][row], sxb[q][col]
-  double* sxi = smem;                       // d x 128
-  double* sxb = smem + d * TILE;            // d x 128
-  double* red = smem + 2 * d * TILE;        // 4 x 128 x d   (6*d KiB <= 96 KiB for d <= MAXD)
-  for (int idx = tid; idx < d * TILE; idx += gemm::THREADS) {
+  double* sxi = smem;                          // d x CT
+  double* sxb = smem + d * CT;                 // d x NT
+  double* red = smem + d * (CT + NT);          // 2 x CT x d      (<= 104 KiB for d <= MAXD)
+  for (int idx = tid; idx < d * CT; idx += PT::NTHREADS) {
     int r = idx / d, q = idx - r * d;
-    int64_t i = (int64_t)it * TILE + r;
-    sxi[q * TILE + r] = (i < Nvalid) ? Xc[i * d + q] / hp.ls[q] : 0.0;
-    int b = bt * TILE + r;
-    sxb[q * TILE + r] = XsAll[((int64_t)hj * n_pad + b) * d + q];
+    int64_t i = (int64_t)it * CT + r;
+    sxi[q * CT + r] = (i < Nvalid) ? Xc[i * d + q] / hp.ls[q] : 0.0;
+  }
+  for (int idx = tid; idx < d * NT; idx += PT::NTHREADS) {
+    int c = idx / d, q = idx - c * d;
+    int b = bt * NT + c;
+    sxb[q * NT + c] = XsAll[((int64_t)hj * n_pad + b) * d + q];
   }
   // wg = Wt * G*
-  const double* Gj = GsT + (int64_t)j * n16 * Nc + (int64_t)it * TILE;
+  const double* Gj = GsT + (int64_t)j * n16 * Nc + (int64_t)it * CT;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = mbase + 8 * i + g;
@@ -216,7 +228,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) dvar_gemm_kernel(
     for (int jn = 0; jn < 4; ++jn)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int b = bt * TILE + nbase + 8 * jn + 2 * t + e;
+        const int b = bt * NT + nbase + 8 * jn + 2 * t + e;
         const double gv = (b < n) ? Gj[(int64_t)b * Nc + r] : 0.0;
         acc[i][jn][e] *= gv;
       }
@@ -226,13 +238,13 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) dvar_gemm_kernel(
     double xb[4][2];
 #pragma unroll
     for (int jn = 0; jn < 4; ++jn) {
-      xb[jn][0] = sxb[q * TILE + nbase + 8 * jn + 2 * t];
-      xb[jn][1] = sxb[q * TILE + nbase + 8 * jn + 2 * t + 1];
+      xb[jn][0] = sxb[q * NT + nbase + 8 * jn + 2 * t];
+      xb[jn][1] = sxb[q * NT + nbase + 8 * jn + 2 * t + 1];
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = mbase + 8 * i + g;
-      const double xi = sxi[q * TILE + r];
+      const double xi = sxi[q * CT + r];
       double s = 0.0;
 #pragma unroll
       for (int jn = 0; jn < 4; ++jn) {
@@ -241,56 +253,58 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) dvar_gemm_kernel(
       }
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (t == 0) red[(wn * TILE + r) * d + q] = s;
+      if (t == 0) red[(wn * CT + r) * d + q] = s;
     }
   }
   __syncthreads();
-  double* out = part_dvar + (((int64_t)j * nb + bt) * Nc + (int64_t)it * TILE) * d;
-  for (int idx = tid; idx < TILE * d; idx += gemm::THREADS) {
-    double s = (red[idx] + red[TILE * d + idx]) + (red[2 * TILE * d + idx] + red[3 * TILE * d + idx]);
-    out[idx] = s;
-  }
+  double* out = part_dvar + (((int64_t)j * nct + bt) * Nc + (int64_t)it * CT) * d;
+  for (int idx = tid; idx < CT * d; idx += PT::NTHREADS) out[idx] = red[idx] + red[CT * d + idx];
 }
 
 // ===================================================================================================
 // var = clip(k** - sum_tiles part_var (+ noise), 1e-10);  dvar = (-2 / l_q) sum_tiles part_dvar
 __global__ void finalize_kernel(const double* __restrict__ part_var, const double* __restrict__ part_dvar,
-                                const OutHyp* __restrict__ hyp, int64_t Nc, int nb, int m, int d, int h, int grad,
+                                const OutHyp* __restrict__ hyp, int64_t Nc, int nct, int m, int d, int h, int grad,
                                 int noiseless, double* __restrict__ var, double* __restrict__ dvar) {
+  // thread idx covers candidate idx (variance) and flat element idx = i*d + q (gradient): both coalesced
   const int j = blockIdx.y;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Nc) return;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const OutHyp& hp = hyp[h * m + j];
-  double s = 0.0;
-  for (int tI = 0; tI < nb; ++tI) s += part_var[((int64_t)j * nb + tI) * Nc + i];
-  double v = hp.variance - s;
-  if (!noiseless) v = hp.noise + v;
-  var[(int64_t)j * Nc + i] = fmax(v, 1e-10);
-  if (grad) {
-    for (int q = 0; q < d; ++q) {
-      double gsum = 0.0;
-      for (int tI = 0; tI < nb; ++tI) gsum += part_dvar[(((int64_t)j * nb + tI) * Nc + i) * d + q];
-      dvar[((int64_t)j * Nc + i) * d + q] = -2.0 * gsum / hp.ls[q];
-    }
+  if (idx < Nc) {
+    double s = 0.0;
+    for (int tI = 0; tI < nct; ++tI) s += part_var[((int64_t)j * nct + tI) * Nc + idx];
+    double v = hp.variance - s;
+    if (!noiseless) v = hp.noise + v;
+    var[(int64_t)j * Nc + idx] = fmax(v, 1e-10);
+  }
+  if (grad && idx < Nc * d) {
+    const int q = (int)(idx % d);
+    double gsum = 0.0;
+    for (int tI = 0; tI < nct; ++tI) gsum += part_dvar[((int64_t)j * nct + tI) * Nc * d + idx];
+    dvar[(int64_t)j * Nc * d + idx] = -2.0 * gsum / hp.ls[q];
   }
 }
 
 // ===================================================================================================
+int candidate_tile() { return CT; }
+
 uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
+  const uint64_t nct = M->n_pad / NT;
   uint64_t per = 0;
   per += (uint64_t)M->m * M->n16;                       // KsT
-  per += (uint64_t)M->m * M->nb;                        // part_var
+  per += (uint64_t)M->m * nct;                          // part_var
   per += 2ull * M->m;                                   // mean, var
   if (grad) {
     per += (uint64_t)M->m * M->n16;                     // GsT
     per += (uint64_t)M->m * M->n_pad;                   // V
-    per += (uint64_t)M->m * M->nb * M->d;               // part_dvar
+    per += (uint64_t)M->m * nct * M->d;                 // part_dvar
     per += 2ull * M->m * M->d;                          // dmean, dvar
   }
   return per * sizeof(double);
 }
 
 void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* cb) {
+  const uint64_t nct = M->n_pad / NT;
   double* p = reinterpret_cast<double*>(base);
   auto take = [&](uint64_t count) {
     double* r = p;
@@ -299,13 +313,13 @@ void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBu
   };
   cb->Nc = Nc;
   cb->KsT = take((uint64_t)M->m * M->n16 * Nc);
-  cb->part_var = take((uint64_t)M->m * M->nb * Nc);
+  cb->part_var = take((uint64_t)M->m * nct * Nc);
   cb->mean = take((uint64_t)M->m * Nc);
   cb->var = take((uint64_t)M->m * Nc);
   if (grad) {
     cb->GsT = take((uint64_t)M->m * M->n16 * Nc);
     cb->V = take((uint64_t)M->m * Nc * M->n_pad);
-    cb->part_dvar = take((uint64_t)M->m * M->nb * Nc * M->d);
+    cb->part_dvar = take((uint64_t)M->m * nct * Nc * M->d);
     cb->dmean = take((uint64_t)M->m * Nc * M->d);
     cb->dvar = take((uint64_t)M->m * Nc * M->d);
   } else {
@@ -342,8 +356,8 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
                            const ChunkBuffers& cb, cudaStream_t st, bool need_var, bool need_dvar) {
   static bool attrs = false;
   if (!attrs) {
-    BOCF_CUDA_OK(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-    BOCF_CUDA_OK(cudaFuncSetAttribute(dvar_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+    BOCF_CUDA_OK(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT::SMEM_BYTES));
+    BOCF_CUDA_OK(cudaFuncSetAttribute(dvar_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT::SMEM_BYTES));
     attrs = true;
   }
   need_dvar = need_dvar && grad;
@@ -361,24 +375,25 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
   }
   if (rc) return rc;
   if (!need_var) return 0;      // mean (and mean gradient) only: no contraction against the factor
-  const unsigned tiles = (unsigned)((cb.Nc / TILE) * M->nb * M->m);
+  const int nct = M->n_pad / NT;
+  const unsigned tiles = (unsigned)((cb.Nc / CT) * nct * M->m);
   {
     ProfScope ps("var_gemm_kernel", st);
-    var_gemm_kernel<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(cb.KsT, M->Linv, cb.V, cb.part_var, cb.Nc, M->n16,
-                                                                    M->n_pad, M->nb, M->m, h, need_dvar ? 1 : 0);
+    var_gemm_kernel<<<tiles, PT::NTHREADS, PT::SMEM_BYTES, st>>>(cb.KsT, M->Linv, cb.V, cb.part_var, cb.Nc, M->n16,
+                                                                  M->n_pad, nct, M->m, h, need_dvar ? 1 : 0);
   }
   BOCF_LAUNCH_OK("var_gemm_kernel");
   if (need_dvar) {
     ProfScope ps("dvar_gemm_kernel", st);
-    dvar_gemm_kernel<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(cb.V, M->Linv, cb.GsT, Xc, Nvalid, M->Xs, M->hyp,
-                                                                    cb.part_dvar, cb.Nc, M->n, M->n16, M->n_pad, M->nb,
-                                                                    M->m, M->d, h);
+    dvar_gemm_kernel<<<tiles, PT::NTHREADS, PT::SMEM_BYTES, st>>>(cb.V, M->Linv, cb.GsT, Xc, Nvalid, M->Xs, M->hyp,
+                                                                  cb.part_dvar, cb.Nc, M->n, M->n16, M->n_pad, nct,
+                                                                  M->m, M->d, h);
   }
   if (need_dvar) BOCF_LAUNCH_OK("dvar_gemm_kernel");
-  dim3 fgrid((unsigned)ceil_div(cb.Nc, 256), (unsigned)M->m);
+  dim3 fgrid((unsigned)ceil_div(need_dvar ? cb.Nc * M->d : cb.Nc, 256), (unsigned)M->m);
   {
     ProfScope ps("finalize_kernel", st);
-    finalize_kernel<<<fgrid, 256, 0, st>>>(cb.part_var, cb.part_dvar, M->hyp, cb.Nc, M->nb, M->m, M->d, h,
+    finalize_kernel<<<fgrid, 256, 0, st>>>(cb.part_var, cb.part_dvar, M->hyp, cb.Nc, nct, M->m, M->d, h,
                                            need_dvar ? 1 : 0, noiseless ? 1 : 0, cb.var, cb.dvar);
   }
   BOCF_LAUNCH_OK("finalize_kernel");
