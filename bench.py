@@ -51,15 +51,48 @@ class ClockSampler(object):
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.5):
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.period = period_s
+        self.nvml = None
+        self._stop = threading.Event()
+
+    def _nvml_loop(self):
+        nv, h = self.nvml
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                flags = ["Active" if (reasons & b) else "Not Active" for b in
+                         (bits["hw_slowdown"], bits["hw_thermal_slowdown"], bits["sw_thermal_slowdown"], bits["sw_power_cap"])]
+                self.rows.append([str(self.gpu), str(sm), str(smax), "0", "0"] + flags)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
+        # in-process NVML at a low rate: `nvidia-smi -lms 200` was measured to slow the timed loop by ~15 %
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml = (nv, h)
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "1000"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -71,13 +104,17 @@ class ClockSampler(object):
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
+        if self.nvml is not None:
+            self._stop.set()
+            self.th.join(timeout=2)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
         sm, smax, reasons = [], [], set()
         for r in self.rows:
             try:
@@ -222,12 +259,22 @@ def run_ours(args, cfg):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
+        marks = []
         for _ in range(steps):
             fn()
             flush.zero_()
+            if os.environ.get("BOCF_BENCH_DEBUG"):
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((ev, time.perf_counter() - t0))
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
+        if marks and rank == 0:
+            prev = e0
+            for ev, cpu_t in marks:
+                sys.stderr.write("  step gpu %.1f ms (cpu enqueue done at %.1f ms)\n" % (prev.elapsed_time(ev), cpu_t * 1e3))
+                prev = ev
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)

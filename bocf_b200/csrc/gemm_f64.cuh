@@ -67,11 +67,18 @@ __device__ __forceinline__ void load_operand(double* s, const double* __restrict
   }
 }
 
+// Triangular B operand: which (k, n) entries are structurally non-zero, in GLOBAL indices (n_glob = tri_col0 + n).
+//   TRI_NONE        dense
+//   TRI_K_LE_N      B(k,n) != 0 only for k <= n_glob   (V = K* Linv^T: Linv[a][b] with b <= a)
+//   TRI_K_GE_N      B(k,n) != 0 only for k >= n_glob   (Wt = V Linv:   Linv[a][b] with a >= b)
+// Inside the k-tiles that straddle the diagonal the MMAs of all-zero 8-column groups are skipped (warp-uniform).
+enum { TRI_NONE = 0, TRI_K_LE_N = 1, TRI_K_GE_N = 2 };
+
 // acc[i][j][e]: row = wm*64 + 8*i + g, col = wn*32 + 8*j + 2*t + e   (lane = 4*g + t, warp = wm*WN + wn)
-template <class T, bool A_KMAJOR, bool B_KMAJOR>
+template <class T, bool A_KMAJOR, bool B_KMAJOR, int TRI = TRI_NONE>
 __device__ __forceinline__ void mainloop(double (&acc)[8][4][2], const double* __restrict__ A, int64_t lda,
                                          const double* __restrict__ B, int64_t ldb, int k_begin, int k_end,
-                                         double* smem) {
+                                         double* smem, int tri_col0 = 0) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -102,19 +109,44 @@ __device__ __forceinline__ void mainloop(double (&acc)[8][4][2], const double* _
     }
     const double* sA = smem + (kt % STAGES) * T::STAGE_DOUBLES;
     const double* sB = sA + T::A_DOUBLES;
+    const int k0 = k_begin + kt * BK;
+    // does this k-tile straddle the diagonal of this warp's columns?  (warp-uniform)
+    bool diag = false;
+    if (TRI == TRI_K_LE_N) diag = (k0 + BK - 1) > (tri_col0 + nbase);            // some k exceeds the first column
+    if (TRI == TRI_K_GE_N) diag = k0 < (tri_col0 + nbase + 31);                  // some k precedes the last column
+    if (!diag) {
 #pragma unroll
-    for (int kk = 0; kk < BK; kk += 4) {
-      double a[8], b[4];
+      for (int kk = 0; kk < BK; kk += 4) {
+        double a[8], b[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        a[i] = A_KMAJOR ? sA[(kk + t) * T::LDA_X + mbase + 8 * i + g] : sA[(mbase + 8 * i + g) * LD_K + kk + t];
+        for (int i = 0; i < 8; ++i)
+          a[i] = A_KMAJOR ? sA[(kk + t) * T::LDA_X + mbase + 8 * i + g] : sA[(mbase + 8 * i + g) * LD_K + kk + t];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        b[j] = B_KMAJOR ? sB[(kk + t) * T::LDB_X + nbase + 8 * j + g] : sB[(nbase + 8 * j + g) * LD_K + kk + t];
+        for (int j = 0; j < 4; ++j)
+          b[j] = B_KMAJOR ? sB[(kk + t) * T::LDB_X + nbase + 8 * j + g] : sB[(nbase + 8 * j + g) * LD_K + kk + t];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < BK; kk += 4) {
+        double a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          a[i] = A_KMAJOR ? sA[(kk + t) * T::LDA_X + mbase + 8 * i + g] : sA[(mbase + 8 * i + g) * LD_K + kk + t];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c_lo = tri_col0 + nbase + 8 * j;     // global columns c_lo .. c_lo+7, k-step rows k0+kk .. +3
+          const bool need = (TRI == TRI_K_LE_N) ? (k0 + kk <= c_lo + 7) : (k0 + kk + 3 >= c_lo);
+          if (need) {
+            const double b = B_KMAJOR ? sB[(kk + t) * T::LDB_X + nbase + 8 * j + g] : sB[(nbase + 8 * j + g) * LD_K + kk + t];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b);
+          }
+        }
+      }
     }
   }
   cp_async_wait<0>();

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) var_gemm_kernel(co
 
   double acc[8][4][2];
   gemm::zero_acc(acc);
-  gemm::mainloop<PT, true, false>(acc, A, Nc, B, n_pad, 0, k_end, smem);
+  gemm::mainloop<PT, true, false, gemm::TRI_K_LE_N>(acc, A, Nc, B, n_pad, 0, k_end, smem, at * NT);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int wn = warp & 1;
@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) dvar_gemm_kernel(
   const double* B = LinvAll + (int64_t)hj * n_pad * n_pad + (int64_t)bt * NT;             // B(k,n) = Linv[k*n_pad + n]
   double acc[8][4][2];
   gemm::zero_acc(acc);
-  if (bt * NT < n16) gemm::mainloop<PT, false, true>(acc, A, n_pad, B, n_pad, bt * NT, n16, smem);
+  if (bt * NT < n16)
+    gemm::mainloop<PT, false, true, gemm::TRI_K_GE_N>(acc, A, n_pad, B, n_pad, bt * NT, n16, smem, bt * NT);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -241,19 +242,37 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) dvar_gemm_kernel(
       xb[jn][0] = sxb[q * NT + nbase + 8 * jn + 2 * t];
       xb[jn][1] = sxb[q * NT + nbase + 8 * jn + 2 * t + 1];
     }
+    double s[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int r = mbase + 8 * i + g;
-      const double xi = sxi[q * CT + r];
-      double s = 0.0;
+      const double xi = sxi[q * CT + mbase + 8 * i + g];
+      double acc_s = 0.0;
 #pragma unroll
       for (int jn = 0; jn < 4; ++jn) {
-        s += acc[i][jn][0] * (xi - xb[jn][0]);
-        s += acc[i][jn][1] * (xi - xb[jn][1]);
+        acc_s += acc[i][jn][0] * (xi - xb[jn][0]);
+        acc_s += acc[i][jn][1] * (xi - xb[jn][1]);
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (t == 0) red[(wn * CT + r) * d + q] = s;
+      s[i] = acc_s;
+    }
+    // reduce over the 4 lanes of a quad AND scatter the 8 row sums over them (6 shuffles instead of 16):
+    // after step 1 a lane holds rows 4*(t&1)+k, k<4, summed over lane pairs; after step 2 rows 4*(t&1)+2*(t>>1)+k, k<2
+    double u[4], w2[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double send = (t & 1) ? s[k] : s[k + 4];
+      const double keep = (t & 1) ? s[k + 4] : s[k];
+      u[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double send = (t & 2) ? u[k] : u[k + 2];
+      const double keep = (t & 2) ? u[k + 2] : u[k];
+      w2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = 4 * (t & 1) + 2 * (t >> 1) + k;
+      red[(wn * CT + mbase + 8 * i + g) * d + q] = w2[k];
     }
   }
   __syncthreads();

@@ -1,0 +1,159 @@
+"""BASELINE.json configurations at (or near) their full sizes on the GPU.
+
+The oracle cannot sweep 10^5..10^6 candidates, so each case combines
+  * oracle spot-checks on a random subset of the very candidates of the sweep, with
+  * size-independent properties of the sweep itself: independence of candidates (a candidate's result does not
+    depend on which chunk / tile / batch it sits in -- bitwise), non-negativity, zero gradient where EI is zero,
+    finite-difference agreement of the pathwise gradient, top-k == argsort.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests.helpers import make_problem, oracle_model, oracle_acq, product_model, product_utility, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _sweep(P, model, variant="uEI_noiseless", grad=True, Xc=None):
+    import bocf_b200
+    acq = getattr(bocf_b200, variant)(model, None, utility=product_utility(P))
+    if hasattr(acq, "W_samples"):
+        acq.W_samples = P.Z
+    model.set_hyperparameters(0)
+    X = P.Xc if Xc is None else Xc
+    if grad:
+        a, g = acq._compute_acq_withGradients(X)
+        return a[:, 0], g, acq
+    return acq._compute_acq(X)[:, 0], None, acq
+
+
+def test_cfg3_million_candidates(cuda_device):
+    """configs[2]: m=16, d=10, n=1000, Matern-5/2 ARD, 1M candidates x 1024 MC samples, with gradients."""
+    import torch
+    P = make_problem(m=16, d=10, n=1000, H=1, kind="matern52", composite="sumsq_target", N=1000000, S=1024, L=1,
+                     seed=0, focus=0.02, focus_scale=0.05)
+    model = product_model(P, cuda_device)
+    Xd = torch.from_numpy(P.Xc).to(cuda_device)
+    a_t, g_t, acq = _sweep(P, model, Xc=Xd)
+    a, g = a_t.cpu().numpy(), g_t.cpu().numpy()
+    assert a.shape == (P.N,) and g.shape == (P.N, P.d)
+    assert np.all(np.isfinite(a)) and np.all(np.isfinite(g)) and np.all(a >= 0)
+    assert np.all(g[a == 0] == 0)                       # no active sample -> no pathwise gradient
+    assert np.mean(a > 0) > 1e-3
+    # (1) oracle spot-check on 48 candidates, half of them with non-zero EI
+    rng = np.random.default_rng(1)
+    nz = np.nonzero(a > 0)[0]
+    idx = np.concatenate([rng.choice(nz, 24, replace=False), rng.choice(P.N, 24, replace=False)])
+    a_o, g_o = oracle_acq(P, grad=True, Xc=P.Xc[idx])
+    assert rel_err(a[idx], a_o) < 1e-8 and rel_err(g[idx], g_o) < 1e-7
+    # (2) independence / determinism: the same candidates alone (other chunk, other tile position) -> bitwise equal
+    a_s, g_s, _ = _sweep(P, model, Xc=P.Xc[idx])
+    assert np.array_equal(a_s, a[idx]) and np.array_equal(g_s, g[idx])
+    # (3) pathwise gradient vs central finite differences of the value at a few improving candidates
+    best = nz[np.argsort(-a[nz])[:3]]
+    eps = 1e-6
+    for i in best:
+        for q in (0, 7):
+            Xp = P.Xc[i:i + 1].copy()
+            Xm = Xp.copy()
+            Xp[0, q] += eps
+            Xm[0, q] -= eps
+            fp = _sweep(P, model, Xc=np.vstack([Xp, Xm]))[0]
+            fd = (fp[0] - fp[1]) / (2 * eps)
+            assert abs(fd - g[i, q]) < 2e-4 * max(1.0, np.abs(g[i]).max())
+    # (4) local top-k on the device == argsort on the host
+    from bocf_b200 import distributed as bd
+    rec = bd.local_topk(a_t, Xd, 16).cpu().numpy()
+    order = np.lexsort((np.arange(P.N), -a))[:16]
+    assert np.array_equal(rec[:, 1].astype(np.int64), order) and np.array_equal(rec[:, 2:], P.Xc[order])
+
+
+def test_cfg2_100k_candidates(cuda_device):
+    """configs[1]: m=4, d=6, n=200, RBF-ARD, sum-of-squares composite, 100k candidates x 256 MC samples."""
+    P = make_problem(m=4, d=6, n=200, H=1, kind="rbf", composite="sumsq_target", N=100000, S=256, L=1, seed=1,
+                     focus=0.05)
+    model = product_model(P, cuda_device)
+    a, g, _ = _sweep(P, model)
+    rng = np.random.default_rng(2)
+    idx = np.concatenate([np.argsort(-a)[:128], rng.choice(P.N, 384, replace=False)])
+    a_o, g_o = oracle_acq(P, grad=True, Xc=P.Xc[idx])
+    assert rel_err(a[idx], a_o) < 1e-8 and rel_err(g[idx], g_o) < 1e-7
+    assert np.argmax(a) == idx[np.argmax(a_o)]                      # same selected next point
+    v, _, _ = _sweep(P, model, grad=False)
+    v_o, _ = oracle_acq(P, grad=False, Xc=P.Xc[idx])
+    assert rel_err(v[idx], v_o) < 1e-8
+
+
+def test_cfg4_parameter_uncertain_maei_upi(cuda_device):
+    """configs[3]: m=8, n=500, 64 utility-parameter samples; maEI (linear U) and uPI (64 targets), 256k candidates
+    swept on the GPU, oracle on a subset."""
+    rng = np.random.default_rng(3)
+    # L = 64 >= 20 -> the reference samples theta instead of using the full support (parameter_distribution.py:18-21);
+    # explicit theta samples are injected on both sides so the comparison is deterministic
+    P = make_problem(m=8, d=8, n=500, H=1, kind="matern52", composite="linear", N=262144, S=256, L=64, seed=4, focus=0.02)
+    model = product_model(P, cuda_device)
+    om = oracle_model(P)
+    import bocf_b200
+    from oracle import acquisitions as OA
+    from tests.helpers import oracle_utility
+    idx = rng.choice(P.N, 96, replace=False)
+    # maEI with the 64 theta samples as an explicit sample set
+    acq = bocf_b200.maEI(model, None, utility=product_utility(P))
+    acq.use_full_support = False
+    acq.utility.parameter_dist.sample = lambda k: P.theta
+    a, g = acq._compute_acq_withGradients(P.Xc)
+    o = OA.maEI(om, utility=oracle_utility(P), utility_params_samples=P.theta)
+    o.use_full_support = False
+    a_o, g_o = o._compute_acq_withGradients(P.Xc[idx])
+    assert a.shape == (P.N, 1) and rel_err(a[idx], a_o) < 1e-8 and rel_err(g[idx], g_o) < 1e-7
+    # uPI with 64 sum-of-squares targets
+    P2 = make_problem(m=8, d=8, n=500, H=1, kind="matern52", composite="sumsq_target", N=32768, S=256, L=64, seed=4,
+                      focus=0.1)
+    model2 = product_model(P2, cuda_device)
+    pi = bocf_b200.uPI(model2, None, utility=product_utility(P2))
+    pi.W_samples = P2.Z
+    pi.use_full_support = False
+    pi.utility_params_samples = P2.theta
+    v = pi._compute_acq(P2.Xc)[:, 0]
+    o2 = OA.uPI(oracle_model(P2), utility=oracle_utility(P2), W_samples=P2.Z, utility_params_samples=P2.theta,
+                vectorised=True)
+    o2.use_full_support = False
+    o2.utility_params_samples = P2.theta
+    idx2 = np.concatenate([np.argsort(-v)[:32], rng.choice(P2.N, 32, replace=False)])
+    v_o = o2._compute_acq(P2.Xc[idx2])[:, 0]
+    assert np.max(np.abs(v[idx2] - v_o)) < 1e-12 and v.max() > 0
+
+
+def test_cfg5_large_n_cholesky_and_variance(cuda_device):
+    """configs[4] (scaled to fit a test: m=4 of the 32 outputs): n=4000 fp64 Cholesky on device, batched
+    triangular-solve variance and its gradient, 512 MC samples."""
+    P = make_problem(m=4, d=10, n=4000, H=1, kind="matern52", composite="sumsq_target", N=4096, S=512, L=1, seed=5,
+                     prior_draw=False, focus=0.2)
+    model = product_model(P, cuda_device)
+    assert np.all(model.jitter_added == 0)
+    om = oracle_model(P)
+    L, Linv, alpha = model.get_factor(0, 2)
+    gp = om.output[2].model_instances[0]
+    assert rel_err(L, gp.woodbury_chol) < 1e-9 and rel_err(alpha, gp.woodbury_vector[:, 0]) < 1e-7
+    idx = np.random.default_rng(6).choice(P.N, 96, replace=False)
+    Xs = P.Xc[idx]
+    assert rel_err(model.posterior_mean(P.Xc)[:, idx], om.posterior_mean(Xs)) < 1e-8
+    v, vo = model.posterior_variance(P.Xc)[:, idx], om.posterior_variance(Xs)
+    assert np.max(np.abs(v - vo) / vo) < 1e-6                                    # north-star bar on the variance
+    assert rel_err(model.posterior_variance_gradient(P.Xc)[:, idx], om.posterior_variance_gradient(Xs)) < 1e-6
+    a, g, _ = _sweep(P, model)
+    a_o, g_o = oracle_acq(P, grad=True, Xc=Xs, model=om)
+    assert rel_err(a[idx], a_o) < 1e-7 and rel_err(g[idx], g_o) < 1e-6
+
+
+def test_small_scratch_limit_gives_identical_results(cuda_device):
+    """Chunking is an implementation detail: a 64 MiB scratch (many tiny chunks) reproduces the default bitwise."""
+    from bocf_b200 import _lib
+    P = make_problem(m=3, d=5, n=300, H=2, kind="se", composite="neg_sum_exp", N=5000, S=64, L=1, seed=7)
+    model = product_model(P, cuda_device)
+    a1, g1, _ = _sweep(P, model)
+    _lib.check(model._lib.bocf_model_set_scratch_limit(model._handle, ctypes.c_uint64(64 << 20)))
+    a2, g2, _ = _sweep(P, model)
+    assert np.array_equal(a1, a2) and np.array_equal(g1, g2)
