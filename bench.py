@@ -263,18 +263,19 @@ def run_ours(args, cfg):
         for _ in range(steps):
             fn()
             flush.zero_()
-            if os.environ.get("BOCF_BENCH_DEBUG"):
-                ev = torch.cuda.Event(enable_timing=True)
-                ev.record()
-                marks.append((ev, time.perf_counter() - t0))
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((ev, time.perf_counter() - t0))
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        if marks and rank == 0:
-            prev = e0
-            for ev, cpu_t in marks:
-                sys.stderr.write("  step gpu %.1f ms (cpu enqueue done at %.1f ms)\n" % (prev.elapsed_time(ev), cpu_t * 1e3))
-                prev = ev
+        step_ms, prev = [], e0
+        for ev, cpu_t in marks:
+            step_ms.append(prev.elapsed_time(ev))
+            if os.environ.get("BOCF_BENCH_DEBUG") and rank == 0:
+                sys.stderr.write("  step gpu %.1f ms (cpu enqueue done at %.1f ms)\n" % (step_ms[-1], cpu_t * 1e3))
+            prev = ev
+        timed.last_step_ms = step_ms
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
@@ -294,6 +295,7 @@ def run_ours(args, cfg):
     if rank == 0:
         sampler.start()
     ms_dev, _, launches, _ = timed(step_device, args.steps)
+    value_step_ms = list(timed.last_step_ms)
     clocks = sampler.stop() if rank == 0 else None
     # separate pass with per-kernel CUDA events (same steps, same data) for the roofline of the dominant kernel
     ms_prof, _, _, prof = timed(step_device, args.steps, profile=True)
@@ -364,7 +366,7 @@ def run_ours(args, cfg):
                 "d2h_bytes_per_step": int(N * 8 + N * c["d"] * 8), "ms_per_step": ms_e2e / args.steps,
                 "api": "uEI_noiseless.acquisition_function_withGradients(numpy (N,d)) -> numpy (N,1),(N,d)"},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "cand_x_samples_per_s": value * c["S"], "factorize_s": t_factor,
+        "cand_x_samples_per_s": value * c["S"], "factorize_s": t_factor, "step_ms": value_step_ms,
     }
     print(json.dumps(line))
     if world > 1:

@@ -93,9 +93,20 @@ class AcquisitionBase(object):
                                          _ptr(acq), _ptr(dacq), st))
         acq = acq.reshape(N, 1)
         if not is_t:
-            acq = acq.cpu().numpy()
-            dacq = None if dacq is None else dacq.cpu().numpy()
+            acq = self._to_host(acq)
+            dacq = None if dacq is None else self._to_host(dacq)
         return (acq, dacq) if grad else acq
+
+    @staticmethod
+    def _to_host(t):
+        """Device -> numpy.  Large results are copied straight into a pinned host buffer (torch's caching host
+        allocator recycles it) and returned as the numpy array that owns that buffer: one DMA, no pageable bounce."""
+        if t.numel() < (1 << 16):
+            return t.cpu().numpy()
+        pin = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+        pin.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return pin.numpy()
 
 
 class uEI_noiseless(AcquisitionBase):

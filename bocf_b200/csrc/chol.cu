@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
 
 // ---------------------------------------------------------------------------------------------------
 // Panel solve: A[I][K] <- A[I][K] . L_KK^-T  (= A . Dinv^T), I > K.   grid (nb-1-K, H*m)
-__global__ void __launch_bounds__(gemm::THREADS, 1) trsm_panel_kernel(double* __restrict__ Lmat,
+__global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) trsm_panel_kernel(double* __restrict__ Lmat,
                                                                       const double* __restrict__ Dinv, int n_pad,
                                                                       int nb, int kb) {
   extern __shared__ __align__(16) double smem[];
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) trsm_panel_kernel(double* __
 }
 
 // Trailing update: A[I][J] -= P_I . P_J^T for K < J <= I.   grid (#pairs, H*m)
-__global__ void __launch_bounds__(gemm::THREADS, 1) syrk_update_kernel(double* __restrict__ Lmat, int n_pad, int nb,
+__global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) syrk_update_kernel(double* __restrict__ Lmat, int n_pad, int nb,
                                                                        int kb) {
   extern __shared__ __align__(16) double smem[];
   const int hj = blockIdx.y;
@@ -234,7 +234,7 @@ __global__ void linv_init_kernel(double* __restrict__ Linv, const double* __rest
 }
 
 template <int STEP>
-__global__ void __launch_bounds__(gemm::THREADS, 1) linv_row_kernel(const double* __restrict__ Lmat,
+__global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) linv_row_kernel(const double* __restrict__ Lmat,
                                                                     double* __restrict__ Linv,
                                                                     const double* __restrict__ Dinv, int n_pad, int nb,
                                                                     int I) {
@@ -352,9 +352,9 @@ int launch_cholesky(bocf_model* M, cudaStream_t st) {
     BOCF_LAUNCH_OK("potrf_diag_kernel");
     const int rem = nb - 1 - kb;
     if (rem > 0) {
-      trsm_panel_kernel<<<dim3(rem, Hm), gemm::THREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Dinv, M->n_pad, nb, kb);
+      trsm_panel_kernel<<<dim3(rem, Hm), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Dinv, M->n_pad, nb, kb);
       BOCF_LAUNCH_OK("trsm_panel_kernel");
-      syrk_update_kernel<<<dim3(rem * (rem + 1) / 2, Hm), gemm::THREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->n_pad, nb, kb);
+      syrk_update_kernel<<<dim3(rem * (rem + 1) / 2, Hm), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->n_pad, nb, kb);
       BOCF_LAUNCH_OK("syrk_update_kernel");
     }
   }
@@ -368,9 +368,9 @@ int launch_inverse_and_alpha(bocf_model* M, cudaStream_t st) {
   linv_init_kernel<<<dim3(nb, Hm), 256, 0, st>>>(M->Linv, M->Dinv, M->n_pad, nb);
   BOCF_LAUNCH_OK("linv_init_kernel");
   for (int I = 1; I < nb; ++I) {
-    linv_row_kernel<1><<<dim3(I, Hm), gemm::THREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
+    linv_row_kernel<1><<<dim3(I, Hm), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
     BOCF_LAUNCH_OK("linv_row_kernel<1>");
-    linv_row_kernel<2><<<dim3(I, Hm), gemm::THREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
+    linv_row_kernel<2><<<dim3(I, Hm), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
     BOCF_LAUNCH_OK("linv_row_kernel<2>");
   }
   linv_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 8), Hm), 256, 0, st>>>(M->Linv, M->yc, M->m, M->n_pad, M->tvec);

@@ -1,13 +1,15 @@
 // gemm_f64.cuh -- fp64 tensor-core (DMMA.8x8x4) tile engine.
 //
-// One CTA (256 threads = 8 warps laid out WM x WN) computes a (64*WM) x (32*WN) fp64 tile
+// One CTA of WM x WN warps computes a (8*MI*WM) x (32*WN) fp64 tile
 //     acc[m][n] = sum_{k in [k_begin,k_end)} A(m,k) * B(k,n)
 // with both operands streamed global -> shared by a 3-stage cp.async ring (BK = 16) and fed to
-// mma.sync.m8n8k4.f64.  Each warp owns a 64 x 32 sub-tile = 8 x 4 MMA tiles (64 fp64 accumulators
-// per thread).  Two tile shapes are used:
-//     Tile<2,4> = 128 x 128   Cholesky panel / trailing updates, blocked triangular inverse
-//     Tile<4,2> = 256 x  64   candidate-side contractions (narrow column tiles waste fewer MMAs on the
-//                             structurally-zero upper triangle of the factor's diagonal blocks)
+// mma.sync.m8n8k4.f64.  Each warp owns an (8*MI) x 32 sub-tile = MI x 4 MMA tiles (8*MI fp64 accumulators per
+// thread).  Tile shapes in use:
+//     Tile<2,4,8> = 128 x 128, 256 threads, 64 acc/thread   Cholesky panel / trailing updates, blocked inverse
+//     Tile<2,2,8> = 128 x  64, 128 threads, 64 acc/thread   candidate-side contractions, two CTAs per SM: their
+//                   barriers are decoupled (+11 % over one 256-thread CTA) and the narrow 64-column tiles waste
+//                   fewer MMAs on the structurally-zero triangle of the factor's diagonal blocks.  Measured
+//                   alternatives: 256x64/256 thr (1 CTA) -12 %; 128x64 with 32x32 warp tiles (16 warps/SM) -3 %.
 // Operand layouts are template switches so the same loop serves
 //     V  = K* . Linv^T      (A k-major, B n-major)         posterior variance (trsm-as-gemm)
 //     Wt = V  . Linv        (A m-major, B k-major)         variance-gradient weights
@@ -22,13 +24,14 @@ namespace gemm {
 
 constexpr int BK = 16;
 constexpr int STAGES = 3;
-constexpr int THREADS = 256;
 constexpr int LD_K = BK + 4;    // operand rows hold BK doubles (k contiguous)
 
-template <int WM, int WN>
+template <int WM_, int WN_, int MI_>
 struct Tile {
+  static constexpr int WM = WM_, WN = WN_, MI = MI_;
   static constexpr int NTHREADS = 32 * WM * WN;
-  static constexpr int BM = 64 * WM;
+  static constexpr int WTM = 8 * MI;          // warp tile rows
+  static constexpr int BM = WTM * WM;
   static constexpr int BN = 32 * WN;
   static constexpr int LDA_X = BM + 4;     // k-major A rows hold BM doubles
   static constexpr int LDB_X = BN + 4;     // k-major B rows hold BN doubles
@@ -37,9 +40,8 @@ struct Tile {
   static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);
 };
-using Tile128 = Tile<2, 4>;      // 128 x 128, 256 threads, 122 880 B
-using TileWide = Tile<4, 2>;     // 256 x  64, 256 threads, 153 600 B
-using TileHalf = Tile<2, 2>;     // 128 x  64, 128 threads,  92 160 B  (2 CTAs / SM)
+using Tile128 = Tile<2, 4, 8>;     // 128 x 128, 256 threads, 122 880 B, 1 CTA / SM
+using TilePost = Tile<2, 2, 8>;    // 128 x  64, 128 threads,  92 160 B, 2 CTAs / SM
 
 // ---- global -> shared stage loads ---------------------------------------------------------------
 // KMAJOR == false: element (x,k) at P[x*ld + k]  (k contiguous)   -> smem s[x*LD_K + k]
@@ -74,15 +76,16 @@ __device__ __forceinline__ void load_operand(double* s, const double* __restrict
 // Inside the k-tiles that straddle the diagonal the MMAs of all-zero 8-column groups are skipped (warp-uniform).
 enum { TRI_NONE = 0, TRI_K_LE_N = 1, TRI_K_GE_N = 2 };
 
-// acc[i][j][e]: row = wm*64 + 8*i + g, col = wn*32 + 8*j + 2*t + e   (lane = 4*g + t, warp = wm*WN + wn)
+// acc[i][j][e]: row = wm*WTM + 8*i + g, col = wn*32 + 8*j + 2*t + e   (lane = 4*g + t, warp = wm*WN + wn)
 template <class T, bool A_KMAJOR, bool B_KMAJOR, int TRI = TRI_NONE>
-__device__ __forceinline__ void mainloop(double (&acc)[8][4][2], const double* __restrict__ A, int64_t lda,
+__device__ __forceinline__ void mainloop(double (&acc)[T::MI][4][2], const double* __restrict__ A, int64_t lda,
                                          const double* __restrict__ B, int64_t ldb, int k_begin, int k_end,
                                          double* smem, int tri_col0 = 0) {
+  constexpr int MI = T::MI;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int mbase = (warp / (T::BN / 32)) * 64, nbase = (warp % (T::BN / 32)) * 32;
+  const int mbase = (warp / T::WN) * T::WTM, nbase = (warp % T::WN) * 32;
   const int KT = (k_end - k_begin) / BK;
 
 #pragma unroll
@@ -117,24 +120,24 @@ __device__ __forceinline__ void mainloop(double (&acc)[8][4][2], const double* _
     if (!diag) {
 #pragma unroll
       for (int kk = 0; kk < BK; kk += 4) {
-        double a[8], b[4];
+        double a[MI], b[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < MI; ++i)
           a[i] = A_KMAJOR ? sA[(kk + t) * T::LDA_X + mbase + 8 * i + g] : sA[(mbase + 8 * i + g) * LD_K + kk + t];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           b[j] = B_KMAJOR ? sB[(kk + t) * T::LDB_X + nbase + 8 * j + g] : sB[(nbase + 8 * j + g) * LD_K + kk + t];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
     } else {
 #pragma unroll
       for (int kk = 0; kk < BK; kk += 4) {
-        double a[8];
+        double a[MI];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < MI; ++i)
           a[i] = A_KMAJOR ? sA[(kk + t) * T::LDA_X + mbase + 8 * i + g] : sA[(mbase + 8 * i + g) * LD_K + kk + t];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -143,7 +146,7 @@ __device__ __forceinline__ void mainloop(double (&acc)[8][4][2], const double* _
           if (need) {
             const double b = B_KMAJOR ? sB[(kk + t) * T::LDB_X + nbase + 8 * j + g] : sB[(nbase + 8 * j + g) * LD_K + kk + t];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b);
+            for (int i = 0; i < MI; ++i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b);
           }
         }
       }
@@ -153,9 +156,10 @@ __device__ __forceinline__ void mainloop(double (&acc)[8][4][2], const double* _
   __syncthreads();   // pipeline smem is free for the epilogue after this
 }
 
-__device__ __forceinline__ void zero_acc(double (&acc)[8][4][2]) {
+template <int MI>
+__device__ __forceinline__ void zero_acc(double (&acc)[MI][4][2]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 }

@@ -18,13 +18,9 @@
 
 namespace bocf {
 
-#ifdef BOCF_TILE_WIDE
-using PT = gemm::TileWide;                 // 256 candidates x 64 factor columns, 256 threads, 1 CTA / SM
-constexpr int PT_MINBLOCKS = 1;
-#else
-using PT = gemm::TileHalf;                 // 128 candidates x 64 factor columns, 128 threads, 2 CTAs / SM
+using PT = gemm::TilePost;                 // 128 candidates x 64 factor columns, 128 threads, 2 CTAs / SM
 constexpr int PT_MINBLOCKS = 2;
-#endif
+constexpr int MI = PT::MI;                 // 8-row MMA tiles per warp (warp tile = 8*MI x 32)
 constexpr int CT = PT::BM;                 // candidate tile
 constexpr int NT = PT::BN;                 // column tile
 
@@ -143,16 +139,16 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) var_gemm_kernel(co
   const double* B = LinvAll + (int64_t)hj * n_pad * n_pad + (int64_t)at * NT * n_pad;   // B(k,n) = Linv[n*n_pad + k]
   const int k_end = min(n16, (at + 1) * NT);
 
-  double acc[8][4][2];
+  double acc[MI][4][2];
   gemm::zero_acc(acc);
   gemm::mainloop<PT, true, false, gemm::TRI_K_LE_N>(acc, A, Nc, B, n_pad, 0, k_end, smem, at * NT);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const int wn = warp & 1;
-  const int mbase = (warp >> 1) * 64, nbase = wn * 32;
-  double* red = smem;   // [2][CT]
+  const int wn = warp % PT::WN;
+  const int mbase = (warp / PT::WN) * PT::WTM, nbase = wn * 32;
+  double* red = smem;   // [WN][CT]
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < MI; ++i) {
     double s = 0.0;
 #pragma unroll
     for (int jn = 0; jn < 4; ++jn) s += acc[i][jn][0] * acc[i][jn][0] + acc[i][jn][1] * acc[i][jn][1];
@@ -163,7 +159,7 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) var_gemm_kernel(co
   if (store_v) {
     double* Vt = V + ((int64_t)j * Nc + (int64_t)it * CT) * n_pad + (int64_t)at * NT;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
       for (int jn = 0; jn < 4; ++jn) {
         int r = mbase + 8 * i + g, c = nbase + 8 * jn + 2 * t;
@@ -171,9 +167,12 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) var_gemm_kernel(co
       }
   }
   __syncthreads();
-  {
-    const int r = threadIdx.x;     // 256 threads == CT rows
-    part_var[((int64_t)j * nct + at) * Nc + (int64_t)it * CT + r] = red[r] + red[CT + r];
+  if (threadIdx.x < CT) {
+    const int r = threadIdx.x;
+    double s = red[r];
+#pragma unroll
+    for (int w = 1; w < PT::WN; ++w) s += red[w * CT + r];
+    part_var[((int64_t)j * nct + at) * Nc + (int64_t)it * CT + r] = s;
   }
 }
 
@@ -195,21 +194,21 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) dvar_gemm_kernel(
 
   const double* A = V + ((int64_t)j * Nc + (int64_t)it * CT) * n_pad;                   // A(m,k) = V[m*n_pad + k]
   const double* B = LinvAll + (int64_t)hj * n_pad * n_pad + (int64_t)bt * NT;             // B(k,n) = Linv[k*n_pad + n]
-  double acc[8][4][2];
+  double acc[MI][4][2];
   gemm::zero_acc(acc);
   if (bt * NT < n16)
     gemm::mainloop<PT, false, true, gemm::TRI_K_GE_N>(acc, A, n_pad, B, n_pad, bt * NT, n16, smem, bt * NT);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int wn = warp & 1;
-  const int mbase = (warp >> 1) * 64, nbase = wn * 32;
+  const int wn = warp % PT::WN;
+  const int mbase = (warp / PT::WN) * PT::WTM, nbase = wn * 32;
   const OutHyp& hp = hyp[hj];
 
   // stage scaled candidate / training coordinates for this tile:  sxi[q][row], sxb[q][col]
   double* sxi = smem;                          // d x CT
   double* sxb = smem + d * CT;                 // d x NT
-  double* red = smem + d * (CT + NT);          // 2 x CT x d      (<= 104 KiB for d <= MAXD)
+  double* red = smem + d * (CT + NT);          // WN x CT x d      (<= 56 KiB for d <= MAXD)
   for (int idx = tid; idx < d * CT; idx += PT::NTHREADS) {
     int r = idx / d, q = idx - r * d;
     int64_t i = (int64_t)it * CT + r;
@@ -223,7 +222,7 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) dvar_gemm_kernel(
   // wg = Wt * G*
   const double* Gj = GsT + (int64_t)j * n16 * Nc + (int64_t)it * CT;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < MI; ++i) {
     const int r = mbase + 8 * i + g;
 #pragma unroll
     for (int jn = 0; jn < 4; ++jn)
@@ -235,6 +234,7 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) dvar_gemm_kernel(
       }
   }
   __syncthreads();
+  static_assert(MI == 4 || MI == 8, "the quad reduce-scatter below handles 4 or 8 row tiles per warp");
   for (int q = 0; q < d; ++q) {
     double xb[4][2];
 #pragma unroll
@@ -242,9 +242,9 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) dvar_gemm_kernel(
       xb[jn][0] = sxb[q * NT + nbase + 8 * jn + 2 * t];
       xb[jn][1] = sxb[q * NT + nbase + 8 * jn + 2 * t + 1];
     }
-    double s[8];
+    double s[MI];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < MI; ++i) {
       const double xi = sxi[q * CT + mbase + 8 * i + g];
       double acc_s = 0.0;
 #pragma unroll
@@ -254,30 +254,36 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) dvar_gemm_kernel(
       }
       s[i] = acc_s;
     }
-    // reduce over the 4 lanes of a quad AND scatter the 8 row sums over them (6 shuffles instead of 16):
-    // after step 1 a lane holds rows 4*(t&1)+k, k<4, summed over lane pairs; after step 2 rows 4*(t&1)+2*(t>>1)+k, k<2
-    double u[4], w2[2];
+    // reduce over the 4 lanes of a quad AND scatter the MI row sums over them (3*MI/4 shuffles instead of 2*MI):
+    // step 1 (lane ^ 1): a lane keeps rows (MI/2)*(t&1)+k, k < MI/2;  step 2 (lane ^ 2): rows ... + (MI/4)*(t>>1)+k
+    constexpr int H1 = MI / 2, H2 = MI / 4;
+    double u[H1], w2[H2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double send = (t & 1) ? s[k] : s[k + 4];
-      const double keep = (t & 1) ? s[k + 4] : s[k];
+    for (int k = 0; k < H1; ++k) {
+      const double send = (t & 1) ? s[k] : s[k + H1];
+      const double keep = (t & 1) ? s[k + H1] : s[k];
       u[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const double send = (t & 2) ? u[k] : u[k + 2];
-      const double keep = (t & 2) ? u[k + 2] : u[k];
+    for (int k = 0; k < H2; ++k) {
+      const double send = (t & 2) ? u[k] : u[k + H2];
+      const double keep = (t & 2) ? u[k + H2] : u[k];
       w2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int i = 4 * (t & 1) + 2 * (t >> 1) + k;
-      red[(wn * CT + mbase + 8 * i + g) * d + q] = w2[k];
+    for (int k = 0; k < H2; ++k) {
+      const int irow = H1 * (t & 1) + H2 * (t >> 1) + k;
+      red[(wn * CT + mbase + 8 * irow + g) * d + q] = w2[k];
     }
   }
   __syncthreads();
   double* out = part_dvar + (((int64_t)j * nct + bt) * Nc + (int64_t)it * CT) * d;
-  for (int idx = tid; idx < CT * d; idx += PT::NTHREADS) out[idx] = red[idx] + red[CT * d + idx];
+  for (int idx = tid; idx < CT * d; idx += PT::NTHREADS) {
+    double sum = red[idx];
+#pragma unroll
+    for (int w = 1; w < PT::WN; ++w) sum += red[w * CT * d + idx];
+    out[idx] = sum;
+  }
 }
 
 // ===================================================================================================
