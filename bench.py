@@ -51,7 +51,7 @@ class ClockSampler(object):
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index, period_s=0.5):
+    def __init__(self, gpu_index, period_s=1.0):
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
@@ -63,10 +63,13 @@ class ClockSampler(object):
         nv, h = self.nvml
         bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        try:
+            smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            smax = 0
         while not self._stop.is_set():
             try:
                 sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:

@@ -10,34 +10,74 @@
 //   Matern52  dK/dr / r = -(5/3) s^2 (1 + sqrt5 r) e^{-sqrt5 r} (stationary.py:532-533: (10/3 r - 5 r - 5 sqrt5/3 r^2) e)
 //   Matern32  dK/dr / r = -3 s^2 e^{-sqrt3 r}                   (stationary.py:443-444: -3 s^2 r e)
 // with the reference's convention that the weight is exactly 0 where r == 0.  Differences are at the 1e-16 level.
+//
+// exp / sqrt: the arguments on this path are exp(x <= 0) and sqrt(r2 >= 0).  The generic libdevice routines spend
+// most of their instructions on special cases (ncu: the K* kernel was issue-bound on non-fp64 instructions with the
+// fp64 pipe 50 % busy), so branch-free versions restricted to these ranges are used: < 2 ulp from the libdevice
+// results, far inside the 1e-6 / 1e-9 parity bars.
 #pragma once
 #include "model.h"
 
 namespace bocf {
 
+// exp(x) for x <= 0.  Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor/Horner (remainder < 4e-18),
+// scaling by 2^k through the exponent field.  x < -700 (result < 1e-304) flushes to 0.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double xc = fmax(x, -700.0);
+  const double kf = rint(xc * 1.4426950408889634074);
+  double r = fma(-kf, 6.93147180369123816490e-01, xc);
+  r = fma(-kf, 1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;          // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);        // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);       // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);       // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);      // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);        // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);       // 1/7!
+  p = fma(p, r, 1.3888888888888889e-03);      // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);       // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);      // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);      // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int k = (int)kf;
+  const double scaled = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  return (x < -700.0) ? 0.0 : scaled;
+}
+
+// sqrt(a) for a >= 0 (finite): one Newton step on a * rsqrt(a).
+__device__ __forceinline__ double sqrt_nonneg(double a) {
+  const double y = rsqrt(a);
+  double s = a * y;
+  const double e = fma(-s, s, a);
+  s = fma(e, 0.5 * y, s);
+  return (a > 0.0) ? s : 0.0;
+}
+
 template <int KIND, bool GRAD>
 __device__ __forceinline__ void kern_eval(double r2, double variance, double& k, double& g) {
   if (KIND == BOCF_KERN_SE) {
     // se.py:60  variance * exp(-0.5 * sqdist)
-    k = variance * exp(-0.5 * r2);
+    k = variance * exp_nonpos(-0.5 * r2);
     if (GRAD) g = -k;
   } else if (KIND == BOCF_KERN_RBF) {
     // rbf.py:42-46 (r*r of the rounded sqrt differs from r2 by <= 1 ulp)
-    k = variance * exp(-0.5 * r2);
+    k = variance * exp_nonpos(-0.5 * r2);
     if (GRAD) g = (r2 != 0.0) ? -k : 0.0;
   } else if (KIND == BOCF_KERN_MATERN52) {
     // stationary.py:529-533
-    const double r = sqrt(r2);
+    const double r = sqrt_nonneg(r2);
     const double s5 = 2.23606797749978969641;   // sqrt(5)
-    const double e = variance * exp(-s5 * r);
+    const double e = variance * exp_nonpos(-s5 * r);
     const double lin = 1.0 + s5 * r;
     k = (lin + 5.0 / 3.0 * r2) * e;
     if (GRAD) g = (r2 != 0.0) ? (-5.0 / 3.0) * (lin * e) : 0.0;
   } else {
     // Matern32, stationary.py:440-444
-    const double r = sqrt(r2);
+    const double r = sqrt_nonneg(r2);
     const double s3 = 1.73205080756887729353;   // sqrt(3)
-    const double e = variance * exp(-s3 * r);
+    const double e = variance * exp_nonpos(-s3 * r);
     k = (1.0 + s3 * r) * e;
     if (GRAD) g = (r2 != 0.0) ? -3.0 * e : 0.0;
   }
