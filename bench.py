@@ -217,6 +217,9 @@ def run_ours(args, cfg):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION/INFO; stdout must carry one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("BOCF_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         ge.build_library()
@@ -390,9 +393,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
-    if args.impl == "reference":
-        return run_reference(args, cfg)
-    return run_ours(args, cfg)
+    # stdout must carry exactly ONE JSON line: libraries (NCCL's version banner, build logs, ...) that write to
+    # fd 1 are diverted to stderr for the whole run; print() below goes to the saved real stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
+    try:
+        if args.impl == "reference":
+            return run_reference(args, cfg)
+        return run_ours(args, cfg)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
