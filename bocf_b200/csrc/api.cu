@@ -2,6 +2,7 @@
 // loop, candidate chunking and the fused sweep  posterior -> acquisition  over all hyper-samples.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -72,6 +73,8 @@ static void free_data(bocf_model* M) {
   dev_free(M->ybar);
 }
 static void free_factor(bocf_model* M) {
+  split_release(M);
+  M->S = 0;
   dev_free(M->Xs);
   dev_free(M->xsq);
   dev_free(M->Lmat);
@@ -105,6 +108,29 @@ static int64_t pick_chunk(const bocf_model* M, int64_t N, bool grad, uint64_t ex
   return nc;
 }
 
+// Resolve the requested contraction precision into the active number of digit planes (M->S; 0 = fp64 DMMA) and build
+// the split operands.  AUTO: predicted relative error of the variance ~ 400 * max|Linv|^2 * 256^-S (measured on the
+// synthetic models of tests/test_gpu_split.py); the smallest S in {4,5,6} that keeps it below 1e-7 is used, and
+// models too ill-conditioned for 6 planes stay on the fp64 tensor path.
+static int apply_precision(bocf_model* M, cudaStream_t st) {
+  int S = 0;
+  if (M->precision == BOCF_PREC_SPLIT_I8) {
+    S = M->slices_req;
+  } else if (M->precision == BOCF_PREC_AUTO) {
+    if (int rc = split_linv_absmax(M, &M->linv_absmax, st)) return rc;
+    const double a2 = M->linv_absmax * M->linv_absmax;
+    for (int s = 4; s <= 6 && S == 0; ++s)
+      if (400.0 * a2 * std::pow(256.0, -s) <= 1e-7) S = s;
+  }
+  if (S == 0) {
+    split_release(M);
+    M->S = 0;
+    return 0;
+  }
+  if (M->split_ready && M->S == S) return 0;
+  return split_prepare(M, S, st);
+}
+
 static int check_ready(const bocf_model* M) {
   if (!M) {
     set_error("null model handle");
@@ -123,7 +149,7 @@ using namespace bocf;
 extern "C" {
 
 const char* bocf_last_error(void) { return g_err.c_str(); }
-const char* bocf_version(void) { return "bocf_b200 0.1 sm_100a fp64-dmma"; }
+const char* bocf_version(void) { return "bocf_b200 0.2 sm_100a fp64-dmma + tcgen05-i8-split"; }
 uint64_t bocf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int bocf_profile_enable(int on) {
@@ -188,8 +214,35 @@ int bocf_model_create(bocf_model** out, int m, int d, int kernel, int device) {
   M->d = d;
   M->kernel = kernel;
   M->device = device;
+  if (const char* env = std::getenv("BOCF_PRECISION")) {      // fp64 | auto | split3 .. split6
+    const std::string v(env);
+    if (v == "auto") M->precision = BOCF_PREC_AUTO;
+    else if (v.rfind("split", 0) == 0 && v.size() == 6 && v[5] >= '3' && v[5] <= '6') {
+      M->precision = BOCF_PREC_SPLIT_I8;
+      M->slices_req = v[5] - '0';
+    }
+  }
   *out = M;
   return 0;
+}
+
+int bocf_model_set_precision(bocf_model* M, int mode, int slices, void* stream) {
+  if (!M || mode < BOCF_PREC_FP64_DMMA || mode > BOCF_PREC_AUTO || (mode == BOCF_PREC_SPLIT_I8 && (slices < 3 || slices > 6))) {
+    set_error("bocf_model_set_precision: mode must be 0 (fp64), 1 (split int8, 3..6 digit planes) or 2 (auto)");
+    return BOCF_ERR_INVALID;
+  }
+  M->precision = mode;
+  if (mode == BOCF_PREC_SPLIT_I8) M->slices_req = slices;
+  if (!M->factorized) return 0;
+  DeviceGuard dg(M->device);
+  return apply_precision(M, static_cast<cudaStream_t>(stream));
+}
+
+int bocf_model_active_slices(const bocf_model* M) { return M ? M->S : -1; }
+
+int bocf_debug_split_gemm(const double* A, const double* B, int R, int N, int K, int slices, int tri, double* out,
+                          void* stream) {
+  return split_debug_gemm(A, B, R, N, K, slices, tri, out, static_cast<cudaStream_t>(stream));
 }
 
 int bocf_model_destroy(bocf_model* M) {
@@ -333,6 +386,8 @@ int bocf_model_factorize(bocf_model* M, double* jitter_out, void* stream) {
   BOCF_CUDA_OK(cudaStreamSynchronize(st));
   if (jitter_out)
     for (int hj = 0; hj < Hm; ++hj) jitter_out[hj] = M->hyp_host[hj].jitter;
+  M->split_ready = false;                  // the digit planes belong to the previous factor
+  if (int rc = apply_precision(M, st)) return rc;
   M->factorized = true;
   return 0;
 }

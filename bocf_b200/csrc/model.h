@@ -47,6 +47,20 @@ struct bocf_model {
   void* scratch = nullptr;
   uint64_t scratch_bytes = 0;
   uint64_t scratch_limit = 4ull << 30;
+
+  // ---- split-integer tensor-core contraction (split_gemm.cu) ---------------------------------------
+  int precision = 0;          // requested mode (bocf_precision)
+  int slices_req = 5;         // requested digit planes for BOCF_PREC_SPLIT_I8
+  int S = 0;                  // ACTIVE digit planes; 0 = fp64 DMMA contractions
+  int NTs = 0, ncts = 0, KCH = 0;   // column tile, number of column tiles, 64-wide K chunks
+  double linv_absmax = 0.0;   // max |Linv| over all (h, j), measured at factorisation
+  uint8_t* B1 = nullptr;      // H*m x ncts x KCH x S x NTs x 64   digit planes of Linv rows   (V  = K* Linv^T)
+  uint8_t* B2 = nullptr;      // same layout, digit planes of Linv columns                      (Wt = V Linv)
+  double* cs1 = nullptr;      // H*m x ncts*NTs   power-of-two output scale per column of the first contraction
+  double* cs2 = nullptr;      //                  ... of the second
+  double* aq = nullptr;       // H*m   2^(8S-2-eA): quantiser of K*   (K* <= sigma_f^2)
+  double* vq = nullptr;       // H*m   2^(8S-2-eV): quantiser of V    (|V| <= sigma_f)
+  bool split_ready = false;
 };
 
 namespace bocf {
@@ -70,6 +84,8 @@ struct ChunkBuffers {          // scratch views for one candidate chunk (Nc rows
   double* var;                 // m x Nc
   double* dmean;               // m x Nc x d
   double* dvar;                // m x Nc x d
+  uint8_t* A1 = nullptr;       // split mode: m x Nc/128 x KCH x S x 128 x 64  digit planes of K* (replaces KsT)
+  uint8_t* A2 = nullptr;       // split mode: same layout, digit planes of V   (replaces V)
 };
 uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad);
 void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* out);
@@ -77,6 +93,17 @@ void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBu
 // grad: also K*-side gradient quantities (dmean, G*); need_var / need_dvar select the two contractions.
 int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, bool noiseless,
                            const ChunkBuffers& cb, cudaStream_t st, bool need_var = true, bool need_dvar = true);
+
+// ---- split_gemm.cu ------------------------------------------------------------------------------
+int split_column_tile(int S);
+int split_prepare(bocf_model* M, int S, cudaStream_t st);          // digit planes of Linv + scales
+void split_release(bocf_model* M);
+int split_linv_absmax(bocf_model* M, double* out_host, cudaStream_t st);
+uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad);
+void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* out);
+int launch_split_var(bocf_model* M, int h, const ChunkBuffers& cb, bool need_dvar, cudaStream_t st);
+int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, const ChunkBuffers& cb, cudaStream_t st);
+int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int S, int tri, double* out, cudaStream_t st);
 
 // ---- acq.cu -------------------------------------------------------------------------------------
 struct AcqParams {

@@ -26,14 +26,23 @@ constexpr int NT = PT::BN;                 // column tile
 
 // ===================================================================================================
 // K*, mean, mean-gradient.  One thread per candidate, training points staged through shared memory.
-template <int KIND, int DP, bool GRAD>
+// SPLIT: instead of the fp64 K* matrix, write the S balanced base-256 digit planes of round(K* 2^(8S-2-eA)) in the
+// packed, 64-byte-swizzled tile layout the tcgen05 contraction streams (split_gemm.cu): plane t of K chunk kc of
+// candidate tile rt holds, for row = candidate, the digits of 64 consecutive training points.
+struct SplitOut {
+  uint8_t* A1;
+  const double* aq;    // [H*m] quantiser 2^(8S-2-eA)
+  int KCH, S;
+};
+
+template <int KIND, int DP, bool GRAD, bool SPLIT>
 __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ Xc, int64_t Nvalid, int64_t Nc, int d,
                                                     int n, int n16, int n_pad, int m, int h,
                                                     const OutHyp* __restrict__ hyp, const double* __restrict__ XsAll,
                                                     const double* __restrict__ xsqAll,
                                                     const double* __restrict__ alphaAll, double* __restrict__ KsT,
                                                     double* __restrict__ GsT, double* __restrict__ mean,
-                                                    double* __restrict__ dmean) {
+                                                    double* __restrict__ dmean, const SplitOut so) {
   __shared__ double sX[128][DP];
   __shared__ double sxsq[128];
   __shared__ double salpha[128];
@@ -61,8 +70,15 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
   const double* Xs = XsAll + (int64_t)hj * n_pad * d;
   const double* xsq = xsqAll + (int64_t)hj * n_pad;
   const double* alpha = alphaAll + (int64_t)hj * n_pad;
-  double* Kout = KsT + (int64_t)j * n16 * Nc;
+  double* Kout = SPLIT ? nullptr : KsT + (int64_t)j * n16 * Nc;
   double* Gout = GRAD ? GsT + (int64_t)j * n16 * Nc : nullptr;
+  // split mode: digit planes of this block's 128 candidates (row = tid) for output j
+  constexpr int MAXS = 6;
+  uint32_t dv[SPLIT ? MAXS : 1][4];
+  const double aq = SPLIT ? so.aq[hj] : 0.0;
+  const unsigned long long dbias = SPLIT ? (0x808080808080ull >> (8 * (MAXS - so.S))) : 0ull;
+  uint8_t* Aout = SPLIT ? so.A1 + ((size_t)((size_t)j * gridDim.x + blockIdx.x) * so.KCH) * so.S * (128 * 64) : nullptr;
+  const uint32_t swz = (uint32_t)((tid >> 1) & 3);
 
   for (int b0 = 0; b0 < n16; b0 += 128) {
     __syncthreads();
@@ -78,36 +94,58 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
     }
     __syncthreads();
     const int bmax = min(128, n16 - b0);
-    for (int bb = 0; bb < bmax; ++bb) {
-      const int b = b0 + bb;
-      double kv = 0.0, gv = 0.0;
-      if (b < n) {
-        double r2;
-        if (KIND == BOCF_KERN_SE) {
-          r2 = 0.0;
+    constexpr int UNR = SPLIT ? 16 : 1;     // split mode: 16 training points = one 16-byte piece of a digit-plane row
+    for (int bb0 = 0; bb0 < bmax; bb0 += UNR) {
+      if (SPLIT) {
 #pragma unroll
-          for (int q = 0; q < DP; ++q) {
-            double df = xs[q] - sX[bb][q];
-            r2 += df * df;
+        for (int t = 0; t < MAXS; ++t) dv[t][0] = dv[t][1] = dv[t][2] = dv[t][3] = 0u;
+      }
+#pragma unroll
+      for (int e = 0; e < UNR; ++e) {
+        const int bb = bb0 + e;
+        const int b = b0 + bb;
+        double kv = 0.0, gv = 0.0;
+        if (b < n) {
+          double r2;
+          if (KIND == BOCF_KERN_SE) {
+            r2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < DP; ++q) {
+              double df = xs[q] - sX[bb][q];
+              r2 += df * df;
+            }
+          } else {
+            double dot = 0.0;
+#pragma unroll
+            for (int q = 0; q < DP; ++q) dot += xs[q] * sX[bb][q];
+            r2 = -2.0 * dot + (xsq_i + sxsq[bb]);
+            r2 = fmax(r2, 0.0);
           }
-        } else {
-          double dot = 0.0;
+          kern_eval<KIND, GRAD>(r2, variance, kv, gv);
+          const double a = salpha[bb];
+          mu += kv * a;
+          if (GRAD) {
+            const double w = gv * a;
 #pragma unroll
-          for (int q = 0; q < DP; ++q) dot += xs[q] * sX[bb][q];
-          r2 = -2.0 * dot + (xsq_i + sxsq[bb]);
-          r2 = fmax(r2, 0.0);
+            for (int q = 0; q < DP; ++q) gm[q] += w * (xs[q] - sX[bb][q]);
+          }
         }
-        kern_eval<KIND, GRAD>(r2, variance, kv, gv);
-        const double a = salpha[bb];
-        mu += kv * a;
-        if (GRAD) {
-          const double w = gv * a;
+        if (GRAD) Gout[(int64_t)b * Nc + i] = gv;
+        if (!SPLIT) {
+          Kout[(int64_t)b * Nc + i] = kv;
+        } else {
+          const unsigned long long dg = ((unsigned long long)__double2ll_rn(kv * aq) + dbias) ^ dbias;
 #pragma unroll
-          for (int q = 0; q < DP; ++q) gm[q] += w * (xs[q] - sX[bb][q]);
+          for (int t = 0; t < MAXS; ++t) dv[t][e >> 2] |= (uint32_t)((dg >> (8 * t)) & 0xFFull) << (8 * (e & 3));
         }
       }
-      Kout[(int64_t)b * Nc + i] = kv;
-      if (GRAD) Gout[(int64_t)b * Nc + i] = gv;
+      if (SPLIT) {
+        const int k0 = b0 + bb0, kc = k0 >> 6, piece = (k0 & 63) >> 4;
+        uint8_t* dst = Aout + (size_t)kc * so.S * (128 * 64) + tid * 64 + ((piece ^ swz) << 4);
+#pragma unroll
+        for (int t = 0; t < MAXS; ++t)
+          if (t < so.S) *reinterpret_cast<uint4*>(dst + (size_t)t * (128 * 64)) = make_uint4(dv[t][0], dv[t][1], dv[t][2], dv[t][3]);
+      }
     }
   }
   mean[(int64_t)j * Nc + i] = mu + hp.ybar;
@@ -314,6 +352,7 @@ __global__ void finalize_kernel(const double* __restrict__ part_var, const doubl
 int candidate_tile() { return CT; }
 
 uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
+  if (M->S > 0) return split_chunk_bytes_per_candidate(M, grad);
   const uint64_t nct = M->n_pad / NT;
   uint64_t per = 0;
   per += (uint64_t)M->m * M->n16;                       // KsT
@@ -329,6 +368,11 @@ uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
 }
 
 void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* cb) {
+  cb->A1 = cb->A2 = nullptr;
+  if (M->S > 0) {
+    split_carve_chunk(M, base, Nc, grad, cb);
+    return;
+  }
   const uint64_t nct = M->n_pad / NT;
   double* p = reinterpret_cast<double*>(base);
   auto take = [&](uint64_t count) {
@@ -356,13 +400,20 @@ template <int KIND, int DP>
 static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, const ChunkBuffers& cb,
                           cudaStream_t st) {
   dim3 grid((unsigned)(cb.Nc / 128), (unsigned)M->m);
-  if (grad)
-    kstar_kernel<KIND, DP, true><<<grid, 128, 0, st>>>(Xc, Nvalid, cb.Nc, M->d, M->n, M->n16, M->n_pad, M->m, h, M->hyp,
-                                                       M->Xs, M->xsq, M->alpha, cb.KsT, cb.GsT, cb.mean, cb.dmean);
-  else
-    kstar_kernel<KIND, DP, false><<<grid, 128, 0, st>>>(Xc, Nvalid, cb.Nc, M->d, M->n, M->n16, M->n_pad, M->m, h,
-                                                        M->hyp, M->Xs, M->xsq, M->alpha, cb.KsT, nullptr, cb.mean,
-                                                        nullptr);
+  SplitOut so;
+  so.A1 = cb.A1;
+  so.aq = M->aq;
+  so.KCH = M->KCH;
+  so.S = M->S;
+  const bool split = (cb.A1 != nullptr);
+#define BOCF_KSTAR(G, SP)                                                                                              \
+  kstar_kernel<KIND, DP, G, SP><<<grid, 128, 0, st>>>(Xc, Nvalid, cb.Nc, M->d, M->n, M->n16, M->n_pad, M->m, h, M->hyp, \
+                                                      M->Xs, M->xsq, M->alpha, cb.KsT, cb.GsT, cb.mean, cb.dmean, so)
+  if (grad && split) BOCF_KSTAR(true, true);
+  else if (grad) BOCF_KSTAR(true, false);
+  else if (split) BOCF_KSTAR(false, true);
+  else BOCF_KSTAR(false, false);
+#undef BOCF_KSTAR
   BOCF_LAUNCH_OK("kstar_kernel");
   return 0;
 }
@@ -400,8 +451,15 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
   }
   if (rc) return rc;
   if (!need_var) return 0;      // mean (and mean gradient) only: no contraction against the factor
-  const int nct = M->n_pad / NT;
+  const bool split = (cb.A1 != nullptr);
+  const int nct = split ? M->ncts : M->n_pad / NT;
   const unsigned tiles = (unsigned)((cb.Nc / CT) * nct * M->m);
+  if (split) {
+    // tcgen05 kind::i8 digit-plane contractions (split_gemm.cu); same partial-sum layout, same finalize
+    if (int rc2 = launch_split_var(M, h, cb, need_dvar, st)) return rc2;
+    if (need_dvar)
+      if (int rc2 = launch_split_dvar(M, h, Xc, Nvalid, cb, st)) return rc2;
+  } else {
   {
     ProfScope ps("var_gemm_kernel", st);
     var_gemm_kernel<<<tiles, PT::NTHREADS, PT::SMEM_BYTES, st>>>(cb.KsT, M->Linv, cb.V, cb.part_var, cb.Nc, M->n16,
@@ -415,6 +473,7 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
                                                                   M->m, M->d, h);
   }
   if (need_dvar) BOCF_LAUNCH_OK("dvar_gemm_kernel");
+  }
   dim3 fgrid((unsigned)ceil_div(need_dvar ? cb.Nc * M->d : cb.Nc, 256), (unsigned)M->m);
   {
     ProfScope ps("finalize_kernel", st);

@@ -1,0 +1,712 @@
+// split_gemm.cu -- the two candidate-side contractions of the GP posterior on the 5th-generation tensor cores.
+//
+//   V  = K* Linv^T   (posterior.py:312, the reference's dtrtrs route)      var  = k** - sum_k V^2
+//   Wt = V  Linv     (= K* W^-1, gp.py:474)                                 dvar = gradients_X(-2 Wt, x*, X)
+//
+// Blackwell's tcgen05 has no fp64 kind, so the fp64 operands are split into S signed 8-bit digits (balanced
+// base-256 expansion of round(x * 2^(8S-2-e)), e a per-row power-of-two scale) and the product is assembled from
+// S(S+1)/2 exact integer GEMMs on `tcgen05.mma.kind::i8` (SASS UTCIMMA): int8 x int8 products accumulated EXACTLY
+// in int32 tensor memory, one accumulator per digit weight 256^(ta+tb).  The only error is the operand
+// quantisation 2^-(8S-2) (relative to the row scale) -- S = 5 carries 38-bit operands and reproduces the fp64 path
+// to ~1e-8 relative on the variance, S = 4 to ~1e-6 (tests/test_gpu_split.py measures both).
+//
+// Kernel structure (persistent, warp specialised, 192 threads, 1 CTA / SM):
+//   warp 0   producer: one lane streams 64-byte-wide K chunks of the packed, pre-swizzled digit planes of A
+//            (128 candidates) and B (NT factor rows) into a STAGES-deep shared-memory ring with bulk async copies
+//            (TMA engine, cp.async.bulk + mbarrier complete_tx).
+//   warp 1   MMA issuer: one lane issues, per 32-byte K step, S instructions  D[128 x (ta+1)NT] += A_ta * [B_tb]^T
+//            whose B operand STACKS the digit planes tb = S-1-ta .. S-1 along N, so every A plane is read from
+//            shared memory once per step while all S(S+1)/2 digit pairs are covered.  Accumulators live in TMEM,
+//            double buffered when 2*S*NT <= 512 columns so the epilogue of tile t overlaps the MMAs of tile t+1.
+//   warps 2-5 epilogue: tcgen05.ld the S int32 levels of a row (lane = candidate), Horner them into one fp64
+//            value, apply the column scale, and fuse the reductions of the reference:
+//            VAR : sum_k V^2 per candidate (+ re-split V into digit planes = the A operand of the second GEMM)
+//            DVAR: sum_b Wt * G* * (xs_i - Xs_b)  -> per column-tile partial variance gradients.
+// Triangular structure of Linv is exploited per column tile at K-chunk granularity.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "model.h"
+#include "tc05.cuh"
+
+namespace bocf {
+namespace sg {
+
+constexpr int KC = 64;        // bytes (= int8 elements) of K per shared-memory row: one SWIZZLE_64B span
+constexpr int TM = 128;       // candidate rows per tile (= TMEM lanes)
+constexpr int NTHREADS = 192;
+constexpr int SMEM_MAX = 232448;
+
+__host__ __device__ __forceinline__ uint32_t sw64(int r, int c) {   // byte offset of (row r, byte c) in a packed plane
+  return (uint32_t)(r * 64 + ((((c >> 4) ^ ((r >> 1) & 3))) << 4) + (c & 15));
+}
+__host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+template <int S, int NT>
+struct Cfg {
+  static constexpr int A_PLANE = TM * KC, B_PLANE = NT * KC;
+  static constexpr int A_STAGE = S * A_PLANE, B_STAGE = S * B_PLANE, STAGE = A_STAGE + B_STAGE;
+  static constexpr int ACC_COLS = S * NT;
+  static constexpr int NBUF = (2 * ACC_COLS <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = pow2_cols(NBUF * ACC_COLS);
+  static constexpr int HEAD = 1024;                                   // barriers, tmem slot, column scales
+  static constexpr int STAGES_FIT = (SMEM_MAX - HEAD - 512) / STAGE;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static constexpr int SMEM_BYTES = HEAD + 512 + STAGES * STAGE;
+  static_assert(S >= 2 && S <= 6 && NT % 16 == 0 && S * NT <= 256, "stacked B operand must fit one MMA (N <= 256)");
+  static_assert(STAGES >= 2, "need at least a double-buffered ring");
+  static_assert(B_STAGE % 512 == 0 && A_STAGE % 512 == 0, "planes must keep the 512-byte swizzle period");
+  static_assert(NT * 8 + (2 * STAGES + 2 * NBUF) * 8 + 16 <= HEAD, "head area too small");
+};
+
+enum { EPI_RAW = 0, EPI_VAR = 1, EPI_DVAR = 2 };
+enum { TRI_FULL = 0, TRI_K_LE_N = 1, TRI_K_GE_N = 2 };
+
+struct GemmParams {
+  const uint8_t* A;        // [m][RT][KCH][S][128][64]   packed digit planes of the candidate-side operand
+  const uint8_t* B;        // [Hm][nct][KCH][S][NT][64]  packed digit planes of the factor-side operand
+  const double* cs;        // [Hm][nct*NT]               column scale (power of two)
+  int m, h, RT, nct, KCH, n, tri;
+  int64_t Nc, Nvalid;
+  // RAW
+  double* raw_out;         // [m*RT*128][ldo]
+  const double* raw_rs;    // [m*RT*128] row scale
+  int ldo;
+  // VAR
+  double* part_var;        // [m][nct][Nc]
+  uint8_t* A2;             // [m][RT][KCH][S][128][64]   digit planes of V (nullptr: not needed)
+  const double* vq;        // [Hm] 2^(8S-2-eV)
+  // DVAR
+  double* part_dvar;       // [m][nct][Nc][d]
+  const double* GsT;       // [m][n16][Nc]
+  const double* Xc;        // [Nvalid][d]
+  const double* Xs;        // [Hm][n_pad][d]
+  const OutHyp* hyp;
+  int d, n16, n_pad;
+};
+
+struct TileInfo {
+  int j, rt, ct, kb, ke;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const GemmParams& P, int NT, int t) {
+  constexpr int RG = 8;                                   // candidate tiles that share one pass over the column tiles
+  TileInfo ti;
+  const int per_j = P.RT * P.nct;
+  ti.j = t / per_j;
+  const int u = t - ti.j * per_j;
+  const int g = u / (RG * P.nct);
+  const int v = u - g * RG * P.nct;
+  const int rows = min(RG, P.RT - g * RG);
+  const int cidx = v / rows;
+  ti.rt = g * RG + (v - cidx * rows);
+  const int kch_used = (P.n + KC - 1) / KC;
+  if (P.tri == TRI_K_LE_N) {                              // K index <= column index: heaviest tiles first
+    ti.ct = P.nct - 1 - cidx;
+    ti.kb = 0;
+    ti.ke = min(kch_used, (min((ti.ct + 1) * NT, P.n) + KC - 1) / KC);
+  } else if (P.tri == TRI_K_GE_N) {                       // K index >= column index
+    ti.ct = cidx;
+    ti.kb = (ti.ct * NT) / KC;
+    ti.ke = kch_used;
+  } else {
+    ti.ct = cidx;
+    ti.kb = 0;
+    ti.ke = kch_used;
+  }
+  return ti;
+}
+
+// digits of a 64-bit integer |Y| < 2^(8S-2): byte t of the result is the balanced base-256 digit of weight 256^t
+template <int S>
+__device__ __forceinline__ unsigned long long balanced_digits(long long Y) {
+  constexpr unsigned long long BIAS = (S == 6)   ? 0x808080808080ull
+                                      : (S == 5) ? 0x8080808080ull
+                                      : (S == 4) ? 0x80808080ull
+                                      : (S == 3) ? 0x808080ull
+                                                 : 0x8080ull;
+  return ((unsigned long long)Y + BIAS) ^ BIAS;
+}
+
+template <int S, int NT, int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParams P) {
+  using C = Cfg<S, NT>;
+  extern __shared__ uint8_t smem_raw[];
+  // head: [0,512) barriers + tmem slot, [512, 1024) column scales; stages start at the next 512-byte boundary
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + C::NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::NBUF);
+  double* s_cs = reinterpret_cast<double*>(smem_raw + 512);
+  const uint32_t raw_addr = tc::smem_u32(smem_raw);
+  const uint32_t stage_off = ((raw_addr + C::HEAD + 511u) & ~511u) - raw_addr;
+  uint8_t* sA = smem_raw + stage_off;
+  uint8_t* sB = sA + C::STAGES * C::A_STAGE;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < C::NBUF; ++b) {
+      tc::mbar_init(&tfull[b], 1);
+      tc::mbar_init(&tempty[b], 128);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = P.m * P.RT * P.nct;
+
+  if (warp == 0) {
+    // ================================ producer =================================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const TileInfo ti = decode_tile(P, NT, t);
+        const uint8_t* gA = P.A + ((size_t)(ti.j * P.RT + ti.rt) * P.KCH) * C::A_STAGE;
+        const uint8_t* gB = P.B + ((size_t)((P.h * P.m + ti.j) * P.nct + ti.ct) * P.KCH) * C::B_STAGE;
+        for (int kc = ti.kb; kc < ti.ke; ++kc) {
+          tc::mbar_wait(&empty[stage], phase ^ 1u);
+          tc::mbar_arrive_expect_tx(&full[stage], C::STAGE);
+          tc::bulk_g2s(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage]);
+          tc::bulk_g2s(sB + stage * C::B_STAGE, gB + (size_t)kc * C::B_STAGE, C::B_STAGE, &full[stage]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===============================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const TileInfo ti = decode_tile(P, NT, t);
+        const int buf = it % C::NBUF;
+        const uint32_t use = (uint32_t)(it / C::NBUF);
+        tc::mbar_wait(&tempty[buf], (use & 1u) ^ 1u);          // epilogue has drained this accumulator buffer
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::ACC_COLS);
+        bool first = true;
+        for (int kc = ti.kb; kc < ti.ke; ++kc) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t a0 = tc::smem_u32(sA + stage * C::A_STAGE);
+          const uint32_t b0 = tc::smem_u32(sB + stage * C::B_STAGE);
+#pragma unroll
+          for (int ks = 0; ks < KC / 32; ++ks) {
+#pragma unroll
+            for (int ta = S - 1; ta >= 0; --ta) {
+              // A digit plane ta against the stacked B planes tb = S-1-ta .. S-1  ->  levels 0 .. ta
+              const uint64_t adesc = tc::smem_desc_sw64(a0 + ta * C::A_PLANE + ks * 32);
+              const uint64_t bdesc = tc::smem_desc_sw64(b0 + (S - 1 - ta) * C::B_PLANE + ks * 32);
+              tc::mma_i8(d_tmem, adesc, bdesc, tc::idesc_i8((ta + 1) * NT), (first && ta == S - 1) ? 0u : 1u);
+            }
+            first = false;
+          }
+          tc::mma_commit(&empty[stage]);                        // stage reusable once these MMAs have read it
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc::mma_commit(&tfull[buf]);                            // accumulators of this tile complete
+      }
+    }
+  } else {
+    // ================================ epilogue (128 threads) ===================================
+    const int et = threadIdx.x - 64;                            // 0..127
+    const int lg = warp & 3;                                    // TMEM lane group this warp may access
+    const int row = lg * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const TileInfo ti = decode_tile(P, NT, t);
+      const int buf = it % C::NBUF;
+      const uint32_t use = (uint32_t)(it / C::NBUF);
+      const int hj = P.h * P.m + ti.j;
+      const int col0 = ti.ct * NT;
+      tc::named_bar_sync(1, 128);                               // previous tile's readers of s_cs are done
+      if (et < NT) s_cs[et] = P.cs[(size_t)hj * P.nct * NT + col0 + et];
+      tc::named_bar_sync(1, 128);
+      const int64_t i = (int64_t)ti.rt * TM + row;              // chunk-local candidate
+
+      // per-tile thread state
+      double sumsq = 0.0;
+      double vq = 0.0;
+      double xs[MAXD], acc[MAXD], s0 = 0.0;
+      const double* Gcol = nullptr;
+      const double* Xb = nullptr;
+      if (EPI == EPI_VAR) vq = P.vq[hj];
+      if (EPI == EPI_DVAR) {
+        const OutHyp& hp = P.hyp[hj];
+#pragma unroll
+        for (int q = 0; q < MAXD; ++q) {
+          xs[q] = (q < P.d && i < P.Nvalid) ? P.Xc[i * P.d + q] / hp.ls[q] : 0.0;
+          acc[q] = 0.0;
+        }
+        Gcol = P.GsT + (size_t)ti.j * P.n16 * P.Nc + i;
+        Xb = P.Xs + (size_t)hj * P.n_pad * P.d;
+      }
+
+      tc::mbar_wait(&tfull[buf], use & 1u);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
+
+#pragma unroll 1
+      for (int cg = 0; cg < NT / 16; ++cg) {
+        uint32_t c[S][16];
+#pragma unroll
+        for (int lb = 0; lb < S; ++lb) tc::tmem_ld16(taddr + (uint32_t)(lb * NT + cg * 16), c[lb]);
+        double gv[16];
+        if (EPI == EPI_DVAR) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int b = col0 + cg * 16 + e;
+            gv[e] = (b < P.n) ? __ldg(Gcol + (size_t)b * P.Nc) : 0.0;
+          }
+        }
+        tc::tmem_ld_wait();
+        uint32_t vec[S][4];
+        if (EPI == EPI_VAR) {
+#pragma unroll
+          for (int tt = 0; tt < S; ++tt)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) vec[tt][w] = 0u;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          double v = (double)(int)c[S - 1][e];
+#pragma unroll
+          for (int lb = S - 2; lb >= 0; --lb) v = fma(v, 256.0, (double)(int)c[lb][e]);
+          v *= s_cs[cg * 16 + e];
+          if (EPI == EPI_RAW) {
+            const int col = col0 + cg * 16 + e;
+            const size_t grow = (size_t)(ti.j * P.RT + ti.rt) * TM + row;
+            if (col < P.ldo) P.raw_out[grow * P.ldo + col] = v * P.raw_rs[grow];
+          } else if (EPI == EPI_VAR) {
+            sumsq = fma(v, v, sumsq);
+            const unsigned long long dg = balanced_digits<S>(__double2ll_rn(v * vq));
+#pragma unroll
+            for (int tt = 0; tt < S; ++tt)
+              vec[tt][e >> 2] |= (uint32_t)((dg >> (8 * tt)) & 0xFFull) << (8 * (e & 3));
+          } else {
+            const double w = v * gv[e];
+            s0 += w;
+            const int b = min(col0 + cg * 16 + e, P.n_pad - 1);
+            const double* xb = Xb + (size_t)b * P.d;
+#pragma unroll
+            for (int q = 0; q < MAXD; ++q)
+              if (q < P.d) acc[q] = fma(w, __ldg(xb + q), acc[q]);
+          }
+        }
+        if (EPI == EPI_VAR && P.A2 != nullptr) {
+          const int k = col0 + cg * 16;
+          if (k < P.KCH * KC) {
+            const int kc = k >> 6, piece = (k & 63) >> 4;
+            uint8_t* dst = P.A2 + (((size_t)(ti.j * P.RT + ti.rt) * P.KCH + kc) * S) * C::A_PLANE + sw64(row, piece * 16);
+#pragma unroll
+            for (int tt = 0; tt < S; ++tt)
+              *reinterpret_cast<uint4*>(dst + (size_t)tt * C::A_PLANE) = make_uint4(vec[tt][0], vec[tt][1], vec[tt][2], vec[tt][3]);
+          }
+        }
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(&tempty[buf]);                            // accumulator buffer may be overwritten
+
+      if (EPI == EPI_VAR) P.part_var[((size_t)ti.j * P.nct + ti.ct) * P.Nc + i] = sumsq;
+      if (EPI == EPI_DVAR) {
+        double* out = P.part_dvar + (((size_t)ti.j * P.nct + ti.ct) * P.Nc + i) * P.d;
+#pragma unroll
+        for (int q = 0; q < MAXD; ++q)
+          if (q < P.d) out[q] = xs[q] * s0 - acc[q];
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc::fence_after_sync();
+    tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---- digit-plane packing of a dense fp64 matrix ------------------------------------------------------------------
+// element (r, k) of matrix `mat`: src[mat*mat_stride + r*sr + k*sk], zero outside r < R, k < K.
+__global__ void row_exp_kernel(const double* __restrict__ src, int64_t mat_stride, int64_t sr, int64_t sk, int R, int K,
+                               int Rpad, int* __restrict__ exps, double* __restrict__ cs,
+                               const int* __restrict__ extra, int base) {
+  const int mat = blockIdx.y;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= Rpad) return;
+  double amax = 0.0;
+  if (row < R)
+    for (int k = lane; k < K; k += 32) amax = fmax(amax, fabs(src[mat * mat_stride + row * sr + k * sk]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (lane == 0) {
+    int e = 0;
+    if (amax > 0.0) frexp(amax * 1.02, &e);
+    exps[(size_t)mat * Rpad + row] = e;
+    if (cs) cs[(size_t)mat * Rpad + row] = ldexp(1.0, e + (extra ? extra[mat] : 0) + base);
+  }
+}
+
+template <int S>
+__global__ void pack_digits_kernel(const double* __restrict__ src, int64_t mat_stride, int64_t sr, int64_t sk, int R,
+                                   int K, const int* __restrict__ exps, int Rpad, int TR, int ntile, int KCH,
+                                   uint8_t* __restrict__ out) {
+  const int kc = blockIdx.x, tile = blockIdx.y, mat = blockIdx.z;
+  uint8_t* obase = out + (((size_t)(mat * ntile + tile) * KCH + kc) * S) * TR * KC;
+  for (int idx = threadIdx.x; idx < TR * 4; idx += blockDim.x) {
+    int r, piece;
+    if (sk == 1) {
+      r = idx >> 2;
+      piece = idx & 3;
+    } else {
+      r = idx % TR;
+      piece = idx / TR;
+    }
+    const int row = tile * TR + r;
+    const int e = exps[(size_t)mat * Rpad + row];
+    const double q = ldexp(1.0, 8 * S - 2 - e);
+    uint32_t vec[S][4];
+#pragma unroll
+    for (int tt = 0; tt < S; ++tt)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) vec[tt][w] = 0u;
+#pragma unroll
+    for (int ee = 0; ee < 16; ++ee) {
+      const int k = kc * KC + piece * 16 + ee;
+      const double x = (row < R && k < K) ? src[mat * mat_stride + row * sr + k * sk] : 0.0;
+      const unsigned long long dg = balanced_digits<S>(__double2ll_rn(x * q));
+#pragma unroll
+      for (int tt = 0; tt < S; ++tt) vec[tt][ee >> 2] |= (uint32_t)((dg >> (8 * tt)) & 0xFFull) << (8 * (ee & 3));
+    }
+#pragma unroll
+    for (int tt = 0; tt < S; ++tt)
+      *reinterpret_cast<uint4*>(obase + (size_t)tt * TR * KC + sw64(r, piece * 16)) =
+          make_uint4(vec[tt][0], vec[tt][1], vec[tt][2], vec[tt][3]);
+  }
+}
+
+__global__ void absmax_kernel(const double* __restrict__ src, size_t count, double* __restrict__ out) {
+  double a = 0.0;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += (size_t)gridDim.x * blockDim.x)
+    a = fmax(a, fabs(src[idx]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+  if ((threadIdx.x & 31) == 0 && a > 0.0)
+    atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(a));
+}
+
+template <int S>
+static int pack_t(const double* src, int64_t mat_stride, int64_t sr, int64_t sk, int R, int K, const int* exps, int Rpad,
+                  int TR, int ntile, int KCH, int mats, uint8_t* out, cudaStream_t st) {
+  dim3 grid((unsigned)KCH, (unsigned)ntile, (unsigned)mats);
+  pack_digits_kernel<S><<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, exps, Rpad, TR, ntile, KCH, out);
+  BOCF_LAUNCH_OK("pack_digits_kernel");
+  return 0;
+}
+static int pack_digits(int S, const double* src, int64_t mat_stride, int64_t sr, int64_t sk, int R, int K,
+                       const int* exps, int Rpad, int TR, int ntile, int KCH, int mats, uint8_t* out, cudaStream_t st) {
+  switch (S) {
+    case 3: return pack_t<3>(src, mat_stride, sr, sk, R, K, exps, Rpad, TR, ntile, KCH, mats, out, st);
+    case 4: return pack_t<4>(src, mat_stride, sr, sk, R, K, exps, Rpad, TR, ntile, KCH, mats, out, st);
+    case 5: return pack_t<5>(src, mat_stride, sr, sk, R, K, exps, Rpad, TR, ntile, KCH, mats, out, st);
+    case 6: return pack_t<6>(src, mat_stride, sr, sk, R, K, exps, Rpad, TR, ntile, KCH, mats, out, st);
+  }
+  set_error("split contraction supports 3..6 digit planes");
+  return BOCF_ERR_INVALID;
+}
+static int row_exps(const double* src, int64_t mat_stride, int64_t sr, int64_t sk, int R, int K, int Rpad, int mats,
+                    int* exps, double* cs, const int* extra, int base, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(Rpad, 8), (unsigned)mats);
+  row_exp_kernel<<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, Rpad, exps, cs, extra, base);
+  BOCF_LAUNCH_OK("row_exp_kernel");
+  return 0;
+}
+
+template <int S, int NT, int EPI>
+static int launch_t(const GemmParams& P, cudaStream_t st) {
+  using C = Cfg<S, NT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    BOCF_CUDA_OK(cudaFuncSetAttribute(split_gemm_kernel<S, NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      C::SMEM_BYTES));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = P.m * P.RT * P.nct;
+  const int grid = tiles < sms ? tiles : sms;
+  split_gemm_kernel<S, NT, EPI><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(P);
+  BOCF_LAUNCH_OK("split_gemm_kernel");
+  return 0;
+}
+template <int EPI>
+static int launch_s(int S, const GemmParams& P, cudaStream_t st) {
+  switch (S) {
+    case 3: return launch_t<3, 64, EPI>(P, st);
+    case 4: return launch_t<4, 64, EPI>(P, st);
+    case 5: return launch_t<5, 48, EPI>(P, st);
+    case 6: return launch_t<6, 32, EPI>(P, st);
+  }
+  set_error("split contraction supports 3..6 digit planes");
+  return BOCF_ERR_INVALID;
+}
+
+}  // namespace sg
+
+int split_column_tile(int S) { return S == 5 ? 48 : (S == 6 ? 32 : 64); }
+
+static void free_split(bocf_model* M) {
+  auto fr = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  fr(M->B1);
+  fr(M->B2);
+  fr(M->cs1);
+  fr(M->cs2);
+  fr(M->aq);
+  fr(M->vq);
+  M->split_ready = false;
+}
+void split_release(bocf_model* M) { free_split(M); }
+
+// Largest |Linv| entry over all (h, j): drives the automatic choice of the number of digit planes.
+int split_linv_absmax(bocf_model* M, double* out_host, cudaStream_t st) {
+  double* d = nullptr;
+  BOCF_CUDA_OK(cudaMalloc(&d, sizeof(double)));
+  BOCF_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(double), st));
+  const size_t count = (size_t)M->H * M->m * M->n_pad * M->n_pad;
+  sg::absmax_kernel<<<1024, 256, 0, st>>>(M->Linv, count, d);
+  BOCF_LAUNCH_OK("absmax_kernel");
+  BOCF_CUDA_OK(cudaMemcpyAsync(out_host, d, sizeof(double), cudaMemcpyDeviceToHost, st));
+  BOCF_CUDA_OK(cudaStreamSynchronize(st));
+  cudaFree(d);
+  return 0;
+}
+
+// Digit planes of Linv for both contractions + all power-of-two scales.  Called after the factorisation.
+int split_prepare(bocf_model* M, int S, cudaStream_t st) {
+  free_split(M);
+  const int Hm = M->H * M->m;
+  const int NT = split_column_tile(S);
+  M->S = S;
+  M->NTs = NT;
+  M->ncts = (int)ceil_div(M->n, NT);
+  M->KCH = (int)ceil_div(M->n, sg::KC);
+  const int Rpad = M->ncts * NT;
+  const size_t plane_bytes = (size_t)Hm * M->ncts * M->KCH * S * NT * sg::KC;
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->B1), plane_bytes));
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->B2), plane_bytes));
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->cs1), sizeof(double) * Hm * Rpad));
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->cs2), sizeof(double) * Hm * Rpad));
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->aq), sizeof(double) * Hm));
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->vq), sizeof(double) * Hm));
+  int *exps = nullptr, *extra = nullptr;
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&exps), sizeof(int) * Hm * Rpad));
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&extra), sizeof(int) * 2 * Hm));
+  // candidate-side scales: K* <= sigma_f^2 (stationary kernels), |V_k| <= sqrt(k**) = sigma_f
+  std::vector<int> ex(2 * Hm);
+  std::vector<double> aq(Hm), vq(Hm);
+  for (int hj = 0; hj < Hm; ++hj) {
+    int eA = 0, eV = 0;
+    std::frexp(M->hyp_host[hj].variance * 1.02, &eA);
+    std::frexp(std::sqrt(M->hyp_host[hj].variance) * 1.02, &eV);
+    ex[hj] = eA;
+    ex[Hm + hj] = eV;
+    aq[hj] = std::ldexp(1.0, 8 * S - 2 - eA);
+    vq[hj] = std::ldexp(1.0, 8 * S - 2 - eV);
+  }
+  BOCF_CUDA_OK(cudaMemcpyAsync(extra, ex.data(), sizeof(int) * 2 * Hm, cudaMemcpyHostToDevice, st));
+  BOCF_CUDA_OK(cudaMemcpyAsync(M->aq, aq.data(), sizeof(double) * Hm, cudaMemcpyHostToDevice, st));
+  BOCF_CUDA_OK(cudaMemcpyAsync(M->vq, vq.data(), sizeof(double) * Hm, cudaMemcpyHostToDevice, st));
+  const int base = -2 * (8 * S - 2) + 8 * (S - 1);
+  const int64_t nn = (int64_t)M->n_pad * M->n_pad;
+  int rc = 0;
+  // first contraction: rows = factor row k, K = b      (element Linv[k][b])
+  if (!rc) rc = sg::row_exps(M->Linv, nn, M->n_pad, 1, M->n, M->n, Rpad, Hm, exps, M->cs1, extra, base, st);
+  if (!rc) rc = sg::pack_digits(S, M->Linv, nn, M->n_pad, 1, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B1, st);
+  // second contraction: rows = factor column b, K = k  (element Linv[k][b])
+  if (!rc) rc = sg::row_exps(M->Linv, nn, 1, M->n_pad, M->n, M->n, Rpad, Hm, exps, M->cs2, extra + Hm, base, st);
+  if (!rc) rc = sg::pack_digits(S, M->Linv, nn, 1, M->n_pad, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B2, st);
+  cudaError_t e = cudaStreamSynchronize(st);      // ex/aq/vq are host vectors going out of scope
+  cudaFree(exps);
+  cudaFree(extra);
+  if (rc) return rc;
+  if (e != cudaSuccess) {
+    set_error(std::string("split_prepare: ") + cudaGetErrorString(e));
+    return BOCF_ERR_CUDA;
+  }
+  M->split_ready = true;
+  return 0;
+}
+
+uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
+  uint64_t per = 0;
+  per += (uint64_t)M->m * M->KCH * sg::KC * M->S;       // A1 digit planes of K*
+  per += (uint64_t)M->m * M->ncts * 8;                  // part_var
+  per += 2ull * M->m * 8;                               // mean, var
+  if (grad) {
+    per += (uint64_t)M->m * M->n16 * 8;                 // GsT
+    per += (uint64_t)M->m * M->KCH * sg::KC * M->S;     // A2 digit planes of V
+    per += (uint64_t)M->m * M->ncts * M->d * 8;         // part_dvar
+    per += 2ull * M->m * M->d * 8;                      // dmean, dvar
+  }
+  return per;
+}
+
+void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* cb) {
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  auto take = [&](uint64_t bytes) {
+    uint8_t* r = p;
+    p += round_up((int64_t)bytes, 1024);
+    return r;
+  };
+  const uint64_t planes = (uint64_t)M->m * Nc * M->KCH * sg::KC * M->S;
+  cb->Nc = Nc;
+  cb->KsT = cb->V = nullptr;
+  cb->A1 = take(planes);
+  cb->part_var = reinterpret_cast<double*>(take((uint64_t)M->m * M->ncts * Nc * 8));
+  cb->mean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
+  cb->var = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
+  if (grad) {
+    cb->GsT = reinterpret_cast<double*>(take((uint64_t)M->m * M->n16 * Nc * 8));
+    cb->A2 = take(planes);
+    cb->part_dvar = reinterpret_cast<double*>(take((uint64_t)M->m * M->ncts * Nc * M->d * 8));
+    cb->dmean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
+    cb->dvar = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
+  } else {
+    cb->GsT = cb->part_dvar = cb->dmean = cb->dvar = nullptr;
+    cb->A2 = nullptr;
+  }
+}
+
+static sg::GemmParams base_params(const bocf_model* M, int h, const ChunkBuffers& cb) {
+  sg::GemmParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.m = M->m;
+  P.h = h;
+  P.RT = (int)(cb.Nc / sg::TM);
+  P.nct = M->ncts;
+  P.KCH = M->KCH;
+  P.n = M->n;
+  P.Nc = cb.Nc;
+  P.d = M->d;
+  P.n16 = M->n16;
+  P.n_pad = M->n_pad;
+  P.hyp = M->hyp;
+  return P;
+}
+
+int launch_split_var(bocf_model* M, int h, const ChunkBuffers& cb, bool need_dvar, cudaStream_t st) {
+  sg::GemmParams P = base_params(M, h, cb);
+  P.A = cb.A1;
+  P.B = M->B1;
+  P.cs = M->cs1;
+  P.tri = sg::TRI_K_LE_N;
+  P.part_var = cb.part_var;
+  P.A2 = need_dvar ? cb.A2 : nullptr;
+  P.vq = M->vq;
+  ProfScope ps("split_var_kernel", st);
+  return sg::launch_s<sg::EPI_VAR>(M->S, P, st);
+}
+
+int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, const ChunkBuffers& cb, cudaStream_t st) {
+  sg::GemmParams P = base_params(M, h, cb);
+  P.A = cb.A2;
+  P.B = M->B2;
+  P.cs = M->cs2;
+  P.tri = sg::TRI_K_GE_N;
+  P.part_dvar = cb.part_dvar;
+  P.GsT = cb.GsT;
+  P.Xc = Xc;
+  P.Nvalid = Nvalid;
+  P.Xs = M->Xs;
+  ProfScope ps("split_dvar_kernel", st);
+  return sg::launch_s<sg::EPI_DVAR>(M->S, P, st);
+}
+
+// Test entry: out (R x N) = A (R x K) * B (N x K)^T through the digit-plane machinery.  All pointers [dev] fp64 row-major.
+int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int S, int tri, double* out, cudaStream_t st) {
+  if (S < 3 || S > 6 || R < 1 || N < 1 || K < 1) {
+    set_error("split_debug_gemm: invalid arguments");
+    return BOCF_ERR_INVALID;
+  }
+  const int NT = split_column_tile(S);
+  const int RT = (int)ceil_div(R, sg::TM), nct = (int)ceil_div(N, NT), KCH = (int)ceil_div(K, sg::KC);
+  const int RpadA = RT * sg::TM, RpadB = nct * NT;
+  uint8_t *pa = nullptr, *pb = nullptr;
+  int *ea = nullptr, *eb = nullptr;
+  double *rs = nullptr, *cs = nullptr, *tmp = nullptr;
+  int rc = 0;
+  do {
+    if (cudaMalloc(reinterpret_cast<void**>(&pa), (size_t)RT * KCH * S * sg::TM * sg::KC) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&pb), (size_t)nct * KCH * S * NT * sg::KC) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&ea), sizeof(int) * RpadA) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&eb), sizeof(int) * RpadB) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&rs), sizeof(double) * RpadA) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&cs), sizeof(double) * RpadB) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&tmp), sizeof(double) * (size_t)RpadA * N) != cudaSuccess) {
+      set_error("split_debug_gemm: out of device memory");
+      rc = BOCF_ERR_CUDA;
+      break;
+    }
+    const int base = -2 * (8 * S - 2) + 8 * (S - 1);
+    if ((rc = sg::row_exps(A, 0, K, 1, R, K, RpadA, 1, ea, rs, nullptr, 0, st))) break;
+    if ((rc = sg::row_exps(B, 0, K, 1, N, K, RpadB, 1, eb, cs, nullptr, base, st))) break;
+    if ((rc = sg::pack_digits(S, A, 0, K, 1, R, K, ea, RpadA, sg::TM, RT, KCH, 1, pa, st))) break;
+    if ((rc = sg::pack_digits(S, B, 0, K, 1, N, K, eb, RpadB, NT, nct, KCH, 1, pb, st))) break;
+    sg::GemmParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.A = pa;
+    P.B = pb;
+    P.cs = cs;
+    P.m = 1;
+    P.h = 0;
+    P.RT = RT;
+    P.nct = nct;
+    P.KCH = KCH;
+    P.n = (tri == sg::TRI_FULL) ? K : (K < N ? K : N);
+    if (tri != sg::TRI_FULL) P.n = K;
+    P.tri = tri;
+    P.Nc = RpadA;
+    P.raw_out = tmp;
+    P.raw_rs = rs;
+    P.ldo = N;
+    if ((rc = sg::launch_s<sg::EPI_RAW>(S, P, st))) break;
+    if (cudaMemcpyAsync(out, tmp, sizeof(double) * (size_t)R * N, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      set_error(std::string("split_debug_gemm: ") + cudaGetErrorString(cudaGetLastError()));
+      rc = BOCF_ERR_CUDA;
+    }
+  } while (0);
+  cudaFree(pa);
+  cudaFree(pb);
+  cudaFree(ea);
+  cudaFree(eb);
+  cudaFree(rs);
+  cudaFree(cs);
+  cudaFree(tmp);
+  return rc;
+}
+
+}  // namespace bocf

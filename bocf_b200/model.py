@@ -26,7 +26,7 @@ class multi_outputGP(object):
     analytical_gradient_prediction = True
 
     def __init__(self, output_dim, kernel=None, noise_var=None, exact_feval=None, n_samples=10, ARD=None,
-                 fixed_hyps=False, device=None):
+                 fixed_hyps=False, device=None, precision=None):
         self.output_dim = int(output_dim)
         self.kernel = [None] * output_dim if kernel is None else list(kernel)
         self.noise_var = [None] * output_dim if noise_var is None else list(noise_var)
@@ -38,6 +38,9 @@ class multi_outputGP(object):
             device = "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cuda:0"
         self.device = torch.device(device)
         self._lib = _lib.load_library()
+        # arithmetic of the two candidate-side contractions: None (library default / BOCF_PRECISION), "fp64",
+        # "auto", or "split3".."split6" (tcgen05 int8 digit planes, include/bocf_b200.h: enum bocf_precision)
+        self.precision = precision
         self._handle = None
         self._handle_sig = None
         self._explicit_hyp = False
@@ -123,6 +126,9 @@ class multi_outputGP(object):
                                              self.device.index or 0))
             self._handle = h
             self._handle_sig = (kind, d)
+            if self.precision is not None:
+                mode, slices = _lib.parse_precision(self.precision)
+                _lib.check(lib.bocf_model_set_precision(self._handle, mode, slices, None))
         with torch.cuda.device(self.device):
             Xd = torch.from_numpy(self.X).to(self.device)
             Yd = torch.from_numpy(self.Y).to(self.device)
@@ -137,6 +143,19 @@ class multi_outputGP(object):
             self.jitter_added = jit
         self._X_dev = Xd
         self._current_h = 0
+
+    def set_precision(self, precision):
+        """Switch the contraction arithmetic ("fp64" | "auto" | "split3".."split6"); rebuilds the digit planes."""
+        self.precision = precision
+        if self._handle is not None:
+            mode, slices = _lib.parse_precision(precision)
+            with torch.cuda.device(self.device):
+                st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+                _lib.check(self._lib.bocf_model_set_precision(self._handle, mode, slices, st))
+
+    def active_slices(self):
+        """Digit planes the tensor-core contraction currently uses (0 = fp64 DMMA)."""
+        return int(self._lib.bocf_model_active_slices(self._handle)) if self._handle is not None else 0
 
     def _destroy(self):
         if getattr(self, "_handle", None) is not None:

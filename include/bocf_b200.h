@@ -61,6 +61,17 @@ enum bocf_acq_variant {
   BOCF_ACQ_MA_PI = 3   /* maPI.py:80-120 / PI.py           analytic PI of theta^T y              */
 };
 
+/* Arithmetic of the two candidate-side contractions  V = K* Linv^T,  Wt = V Linv  (posterior.py:312, gp.py:474).
+ * Everything else (kernel evaluation, mean, MC acquisition, Cholesky) is always IEEE fp64. */
+enum bocf_precision {
+  BOCF_PREC_FP64_DMMA = 0,  /* fp64 tensor-core MMA (mma.sync m8n8k4.f64)                                          */
+  BOCF_PREC_SPLIT_I8 = 1,   /* tcgen05.mma kind::i8: operands split into `slices` signed 8-bit digit planes,
+                               exact int32 accumulation in tensor memory; slices = 5 matches fp64 to ~1e-8 on the
+                               variance of a well-conditioned model, slices = 4 to ~1e-6                           */
+  BOCF_PREC_AUTO = 2        /* pick slices in {4,5,6} from max|L^-1| so the predicted variance error stays below
+                               1e-7 relative; fall back to fp64 DMMA for ill-conditioned factors                   */
+};
+
 const char* bocf_last_error(void);
 /* Library / build identification ("bocf_b200 <ver> sm_100a"). */
 const char* bocf_version(void);
@@ -93,6 +104,18 @@ int bocf_model_get_factor(bocf_model* mdl, int h, int j, double* L, double* Linv
                           void* stream);
 int bocf_model_n(const bocf_model* mdl);
 int bocf_model_H(const bocf_model* mdl);
+
+/* Select the contraction arithmetic (enum bocf_precision).  May be called before or after bocf_model_factorize; the
+ * digit planes of L^-1 are (re)built when needed.  The environment variable BOCF_PRECISION (fp64 | auto | split3..6)
+ * sets the initial mode of new handles.  bocf_model_active_slices: digit planes in use (0 = fp64 DMMA). */
+int bocf_model_set_precision(bocf_model* mdl, int mode, int slices, void* stream);
+int bocf_model_active_slices(const bocf_model* mdl);
+
+/* Test hook of the split-integer tensor-core GEMM: out (R x N) = A (R x K) * B (N x K)^T, all [dev] fp64 row-major,
+ * through the same digit-plane packing, tcgen05 kernel and Horner epilogue the posterior uses.
+ * tri: 0 full, 1 only K <= column (requires N == K), 2 only K >= column. */
+int bocf_debug_split_gemm(const double* A, const double* B, int R, int N, int K, int slices, int tri, double* out,
+                          void* stream);
 
 /* Upper bound, in bytes, of the handle's internal scratch (default 4 GiB). */
 int bocf_model_set_scratch_limit(bocf_model* mdl, uint64_t bytes);
