@@ -175,6 +175,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
         const TileInfo ti = decode_tile(P, NT, t);
         const uint8_t* gA = P.A + ((size_t)(ti.j * P.RT + ti.rt) * P.KCH) * C::A_STAGE;
         const uint8_t* gB = P.B + ((size_t)((P.h * P.m + ti.j) * P.nct + ti.ct) * P.KCH) * C::B_STAGE;
+        if (EPI == EPI_DVAR) {
+          // the epilogue of this tile (one tile later in time) reads 128 G* values of each of its NT columns:
+          // pull those 1 KB rows into L2 now so its loads do not pay HBM latency
+          const double* g0 = P.GsT + (size_t)ti.j * P.n16 * P.Nc + (size_t)ti.rt * TM;
+          const int bend = min(ti.ct * NT + NT, P.n);
+          for (int b = ti.ct * NT; b < bend; ++b) tc::prefetch_l2(g0 + (size_t)b * P.Nc, TM * 8);
+        }
         for (int kc = ti.kb; kc < ti.ke; ++kc) {
           tc::mbar_wait(&empty[stage], phase ^ 1u);
           tc::mbar_arrive_expect_tx(&full[stage], C::STAGE);
@@ -244,21 +251,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       const int64_t i = (int64_t)ti.rt * TM + row;              // chunk-local candidate
 
       // per-tile thread state
+      constexpr int CGW = (EPI == EPI_DVAR) ? 8 : 16;           // columns handled per TMEM load group
+      constexpr int NCG = NT / CGW;
       double sumsq = 0.0;
       double vq = 0.0;
-      double xs[MAXD], acc[MAXD], s0 = 0.0;
+      double acc[MAXD], s0 = 0.0;
+      double gv[CGW];
       const double* Gcol = nullptr;
       const double* Xb = nullptr;
       if (EPI == EPI_VAR) vq = P.vq[hj];
       if (EPI == EPI_DVAR) {
-        const OutHyp& hp = P.hyp[hj];
 #pragma unroll
-        for (int q = 0; q < MAXD; ++q) {
-          xs[q] = (q < P.d && i < P.Nvalid) ? P.Xc[i * P.d + q] / hp.ls[q] : 0.0;
-          acc[q] = 0.0;
-        }
+        for (int q = 0; q < MAXD; ++q) acc[q] = 0.0;
         Gcol = P.GsT + (size_t)ti.j * P.n16 * P.Nc + i;
         Xb = P.Xs + (size_t)hj * P.n_pad * P.d;
+#pragma unroll
+        for (int e = 0; e < CGW; ++e) {                      // first column group: in flight while the MMAs finish
+          const int b = col0 + e;
+          gv[e] = (b < P.n) ? __ldg(Gcol + (size_t)b * P.Nc) : 0.0;
+        }
       }
 
       tc::mbar_wait(&tfull[buf], use & 1u);
@@ -266,18 +277,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
 
 #pragma unroll 1
-      for (int cg = 0; cg < NT / 16; ++cg) {
-        uint32_t c[S][16];
+      for (int cg = 0; cg < NCG; ++cg) {
+        uint32_t c[S][CGW];
 #pragma unroll
-        for (int lb = 0; lb < S; ++lb) tc::tmem_ld16(taddr + (uint32_t)(lb * NT + cg * 16), c[lb]);
-        double gv[16];
-        if (EPI == EPI_DVAR) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int b = col0 + cg * 16 + e;
-            gv[e] = (b < P.n) ? __ldg(Gcol + (size_t)b * P.Nc) : 0.0;
-          }
-        }
+        for (int lb = 0; lb < S; ++lb) tc::tmem_ldw<CGW>(taddr + (uint32_t)(lb * NT + cg * CGW), c[lb]);
         tc::tmem_ld_wait();
         uint32_t vec[S][4];
         if (EPI == EPI_VAR) {
@@ -287,13 +290,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
             for (int w = 0; w < 4; ++w) vec[tt][w] = 0u;
         }
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
+        for (int e = 0; e < CGW; ++e) {
           double v = (double)(int)c[S - 1][e];
 #pragma unroll
           for (int lb = S - 2; lb >= 0; --lb) v = fma(v, 256.0, (double)(int)c[lb][e]);
-          v *= s_cs[cg * 16 + e];
+          v *= s_cs[cg * CGW + e];
           if (EPI == EPI_RAW) {
-            const int col = col0 + cg * 16 + e;
+            const int col = col0 + cg * CGW + e;
             const size_t grow = (size_t)(ti.j * P.RT + ti.rt) * TM + row;
             if (col < P.ldo) P.raw_out[grow * P.ldo + col] = v * P.raw_rs[grow];
           } else if (EPI == EPI_VAR) {
@@ -304,8 +307,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
               vec[tt][e >> 2] |= (uint32_t)((dg >> (8 * tt)) & 0xFFull) << (8 * (e & 3));
           } else {
             const double w = v * gv[e];
+            {                                                  // refill the slot with the next column group's G*
+              const int bn = col0 + (cg + 1) * CGW + e;
+              gv[e] = (cg + 1 < NCG && bn < P.n) ? __ldg(Gcol + (size_t)bn * P.Nc) : 0.0;
+            }
             s0 += w;
-            const int b = min(col0 + cg * 16 + e, P.n_pad - 1);
+            const int b = min(col0 + cg * CGW + e, P.n_pad - 1);
             const double* xb = Xb + (size_t)b * P.d;
 #pragma unroll
             for (int q = 0; q < MAXD; ++q)
@@ -329,9 +336,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       if (EPI == EPI_VAR) P.part_var[((size_t)ti.j * P.nct + ti.ct) * P.Nc + i] = sumsq;
       if (EPI == EPI_DVAR) {
         double* out = P.part_dvar + (((size_t)ti.j * P.nct + ti.ct) * P.Nc + i) * P.d;
+        const OutHyp& hp = P.hyp[hj];
 #pragma unroll
         for (int q = 0; q < MAXD; ++q)
-          if (q < P.d) out[q] = xs[q] * s0 - acc[q];
+          if (q < P.d) {
+            const double xsq = (i < P.Nvalid) ? P.Xc[i * P.d + q] / hp.ls[q] : 0.0;
+            out[q] = xsq * s0 - acc[q];
+          }
       }
     }
   }

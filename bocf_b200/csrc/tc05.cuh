@@ -46,6 +46,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// L2 prefetch of a contiguous global range (multiple of 16 bytes), fire and forget.
+__device__ __forceinline__ void prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ---- tensor memory -------------------------------------------------------------------------------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem) {   // whole warp
@@ -70,6 +75,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+template <int W>
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, uint32_t (&v)[W]);
+template <>
+__device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld8(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 // ---- tcgen05.mma ---------------------------------------------------------------------------------------------

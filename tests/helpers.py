@@ -122,9 +122,9 @@ def oracle_acq(P, grad=True, variant="uEI_noiseless", vectorised=True, Xc=None, 
 
 # ---- product side -----------------------------------------------------------------------------------------
 
-def product_model(P, device="cuda:0"):
+def product_model(P, device="cuda:0", precision=None):
     import bocf_b200
-    mod = bocf_b200.multi_outputGP(P.m, n_samples=P.H, device=device)
+    mod = bocf_b200.multi_outputGP(P.m, n_samples=P.H, device=device, precision=precision)
     mod.set_hyperparameter_samples(P.variance, P.lengthscale, P.noise, kind=P.kind)
     mod.updateModel(P.X, P.Y)
     return mod
@@ -136,9 +136,10 @@ def product_utility(P):
     return bocf_b200.Utility(parameter_dist=pd, composite=P.composite)
 
 
-def product_acq(P, grad=True, variant="uEI_noiseless", device="cuda:0", Xc=None, model=None, parallel=True):
+def product_acq(P, grad=True, variant="uEI_noiseless", device="cuda:0", Xc=None, model=None, parallel=True,
+                precision=None):
     import bocf_b200
-    mod = product_model(P, device) if model is None else model
+    mod = product_model(P, device, precision) if model is None else model
     U = product_utility(P)
     Xc = P.Xc if Xc is None else Xc
     mod.set_hyperparameters(0)
