@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
         if (!SPLIT) {
           Kout[(int64_t)b * Nc + i] = kv;
         } else {
-          const unsigned long long dg = ((unsigned long long)__double2ll_rn(kv * aq) + dbias) ^ dbias;
+          const unsigned long long dg = ((unsigned long long)__double_as_longlong(fma(kv, aq, 6755399441055744.0)) + dbias) ^ dbias;
 #pragma unroll
           for (int t = 0; t < MAXS; ++t) dv[t][e >> 2] |= (uint32_t)((dg >> (8 * t)) & 0xFFull) << (8 * (e & 3));
         }

@@ -24,6 +24,7 @@
 //            DVAR: sum_b Wt * G* * (xs_i - Xs_b)  -> per column-tile partial variance gradients.
 // Triangular structure of Linv is exploited per column tile at K-chunk granularity.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -44,21 +45,22 @@ __host__ __device__ __forceinline__ uint32_t sw64(int r, int c) {   // byte offs
 }
 __host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int S, int NT>
+template <int S, int NT, int DP = 0>
 struct Cfg {
   static constexpr int A_PLANE = TM * KC, B_PLANE = NT * KC;
   static constexpr int A_STAGE = S * A_PLANE, B_STAGE = S * B_PLANE, STAGE = A_STAGE + B_STAGE;
   static constexpr int ACC_COLS = S * NT;
   static constexpr int NBUF = (2 * ACC_COLS <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = pow2_cols(NBUF * ACC_COLS);
-  static constexpr int HEAD = 1024;                                   // barriers, tmem slot, column scales
+  static constexpr int XB_BYTES = NT * DP * 8;                       // DVAR: scaled training inputs of the column tile
+  static constexpr int HEAD = 1024 + XB_BYTES;                        // barriers, tmem slot, column scales, xb tile
   static constexpr int STAGES_FIT = (SMEM_MAX - HEAD - 512) / STAGE;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int SMEM_BYTES = HEAD + 512 + STAGES * STAGE;
   static_assert(S >= 2 && S <= 6 && NT % 16 == 0 && S * NT <= 256, "stacked B operand must fit one MMA (N <= 256)");
   static_assert(STAGES >= 2, "need at least a double-buffered ring");
   static_assert(B_STAGE % 512 == 0 && A_STAGE % 512 == 0, "planes must keep the 512-byte swizzle period");
-  static_assert(NT * 8 + (2 * STAGES + 2 * NBUF) * 8 + 16 <= HEAD, "head area too small");
+  static_assert(NT * 8 <= 512 && (2 * STAGES + 2 * NBUF) * 8 + 16 <= 512, "head area too small");
 };
 
 enum { EPI_RAW = 0, EPI_VAR = 1, EPI_DVAR = 2 };
@@ -130,9 +132,19 @@ __device__ __forceinline__ unsigned long long balanced_digits(long long Y) {
   return ((unsigned long long)Y + BIAS) ^ BIAS;
 }
 
-template <int S, int NT, int EPI>
+// int32 -> double without the (slow) I2F.F64 conversion pipe: (2^52 + 2^31 + c) is exactly representable, one DADD.
+__device__ __forceinline__ double i32_to_f64(uint32_t c) {
+  return __hiloint2double(0x43300000, (int)(c ^ 0x80000000u)) - 4503601774854144.0;
+}
+// digits of rint(x) for |x| < 2^46 without F2I: adding 1.5 * 2^52 leaves rint(x) (two's complement) in the low mantissa bits
+template <int S>
+__device__ __forceinline__ unsigned long long balanced_digits_of(double x) {
+  return balanced_digits<S>(__double_as_longlong(x + 6755399441055744.0));
+}
+
+template <int S, int NT, int EPI, int DP>
 __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParams P) {
-  using C = Cfg<S, NT>;
+  using C = Cfg<S, NT, DP>;
   extern __shared__ uint8_t smem_raw[];
   // head: [0,512) barriers + tmem slot, [512, 1024) column scales; stages start at the next 512-byte boundary
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -142,6 +154,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
   uint64_t* tempty = tfull + C::NBUF;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::NBUF);
   double* s_cs = reinterpret_cast<double*>(smem_raw + 512);
+  double* s_xb = reinterpret_cast<double*>(smem_raw + 1024);      // [NT][DP]
   const uint32_t raw_addr = tc::smem_u32(smem_raw);
   const uint32_t stage_off = ((raw_addr + C::HEAD + 511u) & ~511u) - raw_addr;
   uint8_t* sA = smem_raw + stage_off;
@@ -245,26 +258,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       const uint32_t use = (uint32_t)(it / C::NBUF);
       const int hj = P.h * P.m + ti.j;
       const int col0 = ti.ct * NT;
-      tc::named_bar_sync(1, 128);                               // previous tile's readers of s_cs are done
+      tc::named_bar_sync(1, 128);                               // previous tile's readers of s_cs / s_xb are done
       if (et < NT) s_cs[et] = P.cs[(size_t)hj * P.nct * NT + col0 + et];
+      if (EPI == EPI_DVAR) {
+        const double* Xb = P.Xs + (size_t)hj * P.n_pad * P.d;
+        for (int idx = et; idx < NT * DP; idx += 128) {
+          const int cc = idx / DP, q = idx - cc * DP;
+          const int b = col0 + cc;
+          s_xb[idx] = (q < P.d && b < P.n) ? Xb[(size_t)b * P.d + q] : 0.0;
+        }
+      }
       tc::named_bar_sync(1, 128);
       const int64_t i = (int64_t)ti.rt * TM + row;              // chunk-local candidate
 
       // per-tile thread state
       constexpr int CGW = (EPI == EPI_DVAR) ? 8 : 16;           // columns handled per TMEM load group
       constexpr int NCG = NT / CGW;
+      constexpr int DPA = DP > 0 ? DP : 2;
       double sumsq = 0.0;
       double vq = 0.0;
-      double acc[MAXD], s0 = 0.0;
+      double acc[DPA], s0 = 0.0;
       double gv[CGW];
       const double* Gcol = nullptr;
-      const double* Xb = nullptr;
       if (EPI == EPI_VAR) vq = P.vq[hj];
       if (EPI == EPI_DVAR) {
 #pragma unroll
-        for (int q = 0; q < MAXD; ++q) acc[q] = 0.0;
+        for (int q = 0; q < DPA; ++q) acc[q] = 0.0;
         Gcol = P.GsT + (size_t)ti.j * P.n16 * P.Nc + i;
-        Xb = P.Xs + (size_t)hj * P.n_pad * P.d;
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {                      // first column group: in flight while the MMAs finish
           const int b = col0 + e;
@@ -291,9 +311,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
         }
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {
-          double v = (double)(int)c[S - 1][e];
+          double v = i32_to_f64(c[S - 1][e]);
 #pragma unroll
-          for (int lb = S - 2; lb >= 0; --lb) v = fma(v, 256.0, (double)(int)c[lb][e]);
+          for (int lb = S - 2; lb >= 0; --lb) v = fma(v, 256.0, i32_to_f64(c[lb][e]));
           v *= s_cs[cg * CGW + e];
           if (EPI == EPI_RAW) {
             const int col = col0 + cg * CGW + e;
@@ -301,7 +321,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
             if (col < P.ldo) P.raw_out[grow * P.ldo + col] = v * P.raw_rs[grow];
           } else if (EPI == EPI_VAR) {
             sumsq = fma(v, v, sumsq);
-            const unsigned long long dg = balanced_digits<S>(__double2ll_rn(v * vq));
+            const unsigned long long dg = balanced_digits_of<S>(v * vq);
 #pragma unroll
             for (int tt = 0; tt < S; ++tt)
               vec[tt][e >> 2] |= (uint32_t)((dg >> (8 * tt)) & 0xFFull) << (8 * (e & 3));
@@ -312,11 +332,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
               gv[e] = (cg + 1 < NCG && bn < P.n) ? __ldg(Gcol + (size_t)bn * P.Nc) : 0.0;
             }
             s0 += w;
-            const int b = min(col0 + cg * CGW + e, P.n_pad - 1);
-            const double* xb = Xb + (size_t)b * P.d;
+            const double2* xb2 = reinterpret_cast<const double2*>(s_xb + (cg * CGW + e) * DPA);
 #pragma unroll
-            for (int q = 0; q < MAXD; ++q)
-              if (q < P.d) acc[q] = fma(w, __ldg(xb + q), acc[q]);
+            for (int q2 = 0; q2 < DPA / 2; ++q2) {
+              const double2 x2 = xb2[q2];
+              acc[2 * q2] = fma(w, x2.x, acc[2 * q2]);
+              acc[2 * q2 + 1] = fma(w, x2.y, acc[2 * q2 + 1]);
+            }
           }
         }
         if (EPI == EPI_VAR && P.A2 != nullptr) {
@@ -338,7 +360,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
         double* out = P.part_dvar + (((size_t)ti.j * P.nct + ti.ct) * P.Nc + i) * P.d;
         const OutHyp& hp = P.hyp[hj];
 #pragma unroll
-        for (int q = 0; q < MAXD; ++q)
+        for (int q = 0; q < DPA; ++q)
           if (q < P.d) {
             const double xsq = (i < P.Nvalid) ? P.Xc[i * P.d + q] / hp.ls[q] : 0.0;
             out[q] = xsq * s0 - acc[q];
@@ -404,7 +426,7 @@ __global__ void pack_digits_kernel(const double* __restrict__ src, int64_t mat_s
     for (int ee = 0; ee < 16; ++ee) {
       const int k = kc * KC + piece * 16 + ee;
       const double x = (row < R && k < K) ? src[mat * mat_stride + row * sr + k * sk] : 0.0;
-      const unsigned long long dg = balanced_digits<S>(__double2ll_rn(x * q));
+      const unsigned long long dg = balanced_digits_of<S>(x * q);
 #pragma unroll
       for (int tt = 0; tt < S; ++tt) vec[tt][ee >> 2] |= (uint32_t)((dg >> (8 * tt)) & 0xFFull) << (8 * (ee & 3));
     }
@@ -452,12 +474,12 @@ static int row_exps(const double* src, int64_t mat_stride, int64_t sr, int64_t s
   return 0;
 }
 
-template <int S, int NT, int EPI>
+template <int S, int NT, int EPI, int DP = 0>
 static int launch_t(const GemmParams& P, cudaStream_t st) {
-  using C = Cfg<S, NT>;
+  using C = Cfg<S, NT, DP>;
   static bool attr_done = false;
   if (!attr_done) {
-    BOCF_CUDA_OK(cudaFuncSetAttribute(split_gemm_kernel<S, NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    BOCF_CUDA_OK(cudaFuncSetAttribute(split_gemm_kernel<S, NT, EPI, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       C::SMEM_BYTES));
     attr_done = true;
   }
@@ -465,21 +487,31 @@ static int launch_t(const GemmParams& P, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = P.m * P.RT * P.nct;
+  if (const char* env = std::getenv("BOCF_SPLIT_GRID")) {          // experiment knob: persistent CTAs launched
+    const int g = std::atoi(env);
+    if (g > 0 && g < sms) sms = g;
+  }
   const int grid = tiles < sms ? tiles : sms;
-  split_gemm_kernel<S, NT, EPI><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(P);
+  split_gemm_kernel<S, NT, EPI, DP><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(P);
   BOCF_LAUNCH_OK("split_gemm_kernel");
   return 0;
 }
-template <int EPI>
+template <int EPI, int DP = 0>
 static int launch_s(int S, const GemmParams& P, cudaStream_t st) {
   switch (S) {
-    case 3: return launch_t<3, 64, EPI>(P, st);
-    case 4: return launch_t<4, 64, EPI>(P, st);
-    case 5: return launch_t<5, 48, EPI>(P, st);
-    case 6: return launch_t<6, 32, EPI>(P, st);
+    case 3: return launch_t<3, 64, EPI, DP>(P, st);
+    case 4: return launch_t<4, 64, EPI, DP>(P, st);
+    case 5: return launch_t<5, 48, EPI, DP>(P, st);
+    case 6: return launch_t<6, 32, EPI, DP>(P, st);
   }
   set_error("split contraction supports 3..6 digit planes");
   return BOCF_ERR_INVALID;
+}
+static int launch_dvar(int S, int d, const GemmParams& P, cudaStream_t st) {
+  if (d <= 4) return launch_s<EPI_DVAR, 4>(S, P, st);
+  if (d <= 8) return launch_s<EPI_DVAR, 8>(S, P, st);
+  if (d <= 12) return launch_s<EPI_DVAR, 12>(S, P, st);
+  return launch_s<EPI_DVAR, 16>(S, P, st);
 }
 
 }  // namespace sg
@@ -653,7 +685,7 @@ int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, co
   P.Nvalid = Nvalid;
   P.Xs = M->Xs;
   ProfScope ps("split_dvar_kernel", st);
-  return sg::launch_s<sg::EPI_DVAR>(M->S, P, st);
+  return sg::launch_dvar(M->S, M->d, P, st);
 }
 
 // Test entry: out (R x N) = A (R x K) * B (N x K)^T through the digit-plane machinery.  All pointers [dev] fp64 row-major.
