@@ -84,6 +84,7 @@ struct ChunkBuffers {          // scratch views for one candidate chunk (Nc rows
   double* var;                 // m x Nc
   double* dmean;               // m x Nc x d
   double* dvar;                // m x Nc x d
+  double* part_s0 = nullptr;   // split mode: m x parts x Nc  per column-tile partial sums of Wt * G*
   uint8_t* A1 = nullptr;       // split mode: m x Nc/128 x KCH x S x 128 x 64  digit planes of K* (replaces KsT)
   uint8_t* A2 = nullptr;       // split mode: same layout, digit planes of V   (replaces V)
 };
@@ -96,6 +97,7 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
 
 // ---- split_gemm.cu ------------------------------------------------------------------------------
 int split_column_tile(int S);
+int split_partials_per_tile();   // partial sums the split epilogue writes per column tile
 int split_prepare(bocf_model* M, int S, cudaStream_t st);          // digit planes of Linv + scales
 void split_release(bocf_model* M);
 int split_linv_absmax(bocf_model* M, double* out_host, cudaStream_t st);

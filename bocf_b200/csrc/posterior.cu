@@ -326,9 +326,12 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) dvar_gemm_kernel(
 
 // ===================================================================================================
 // var = clip(k** - sum_tiles part_var (+ noise), 1e-10);  dvar = (-2 / l_q) sum_tiles part_dvar
+// split mode: part_dvar holds sum_b T_b Xs_bq and part_s0 holds sum_b T_b (T = Wt * G*), so that
+//   sum_b T_b (xs_iq - Xs_bq) = xs_iq * S0 - ACC_q   with xs_i = x_i / l formed here, once per candidate.
 __global__ void finalize_kernel(const double* __restrict__ part_var, const double* __restrict__ part_dvar,
                                 const OutHyp* __restrict__ hyp, int64_t Nc, int nct, int m, int d, int h, int grad,
-                                int noiseless, double* __restrict__ var, double* __restrict__ dvar) {
+                                int noiseless, double* __restrict__ var, double* __restrict__ dvar,
+                                const double* __restrict__ part_s0, const double* __restrict__ Xc, int64_t Nvalid) {
   // thread idx covers candidate idx (variance) and flat element idx = i*d + q (gradient): both coalesced
   const int j = blockIdx.y;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,6 +347,13 @@ __global__ void finalize_kernel(const double* __restrict__ part_var, const doubl
     const int q = (int)(idx % d);
     double gsum = 0.0;
     for (int tI = 0; tI < nct; ++tI) gsum += part_dvar[((int64_t)j * nct + tI) * Nc * d + idx];
+    if (part_s0 != nullptr) {
+      const int64_t i = idx / d;
+      double s0 = 0.0;
+      for (int tI = 0; tI < nct; ++tI) s0 += part_s0[((int64_t)j * nct + tI) * Nc + i];
+      const double xs = (i < Nvalid) ? Xc[i * d + q] / hp.ls[q] : 0.0;
+      gsum = xs * s0 - gsum;
+    }
     dvar[(int64_t)j * Nc * d + idx] = -2.0 * gsum / hp.ls[q];
   }
 }
@@ -452,7 +462,7 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
   if (rc) return rc;
   if (!need_var) return 0;      // mean (and mean gradient) only: no contraction against the factor
   const bool split = (cb.A1 != nullptr);
-  const int nct = split ? M->ncts : M->n_pad / NT;
+  const int nct = split ? M->ncts * split_partials_per_tile() : M->n_pad / NT;   // partial sums per candidate
   const unsigned tiles = (unsigned)((cb.Nc / CT) * nct * M->m);
   if (split) {
     // tcgen05 kind::i8 digit-plane contractions (split_gemm.cu); same partial-sum layout, same finalize
@@ -478,7 +488,8 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
   {
     ProfScope ps("finalize_kernel", st);
     finalize_kernel<<<fgrid, 256, 0, st>>>(cb.part_var, cb.part_dvar, M->hyp, cb.Nc, nct, M->m, M->d, h,
-                                           need_dvar ? 1 : 0, noiseless ? 1 : 0, cb.var, cb.dvar);
+                                           need_dvar ? 1 : 0, noiseless ? 1 : 0, cb.var, cb.dvar,
+                                           split ? cb.part_s0 : nullptr, Xc, Nvalid);
   }
   BOCF_LAUNCH_OK("finalize_kernel");
   return 0;

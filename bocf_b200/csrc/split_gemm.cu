@@ -37,7 +37,10 @@ namespace sg {
 
 constexpr int KC = 64;        // bytes (= int8 elements) of K per shared-memory row: one SWIZZLE_64B span
 constexpr int TM = 128;       // candidate rows per tile (= TMEM lanes)
-constexpr int NTHREADS = 192;
+constexpr int EPI_WARPS = 8;     // two warps per TMEM lane group: latency hiding on the fp64 epilogue math
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int NTHREADS = 64 + EPI_THREADS;
+constexpr int PART_SPLIT = EPI_WARPS / 4;   // partial sums per column tile (one per warp of a lane group)
 constexpr int SMEM_MAX = 232448;
 
 __host__ __device__ __forceinline__ uint32_t sw64(int r, int c) {   // byte offset of (row r, byte c) in a packed plane
@@ -81,12 +84,14 @@ struct GemmParams {
   uint8_t* A2;             // [m][RT][KCH][S][128][64]   digit planes of V (nullptr: not needed)
   const double* vq;        // [Hm] 2^(8S-2-eV)
   // DVAR
-  double* part_dvar;       // [m][nct][Nc][d]
+  double* part_dvar;       // [m][nct*PART_SPLIT][Nc][d]   sum_b T_b Xs_bq
+  double* part_s0;         // [m][nct*PART_SPLIT][Nc]      sum_b T_b
   const double* GsT;       // [m][n16][Nc]
   const double* Xc;        // [Nvalid][d]
   const double* Xs;        // [Hm][n_pad][d]
   const OutHyp* hyp;
   int d, n16, n_pad;
+  int exp;                 // experiment knob (BOCF_SPLIT_EXP): 1 = skip the MMAs, 2 = skip the bulk loads (results invalid)
 };
 
 struct TileInfo {
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
     }
     for (int b = 0; b < C::NBUF; ++b) {
       tc::mbar_init(&tfull[b], 1);
-      tc::mbar_init(&tempty[b], 128);
+      tc::mbar_init(&tempty[b], EPI_THREADS);
     }
     tc::fence_barrier_init();
   }
@@ -197,9 +202,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
         }
         for (int kc = ti.kb; kc < ti.ke; ++kc) {
           tc::mbar_wait(&empty[stage], phase ^ 1u);
-          tc::mbar_arrive_expect_tx(&full[stage], C::STAGE);
-          tc::bulk_g2s(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage]);
-          tc::bulk_g2s(sB + stage * C::B_STAGE, gB + (size_t)kc * C::B_STAGE, C::B_STAGE, &full[stage]);
+          if (P.exp == 2) {
+            tc::mbar_arrive(&full[stage]);
+          } else {
+            tc::mbar_arrive_expect_tx(&full[stage], C::STAGE);
+            tc::bulk_g2s(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage]);
+            tc::bulk_g2s(sB + stage * C::B_STAGE, gB + (size_t)kc * C::B_STAGE, C::B_STAGE, &full[stage]);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
               // A digit plane ta against the stacked B planes tb = S-1-ta .. S-1  ->  levels 0 .. ta
               const uint64_t adesc = tc::smem_desc_sw64(a0 + ta * C::A_PLANE + ks * 32);
               const uint64_t bdesc = tc::smem_desc_sw64(b0 + (S - 1 - ta) * C::B_PLANE + ks * 32);
-              tc::mma_i8(d_tmem, adesc, bdesc, tc::idesc_i8((ta + 1) * NT), (first && ta == S - 1) ? 0u : 1u);
+              if (P.exp != 1) tc::mma_i8(d_tmem, adesc, bdesc, tc::idesc_i8((ta + 1) * NT), (first && ta == S - 1) ? 0u : 1u);
             }
             first = false;
           }
@@ -247,47 +256,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       }
     }
   } else {
-    // ================================ epilogue (128 threads) ===================================
-    const int et = threadIdx.x - 64;                            // 0..127
+    // ================================ epilogue (EPI_WARPS warps) ===============================
+    const int et = threadIdx.x - 64;
     const int lg = warp & 3;                                    // TMEM lane group this warp may access
+    const int hw = (warp - 2) >> 2;                             // which of the lane group's warps: owns column groups hw, hw+PART_SPLIT, ..
     const int row = lg * 32 + lane;
     int it = 0;
+    // per-tile constants (column scales, scaled training inputs of the column tile) are fetched one tile AHEAD into
+    // registers and parked in shared memory at the top of the tile, so their global-load latency is never exposed
+    constexpr int DPA0 = DP > 0 ? DP : 1;
+    constexpr int XPT = (EPI == EPI_DVAR) ? (NT * DPA0 + EPI_THREADS - 1) / EPI_THREADS : 1;
+    double pre_cs = 0.0, pre_vq = 0.0, pre_xb[XPT];
+    auto prefetch_tile_consts = [&](int tnext) {
+      if (tnext >= num_tiles) return;
+      const TileInfo tn = decode_tile(P, NT, tnext);
+      const int hjn = P.h * P.m + tn.j;
+      if (et < NT) pre_cs = __ldg(P.cs + (size_t)hjn * P.nct * NT + tn.ct * NT + et);
+      if (EPI == EPI_VAR) pre_vq = __ldg(P.vq + hjn);
+      if (EPI == EPI_DVAR) {
+        const double* Xb = P.Xs + (size_t)hjn * P.n_pad * P.d;
+#pragma unroll
+        for (int x = 0; x < XPT; ++x) {
+          const int idx = et + x * EPI_THREADS;
+          const int cc = idx / DPA0, q = idx - cc * DPA0;
+          const int b = tn.ct * NT + cc;
+          pre_xb[x] = (idx < NT * DPA0 && q < P.d && b < P.n) ? __ldg(Xb + (size_t)b * P.d + q) : 0.0;
+        }
+      }
+    };
+    prefetch_tile_consts(blockIdx.x);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const TileInfo ti = decode_tile(P, NT, t);
       const int buf = it % C::NBUF;
       const uint32_t use = (uint32_t)(it / C::NBUF);
-      const int hj = P.h * P.m + ti.j;
       const int col0 = ti.ct * NT;
-      tc::named_bar_sync(1, 128);                               // previous tile's readers of s_cs / s_xb are done
-      if (et < NT) s_cs[et] = P.cs[(size_t)hj * P.nct * NT + col0 + et];
+      tc::named_bar_sync(1, EPI_THREADS);                       // previous tile's readers of s_cs / s_xb are done
+      if (et < NT) s_cs[et] = pre_cs;
       if (EPI == EPI_DVAR) {
-        const double* Xb = P.Xs + (size_t)hj * P.n_pad * P.d;
-        for (int idx = et; idx < NT * DP; idx += 128) {
-          const int cc = idx / DP, q = idx - cc * DP;
-          const int b = col0 + cc;
-          s_xb[idx] = (q < P.d && b < P.n) ? Xb[(size_t)b * P.d + q] : 0.0;
+#pragma unroll
+        for (int x = 0; x < XPT; ++x) {
+          const int idx = et + x * EPI_THREADS;
+          if (idx < NT * DPA0) s_xb[idx] = pre_xb[x];
         }
       }
-      tc::named_bar_sync(1, 128);
+      const double vq = pre_vq;
+      tc::named_bar_sync(1, EPI_THREADS);
+      prefetch_tile_consts(t + gridDim.x);
       const int64_t i = (int64_t)ti.rt * TM + row;              // chunk-local candidate
 
       // per-tile thread state
-      constexpr int CGW = (EPI == EPI_DVAR) ? 8 : 16;           // columns handled per TMEM load group
+      constexpr int CGW = 8;                                    // columns per TMEM load group
       constexpr int NCG = NT / CGW;
       constexpr int DPA = DP > 0 ? DP : 2;
       double sumsq = 0.0;
-      double vq = 0.0;
       double acc[DPA], s0 = 0.0;
       double gv[CGW];
       const double* Gcol = nullptr;
-      if (EPI == EPI_VAR) vq = P.vq[hj];
       if (EPI == EPI_DVAR) {
 #pragma unroll
         for (int q = 0; q < DPA; ++q) acc[q] = 0.0;
         Gcol = P.GsT + (size_t)ti.j * P.n16 * P.Nc + i;
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {                      // first column group: in flight while the MMAs finish
-          const int b = col0 + e;
+          const int b = col0 + hw * CGW + e;
           gv[e] = (b < P.n) ? __ldg(Gcol + (size_t)b * P.Nc) : 0.0;
         }
       }
@@ -297,17 +328,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
 
 #pragma unroll 1
-      for (int cg = 0; cg < NCG; ++cg) {
+      for (int cg = hw; cg < NCG; cg += PART_SPLIT) {
         uint32_t c[S][CGW];
 #pragma unroll
         for (int lb = 0; lb < S; ++lb) tc::tmem_ldw<CGW>(taddr + (uint32_t)(lb * NT + cg * CGW), c[lb]);
         tc::tmem_ld_wait();
-        uint32_t vec[S][4];
+        uint32_t vec[S][2];
         if (EPI == EPI_VAR) {
 #pragma unroll
-          for (int tt = 0; tt < S; ++tt)
-#pragma unroll
-            for (int w = 0; w < 4; ++w) vec[tt][w] = 0u;
+          for (int tt = 0; tt < S; ++tt) vec[tt][0] = vec[tt][1] = 0u;
         }
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {
@@ -327,9 +356,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
               vec[tt][e >> 2] |= (uint32_t)((dg >> (8 * tt)) & 0xFFull) << (8 * (e & 3));
           } else {
             const double w = v * gv[e];
-            {                                                  // refill the slot with the next column group's G*
-              const int bn = col0 + (cg + 1) * CGW + e;
-              gv[e] = (cg + 1 < NCG && bn < P.n) ? __ldg(Gcol + (size_t)bn * P.Nc) : 0.0;
+            {                                                  // refill the slot with this warp's next column group's G*
+              const int bn = col0 + (cg + PART_SPLIT) * CGW + e;
+              gv[e] = (cg + PART_SPLIT < NCG && bn < P.n) ? __ldg(Gcol + (size_t)bn * P.Nc) : 0.0;
             }
             s0 += w;
             const double2* xb2 = reinterpret_cast<const double2*>(s_xb + (cg * CGW + e) * DPA);
@@ -342,29 +371,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
           }
         }
         if (EPI == EPI_VAR && P.A2 != nullptr) {
-          const int k = col0 + cg * 16;
+          const int k = col0 + cg * CGW;
           if (k < P.KCH * KC) {
-            const int kc = k >> 6, piece = (k & 63) >> 4;
-            uint8_t* dst = P.A2 + (((size_t)(ti.j * P.RT + ti.rt) * P.KCH + kc) * S) * C::A_PLANE + sw64(row, piece * 16);
+            const int kc = k >> 6;
+            uint8_t* dst = P.A2 + (((size_t)(ti.j * P.RT + ti.rt) * P.KCH + kc) * S) * C::A_PLANE + sw64(row, k & 63);
 #pragma unroll
             for (int tt = 0; tt < S; ++tt)
-              *reinterpret_cast<uint4*>(dst + (size_t)tt * C::A_PLANE) = make_uint4(vec[tt][0], vec[tt][1], vec[tt][2], vec[tt][3]);
+              *reinterpret_cast<uint2*>(dst + (size_t)tt * C::A_PLANE) = make_uint2(vec[tt][0], vec[tt][1]);
           }
         }
       }
       tc::fence_before_sync();
       tc::mbar_arrive(&tempty[buf]);                            // accumulator buffer may be overwritten
 
-      if (EPI == EPI_VAR) P.part_var[((size_t)ti.j * P.nct + ti.ct) * P.Nc + i] = sumsq;
+      // one partial per (column tile, warp of the lane group): summed in fixed order by finalize_kernel
+      const size_t pidx = ((size_t)ti.j * P.nct + ti.ct) * PART_SPLIT + hw;
+      if (EPI == EPI_VAR) P.part_var[pidx * P.Nc + i] = sumsq;
       if (EPI == EPI_DVAR) {
-        double* out = P.part_dvar + (((size_t)ti.j * P.nct + ti.ct) * P.Nc + i) * P.d;
-        const OutHyp& hp = P.hyp[hj];
+        // xs_iq * S0 - ACC_q is formed by finalize_kernel (one division per candidate instead of one per tile)
+        P.part_s0[pidx * P.Nc + i] = s0;
+        double* out = P.part_dvar + (pidx * P.Nc + i) * P.d;
 #pragma unroll
         for (int q = 0; q < DPA; ++q)
-          if (q < P.d) {
-            const double xsq = (i < P.Nvalid) ? P.Xc[i * P.d + q] / hp.ls[q] : 0.0;
-            out[q] = xsq * s0 - acc[q];
-          }
+          if (q < P.d) out[q] = acc[q];
       }
     }
   }
@@ -517,6 +546,7 @@ static int launch_dvar(int S, int d, const GemmParams& P, cudaStream_t st) {
 }  // namespace sg
 
 int split_column_tile(int S) { return S == 5 ? 48 : (S == 6 ? 32 : 64); }
+int split_partials_per_tile() { return sg::PART_SPLIT; }
 
 static void free_split(bocf_model* M) {
   auto fr = [](auto*& p) {
@@ -606,12 +636,12 @@ int split_prepare(bocf_model* M, int S, cudaStream_t st) {
 uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
   uint64_t per = 0;
   per += (uint64_t)M->m * M->KCH * sg::KC * M->S;       // A1 digit planes of K*
-  per += (uint64_t)M->m * M->ncts * 8;                  // part_var
+  per += (uint64_t)M->m * M->ncts * sg::PART_SPLIT * 8;  // part_var
   per += 2ull * M->m * 8;                               // mean, var
   if (grad) {
     per += (uint64_t)M->m * M->n16 * 8;                 // GsT
     per += (uint64_t)M->m * M->KCH * sg::KC * M->S;     // A2 digit planes of V
-    per += (uint64_t)M->m * M->ncts * M->d * 8;         // part_dvar
+    per += (uint64_t)M->m * M->ncts * sg::PART_SPLIT * (M->d + 1) * 8;   // part_dvar, part_s0
     per += 2ull * M->m * M->d * 8;                      // dmean, dvar
   }
   return per;
@@ -628,13 +658,14 @@ void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, C
   cb->Nc = Nc;
   cb->KsT = cb->V = nullptr;
   cb->A1 = take(planes);
-  cb->part_var = reinterpret_cast<double*>(take((uint64_t)M->m * M->ncts * Nc * 8));
+  cb->part_var = reinterpret_cast<double*>(take((uint64_t)M->m * M->ncts * sg::PART_SPLIT * Nc * 8));
   cb->mean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
   cb->var = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
   if (grad) {
     cb->GsT = reinterpret_cast<double*>(take((uint64_t)M->m * M->n16 * Nc * 8));
     cb->A2 = take(planes);
-    cb->part_dvar = reinterpret_cast<double*>(take((uint64_t)M->m * M->ncts * Nc * M->d * 8));
+    cb->part_dvar = reinterpret_cast<double*>(take((uint64_t)M->m * M->ncts * sg::PART_SPLIT * Nc * M->d * 8));
+    cb->part_s0 = reinterpret_cast<double*>(take((uint64_t)M->m * M->ncts * sg::PART_SPLIT * Nc * 8));
     cb->dmean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
     cb->dvar = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
   } else {
@@ -657,6 +688,7 @@ static sg::GemmParams base_params(const bocf_model* M, int h, const ChunkBuffers
   P.n16 = M->n16;
   P.n_pad = M->n_pad;
   P.hyp = M->hyp;
+  if (const char* env = std::getenv("BOCF_SPLIT_EXP")) P.exp = std::atoi(env);
   return P;
 }
 
@@ -680,6 +712,7 @@ int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, co
   P.cs = M->cs2;
   P.tri = sg::TRI_K_GE_N;
   P.part_dvar = cb.part_dvar;
+  P.part_s0 = cb.part_s0;
   P.GsT = cb.GsT;
   P.Xc = Xc;
   P.Nvalid = Nvalid;
