@@ -245,11 +245,22 @@ def run_ours(args, cfg):
     Xd = Xh.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    dbg = bool(os.environ.get("BOCF_BENCH_DEBUG"))
+
     def step_device():
         model.set_hyperparameters(0)
+        t0 = time.perf_counter()
         a, g = acq._compute_acq_withGradients(Xd)
+        t1 = time.perf_counter()
         rec = bd.local_topk(a, Xd, K_TOP, index_offset=rank * N)
-        return bd.allgather_topk(rec, K_TOP) if world > 1 else rec
+        t2 = time.perf_counter()
+        out = bd.allgather_topk(rec, K_TOP) if world > 1 else rec
+        if dbg and rank == 0:
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            sys.stderr.write("    host: acq enqueue %.1f ms, topk enqueue %.1f ms, gather %.1f ms, drain %.1f ms\n"
+                             % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, 0.0, (t3 - t2) * 1e3))
+        return out
 
     def step_host():
         model.set_hyperparameters(0)
@@ -299,11 +310,11 @@ def run_ours(args, cfg):
         step_device()
         flush.zero_()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BOCF_BENCH_NO_SAMPLER"):
         sampler.start()
     ms_dev, _, launches, _ = timed(step_device, args.steps)
     value_step_ms = list(timed.last_step_ms)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and not os.environ.get("BOCF_BENCH_NO_SAMPLER")) else None
     # separate pass with per-kernel CUDA events (same steps, same data) for the roofline of the dominant kernel
     ms_prof, _, _, prof = timed(step_device, args.steps, profile=True)
     step_host()                                                     # warm the host path (pinned staging, allocator)

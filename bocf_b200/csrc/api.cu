@@ -587,11 +587,25 @@ int bocf_topk(const double* acq, const double* Xc, int64_t N, int d, int k, int6
     return BOCF_ERR_INVALID;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  void* ws = nullptr;
-  BOCF_CUDA_OK(cudaMallocAsync(&ws, topk_workspace_bytes(N, k), st));
-  int rc = launch_topk(acq, Xc, N, d, k, index_offset, out_rec, ws, st);
-  cudaFreeAsync(ws, st);
-  return rc;
+  // grow-only workspace per device (stream-ordered pool allocations are trimmed back to the OS at every
+  // synchronisation with the default release threshold, which stalls the device between steps)
+  static void* ws_cache[64] = {nullptr};
+  static uint64_t ws_bytes[64] = {0};
+  int dev = 0;
+  BOCF_CUDA_OK(cudaGetDevice(&dev));
+  const uint64_t need = topk_workspace_bytes(N, k);
+  if (dev < 0 || dev >= 64) {
+    set_error("bocf_topk: unsupported device ordinal");
+    return BOCF_ERR_INVALID;
+  }
+  if (ws_bytes[dev] < need) {
+    if (ws_cache[dev]) cudaFree(ws_cache[dev]);
+    ws_cache[dev] = nullptr;
+    ws_bytes[dev] = 0;
+    BOCF_CUDA_OK(cudaMalloc(&ws_cache[dev], need));
+    ws_bytes[dev] = need;
+  }
+  return launch_topk(acq, Xc, N, d, k, index_offset, out_rec, ws_cache[dev], st);
 }
 
 }  // extern "C"

@@ -462,7 +462,7 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
   if (rc) return rc;
   if (!need_var) return 0;      // mean (and mean gradient) only: no contraction against the factor
   const bool split = (cb.A1 != nullptr);
-  const int nct = split ? M->ncts * split_partials_per_tile() : M->n_pad / NT;   // partial sums per candidate
+  const int nct = split ? split_partials_per_tile() : M->n_pad / NT;   // partial sums per candidate
   const unsigned tiles = (unsigned)((cb.Nc / CT) * nct * M->m);
   if (split) {
     // tcgen05 kind::i8 digit-plane contractions (split_gemm.cu); same partial-sum layout, same finalize

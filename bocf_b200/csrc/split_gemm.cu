@@ -94,32 +94,47 @@ struct GemmParams {
   int exp;                 // experiment knob (BOCF_SPLIT_EXP): 1 = skip the MMAs, 2 = skip the bulk loads (results invalid)
 };
 
+// Work decomposition.  A UNIT is (output j, candidate tile rt, part p of NP): the column tiles ct = p, p+NP, ... of one
+// 128-candidate tile.  A persistent CTA owns whole units and walks their column tiles back to back, so the epilogue
+// keeps its per-candidate reductions in registers across the unit and writes ONE partial per (unit, epilogue warp)
+// instead of one per column tile; the NP parts of a candidate tile run on neighbouring CTAs at the same time, which
+// keeps the digit planes of the tile (re-read by every column tile) L2 resident.
+constexpr int NP = 2;
+
 struct TileInfo {
-  int j, rt, ct, kb, ke;
+  int j, rt, p, ct, kb, ke;
+  bool valid, first, last;      // first / last column tile of the unit
 };
 
-__device__ __forceinline__ TileInfo decode_tile(const GemmParams& P, int NT, int t) {
-  constexpr int RG = 8;                                   // candidate tiles that share one pass over the column tiles
+__device__ __forceinline__ int tiles_per_unit(const GemmParams& P) { return (P.nct + NP - 1) / NP; }
+__device__ __forceinline__ int local_tile_count(const GemmParams& P) {      // slots this CTA walks (some may be empty)
+  const int units = P.m * P.RT * NP;
+  const int mine = (units > (int)blockIdx.x) ? (units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  return mine * tiles_per_unit(P);
+}
+
+// slot l of this CTA: unit = blockIdx.x + (l / TPU) * gridDim.x, position l % TPU inside the unit
+__device__ __forceinline__ TileInfo decode_tile(const GemmParams& P, int NT, int l) {
   TileInfo ti;
-  const int per_j = P.RT * P.nct;
-  ti.j = t / per_j;
-  const int u = t - ti.j * per_j;
-  const int g = u / (RG * P.nct);
-  const int v = u - g * RG * P.nct;
-  const int rows = min(RG, P.RT - g * RG);
-  const int cidx = v / rows;
-  ti.rt = g * RG + (v - cidx * rows);
+  const int tpu = tiles_per_unit(P);
+  const int k = l / tpu, pos = l - k * tpu;
+  const int u = (int)blockIdx.x + k * (int)gridDim.x;
+  ti.j = u / (P.RT * NP);
+  const int r = u - ti.j * (P.RT * NP);
+  ti.rt = r / NP;
+  ti.p = r - ti.rt * NP;
+  ti.ct = ti.p + pos * NP;
+  ti.valid = ti.ct < P.nct;
+  ti.first = (pos == 0);
+  ti.last = (ti.ct + NP >= P.nct);
   const int kch_used = (P.n + KC - 1) / KC;
-  if (P.tri == TRI_K_LE_N) {                              // K index <= column index: heaviest tiles first
-    ti.ct = P.nct - 1 - cidx;
+  if (P.tri == TRI_K_LE_N) {                              // K index <= column index
     ti.kb = 0;
     ti.ke = min(kch_used, (min((ti.ct + 1) * NT, P.n) + KC - 1) / KC);
   } else if (P.tri == TRI_K_GE_N) {                       // K index >= column index
-    ti.ct = cidx;
     ti.kb = (ti.ct * NT) / KC;
     ti.ke = kch_used;
   } else {
-    ti.ct = cidx;
     ti.kb = 0;
     ti.ke = kch_used;
   }
@@ -182,15 +197,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const int num_tiles = P.m * P.RT * P.nct;
+  const int num_tiles = local_tile_count(P);   // slots of THIS CTA
 
   if (warp == 0) {
     // ================================ producer =================================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = 0; t < num_tiles; ++t) {
         const TileInfo ti = decode_tile(P, NT, t);
+        if (!ti.valid) continue;
         const uint8_t* gA = P.A + ((size_t)(ti.j * P.RT + ti.rt) * P.KCH) * C::A_STAGE;
         const uint8_t* gB = P.B + ((size_t)((P.h * P.m + ti.j) * P.nct + ti.ct) * P.KCH) * C::B_STAGE;
         if (EPI == EPI_DVAR) {
@@ -222,10 +238,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = 0; t < num_tiles; ++t) {
         const TileInfo ti = decode_tile(P, NT, t);
+        if (!ti.valid) continue;
         const int buf = it % C::NBUF;
         const uint32_t use = (uint32_t)(it / C::NBUF);
+        ++it;
         tc::mbar_wait(&tempty[buf], (use & 1u) ^ 1u);          // epilogue has drained this accumulator buffer
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::ACC_COLS);
@@ -268,8 +286,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
     constexpr int XPT = (EPI == EPI_DVAR) ? (NT * DPA0 + EPI_THREADS - 1) / EPI_THREADS : 1;
     double pre_cs = 0.0, pre_vq = 0.0, pre_xb[XPT];
     auto prefetch_tile_consts = [&](int tnext) {
-      if (tnext >= num_tiles) return;
-      const TileInfo tn = decode_tile(P, NT, tnext);
+      TileInfo tn;
+      tn.valid = false;
+      while (tnext < num_tiles && !(tn = decode_tile(P, NT, tnext)).valid) ++tnext;
+      if (!tn.valid) return;
       const int hjn = P.h * P.m + tn.j;
       if (et < NT) pre_cs = __ldg(P.cs + (size_t)hjn * P.nct * NT + tn.ct * NT + et);
       if (EPI == EPI_VAR) pre_vq = __ldg(P.vq + hjn);
@@ -284,12 +304,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
         }
       }
     };
-    prefetch_tile_consts(blockIdx.x);
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    prefetch_tile_consts(0);
+    // reductions over the column tiles of a unit live in registers
+    constexpr int DPA = DP > 0 ? DP : 2;
+    double sumsq = 0.0, s0 = 0.0, acc[DPA];
+    for (int t = 0; t < num_tiles; ++t) {
       const TileInfo ti = decode_tile(P, NT, t);
+      if (!ti.valid) continue;
       const int buf = it % C::NBUF;
       const uint32_t use = (uint32_t)(it / C::NBUF);
+      ++it;
       const int col0 = ti.ct * NT;
+      if (ti.first) {
+        sumsq = 0.0;
+        s0 = 0.0;
+#pragma unroll
+        for (int q = 0; q < DPA; ++q) acc[q] = 0.0;
+      }
       tc::named_bar_sync(1, EPI_THREADS);                       // previous tile's readers of s_cs / s_xb are done
       if (et < NT) s_cs[et] = pre_cs;
       if (EPI == EPI_DVAR) {
@@ -301,20 +332,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       }
       const double vq = pre_vq;
       tc::named_bar_sync(1, EPI_THREADS);
-      prefetch_tile_consts(t + gridDim.x);
+      prefetch_tile_consts(t + 1);
       const int64_t i = (int64_t)ti.rt * TM + row;              // chunk-local candidate
 
       // per-tile thread state
       constexpr int CGW = 8;                                    // columns per TMEM load group
       constexpr int NCG = NT / CGW;
-      constexpr int DPA = DP > 0 ? DP : 2;
-      double sumsq = 0.0;
-      double acc[DPA], s0 = 0.0;
       double gv[CGW];
       const double* Gcol = nullptr;
       if (EPI == EPI_DVAR) {
-#pragma unroll
-        for (int q = 0; q < DPA; ++q) acc[q] = 0.0;
         Gcol = P.GsT + (size_t)ti.j * P.n16 * P.Nc + i;
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {                      // first column group: in flight while the MMAs finish
@@ -384,10 +410,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       tc::fence_before_sync();
       tc::mbar_arrive(&tempty[buf]);                            // accumulator buffer may be overwritten
 
-      // one partial per (column tile, warp of the lane group): summed in fixed order by finalize_kernel
-      const size_t pidx = ((size_t)ti.j * P.nct + ti.ct) * PART_SPLIT + hw;
-      if (EPI == EPI_VAR) P.part_var[pidx * P.Nc + i] = sumsq;
-      if (EPI == EPI_DVAR) {
+      // one partial per (unit part, warp of the lane group): summed in fixed order by finalize_kernel
+      const size_t pidx = ((size_t)ti.j * NP + ti.p) * PART_SPLIT + hw;
+      if (EPI == EPI_VAR && ti.last) P.part_var[pidx * P.Nc + i] = sumsq;
+      if (EPI == EPI_DVAR && ti.last) {
         // xs_iq * S0 - ACC_q is formed by finalize_kernel (one division per candidate instead of one per tile)
         P.part_s0[pidx * P.Nc + i] = s0;
         double* out = P.part_dvar + (pidx * P.Nc + i) * P.d;
@@ -515,7 +541,7 @@ static int launch_t(const GemmParams& P, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tiles = P.m * P.RT * P.nct;
+  const int tiles = P.m * P.RT * NP;             // units
   if (const char* env = std::getenv("BOCF_SPLIT_GRID")) {          // experiment knob: persistent CTAs launched
     const int g = std::atoi(env);
     if (g > 0 && g < sms) sms = g;
@@ -546,7 +572,7 @@ static int launch_dvar(int S, int d, const GemmParams& P, cudaStream_t st) {
 }  // namespace sg
 
 int split_column_tile(int S) { return S == 5 ? 48 : (S == 6 ? 32 : 64); }
-int split_partials_per_tile() { return sg::PART_SPLIT; }
+int split_partials_per_tile() { return sg::PART_SPLIT * sg::NP; }   // partial sums per candidate and output
 
 static void free_split(bocf_model* M) {
   auto fr = [](auto*& p) {
@@ -636,12 +662,12 @@ int split_prepare(bocf_model* M, int S, cudaStream_t st) {
 uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
   uint64_t per = 0;
   per += (uint64_t)M->m * M->KCH * sg::KC * M->S;       // A1 digit planes of K*
-  per += (uint64_t)M->m * M->ncts * sg::PART_SPLIT * 8;  // part_var
+  per += (uint64_t)M->m * sg::NP * sg::PART_SPLIT * 8;  // part_var
   per += 2ull * M->m * 8;                               // mean, var
   if (grad) {
     per += (uint64_t)M->m * M->n16 * 8;                 // GsT
     per += (uint64_t)M->m * M->KCH * sg::KC * M->S;     // A2 digit planes of V
-    per += (uint64_t)M->m * M->ncts * sg::PART_SPLIT * (M->d + 1) * 8;   // part_dvar, part_s0
+    per += (uint64_t)M->m * sg::NP * sg::PART_SPLIT * (M->d + 1) * 8;   // part_dvar, part_s0
     per += 2ull * M->m * M->d * 8;                      // dmean, dvar
   }
   return per;
@@ -658,14 +684,14 @@ void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, C
   cb->Nc = Nc;
   cb->KsT = cb->V = nullptr;
   cb->A1 = take(planes);
-  cb->part_var = reinterpret_cast<double*>(take((uint64_t)M->m * M->ncts * sg::PART_SPLIT * Nc * 8));
+  cb->part_var = reinterpret_cast<double*>(take((uint64_t)M->m * sg::NP * sg::PART_SPLIT * Nc * 8));
   cb->mean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
   cb->var = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
   if (grad) {
     cb->GsT = reinterpret_cast<double*>(take((uint64_t)M->m * M->n16 * Nc * 8));
     cb->A2 = take(planes);
-    cb->part_dvar = reinterpret_cast<double*>(take((uint64_t)M->m * M->ncts * sg::PART_SPLIT * Nc * M->d * 8));
-    cb->part_s0 = reinterpret_cast<double*>(take((uint64_t)M->m * M->ncts * sg::PART_SPLIT * Nc * 8));
+    cb->part_dvar = reinterpret_cast<double*>(take((uint64_t)M->m * sg::NP * sg::PART_SPLIT * Nc * M->d * 8));
+    cb->part_s0 = reinterpret_cast<double*>(take((uint64_t)M->m * sg::NP * sg::PART_SPLIT * Nc * 8));
     cb->dmean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
     cb->dvar = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
   } else {
@@ -701,6 +727,8 @@ int launch_split_var(bocf_model* M, int h, const ChunkBuffers& cb, bool need_dva
   P.part_var = cb.part_var;
   P.A2 = need_dvar ? cb.A2 : nullptr;
   P.vq = M->vq;
+  if (M->ncts < sg::NP)      // parts without a column tile never write their partial
+    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_var, 0, sizeof(double) * M->m * sg::NP * sg::PART_SPLIT * cb.Nc, st));
   ProfScope ps("split_var_kernel", st);
   return sg::launch_s<sg::EPI_VAR>(M->S, P, st);
 }
@@ -717,6 +745,10 @@ int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, co
   P.Xc = Xc;
   P.Nvalid = Nvalid;
   P.Xs = M->Xs;
+  if (M->ncts < sg::NP) {
+    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_dvar, 0, sizeof(double) * M->m * sg::NP * sg::PART_SPLIT * cb.Nc * M->d, st));
+    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_s0, 0, sizeof(double) * M->m * sg::NP * sg::PART_SPLIT * cb.Nc, st));
+  }
   ProfScope ps("split_dvar_kernel", st);
   return sg::launch_dvar(M->S, M->d, P, st);
 }
