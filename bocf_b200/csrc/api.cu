@@ -214,9 +214,11 @@ int bocf_model_create(bocf_model** out, int m, int d, int kernel, int device) {
   M->d = d;
   M->kernel = kernel;
   M->device = device;
+  M->precision = BOCF_PREC_AUTO;                                // library default
   if (const char* env = std::getenv("BOCF_PRECISION")) {      // fp64 | auto | split3 .. split6
     const std::string v(env);
     if (v == "auto") M->precision = BOCF_PREC_AUTO;
+    else if (v == "fp64") M->precision = BOCF_PREC_FP64_DMMA;
     else if (v.rfind("split", 0) == 0 && v.size() == 6 && v[5] >= '3' && v[5] <= '6') {
       M->precision = BOCF_PREC_SPLIT_I8;
       M->slices_req = v[5] - '0';

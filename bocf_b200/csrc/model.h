@@ -49,7 +49,7 @@ struct bocf_model {
   uint64_t scratch_limit = 4ull << 30;
 
   // ---- split-integer tensor-core contraction (split_gemm.cu) ---------------------------------------
-  int precision = 0;          // requested mode (bocf_precision)
+  int precision = 2;          // requested mode (bocf_precision); default BOCF_PREC_AUTO
   int slices_req = 5;         // requested digit planes for BOCF_PREC_SPLIT_I8
   int S = 0;                  // ACTIVE digit planes; 0 = fp64 DMMA contractions
   int NTs = 0, ncts = 0, KCH = 0;   // column tile, number of column tiles, 64-wide K chunks

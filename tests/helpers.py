@@ -154,6 +154,14 @@ def product_acq(P, grad=True, variant="uEI_noiseless", device="cuda:0", Xc=None,
     return acq._compute_acq(Xc)[:, 0], None
 
 
+def tol(fp64_tol, floor=1e-6):
+    """Tolerance of a GPU parity check: the fp64-tight value when the contractions run in fp64 (BOCF_PRECISION=fp64),
+    otherwise at least `floor` -- the north-star fp64-mode bar of 1e-6 on mean / variance, which the split-integer
+    tensor-core mode is also held to for everything derived from the variance (north star allows 1e-4 on EI-CF)."""
+    import os
+    return fp64_tol if os.environ.get("BOCF_PRECISION", "auto") == "fp64" else max(fp64_tol, floor)
+
+
 def rel_err(a, b):
     a = np.asarray(a)
     b = np.asarray(b)

@@ -8,7 +8,7 @@ the EI-CF value / gradient bar of 1e-4 is the mixed-precision bar and is trivial
 import numpy as np
 import pytest
 
-from tests.helpers import (make_problem, oracle_model, oracle_acq, product_model, product_acq, product_utility,
+from tests.helpers import (tol, make_problem, oracle_model, oracle_acq, product_model, product_acq, product_utility,
                            rel_err)
 
 pytestmark = pytest.mark.gpu
@@ -49,14 +49,14 @@ def test_posterior_matches_oracle(cuda_device, kind, shape):
         mu, v = pm.posterior_mean(P.Xc), pm.posterior_variance(P.Xc)
         dm, dv = pm.posterior_mean_gradient(P.Xc), pm.posterior_variance_gradient(P.Xc)
         assert mu.shape == (m, N) and v.shape == (m, N) and dm.shape == (m, N, d) and dv.shape == (m, N, d)
-        assert rel_err(mu, mu_o) < TOL_MEANVAR and rel_err(v, v_o) < TOL_MEANVAR
-        assert rel_err(mu, mu_o) < TOL_TIGHT and np.max(np.abs(v - v_o) / np.abs(v_o)) < 1e-7
-        assert rel_err(dm, dm_o) < TOL_TIGHT and rel_err(dv, dv_o) < 1e-7
+        assert rel_err(mu, mu_o) < tol(TOL_MEANVAR) and rel_err(v, v_o) < tol(TOL_MEANVAR)
+        assert rel_err(mu, mu_o) < tol(TOL_TIGHT) and np.max(np.abs(v - v_o) / np.abs(v_o)) < tol(1e-7)
+        assert rel_err(dm, dm_o) < tol(TOL_TIGHT) and rel_err(dv, dv_o) < tol(1e-7)
         mp, vp = pm.predict(P.Xc)
         mo, vo = om.predict(P.Xc)
-        assert rel_err(mp, mo) < TOL_TIGHT and rel_err(vp, vo) < 1e-7
+        assert rel_err(mp, mo) < tol(TOL_TIGHT) and rel_err(vp, vo) < tol(1e-7)
         vn = pm.posterior_variance_noiseless(P.Xc)
-        assert rel_err(vn, om.posterior_variance_noiseless(P.Xc)) < 1e-6
+        assert rel_err(vn, om.posterior_variance_noiseless(P.Xc)) < tol(1e-6)
 
 
 def test_posterior_at_training_points_and_clip(cuda_device):
@@ -67,9 +67,9 @@ def test_posterior_at_training_points_and_clip(cuda_device):
     v = pm.posterior_variance(P.X)
     vo = om.posterior_variance(P.X)
     assert np.all(v >= 1e-10) and np.all(vo >= 1e-10)
-    assert np.max(np.abs(v - vo)) < 1e-7
+    assert np.max(np.abs(v - vo)) < tol(1e-7)
     f = pm.posterior_mean_at_evaluated_points()
-    assert rel_err(f, om.posterior_mean_at_evaluated_points()) < 1e-7
+    assert rel_err(f, om.posterior_mean_at_evaluated_points()) < tol(1e-7)
 
 
 @pytest.mark.parametrize("composite", ["sumsq_target", "neg_sum_exp", "exp_cos", "rosen_composite", "linear"])
@@ -79,12 +79,12 @@ def test_eicf_value_and_gradient(cuda_device, composite, kind):
     a_o, g_o = oracle_acq(P, grad=True)
     a, g = product_acq(P, grad=True, device=cuda_device)
     assert np.mean(a_o > 0) > 0.02, "degenerate test problem"
-    assert rel_err(a, a_o) < 1e-8, rel_err(a, a_o)
-    assert rel_err(g, g_o) < 1e-7, rel_err(g, g_o)
+    assert rel_err(a, a_o) < tol(1e-8), rel_err(a, a_o)
+    assert rel_err(g, g_o) < tol(1e-7), rel_err(g, g_o)
     assert np.argmax(a) == np.argmax(a_o)                      # same selected candidate
     av, _ = product_acq(P, grad=False, device=cuda_device)
     avo, _ = oracle_acq(P, grad=False)
-    assert rel_err(av, avo) < 1e-8
+    assert rel_err(av, avo) < tol(1e-8)
 
 
 def test_eicf_matches_literal_reference_loops(cuda_device):
@@ -92,7 +92,7 @@ def test_eicf_matches_literal_reference_loops(cuda_device):
     P = make_problem(m=3, d=4, n=50, H=2, kind="rbf", composite="sumsq_target", N=40, S=25, L=1, seed=4)
     a_o, g_o = oracle_acq(P, grad=True, vectorised=False)
     a, g = product_acq(P, grad=True, device=cuda_device)
-    assert rel_err(a, a_o) < 1e-9 and rel_err(g, g_o) < 1e-8
+    assert rel_err(a, a_o) < tol(1e-9) and rel_err(g, g_o) < tol(1e-8)
 
 
 @pytest.mark.parametrize("S", [1, 25, 1024, 1500])
@@ -100,7 +100,7 @@ def test_eicf_sample_counts(cuda_device, S):
     P = make_problem(m=3, d=5, n=64, H=1, kind="matern32", composite="neg_sum_exp", N=130, S=S, seed=S)
     a_o, g_o = oracle_acq(P, grad=True)
     a, g = product_acq(P, grad=True, device=cuda_device)
-    assert rel_err(a, a_o) < 1e-8 and rel_err(g, g_o) < 1e-7
+    assert rel_err(a, a_o) < tol(1e-8) and rel_err(g, g_o) < tol(1e-7)
 
 
 def test_upi_value_only(cuda_device):
@@ -108,7 +108,7 @@ def test_upi_value_only(cuda_device):
     a_o, _ = oracle_acq(P, grad=False, variant="uPI")
     a, _ = product_acq(P, grad=False, variant="uPI", device=cuda_device)
     assert np.mean(a_o > 0) > 0.02
-    assert np.max(np.abs(a - a_o)) < 1e-12         # counts / (H*S): exact up to the final scaling
+    assert np.max(np.abs(a - a_o)) < tol(1e-12)         # counts / (H*S): exact up to the final scaling
     with pytest.raises(NotImplementedError):
         product_acq(P, grad=True, variant="uPI", device=cuda_device)
 
@@ -118,10 +118,10 @@ def test_analytic_variants(cuda_device, variant):
     P = make_problem(m=5, d=4, n=90, H=3, kind="matern52", composite="linear", N=260, S=4, L=4, seed=6)
     a_o, g_o = oracle_acq(P, grad=True, variant=variant)
     a, g = product_acq(P, grad=True, variant=variant, device=cuda_device)
-    assert rel_err(a, a_o) < 1e-8 and rel_err(g, g_o) < 1e-7
+    assert rel_err(a, a_o) < tol(1e-8) and rel_err(g, g_o) < tol(1e-7)
     av_o, _ = oracle_acq(P, grad=False, variant=variant)
     av, _ = product_acq(P, grad=False, variant=variant, device=cuda_device)
-    assert rel_err(av, av_o) < 1e-8
+    assert rel_err(av, av_o) < tol(1e-8)
 
 
 @pytest.mark.parametrize("variant", ["EI", "PI"])
@@ -130,7 +130,7 @@ def test_single_output_ei_pi(cuda_device, variant):
     P.theta = np.ones((1, 1))
     a_o, g_o = oracle_acq(P, grad=True, variant=variant)
     a, g = product_acq(P, grad=True, variant=variant, device=cuda_device)
-    assert rel_err(a, a_o) < 1e-8 and rel_err(g, g_o) < 1e-7
+    assert rel_err(a, a_o) < tol(1e-8) and rel_err(g, g_o) < tol(1e-7)
 
 
 def test_torch_tensors_stay_on_device(cuda_device):

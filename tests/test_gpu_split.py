@@ -18,6 +18,14 @@ from tests.helpers import make_problem, oracle_model, oracle_acq, product_model,
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture
+def cuda_device(built_library):      # every test here names its precision explicitly: no mode parametrisation
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return "cuda:0"
+
+
 def _split_gemm(A, B, S, tri=0):
     import torch
     from bocf_b200 import _lib
