@@ -22,28 +22,42 @@ namespace bocf {
 
 // exp(x) for x <= 0.  Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor/Horner (remainder < 4e-18),
 // scaling by 2^k through the exponent field.  x < -700 (result < 1e-304) flushes to 0.
+// Coefficients live in constant memory so every DFMA takes them as a constant-bank operand: as immediates each 64-bit
+// literal costs two extra move instructions per use (the K* kernel was issue-bound on exactly those moves).
+static __constant__ double EXPC[16] = {
+    1.6059043836821613e-10,      // 1/13!
+    2.08767569878681e-09,        // 1/12!
+    2.505210838544172e-08,       // 1/11!
+    2.755731922398589e-07,       // 1/10!
+    2.7557319223985893e-06,      // 1/9!
+    2.48015873015873e-05,        // 1/8!
+    1.984126984126984e-04,       // 1/7!
+    1.3888888888888889e-03,      // 1/6!
+    8.333333333333333e-03,       // 1/5!
+    4.1666666666666664e-02,      // 1/4!
+    1.6666666666666666e-01,      // 1/3!
+    1.4426950408889634074,       // [11] log2(e)
+    6755399441055744.0,          // [12] 1.5 * 2^52
+    6.93147180369123816490e-01,  // [13] ln2 high
+    1.90821492927058770002e-10,  // [14] ln2 low
+    -700.0};
 __device__ __forceinline__ double exp_nonpos(double x) {
-  const double xc = fmax(x, -700.0);
-  const double kf = rint(xc * 1.4426950408889634074);
-  double r = fma(-kf, 6.93147180369123816490e-01, xc);
-  r = fma(-kf, 1.90821492927058770002e-10, r);
-  double p = 1.6059043836821613e-10;          // 1/13!
-  p = fma(p, r, 2.08767569878681e-09);        // 1/12!
-  p = fma(p, r, 2.505210838544172e-08);       // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);       // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);      // 1/9!
-  p = fma(p, r, 2.48015873015873e-05);        // 1/8!
-  p = fma(p, r, 1.984126984126984e-04);       // 1/7!
-  p = fma(p, r, 1.3888888888888889e-03);      // 1/6!
-  p = fma(p, r, 8.333333333333333e-03);       // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);      // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);      // 1/3!
+  const double xc = fmax(x, EXPC[15]);
+  // round-to-nearest integer of xc * log2(e) through the 1.5 * 2^52 shift: no FRND / F2I conversion instructions,
+  // and the integer is available in the low word of the shifted value
+  const double sh = fma(xc, EXPC[11], EXPC[12]);
+  const double kf = sh - EXPC[12];
+  double r = fma(-kf, EXPC[13], xc);
+  r = fma(-kf, EXPC[14], r);
+  double p = EXPC[0];
+#pragma unroll
+  for (int c = 1; c <= 10; ++c) p = fma(p, r, EXPC[c]);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  const int k = (int)kf;
+  const int k = __double2loint(sh);
   const double scaled = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-  return (x < -700.0) ? 0.0 : scaled;
+  return (x < EXPC[15]) ? 0.0 : scaled;
 }
 
 // sqrt(a) for a >= 0 (finite): one Newton step on a * rsqrt(a).

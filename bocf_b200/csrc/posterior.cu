@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
     xs[q] = v;
     xsq_i += v * v;
   }
-  double mu = 0.0;
-  double gm[DP];
+  double mu = 0.0, wsum = 0.0;
+  double gm[DP];       // sum_b w_b Xs_bq ;  dmean_q = (xs_q * sum_b w_b - gm_q) / l_q
 #pragma unroll
   for (int q = 0; q < DP; ++q) gm[q] = 0.0;
 
@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
     }
     __syncthreads();
     const int bmax = min(128, n16 - b0);
-    constexpr int UNR = SPLIT ? 16 : 1;     // split mode: 16 training points = one 16-byte piece of a digit-plane row
+    // 16 (split: one 16-byte piece of a digit-plane row) or 4 training points per trip, evaluated branch-free so the
+    // independent chains interleave; padded points b >= n are evaluated like the others and masked at the end
+    constexpr int UNR = SPLIT ? 16 : 4;
     for (int bb0 = 0; bb0 < bmax; bb0 += UNR) {
       if (SPLIT) {
 #pragma unroll
@@ -104,16 +106,21 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
       for (int e = 0; e < UNR; ++e) {
         const int bb = bb0 + e;
         const int b = b0 + bb;
-        double kv = 0.0, gv = 0.0;
-        if (b < n) {
+        double kv, gv;
+        {
           double r2;
           if (KIND == BOCF_KERN_SE) {
-            r2 = 0.0;
+            double r2a = 0.0, r2b = 0.0;
 #pragma unroll
-            for (int q = 0; q < DP; ++q) {
-              double df = xs[q] - sX[bb][q];
-              r2 += df * df;
+            for (int q = 0; q < DP; q += 2) {
+              const double d0 = xs[q] - sX[bb][q];
+              r2a = fma(d0, d0, r2a);
+              if (q + 1 < DP) {
+                const double d1 = xs[q + 1] - sX[bb][q + 1];
+                r2b = fma(d1, d1, r2b);
+              }
             }
+            r2 = r2a + r2b;
           } else {
             double dot = 0.0;
 #pragma unroll
@@ -122,12 +129,17 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
             r2 = fmax(r2, 0.0);
           }
           kern_eval<KIND, GRAD>(r2, variance, kv, gv);
+          if (b >= n) {
+            kv = 0.0;
+            gv = 0.0;
+          }
           const double a = salpha[bb];
           mu += kv * a;
           if (GRAD) {
             const double w = gv * a;
+            wsum += w;
 #pragma unroll
-            for (int q = 0; q < DP; ++q) gm[q] += w * (xs[q] - sX[bb][q]);
+            for (int q = 0; q < DP; ++q) gm[q] = fma(w, sX[bb][q], gm[q]);
           }
         }
         if (GRAD) Gout[(int64_t)b * Nc + i] = gv;
@@ -152,7 +164,7 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
   if (GRAD) {
 #pragma unroll
     for (int q = 0; q < DP; ++q)
-      if (q < d) dmean[((int64_t)j * Nc + i) * d + q] = gm[q] / hp.ls[q];
+      if (q < d) dmean[((int64_t)j * Nc + i) * d + q] = (xs[q] * wsum - gm[q]) / hp.ls[q];
   }
 }
 
@@ -433,7 +445,9 @@ static int launch_kstar_k(bocf_model* M, int h, const double* Xc, int64_t Nvalid
                           cudaStream_t st) {
   const int d = M->d;
   if (d <= 4) return launch_kstar_t<KIND, 4>(M, h, Xc, Nvalid, grad, cb, st);
+  if (d <= 6) return launch_kstar_t<KIND, 6>(M, h, Xc, Nvalid, grad, cb, st);
   if (d <= 8) return launch_kstar_t<KIND, 8>(M, h, Xc, Nvalid, grad, cb, st);
+  if (d <= 10) return launch_kstar_t<KIND, 10>(M, h, Xc, Nvalid, grad, cb, st);
   if (d <= 12) return launch_kstar_t<KIND, 12>(M, h, Xc, Nvalid, grad, cb, st);
   return launch_kstar_t<KIND, MAXD>(M, h, Xc, Nvalid, grad, cb, st);
 }
