@@ -53,6 +53,7 @@ struct bocf_model {
   int slices_req = 5;         // requested digit planes for BOCF_PREC_SPLIT_I8
   int S = 0;                  // ACTIVE digit planes; 0 = fp64 DMMA contractions
   int NTs = 0, ncts = 0, KCH = 0;   // column tile, number of column tiles, 64-wide K chunks
+  int split_cg = 1;           // CTAs per tile group of the split contraction: 1 = single CTAs (default), 2 = cta_group::2 pairs
   double linv_absmax = 0.0;   // max |Linv| over all (h, j), measured at factorisation
   uint8_t* B1 = nullptr;      // H*m x ncts x KCH x S x NTs x 64   digit planes of Linv rows   (V  = K* Linv^T)
   uint8_t* B2 = nullptr;      // same layout, digit planes of Linv columns                      (Wt = V Linv)

@@ -48,10 +48,24 @@ __host__ __device__ __forceinline__ uint32_t sw64(int r, int c) {   // byte offs
 }
 __host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int S, int NT, int DP = 0>
+// CG = 1: one CTA per tile (M = 128).  CG = 2: the two CTAs of a cluster form an M = 256 tile (cta_group::2): each CTA
+// brings its own 128 candidates (A planes, accumulators, epilogue) and HALF of the rows of every stacked B operand, so
+// the shared-memory operand traffic per SM -- the measured limiter of the 1-CTA stream -- drops from 42.5 to 31 KB per
+// K step.  Because the stacked operand of instruction ta starts at a different plane for every ta, its halves cannot
+// alias one natural plane layout: the pair layout stores, per CTA rank, one region per instruction
+// (rows [rank N_ta/2, (rank+1) N_ta/2) of the stack), S(S+1)/2 * NT/2 rows in total.
+template <int S, int NT, int DP = 0, int CG = 1>
 struct Cfg {
   static constexpr int A_PLANE = TM * KC, B_PLANE = NT * KC;
-  static constexpr int A_STAGE = S * A_PLANE, B_STAGE = S * B_PLANE, STAGE = A_STAGE + B_STAGE;
+  static constexpr int B_ROWS = (CG == 1) ? S * NT : (S * (S + 1) / 2) * (NT / 2);
+  static constexpr int A_STAGE = S * A_PLANE, B_STAGE = B_ROWS * KC, STAGE = A_STAGE + B_STAGE;
+  // byte offset of the B operand of instruction ta (A plane ta against planes S-1-ta .. S-1) inside a stage
+  __host__ __device__ static constexpr int b_off(int ta) {
+    if (CG == 1) return (S - 1 - ta) * B_PLANE;
+    int rows = 0;                                        // regions ordered ta = S-1 (largest) first
+    for (int t = S - 1; t > ta; --t) rows += (t + 1) * (NT / 2);
+    return rows * KC;
+  }
   static constexpr int ACC_COLS = S * NT;
   static constexpr int NBUF = (2 * ACC_COLS <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = pow2_cols(NBUF * ACC_COLS);
@@ -63,7 +77,8 @@ struct Cfg {
   static_assert(S >= 2 && S <= 6 && NT % 16 == 0 && S * NT <= 256, "stacked B operand must fit one MMA (N <= 256)");
   static_assert(STAGES >= 2, "need at least a double-buffered ring");
   static_assert(B_STAGE % 512 == 0 && A_STAGE % 512 == 0, "planes must keep the 512-byte swizzle period");
-  static_assert(NT * 8 <= 512 && (2 * STAGES + 2 * NBUF) * 8 + 16 <= 512, "head area too small");
+  static_assert(NT * 8 <= 512 && (3 * STAGES + 3 * NBUF) * 8 + 16 <= 512, "head area too small");
+  static_assert(CG == 1 || (NT / 2) % 8 == 0, "half operands must be whole 8-row groups");
 };
 
 enum { EPI_RAW = 0, EPI_VAR = 1, EPI_DVAR = 2 };
@@ -91,6 +106,7 @@ struct GemmParams {
   const double* Xs;        // [Hm][n_pad][d]
   const OutHyp* hyp;
   int d, n16, n_pad;
+  int cg;                  // CTAs per tile group (1 or 2)
   int exp;                 // experiment knob (BOCF_SPLIT_EXP): 1 = skip the MMAs, 2 = skip the bulk loads (results invalid)
 };
 
@@ -107,22 +123,27 @@ struct TileInfo {
 };
 
 __device__ __forceinline__ int tiles_per_unit(const GemmParams& P) { return (P.nct + NP - 1) / NP; }
+// With CTA pairs (P.cg == 2) the pair is the scheduling entity: both CTAs walk the same (output, part, column tile)
+// sequence and CTA rank r of the pair owns candidate tile 2 * (pair's tile index) + r  (RT is even).
 __device__ __forceinline__ int local_tile_count(const GemmParams& P) {      // slots this CTA walks (some may be empty)
-  const int units = P.m * P.RT * NP;
-  const int mine = (units > (int)blockIdx.x) ? (units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int units = P.m * (P.RT / P.cg) * NP;
+  const int me = (int)blockIdx.x / P.cg, groups = (int)gridDim.x / P.cg;
+  const int mine = (units > me) ? (units - 1 - me) / groups + 1 : 0;
   return mine * tiles_per_unit(P);
 }
 
-// slot l of this CTA: unit = blockIdx.x + (l / TPU) * gridDim.x, position l % TPU inside the unit
+// slot l of this CTA: unit = group + (l / TPU) * groups, position l % TPU inside the unit
 __device__ __forceinline__ TileInfo decode_tile(const GemmParams& P, int NT, int l) {
   TileInfo ti;
   const int tpu = tiles_per_unit(P);
   const int k = l / tpu, pos = l - k * tpu;
-  const int u = (int)blockIdx.x + k * (int)gridDim.x;
-  ti.j = u / (P.RT * NP);
-  const int r = u - ti.j * (P.RT * NP);
-  ti.rt = r / NP;
-  ti.p = r - ti.rt * NP;
+  const int me = (int)blockIdx.x / P.cg, groups = (int)gridDim.x / P.cg;
+  const int u = me + k * groups;
+  const int rtg = P.RT / P.cg;
+  ti.j = u / (rtg * NP);
+  const int r = u - ti.j * (rtg * NP);
+  ti.rt = (r / NP) * P.cg + ((int)blockIdx.x % P.cg);
+  ti.p = r - (r / NP) * NP;
   ti.ct = ti.p + pos * NP;
   ti.valid = ti.ct < P.nct;
   ti.first = (pos == 0);
@@ -162,9 +183,9 @@ __device__ __forceinline__ unsigned long long balanced_digits_of(double x) {
   return balanced_digits<S>(__double_as_longlong(x + 6755399441055744.0));
 }
 
-template <int S, int NT, int EPI, int DP>
+template <int S, int NT, int EPI, int DP, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParams P) {
-  using C = Cfg<S, NT, DP>;
+  using C = Cfg<S, NT, DP, CG>;
   extern __shared__ uint8_t smem_raw[];
   // head: [0,512) barriers + tmem slot, [512, 1024) column scales; stages start at the next 512-byte boundary
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -172,7 +193,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
   uint64_t* empty = bars + C::STAGES;
   uint64_t* tfull = bars + 2 * C::STAGES;
   uint64_t* tempty = tfull + C::NBUF;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::NBUF);
+  uint64_t* pfull = tempty + C::NBUF;          // CG = 2, leader only: the peer CTA's stage has landed (relayed)
+  uint64_t* ptempty = pfull + C::STAGES;       // CG = 2, leader only: the peer CTA's epilogue has drained the buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ptempty + C::NBUF);
   double* s_cs = reinterpret_cast<double*>(smem_raw + 512);
   double* s_xb = reinterpret_cast<double*>(smem_raw + 1024);      // [NT][DP]
   const uint32_t raw_addr = tc::smem_u32(smem_raw);
@@ -189,14 +212,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
     for (int b = 0; b < C::NBUF; ++b) {
       tc::mbar_init(&tfull[b], 1);
       tc::mbar_init(&tempty[b], EPI_THREADS);
+      tc::mbar_init(&ptempty[b], 1);
     }
+    for (int s = 0; s < C::STAGES; ++s) tc::mbar_init(&pfull[s], 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (CG == 2) tc::tmem_alloc2<C::TMEM_COLS>(tmem_slot);
+    else tc::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  }
   tc::fence_before_sync();
-  __syncthreads();
+  if (CG == 2) tc::cluster_sync_all();         // peer barriers are initialised before any remote arrive / multicast commit
+  else __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = (CG == 2) ? tc::cluster_ctarank() : 0u;
   const int num_tiles = local_tile_count(P);   // slots of THIS CTA
 
   if (warp == 0) {
@@ -208,7 +238,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
         const TileInfo ti = decode_tile(P, NT, t);
         if (!ti.valid) continue;
         const uint8_t* gA = P.A + ((size_t)(ti.j * P.RT + ti.rt) * P.KCH) * C::A_STAGE;
-        const uint8_t* gB = P.B + ((size_t)((P.h * P.m + ti.j) * P.nct + ti.ct) * P.KCH) * C::B_STAGE;
+        // CG = 2: [..][kc][rank][regions]  -- this CTA streams its own half-operand block
+        const uint8_t* gB = P.B + ((size_t)((P.h * P.m + ti.j) * P.nct + ti.ct) * P.KCH) * (C::B_STAGE * CG) +
+                            (size_t)crank * C::B_STAGE;
         if (EPI == EPI_DVAR) {
           // the epilogue of this tile (one tile later in time) reads 128 G* values of each of its NT columns:
           // pull those 1 KB rows into L2 now so its loads do not pay HBM latency
@@ -223,7 +255,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
           } else {
             tc::mbar_arrive_expect_tx(&full[stage], C::STAGE);
             tc::bulk_g2s(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage]);
-            tc::bulk_g2s(sB + stage * C::B_STAGE, gB + (size_t)kc * C::B_STAGE, C::B_STAGE, &full[stage]);
+            tc::bulk_g2s(sB + stage * C::B_STAGE, gB + (size_t)kc * (C::B_STAGE * CG), C::B_STAGE, &full[stage]);
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -233,6 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       }
     }
   } else if (warp == 1) {
+#define WAITFN(bar, par) tc::mbar_wait(bar, par)
     // ================================ MMA issuer ===============================================
     if (lane == 0) {
       int stage = 0;
@@ -244,12 +277,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
         const int buf = it % C::NBUF;
         const uint32_t use = (uint32_t)(it / C::NBUF);
         ++it;
-        tc::mbar_wait(&tempty[buf], (use & 1u) ^ 1u);          // epilogue has drained this accumulator buffer
+        if (CG == 2 && crank != 0) {
+          // follower of the pair: issues nothing; relays "my epilogue drained the buffer" and "my stage landed" to the
+          // leader, whose MMAs read this CTA's shared memory and write this CTA's tensor memory
+          WAITFN(&tempty[buf], (use & 1u) ^ 1u);
+          tc::mbar_arrive_remote(&ptempty[buf], 0);
+          for (int kc = ti.kb; kc < ti.ke; ++kc) {
+            WAITFN(&full[stage], phase);
+            tc::mbar_arrive_remote(&pfull[stage], 0);
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          continue;
+        }
+        WAITFN(&tempty[buf], (use & 1u) ^ 1u);          // epilogue has drained this accumulator buffer
+        if (CG == 2) WAITFN(&ptempty[buf], use & 1u);   // ... in the peer CTA too
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::ACC_COLS);
         bool first = true;
         for (int kc = ti.kb; kc < ti.ke; ++kc) {
-          tc::mbar_wait(&full[stage], phase);
+          WAITFN(&full[stage], phase);
+          if (CG == 2) WAITFN(&pfull[stage], phase);
           tc::fence_after_sync();
           const uint32_t a0 = tc::smem_u32(sA + stage * C::A_STAGE);
           const uint32_t b0 = tc::smem_u32(sB + stage * C::B_STAGE);
@@ -259,20 +309,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
             for (int ta = S - 1; ta >= 0; --ta) {
               // A digit plane ta against the stacked B planes tb = S-1-ta .. S-1  ->  levels 0 .. ta
               const uint64_t adesc = tc::smem_desc_sw64(a0 + ta * C::A_PLANE + ks * 32);
-              const uint64_t bdesc = tc::smem_desc_sw64(b0 + (S - 1 - ta) * C::B_PLANE + ks * 32);
-              if (P.exp != 1) tc::mma_i8(d_tmem, adesc, bdesc, tc::idesc_i8((ta + 1) * NT), (first && ta == S - 1) ? 0u : 1u);
+              const uint64_t bdesc = tc::smem_desc_sw64(b0 + C::b_off(ta) + ks * 32);
+              const uint32_t acc = (first && ta == S - 1) ? 0u : 1u;
+              if (P.exp != 1) {
+                if (CG == 2) tc::mma_i8_pair(d_tmem, adesc, bdesc, tc::idesc_i8_m256((ta + 1) * NT), acc);
+                else tc::mma_i8(d_tmem, adesc, bdesc, tc::idesc_i8((ta + 1) * NT), acc);
+              }
             }
             first = false;
           }
-          tc::mma_commit(&empty[stage]);                        // stage reusable once these MMAs have read it
+          // stage reusable once these MMAs have read it (both CTAs' stages for a pair)
+          if (CG == 2) tc::mma_commit_pair(&empty[stage]);
+          else tc::mma_commit(&empty[stage]);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc::mma_commit(&tfull[buf]);                            // accumulators of this tile complete
+        // accumulators of this tile complete (in both CTAs' tensor memory for a pair)
+        if (CG == 2) tc::mma_commit_pair(&tfull[buf]);
+        else tc::mma_commit(&tfull[buf]);
       }
     }
+#undef WAITFN
   } else {
     // ================================ epilogue (EPI_WARPS warps) ===============================
     const int et = threadIdx.x - 64;
@@ -424,11 +483,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
     }
   }
   tc::fence_before_sync();
-  __syncthreads();
+  if (CG == 2) tc::cluster_sync_all();         // no CTA leaves while its peer may still signal it / use its memories
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc::fence_after_sync();
-    tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if (CG == 2) tc::tmem_dealloc2<C::TMEM_COLS>(tmem_base);
+    else tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -492,6 +553,52 @@ __global__ void pack_digits_kernel(const double* __restrict__ src, int64_t mat_s
   }
 }
 
+// Pair layout of the factor-side operand (cta_group::2, see Cfg): per (tile, K chunk) two blocks (CTA rank 0 / 1), each
+// holding for every instruction ta = S-1 .. 0 the rows [rank N_ta/2, (rank+1) N_ta/2) of the stack of planes S-1-ta .. S-1.
+template <int S>
+__global__ void pack_digits_pair_kernel(const double* __restrict__ src, int64_t mat_stride, int64_t sr, int64_t sk,
+                                        int R, int K, const int* __restrict__ exps, int Rpad, int NTr, int ntile,
+                                        int KCH, uint8_t* __restrict__ out) {
+  const int kc = blockIdx.x, tile = blockIdx.y, mat = blockIdx.z;
+  const int half = NTr / 2;
+  const int rows_per_rank = (S * (S + 1) / 2) * half;
+  uint8_t* obase = out + ((size_t)(mat * ntile + tile) * KCH + kc) * (size_t)(2 * rows_per_rank * KC);
+  for (int idx = threadIdx.x; idx < 2 * rows_per_rank * 4; idx += blockDim.x) {
+    int piece, rr_all;
+    if (sk == 1) {
+      rr_all = idx >> 2;
+      piece = idx & 3;
+    } else {
+      rr_all = idx % (2 * rows_per_rank);
+      piece = idx / (2 * rows_per_rank);
+    }
+    const int rank = rr_all / rows_per_rank;
+    int rem = rr_all - rank * rows_per_rank;
+    int ta = S - 1, off_rows = 0;
+    while (rem >= (ta + 1) * half) {                     // regions ordered ta = S-1 first
+      rem -= (ta + 1) * half;
+      off_rows += (ta + 1) * half;
+      --ta;
+    }
+    const int sidx = rank * (ta + 1) * half + rem;       // row inside the stack of instruction ta
+    const int tb = (S - 1 - ta) + sidx / NTr;
+    const int r = sidx % NTr;
+    const int row = tile * NTr + r;
+    const int e = exps[(size_t)mat * Rpad + row];
+    const double q = ldexp(1.0, 8 * S - 2 - e);
+    uint32_t vec[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int ee = 0; ee < 16; ++ee) {
+      const int k = kc * KC + piece * 16 + ee;
+      const double x = (row < R && k < K) ? src[mat * mat_stride + row * sr + k * sk] : 0.0;
+      const unsigned long long dg = balanced_digits_of<S>(x * q);
+      vec[ee >> 2] |= (uint32_t)((dg >> (8 * tb)) & 0xFFull) << (8 * (ee & 3));
+    }
+    *reinterpret_cast<uint4*>(obase + (size_t)rank * rows_per_rank * KC + (size_t)off_rows * KC + sw64(rem, piece * 16)) =
+        make_uint4(vec[0], vec[1], vec[2], vec[3]);
+  }
+}
+
 __global__ void absmax_kernel(const double* __restrict__ src, size_t count, double* __restrict__ out) {
   double a = 0.0;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += (size_t)gridDim.x * blockDim.x)
@@ -508,6 +615,20 @@ static int pack_t(const double* src, int64_t mat_stride, int64_t sr, int64_t sk,
   dim3 grid((unsigned)KCH, (unsigned)ntile, (unsigned)mats);
   pack_digits_kernel<S><<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, exps, Rpad, TR, ntile, KCH, out);
   BOCF_LAUNCH_OK("pack_digits_kernel");
+  return 0;
+}
+static int pack_digits_pair(int S, const double* src, int64_t mat_stride, int64_t sr, int64_t sk, int R, int K,
+                            const int* exps, int Rpad, int NTr, int ntile, int KCH, int mats, uint8_t* out,
+                            cudaStream_t st) {
+  dim3 grid((unsigned)KCH, (unsigned)ntile, (unsigned)mats);
+  switch (S) {
+    case 3: pack_digits_pair_kernel<3><<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, exps, Rpad, NTr, ntile, KCH, out); break;
+    case 4: pack_digits_pair_kernel<4><<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, exps, Rpad, NTr, ntile, KCH, out); break;
+    case 5: pack_digits_pair_kernel<5><<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, exps, Rpad, NTr, ntile, KCH, out); break;
+    case 6: pack_digits_pair_kernel<6><<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, exps, Rpad, NTr, ntile, KCH, out); break;
+    default: set_error("split contraction supports 3..6 digit planes"); return BOCF_ERR_INVALID;
+  }
+  BOCF_LAUNCH_OK("pack_digits_pair_kernel");
   return 0;
 }
 static int pack_digits(int S, const double* src, int64_t mat_stride, int64_t sr, int64_t sk, int R, int K,
@@ -529,27 +650,50 @@ static int row_exps(const double* src, int64_t mat_stride, int64_t sr, int64_t s
   return 0;
 }
 
-template <int S, int NT, int EPI, int DP = 0>
-static int launch_t(const GemmParams& P, cudaStream_t st) {
-  using C = Cfg<S, NT, DP>;
+template <int S, int NT, int EPI, int DP, int CG>
+static int launch_cg(const GemmParams& P, cudaStream_t st) {
+  using C = Cfg<S, NT, DP, CG>;
   static bool attr_done = false;
   if (!attr_done) {
-    BOCF_CUDA_OK(cudaFuncSetAttribute(split_gemm_kernel<S, NT, EPI, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    BOCF_CUDA_OK(cudaFuncSetAttribute(split_gemm_kernel<S, NT, EPI, DP, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       C::SMEM_BYTES));
     attr_done = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tiles = P.m * P.RT * NP;             // units
+  const int units = P.m * (P.RT / CG) * NP;       // scheduling entities (CTAs, or CTA pairs)
   if (const char* env = std::getenv("BOCF_SPLIT_GRID")) {          // experiment knob: persistent CTAs launched
     const int g = std::atoi(env);
     if (g > 0 && g < sms) sms = g;
   }
-  const int grid = tiles < sms ? tiles : sms;
-  split_gemm_kernel<S, NT, EPI, DP><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(P);
-  BOCF_LAUNCH_OK("split_gemm_kernel");
+  int groups = sms / CG;
+  if (units < groups) groups = units;
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(groups * CG));
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, split_gemm_kernel<S, NT, EPI, DP, CG>, P);
+  count_launch();
+  if (e != cudaSuccess) {
+    set_error(std::string("launch split_gemm_kernel: ") + cudaGetErrorString(e));
+    return -2;
+  }
   return 0;
+}
+template <int S, int NT, int EPI, int DP = 0>
+static int launch_t(const GemmParams& P, cudaStream_t st) {
+  if (P.cg == 2) return launch_cg<S, NT, EPI, DP, 2>(P, st);
+  return launch_cg<S, NT, EPI, DP, 1>(P, st);
 }
 template <int EPI, int DP = 0>
 static int launch_s(int S, const GemmParams& P, cudaStream_t st) {
@@ -613,7 +757,13 @@ int split_prepare(bocf_model* M, int S, cudaStream_t st) {
   M->ncts = (int)ceil_div(M->n, NT);
   M->KCH = (int)ceil_div(M->n, sg::KC);
   const int Rpad = M->ncts * NT;
-  const size_t plane_bytes = (size_t)Hm * M->ncts * M->KCH * S * NT * sg::KC;
+  // CTA pairs (cta_group::2, BOCF_SPLIT_CG=2) are implemented and bit-exact but measured SLOWER on B200 (first
+  // contraction 26.6 vs 15.6 ms per 131072 candidates, profiles/r1_split_experiments.md): single CTAs are the default.
+  M->split_cg = 1;
+  if (const char* env = std::getenv("BOCF_SPLIT_CG"))
+    if (std::atoi(env) == 2) M->split_cg = 2;
+  const size_t rows_per_tile = (M->split_cg == 2) ? (size_t)S * (S + 1) / 2 * NT : (size_t)S * NT;   // both ranks
+  const size_t plane_bytes = (size_t)Hm * M->ncts * M->KCH * rows_per_tile * sg::KC;
   BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->B1), plane_bytes));
   BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->B2), plane_bytes));
   BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->cs1), sizeof(double) * Hm * Rpad));
@@ -643,10 +793,16 @@ int split_prepare(bocf_model* M, int S, cudaStream_t st) {
   int rc = 0;
   // first contraction: rows = factor row k, K = b      (element Linv[k][b])
   if (!rc) rc = sg::row_exps(M->Linv, nn, M->n_pad, 1, M->n, M->n, Rpad, Hm, exps, M->cs1, extra, base, st);
-  if (!rc) rc = sg::pack_digits(S, M->Linv, nn, M->n_pad, 1, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B1, st);
+  if (!rc)
+    rc = (M->split_cg == 2)
+             ? sg::pack_digits_pair(S, M->Linv, nn, M->n_pad, 1, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B1, st)
+             : sg::pack_digits(S, M->Linv, nn, M->n_pad, 1, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B1, st);
   // second contraction: rows = factor column b, K = k  (element Linv[k][b])
   if (!rc) rc = sg::row_exps(M->Linv, nn, 1, M->n_pad, M->n, M->n, Rpad, Hm, exps, M->cs2, extra + Hm, base, st);
-  if (!rc) rc = sg::pack_digits(S, M->Linv, nn, 1, M->n_pad, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B2, st);
+  if (!rc)
+    rc = (M->split_cg == 2)
+             ? sg::pack_digits_pair(S, M->Linv, nn, 1, M->n_pad, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B2, st)
+             : sg::pack_digits(S, M->Linv, nn, 1, M->n_pad, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B2, st);
   cudaError_t e = cudaStreamSynchronize(st);      // ex/aq/vq are host vectors going out of scope
   cudaFree(exps);
   cudaFree(extra);
@@ -714,6 +870,7 @@ static sg::GemmParams base_params(const bocf_model* M, int h, const ChunkBuffers
   P.n16 = M->n16;
   P.n_pad = M->n_pad;
   P.hyp = M->hyp;
+  P.cg = M->split_cg;
   if (const char* env = std::getenv("BOCF_SPLIT_EXP")) P.exp = std::atoi(env);
   return P;
 }
@@ -760,7 +917,7 @@ int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int 
     return BOCF_ERR_INVALID;
   }
   const int NT = split_column_tile(S);
-  const int RT = (int)ceil_div(R, sg::TM), nct = (int)ceil_div(N, NT), KCH = (int)ceil_div(K, sg::KC);
+  const int RT = (int)round_up(ceil_div(R, sg::TM), 2), nct = (int)ceil_div(N, NT), KCH = (int)ceil_div(K, sg::KC);
   const int RpadA = RT * sg::TM, RpadB = nct * NT;
   uint8_t *pa = nullptr, *pb = nullptr;
   int *ea = nullptr, *eb = nullptr;
@@ -768,7 +925,7 @@ int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int 
   int rc = 0;
   do {
     if (cudaMalloc(reinterpret_cast<void**>(&pa), (size_t)RT * KCH * S * sg::TM * sg::KC) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&pb), (size_t)nct * KCH * S * NT * sg::KC) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&pb), (size_t)nct * KCH * (S * (S + 1) / 2) * NT * sg::KC) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&ea), sizeof(int) * RpadA) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&eb), sizeof(int) * RpadB) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&rs), sizeof(double) * RpadA) != cudaSuccess ||
@@ -782,7 +939,12 @@ int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int 
     if ((rc = sg::row_exps(A, 0, K, 1, R, K, RpadA, 1, ea, rs, nullptr, 0, st))) break;
     if ((rc = sg::row_exps(B, 0, K, 1, N, K, RpadB, 1, eb, cs, nullptr, base, st))) break;
     if ((rc = sg::pack_digits(S, A, 0, K, 1, R, K, ea, RpadA, sg::TM, RT, KCH, 1, pa, st))) break;
-    if ((rc = sg::pack_digits(S, B, 0, K, 1, N, K, eb, RpadB, NT, nct, KCH, 1, pb, st))) break;
+    int cg = 1;
+    if (const char* env = std::getenv("BOCF_SPLIT_CG"))
+      if (std::atoi(env) == 2) cg = 2;
+    if (cg == 2) {
+      if ((rc = sg::pack_digits_pair(S, B, 0, K, 1, N, K, eb, RpadB, NT, nct, KCH, 1, pb, st))) break;
+    } else if ((rc = sg::pack_digits(S, B, 0, K, 1, N, K, eb, RpadB, NT, nct, KCH, 1, pb, st))) break;
     sg::GemmParams P;
     std::memset(&P, 0, sizeof(P));
     P.A = pa;
@@ -790,6 +952,7 @@ int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int 
     P.cs = cs;
     P.m = 1;
     P.h = 0;
+    P.cg = cg;
     P.RT = RT;
     P.nct = nct;
     P.KCH = KCH;

@@ -136,3 +136,19 @@ def test_auto_precision_follows_conditioning(cuda_device):
     assert pm.active_slices() == 0                                                                # stays on fp64 DMMA
     om = oracle_model(ill)
     assert np.max(np.abs(pm.posterior_variance(ill.Xc) - om.posterior_variance(ill.Xc))) < 1e-7
+
+
+def test_cta_pair_variant_is_exact_too(cuda_device, monkeypatch):
+    # cta_group::2 (M = 256 across a cluster of two CTAs, BOCF_SPLIT_CG=2): experimental, slower on B200, but it must
+    # produce the same exact integer products -- through the raw GEMM and through the posterior
+    monkeypatch.setenv("BOCF_SPLIT_CG", "2")
+    rng = np.random.default_rng(5)
+    A = rng.integers(-100, 101, size=(300, 500)).astype(np.float64)
+    B = rng.integers(-100, 101, size=(500, 500)).astype(np.float64)
+    assert np.array_equal(_split_gemm(A, B, 5), A @ B.T)
+    P = make_problem(m=2, d=5, n=257, H=1, kind="matern52", N=700, S=4, seed=3)
+    om = oracle_model(P)
+    pm = product_model(P, cuda_device, precision="split5")
+    v, v_o = pm.posterior_variance(P.Xc), om.posterior_variance(P.Xc)
+    assert np.max(np.abs(v - v_o) / np.abs(v_o)) < 1e-6
+    assert rel_err(pm.posterior_variance_gradient(P.Xc), om.posterior_variance_gradient(P.Xc)) < 1e-6
