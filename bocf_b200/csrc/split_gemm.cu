@@ -107,6 +107,7 @@ struct GemmParams {
   const OutHyp* hyp;
   int d, n16, n_pad;
   int cg;                  // CTAs per tile group (1 or 2)
+  int np;                  // parts per candidate tile
   int exp;                 // experiment knob (BOCF_SPLIT_EXP): 1 = skip the MMAs, 2 = skip the bulk loads (results invalid)
 };
 
@@ -115,18 +116,29 @@ struct GemmParams {
 // keeps its per-candidate reductions in registers across the unit and writes ONE partial per (unit, epilogue warp)
 // instead of one per column tile; the NP parts of a candidate tile run on neighbouring CTAs at the same time, which
 // keeps the digit planes of the tile (re-read by every column tile) L2 resident.
-constexpr int NP = 2;
+constexpr int NP_DEFAULT = 2;   // parts per candidate tile (BOCF_SPLIT_NP overrides: 1, 2 or 4)
+inline int parts_per_tile() {
+  static int np = 0;
+  if (np == 0) {
+    np = NP_DEFAULT;
+    if (const char* env = std::getenv("BOCF_SPLIT_NP")) {
+      const int v = std::atoi(env);
+      if (v == 1 || v == 2 || v == 4) np = v;
+    }
+  }
+  return np;
+}
 
 struct TileInfo {
   int j, rt, p, ct, kb, ke;
   bool valid, first, last;      // first / last column tile of the unit
 };
 
-__device__ __forceinline__ int tiles_per_unit(const GemmParams& P) { return (P.nct + NP - 1) / NP; }
+__device__ __forceinline__ int tiles_per_unit(const GemmParams& P) { return (P.nct + P.np - 1) / P.np; }
 // With CTA pairs (P.cg == 2) the pair is the scheduling entity: both CTAs walk the same (output, part, column tile)
 // sequence and CTA rank r of the pair owns candidate tile 2 * (pair's tile index) + r  (RT is even).
 __device__ __forceinline__ int local_tile_count(const GemmParams& P) {      // slots this CTA walks (some may be empty)
-  const int units = P.m * (P.RT / P.cg) * NP;
+  const int units = P.m * (P.RT / P.cg) * P.np;
   const int me = (int)blockIdx.x / P.cg, groups = (int)gridDim.x / P.cg;
   const int mine = (units > me) ? (units - 1 - me) / groups + 1 : 0;
   return mine * tiles_per_unit(P);
@@ -140,14 +152,14 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& P, int NT, int
   const int me = (int)blockIdx.x / P.cg, groups = (int)gridDim.x / P.cg;
   const int u = me + k * groups;
   const int rtg = P.RT / P.cg;
-  ti.j = u / (rtg * NP);
-  const int r = u - ti.j * (rtg * NP);
-  ti.rt = (r / NP) * P.cg + ((int)blockIdx.x % P.cg);
-  ti.p = r - (r / NP) * NP;
-  ti.ct = ti.p + pos * NP;
+  ti.j = u / (rtg * P.np);
+  const int r = u - ti.j * (rtg * P.np);
+  ti.rt = (r / P.np) * P.cg + ((int)blockIdx.x % P.cg);
+  ti.p = r - (r / P.np) * P.np;
+  ti.ct = ti.p + pos * P.np;
   ti.valid = ti.ct < P.nct;
   ti.first = (pos == 0);
-  ti.last = (ti.ct + NP >= P.nct);
+  ti.last = (ti.ct + P.np >= P.nct);
   const int kch_used = (P.n + KC - 1) / KC;
   if (P.tri == TRI_K_LE_N) {                              // K index <= column index
     ti.kb = 0;
@@ -470,7 +482,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       tc::mbar_arrive(&tempty[buf]);                            // accumulator buffer may be overwritten
 
       // one partial per (unit part, warp of the lane group): summed in fixed order by finalize_kernel
-      const size_t pidx = ((size_t)ti.j * NP + ti.p) * PART_SPLIT + hw;
+      const size_t pidx = ((size_t)ti.j * P.np + ti.p) * PART_SPLIT + hw;
       if (EPI == EPI_VAR && ti.last) P.part_var[pidx * P.Nc + i] = sumsq;
       if (EPI == EPI_DVAR && ti.last) {
         // xs_iq * S0 - ACC_q is formed by finalize_kernel (one division per candidate instead of one per tile)
@@ -662,7 +674,7 @@ static int launch_cg(const GemmParams& P, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int units = P.m * (P.RT / CG) * NP;       // scheduling entities (CTAs, or CTA pairs)
+  const int units = P.m * (P.RT / CG) * P.np;     // scheduling entities (CTAs, or CTA pairs)
   if (const char* env = std::getenv("BOCF_SPLIT_GRID")) {          // experiment knob: persistent CTAs launched
     const int g = std::atoi(env);
     if (g > 0 && g < sms) sms = g;
@@ -716,7 +728,7 @@ static int launch_dvar(int S, int d, const GemmParams& P, cudaStream_t st) {
 }  // namespace sg
 
 int split_column_tile(int S) { return S == 5 ? 48 : (S == 6 ? 32 : 64); }
-int split_partials_per_tile() { return sg::PART_SPLIT * sg::NP; }   // partial sums per candidate and output
+int split_partials_per_tile() { return sg::PART_SPLIT * sg::parts_per_tile(); }   // partial sums per candidate and output
 
 static void free_split(bocf_model* M) {
   auto fr = [](auto*& p) {
@@ -818,12 +830,12 @@ int split_prepare(bocf_model* M, int S, cudaStream_t st) {
 uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
   uint64_t per = 0;
   per += (uint64_t)M->m * M->KCH * sg::KC * M->S;       // A1 digit planes of K*
-  per += (uint64_t)M->m * sg::NP * sg::PART_SPLIT * 8;  // part_var
+  per += (uint64_t)M->m * sg::parts_per_tile() * sg::PART_SPLIT * 8;  // part_var
   per += 2ull * M->m * 8;                               // mean, var
   if (grad) {
     per += (uint64_t)M->m * M->n16 * 8;                 // GsT
     per += (uint64_t)M->m * M->KCH * sg::KC * M->S;     // A2 digit planes of V
-    per += (uint64_t)M->m * sg::NP * sg::PART_SPLIT * (M->d + 1) * 8;   // part_dvar, part_s0
+    per += (uint64_t)M->m * sg::parts_per_tile() * sg::PART_SPLIT * (M->d + 1) * 8;   // part_dvar, part_s0
     per += 2ull * M->m * M->d * 8;                      // dmean, dvar
   }
   return per;
@@ -840,14 +852,14 @@ void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, C
   cb->Nc = Nc;
   cb->KsT = cb->V = nullptr;
   cb->A1 = take(planes);
-  cb->part_var = reinterpret_cast<double*>(take((uint64_t)M->m * sg::NP * sg::PART_SPLIT * Nc * 8));
+  cb->part_var = reinterpret_cast<double*>(take((uint64_t)M->m * sg::parts_per_tile() * sg::PART_SPLIT * Nc * 8));
   cb->mean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
   cb->var = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
   if (grad) {
     cb->GsT = reinterpret_cast<double*>(take((uint64_t)M->m * M->n16 * Nc * 8));
     cb->A2 = take(planes);
-    cb->part_dvar = reinterpret_cast<double*>(take((uint64_t)M->m * sg::NP * sg::PART_SPLIT * Nc * M->d * 8));
-    cb->part_s0 = reinterpret_cast<double*>(take((uint64_t)M->m * sg::NP * sg::PART_SPLIT * Nc * 8));
+    cb->part_dvar = reinterpret_cast<double*>(take((uint64_t)M->m * sg::parts_per_tile() * sg::PART_SPLIT * Nc * M->d * 8));
+    cb->part_s0 = reinterpret_cast<double*>(take((uint64_t)M->m * sg::parts_per_tile() * sg::PART_SPLIT * Nc * 8));
     cb->dmean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
     cb->dvar = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
   } else {
@@ -871,6 +883,7 @@ static sg::GemmParams base_params(const bocf_model* M, int h, const ChunkBuffers
   P.n_pad = M->n_pad;
   P.hyp = M->hyp;
   P.cg = M->split_cg;
+  P.np = sg::parts_per_tile();
   if (const char* env = std::getenv("BOCF_SPLIT_EXP")) P.exp = std::atoi(env);
   return P;
 }
@@ -884,8 +897,8 @@ int launch_split_var(bocf_model* M, int h, const ChunkBuffers& cb, bool need_dva
   P.part_var = cb.part_var;
   P.A2 = need_dvar ? cb.A2 : nullptr;
   P.vq = M->vq;
-  if (M->ncts < sg::NP)      // parts without a column tile never write their partial
-    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_var, 0, sizeof(double) * M->m * sg::NP * sg::PART_SPLIT * cb.Nc, st));
+  if (M->ncts < sg::parts_per_tile())      // parts without a column tile never write their partial
+    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_var, 0, sizeof(double) * M->m * sg::parts_per_tile() * sg::PART_SPLIT * cb.Nc, st));
   ProfScope ps("split_var_kernel", st);
   return sg::launch_s<sg::EPI_VAR>(M->S, P, st);
 }
@@ -902,9 +915,9 @@ int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, co
   P.Xc = Xc;
   P.Nvalid = Nvalid;
   P.Xs = M->Xs;
-  if (M->ncts < sg::NP) {
-    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_dvar, 0, sizeof(double) * M->m * sg::NP * sg::PART_SPLIT * cb.Nc * M->d, st));
-    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_s0, 0, sizeof(double) * M->m * sg::NP * sg::PART_SPLIT * cb.Nc, st));
+  if (M->ncts < sg::parts_per_tile()) {
+    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_dvar, 0, sizeof(double) * M->m * sg::parts_per_tile() * sg::PART_SPLIT * cb.Nc * M->d, st));
+    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_s0, 0, sizeof(double) * M->m * sg::parts_per_tile() * sg::PART_SPLIT * cb.Nc, st));
   }
   ProfScope ps("split_dvar_kernel", st);
   return sg::launch_dvar(M->S, M->d, P, st);
@@ -953,6 +966,7 @@ int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int 
     P.m = 1;
     P.h = 0;
     P.cg = cg;
+    P.np = sg::parts_per_tile();
     P.RT = RT;
     P.nct = nct;
     P.KCH = KCH;
