@@ -112,21 +112,31 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
     double val_l = 0.0;
     for (int sb = 0; sb < S; sb += 1024) {
       unsigned mask = 0u;
+      // four sample groups per trip: their 4 x m base-sample loads are independent and issued together (the kernel
+      // was latency bound on one dependent load -> fma chain per sample, ncu: long_scoreboard)
 #pragma unroll 1
-      for (int k = 0; k < 32; ++k) {
-        const int s = sb + k * 32 + lane;
-        if (s < S) {
-          double U = 0.0;
-          for (int j = 0; j < m; ++j) {
-            const CompCtx c = comp_ctx<COMP>(th, j, m);
-            const double a = s_mu[warp][j] + s_sig[warp][j] * Zt[(int64_t)j * S + s];
-            U += comp_phi<COMP>(c, a);
-          }
-          if (MODE == 2) {
-            val_l += ((U - fs) > 0.0) ? 1.0 : 0.0;
-          } else {
-            val_l += fmax(U - fs, 0.0);                                   // uEI_noiseless.py:80,161
-            if (U > fs) mask |= (1u << k);                                // :162 strict >
+      for (int k0 = 0; k0 < 32; k0 += 4) {
+        double U[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int j = 0; j < m; ++j) {
+          const CompCtx c = comp_ctx<COMP>(th, j, m);
+          const double muj = s_mu[warp][j], sgj = s_sig[warp][j];
+          const double* zr = Zt + (int64_t)j * S + sb + lane;
+          double z[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) z[u] = (sb + (k0 + u) * 32 + lane < S) ? zr[(k0 + u) * 32] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) U[u] += comp_phi<COMP>(c, muj + sgj * z[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u;
+          if (sb + k * 32 + lane < S) {
+            if (MODE == 2) {
+              val_l += ((U[u] - fs) > 0.0) ? 1.0 : 0.0;
+            } else {
+              val_l += fmax(U[u] - fs, 0.0);                              // uEI_noiseless.py:80,161
+              if (U[u] > fs) mask |= (1u << k);                           // :162 strict >
+            }
           }
         }
       }
