@@ -394,6 +394,28 @@ int bocf_model_factorize(bocf_model* M, double* jitter_out, void* stream) {
   return 0;
 }
 
+int bocf_model_log_likelihood(bocf_model* M, double* lml, double* g_variance, double* g_lengthscale, double* g_noise,
+                              void* stream) {
+  if (int rc = check_ready(M)) return rc;
+  if (!lml) {
+    set_error("bocf_model_log_likelihood: lml must not be NULL");
+    return BOCF_ERR_INVALID;
+  }
+  DeviceGuard dg(M->device);
+  const int Hm = M->H * M->m;
+  std::vector<double> buf((size_t)Hm * (MAXD + 3));
+  if (int rc = launch_log_likelihood(M, buf.data(), static_cast<cudaStream_t>(stream))) return rc;
+  for (int hj = 0; hj < Hm; ++hj) {
+    const double* o = buf.data() + (size_t)hj * (MAXD + 3);
+    lml[hj] = o[0];
+    if (g_variance) g_variance[hj] = o[1];
+    if (g_noise) g_noise[hj] = o[2];
+    if (g_lengthscale)
+      for (int q = 0; q < M->d; ++q) g_lengthscale[(size_t)hj * M->d + q] = o[3 + q];
+  }
+  return 0;
+}
+
 int bocf_model_get_factor(bocf_model* M, int h, int j, double* L, double* Linv, double* alpha, void* stream) {
   if (int rc = check_ready(M)) return rc;
   if (h < 0 || h >= M->H || j < 0 || j >= M->m) {

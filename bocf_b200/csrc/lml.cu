@@ -1,0 +1,212 @@
+// lml.cu -- log marginal likelihood of every (hyper-sample, output) GP and its gradient with respect to the kernel
+// variance, the ARD lengthscales and the Gaussian noise variance, on device in fp64 (the
+// objective / gradient pair that ML-II and HMC evaluate thousands of times per BO iteration).
+//
+//   log p(y)  = -1/2 (n log 2pi + log|Ky| + (y-ybar)^T alpha)          exact_gaussian_inference.py:53
+//   dL_dK     =  1/2 (alpha alpha^T - Ky^-1)                            exact_gaussian_inference.py:61
+//   d/d var   =  sum K o dL_dK / var                                    stationary.py:197, se.py:181
+//   d/d l_q   = -sum dL_dK (dK/dr / r) (x_aq - x_bq)^2 / l_q^3          stationary.py:203-240 + stationary_utils.c:34-48,
+//                                                                       se.py:183 (same expression with dK/dr / r = -K)
+//   d/d noise =  tr dL_dK                                               gaussian.py:64-71
+//
+// Ky^-1 = Linv^T Linv is never stored: one CTA per 128 x 128 tile of the lower triangle contracts the two column
+// blocks of Linv on the fp64 tensor-core tile engine (k >= the tile's row block only -- Linv is lower triangular) and
+// reduces its tile of dL_dK against K, dK/dr/r and the squared coordinate differences in the epilogue.  Tiles are
+// summed in a fixed order by a second kernel (no atomics: results are reproducible bit for bit).
+#include "gemm_f64.cuh"
+#include "kernfn.cuh"
+#include "model.h"
+
+namespace bocf {
+
+using LT = gemm::Tile128;
+
+template <int KIND>
+__global__ void __launch_bounds__(LT::NTHREADS, 1) lml_tile_kernel(const double* __restrict__ LinvAll,
+                                                                    const double* __restrict__ alphaAll,
+                                                                    const double* __restrict__ XsAll,
+                                                                    const double* __restrict__ xsqAll,
+                                                                    const OutHyp* __restrict__ hyp, int n, int n_pad, int d,
+                                                                    int ntiles, double* __restrict__ part) {
+  extern __shared__ __align__(16) double smem[];
+  const int hj = blockIdx.y;
+  int p = blockIdx.x;                                   // lower-triangular tile pair (I >= J)
+  int I = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+  while ((I + 1) * (I + 2) / 2 <= p) ++I;
+  while (I * (I + 1) / 2 > p) --I;
+  const int J = p - I * (I + 1) / 2;
+  const double* Linv = LinvAll + (int64_t)hj * n_pad * n_pad;
+  // Wi[a][b] = sum_k Linv[k][a] Linv[k][b]:  A(m = a, k) = Linv[k*ld + a], B(k, n = b) = Linv[k*ld + b]
+  double acc[8][4][2];
+  gemm::zero_acc(acc);
+  gemm::mainloop<LT, true, true>(acc, Linv + I * TILE, n_pad, Linv + J * TILE, n_pad, I * TILE, n_pad, smem);
+
+  // stage the scaled inputs / alpha of both blocks (the pipeline buffers are free now)
+  double* sxa = smem;                         // TILE x d
+  double* sxb = sxa + TILE * MAXD;            // TILE x d
+  double* sal = sxb + TILE * MAXD;            // 2 x TILE alpha
+  double* ssq = sal + 2 * TILE;               // 2 x TILE |xs|^2
+  double* red = ssq + 2 * TILE;               // warps x (MAXD + 2)
+  const int tid = threadIdx.x;
+  const double* Xs = XsAll + (int64_t)hj * n_pad * d;
+  for (int idx = tid; idx < TILE * d; idx += LT::NTHREADS) {
+    const int r = idx / d, q = idx - r * d;
+    sxa[r * MAXD + q] = Xs[(int64_t)(I * TILE + r) * d + q];
+    sxb[r * MAXD + q] = Xs[(int64_t)(J * TILE + r) * d + q];
+  }
+  for (int r = tid; r < TILE; r += LT::NTHREADS) {
+    sal[r] = alphaAll[(int64_t)hj * n_pad + I * TILE + r];
+    sal[TILE + r] = alphaAll[(int64_t)hj * n_pad + J * TILE + r];
+    ssq[r] = xsqAll[(int64_t)hj * n_pad + I * TILE + r];
+    ssq[TILE + r] = xsqAll[(int64_t)hj * n_pad + J * TILE + r];
+  }
+  __syncthreads();
+
+  const OutHyp& hp = hyp[hj];
+  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int mbase = (warp >> 2) * 64, nbase = (warp & 3) * 32;
+  double gvar = 0.0, gnoise = 0.0, gl[MAXD];
+#pragma unroll
+  for (int q = 0; q < MAXD; ++q) gl[q] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = mbase + 8 * i + g, c = nbase + 8 * jn + 2 * t + e;
+        const int a = I * TILE + r, b = J * TILE + c;
+        if (a >= n || b >= n || b > a) continue;                 // lower triangle of the n x n problem only
+        const double w = (a == b) ? 1.0 : 2.0;                   // symmetric: count (a,b) and (b,a)
+        const double dLdK = 0.5 * (sal[r] * sal[TILE + c] - acc[i][jn][e]);
+        double r2;
+        if (KIND == BOCF_KERN_SE) {
+          r2 = 0.0;
+          for (int q = 0; q < d; ++q) {
+            const double df = sxa[r * MAXD + q] - sxb[c * MAXD + q];
+            r2 += df * df;
+          }
+        } else {
+          double dot = 0.0;
+          for (int q = 0; q < d; ++q) dot += sxa[r * MAXD + q] * sxb[c * MAXD + q];
+          r2 = -2.0 * dot + (ssq[r] + ssq[TILE + c]);
+          r2 = fmax(r2, 0.0);
+        }
+        if (a == b) r2 = 0.0;                                    // stationary.py:136, se.py:58
+        double kv, gv;
+        kern_eval<KIND, true>(r2, hp.variance, kv, gv);
+        gvar += w * dLdK * kv;
+        if (a == b) gnoise += dLdK;
+        const double wg = w * dLdK * gv;
+        for (int q = 0; q < d; ++q) {
+          const double df = sxa[r * MAXD + q] - sxb[c * MAXD + q];
+          gl[q] += wg * df * df;
+        }
+      }
+  // block reduction of d + 2 values
+  gvar = warp_sum(gvar);
+  gnoise = warp_sum(gnoise);
+  for (int q = 0; q < d; ++q) gl[q] = warp_sum(gl[q]);
+  __syncthreads();
+  if (lane == 0) {
+    red[warp * (MAXD + 2) + 0] = gvar;
+    red[warp * (MAXD + 2) + 1] = gnoise;
+    for (int q = 0; q < d; ++q) red[warp * (MAXD + 2) + 2 + q] = gl[q];
+  }
+  __syncthreads();
+  if (tid < d + 2) {
+    double s = 0.0;
+    for (int w8 = 0; w8 < LT::NTHREADS / 32; ++w8) s += red[w8 * (MAXD + 2) + tid];
+    part[((int64_t)hj * ntiles + p) * (MAXD + 2) + tid] = s;
+  }
+}
+
+// sums the tile partials in order, applies the 1/var and -1/l scalings, and forms log p(y)
+__global__ void lml_finish_kernel(const double* __restrict__ part, const double* __restrict__ Lmat,
+                                  const double* __restrict__ alphaAll, const double* __restrict__ yc,
+                                  const OutHyp* __restrict__ hyp, int n, int n_pad, int d, int m, int ntiles,
+                                  double* __restrict__ out) {
+  __shared__ double s_ld[32], s_fit[32];
+  const int hj = blockIdx.x, j = hj % m;
+  const int tid = threadIdx.x;
+  double ld = 0.0, fit = 0.0;
+  const double* L = Lmat + (int64_t)hj * n_pad * n_pad;
+  for (int a = tid; a < n; a += blockDim.x) {
+    ld += log(L[(int64_t)a * n_pad + a]);
+    fit += alphaAll[(int64_t)hj * n_pad + a] * yc[(int64_t)j * n_pad + a];
+  }
+  ld = warp_sum(ld);
+  fit = warp_sum(fit);
+  if ((tid & 31) == 0) {
+    s_ld[tid >> 5] = ld;
+    s_fit[tid >> 5] = fit;
+  }
+  __syncthreads();
+  const OutHyp& hp = hyp[hj];
+  double* o = out + (int64_t)hj * (MAXD + 3);          // [lml, g_var, g_noise, g_len[0..d)]
+  if (tid == 0) {
+    double lds = 0.0, fits = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      lds += s_ld[w];
+      fits += s_fit[w];
+    }
+    o[0] = 0.5 * (-(double)n * 1.8378770664093453 - 2.0 * lds - fits);     // log(2 pi)
+  }
+  if (tid < d + 2) {
+    double s = 0.0;
+    for (int p = 0; p < ntiles; ++p) s += part[((int64_t)hj * ntiles + p) * (MAXD + 2) + tid];
+    if (tid == 0) o[1] = s / hp.variance;
+    else if (tid == 1) o[2] = s;
+    else o[3 + (tid - 2)] = -s / hp.ls[tid - 2];
+  }
+}
+
+template <int KIND>
+static int launch_tiles(bocf_model* M, int ntiles, double* part, cudaStream_t st) {
+  static bool done = false;
+  if (!done) {
+    BOCF_CUDA_OK(cudaFuncSetAttribute(lml_tile_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::SMEM_BYTES));
+    done = true;
+  }
+  lml_tile_kernel<KIND><<<dim3((unsigned)ntiles, (unsigned)(M->H * M->m)), LT::NTHREADS, LT::SMEM_BYTES, st>>>(
+      M->Linv, M->alpha, M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, ntiles, part);
+  BOCF_LAUNCH_OK("lml_tile_kernel");
+  return 0;
+}
+
+// out_host: H*m x (MAXD + 3) doubles [lml, d/dvariance, d/dnoise, d/dlengthscale[0..d)]
+int launch_log_likelihood(bocf_model* M, double* out_host, cudaStream_t st) {
+  static_assert(2 * TILE * MAXD + 4 * TILE + 8 * (MAXD + 2) <= LT::SMEM_BYTES / (int)sizeof(double), "epilogue staging fits");
+  const int Hm = M->H * M->m;
+  const int ntiles = M->nb * (M->nb + 1) / 2;
+  double *part = nullptr, *out = nullptr;
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&part), sizeof(double) * Hm * ntiles * (MAXD + 2)));
+  if (cudaMalloc(reinterpret_cast<void**>(&out), sizeof(double) * Hm * (MAXD + 3)) != cudaSuccess) {
+    cudaFree(part);
+    set_error("bocf_model_log_likelihood: out of device memory");
+    return BOCF_ERR_CUDA;
+  }
+  int rc = 0;
+  switch (M->kernel) {
+    case BOCF_KERN_SE: rc = launch_tiles<BOCF_KERN_SE>(M, ntiles, part, st); break;
+    case BOCF_KERN_RBF: rc = launch_tiles<BOCF_KERN_RBF>(M, ntiles, part, st); break;
+    case BOCF_KERN_MATERN52: rc = launch_tiles<BOCF_KERN_MATERN52>(M, ntiles, part, st); break;
+    default: rc = launch_tiles<BOCF_KERN_MATERN32>(M, ntiles, part, st); break;
+  }
+  if (!rc) {
+    lml_finish_kernel<<<Hm, 256, 0, st>>>(part, M->Lmat, M->alpha, M->yc, M->hyp, M->n, M->n_pad, M->d, M->m, ntiles, out);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, out, sizeof(double) * Hm * (MAXD + 3), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      set_error(std::string("bocf_model_log_likelihood: ") + cudaGetErrorString(e));
+      rc = BOCF_ERR_CUDA;
+    }
+  }
+  cudaFree(part);
+  cudaFree(out);
+  return rc;
+}
+
+}  // namespace bocf

@@ -73,6 +73,10 @@ int launch_cholesky(bocf_model* M, cudaStream_t st);                      // blo
 int launch_inverse_and_alpha(bocf_model* M, cudaStream_t st);             // Linv, alpha
 int launch_copy_factor(bocf_model* M, int hj, double* L, double* Linv, double* alpha, cudaStream_t st);
 
+// ---- lml.cu -------------------------------------------------------------------------------------
+// out_host: H*m x (MAXD + 3) doubles [log p(y), d/dvariance, d/dnoise, d/dlengthscale[0..d)]
+int launch_log_likelihood(bocf_model* M, double* out_host, cudaStream_t st);
+
 // ---- posterior.cu -------------------------------------------------------------------------------
 struct ChunkBuffers {          // scratch views for one candidate chunk (Nc rows, multiple of 128)
   int64_t Nc;

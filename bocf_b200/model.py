@@ -247,6 +247,81 @@ class multi_outputGP(object):
     def posterior_variance_gradient(self, X):
         return self._posterior(X, want_dvar=True)[3]
 
+    # ---- marginal likelihood ---------------------------------------------------
+    def log_likelihood_and_gradients(self):
+        """log p(y) of every (hyper-sample, output) GP and its gradient w.r.t. variance, lengthscales and noise.
+
+        Returns (lml (H,m), g_variance (H,m), g_lengthscale (H,m,d), g_noise (H,m)): what GP.log_likelihood() and the
+        .gradient attributes hold after GP.parameters_changed (gp.py:247-266) for each of the reference's model
+        instances.  One fused device pass (bocf_model_log_likelihood)."""
+        if self._handle is None:
+            raise RuntimeError("model has no data: call updateModel first")
+        H, m, d = self.n_hyper_samples_loaded(), self.output_dim, self.input_dim
+        lml = np.empty((H, m))
+        gv = np.empty((H, m))
+        gl = np.empty((H, m, d))
+        gn = np.empty((H, m))
+        with torch.cuda.device(self.device):
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(self._lib.bocf_model_log_likelihood(
+                self._handle, lml.ctypes.data_as(ctypes.c_void_p), gv.ctypes.data_as(ctypes.c_void_p),
+                gl.ctypes.data_as(ctypes.c_void_p), gn.ctypes.data_as(ctypes.c_void_p), st))
+        return lml, gv, gl, gn
+
+    def log_likelihood(self):
+        return self.log_likelihood_and_gradients()[0]
+
+    def fit_hyperparameters(self, max_iters=200, fit_noise=True, bounds=(1e-6, 1e6), verbose=False):
+        """ML-II: maximise sum_j log p(y_j) over (variance, lengthscales[, noise]) of every output, all outputs in ONE
+        L-BFGS-B run whose objective and gradient are a single device pass per iteration (Gram, Cholesky, L^-1, alpha,
+        likelihood, gradients for all m outputs at once).  Optimises in log space (the positivity constraint of the
+        reference's Logexp transform, gpmodel.py:84-100); keeps H = 1.  This is the deterministic part of
+        GPModel.updateModel (gpmodel.py:117: model.optimize(max_iters=200)); the HMC sampling around it is out of scope.
+        Returns the final (H = 1) log likelihoods (m,)."""
+        import scipy.optimize
+        if self.X is None:
+            raise RuntimeError("model has no data: call updateModel first")
+        kind, variance, lengthscale, noise = self._hyp
+        m, d = self.output_dim, self.input_dim
+        if lengthscale.shape[2] != d:
+            lengthscale = np.ascontiguousarray(np.broadcast_to(lengthscale, lengthscale.shape[:2] + (d,)))
+        v0, l0, n0 = variance[:1].copy(), lengthscale[:1].copy(), np.maximum(noise[:1].copy(), bounds[0])
+        npar = (d + 2) if fit_noise else (d + 1)
+
+        def unpack(theta):
+            th = np.exp(theta.reshape(m, npar))
+            var = th[:, 0][None, :]
+            ls = th[:, 1:1 + d][None, :, :]
+            nz = th[:, 1 + d][None, :] if fit_noise else n0
+            return np.ascontiguousarray(var), np.ascontiguousarray(ls), np.ascontiguousarray(nz)
+
+        def f_df(theta):
+            var, ls, nz = unpack(theta)
+            self._hyp = (kind, var, ls, nz)
+            self._explicit_hyp = True
+            try:
+                self._upload_and_factorize()
+            except _lib.NotPositiveDefiniteError:
+                return 1e25, np.zeros_like(theta)
+            lml, gv, gl, gn = self.log_likelihood_and_gradients()
+            g = np.zeros((m, npar))
+            g[:, 0] = gv[0] * var[0]                       # d/d log(theta) = theta * d/d theta
+            g[:, 1:1 + d] = gl[0] * ls[0]
+            if fit_noise:
+                g[:, 1 + d] = gn[0] * nz[0]
+            if verbose:
+                print("fit_hyperparameters: log p(y) = %.6f" % lml.sum())
+            return -float(lml.sum()), -g.reshape(-1)
+
+        cols = [np.log(v0[0])[:, None], np.log(l0[0])]
+        if fit_noise:
+            cols.append(np.log(n0[0])[:, None])
+        theta0 = np.concatenate(cols, axis=1).reshape(-1)
+        lo, hi = np.log(bounds[0]), np.log(bounds[1])
+        res = scipy.optimize.fmin_l_bfgs_b(f_df, theta0, bounds=[(lo, hi)] * theta0.size, maxiter=max_iters)
+        f_df(res[0])                                       # leave the model factorised at the optimum
+        return self.log_likelihood()[0]
+
     # ---- inspection (tests) ---------------------------------------------------------------------------
     def get_factor(self, h, j):
         """(L, Linv, alpha) of output j under hyper-sample h as numpy arrays."""

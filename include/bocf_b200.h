@@ -99,6 +99,15 @@ int bocf_model_set_hypers(bocf_model* mdl, int H, const double* variance, const 
  * jitter jitchol had to add (0 if none).  Synchronises the stream (needs the device info flag). */
 int bocf_model_factorize(bocf_model* mdl, double* jitter_out, void* stream);
 
+/* Log marginal likelihood of every (h, j) GP and its gradient w.r.t. the kernel variance, the ARD lengthscales and the
+ * noise variance -- the objective / gradient pair of GPModel.updateModel's ML-II + HMC (gpmodel.py:117-119).  Replaces
+ * ExactGaussianInference.inference's log_marginal and dL_dK (exact_gaussian_inference.py:53-63), Stationary /
+ * SE.update_gradients_full (stationary.py:191-215, se.py:169-185, stationary_utils.c:34-48) and Gaussian.update_gradients
+ * (gaussian.py:64-71).  All outputs [host]: lml H x m, g_variance H x m, g_lengthscale H x m x d, g_noise H x m
+ * (gradient pointers may be NULL).  Synchronises the stream. */
+int bocf_model_log_likelihood(bocf_model* mdl, double* lml, double* g_variance, double* g_lengthscale,
+                              double* g_noise, void* stream);
+
 /* Copy one factor out for inspection (tests): L, Linv n x n row-major, alpha n, [dev] or NULL. */
 int bocf_model_get_factor(bocf_model* mdl, int h, int j, double* L, double* Linv, double* alpha,
                           void* stream);

@@ -36,6 +36,23 @@ class GPRegression(object):
         self.woodbury_vector = alpha
         self._woodbury_inv = None
         self.K_train = K
+        # exact_gaussian_inference.py:53-63 (single-output Y: Y.size = n, Y.shape[1] = 1)
+        n = self.Y_normalized.shape[0]
+        self._log_marginal_likelihood = 0.5 * (-n * np.log(2. * np.pi) - self.Y_normalized.shape[1] * W_logdet
+                                               - np.sum(alpha * self.Y_normalized))
+        self._dL_dK = 0.5 * (np.dot(alpha, alpha.T) - self.Y_normalized.shape[1] * Wi)
+
+    # gp.py:262-266
+    def log_likelihood(self):
+        return float(self._log_marginal_likelihood)
+
+    def likelihood_gradients(self):
+        """d log p(y) / d (kernel variance, lengthscales, Gaussian noise variance): what GP.parameters_changed leaves
+        in kern.variance.gradient, kern.lengthscale.gradient and likelihood.variance.gradient (gp.py:256-258,
+        gaussian.py:64-71: the noise gradient is the trace of dL_dK)."""
+        g_var, g_len = self.kern.update_gradients_full(self._dL_dK, self.X)
+        g_noise = float(np.diag(self._dL_dK).sum())
+        return g_var, g_len, g_noise
 
     @property
     def woodbury_inv(self):

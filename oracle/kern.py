@@ -127,6 +127,29 @@ class Kern(object):
         r = self._scaled_dist(X, X2)
         return self.K_of_r(r)
 
+    # ---- hyper-parameter gradients --------------------
+    def update_gradients_full(self, dL_dK, X):
+        """(d/d variance, d/d lengthscale) of an objective with derivative dL_dK wrt K(X, X).
+
+        Stationary kinds: stationary.py:191-215 with the native loop of stationary_utils.c:34-48
+        (_lengthscale_grads); SE: se.py:169-185 (X2 is None branch).  ARD only (the fork's models are ARD)."""
+        assert self.ARD
+        if self.kind == 'se':
+            squared_dist = self._se_scaled_squared_dist(X)
+            exp_squared_dist = np.exp(-0.5 * squared_dist)
+            tmp = scipy.spatial.distance.squareform(exp_squared_dist, checks=False)
+            np.fill_diagonal(tmp, 1.)
+            g_var = np.sum(tmp * dL_dK)                                                  # se.py:181
+            g_len = (self.variance * np.sum((tmp * dL_dK)[:, :, None] *
+                                            np.square(X[:, None, :] - X[None, :, :]), axis=(0, 1))) / (self.lengthscale**3)
+            return float(g_var), np.asarray(g_len, dtype=float)
+        g_var = np.sum(self.K(X) * dL_dK) / self.variance                               # stationary.py:197
+        r = self._scaled_dist(X)
+        dL_dr = self.dK_dr(r) * dL_dK                                                    # :203 (dK_dr_via_X)
+        tmp = dL_dr * self._inv_dist(X)                                                  # :206
+        grads = np.array([np.sum(tmp * np.square(X[:, q:q + 1] - X[:, q:q + 1].T)) for q in range(self.input_dim)])
+        return float(np.asarray(g_var).reshape(-1)[0]), -grads / self.lengthscale**3    # :232-240
+
     def Kdiag(self, X):
         # stationary.py:168-171 / se.py:102-111
         ret = np.empty(X.shape[0])
