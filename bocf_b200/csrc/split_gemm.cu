@@ -665,14 +665,14 @@ static int row_exps(const double* src, int64_t mat_stride, int64_t sr, int64_t s
 template <int S, int NT, int EPI, int DP, int CG>
 static int launch_cg(const GemmParams& P, cudaStream_t st) {
   using C = Cfg<S, NT, DP, CG>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    BOCF_CUDA_OK(cudaFuncSetAttribute(split_gemm_kernel<S, NT, EPI, DP, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      C::SMEM_BYTES));
-    attr_done = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
+  static bool attr_done[64] = {false};          // per device: function attributes belong to the device's context
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    BOCF_CUDA_OK(cudaFuncSetAttribute(split_gemm_kernel<S, NT, EPI, DP, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      C::SMEM_BYTES));
+    attr_done[dev] = true;
+  }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int units = P.m * (P.RT / CG) * P.np;     // scheduling entities (CTAs, or CTA pairs)
   if (const char* env = std::getenv("BOCF_SPLIT_GRID")) {          // experiment knob: persistent CTAs launched
