@@ -35,7 +35,8 @@ struct SplitOut {
   int KCH, S;
 };
 
-template <int KIND, int DP, bool GRAD, bool SPLIT>
+// SPL: 0 = fp64 K* output; 5 = exactly five digit planes (the common case, fewer registers); 6 = up to six (so.S)
+template <int KIND, int DP, bool GRAD, int SPL>
 __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ Xc, int64_t Nvalid, int64_t Nc, int d,
                                                     int n, int n16, int n_pad, int m, int h,
                                                     const OutHyp* __restrict__ hyp, const double* __restrict__ XsAll,
@@ -70,13 +71,14 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
   const double* Xs = XsAll + (int64_t)hj * n_pad * d;
   const double* xsq = xsqAll + (int64_t)hj * n_pad;
   const double* alpha = alphaAll + (int64_t)hj * n_pad;
+  constexpr bool SPLIT = SPL > 0;
   double* Kout = SPLIT ? nullptr : KsT + (int64_t)j * n16 * Nc;
   double* Gout = GRAD ? GsT + (int64_t)j * n16 * Nc : nullptr;
   // split mode: digit planes of this block's 128 candidates (row = tid) for output j
-  constexpr int MAXS = 6;
-  uint32_t dv[SPLIT ? MAXS : 1][4];
+  constexpr int MAXS = SPLIT ? SPL : 1;
+  uint32_t dv[MAXS][4];
   const double aq = SPLIT ? so.aq[hj] : 0.0;
-  const unsigned long long dbias = SPLIT ? (0x808080808080ull >> (8 * (MAXS - so.S))) : 0ull;
+  const unsigned long long dbias = SPLIT ? (0x808080808080ull >> (8 * (6 - so.S))) : 0ull;
   uint8_t* Aout = SPLIT ? so.A1 + ((size_t)((size_t)j * gridDim.x + blockIdx.x) * so.KCH) * so.S * (128 * 64) : nullptr;
   const uint32_t swz = (uint32_t)((tid >> 1) & 3);
 
@@ -427,14 +429,16 @@ static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid
   so.aq = M->aq;
   so.KCH = M->KCH;
   so.S = M->S;
-  const bool split = (cb.A1 != nullptr);
+  const int spl = (cb.A1 == nullptr) ? 0 : (M->S == 5 ? 5 : 6);
 #define BOCF_KSTAR(G, SP)                                                                                              \
   kstar_kernel<KIND, DP, G, SP><<<grid, 128, 0, st>>>(Xc, Nvalid, cb.Nc, M->d, M->n, M->n16, M->n_pad, M->m, h, M->hyp, \
                                                       M->Xs, M->xsq, M->alpha, cb.KsT, cb.GsT, cb.mean, cb.dmean, so)
-  if (grad && split) BOCF_KSTAR(true, true);
-  else if (grad) BOCF_KSTAR(true, false);
-  else if (split) BOCF_KSTAR(false, true);
-  else BOCF_KSTAR(false, false);
+  if (grad && spl == 5) BOCF_KSTAR(true, 5);
+  else if (grad && spl == 6) BOCF_KSTAR(true, 6);
+  else if (grad) BOCF_KSTAR(true, 0);
+  else if (spl == 5) BOCF_KSTAR(false, 5);
+  else if (spl == 6) BOCF_KSTAR(false, 6);
+  else BOCF_KSTAR(false, 0);
 #undef BOCF_KSTAR
   BOCF_LAUNCH_OK("kstar_kernel");
   return 0;
