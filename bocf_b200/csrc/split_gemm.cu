@@ -131,6 +131,7 @@ inline int parts_per_tile() {
 
 struct TileInfo {
   int j, rt, p, ct, kb, ke;
+  int sb, se;                   // first / one-past-last 32-byte K STEP that touches the triangle (MMA issue range)
   bool valid, first, last;      // first / last column tile of the unit
 };
 
@@ -164,12 +165,18 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& P, int NT, int
   if (P.tri == TRI_K_LE_N) {                              // K index <= column index
     ti.kb = 0;
     ti.ke = min(kch_used, (min((ti.ct + 1) * NT, P.n) + KC - 1) / KC);
+    ti.sb = 0;
+    ti.se = min(ti.ke * (KC / 32), (min((ti.ct + 1) * NT, P.n) + 31) / 32);
   } else if (P.tri == TRI_K_GE_N) {                       // K index >= column index
     ti.kb = (ti.ct * NT) / KC;
     ti.ke = kch_used;
+    ti.sb = (ti.ct * NT) / 32;
+    ti.se = ti.ke * (KC / 32);
   } else {
     ti.kb = 0;
     ti.ke = kch_used;
+    ti.sb = 0;
+    ti.se = ti.ke * (KC / 32);
   }
   return ti;
 }
@@ -317,6 +324,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
           const uint32_t b0 = tc::smem_u32(sB + stage * C::B_STAGE);
 #pragma unroll
           for (int ks = 0; ks < KC / 32; ++ks) {
+            const int kstep = kc * (KC / 32) + ks;            // K steps wholly outside the triangle multiply zeros: skip
+            if (kstep < ti.sb || kstep >= ti.se) continue;
 #pragma unroll
             for (int ta = S - 1; ta >= 0; --ta) {
               // A digit plane ta against the stacked B planes tb = S-1-ta .. S-1  ->  levels 0 .. ta
