@@ -152,3 +152,19 @@ def test_cta_pair_variant_is_exact_too(cuda_device, monkeypatch):
     v, v_o = pm.posterior_variance(P.Xc), om.posterior_variance(P.Xc)
     assert np.max(np.abs(v - v_o) / np.abs(v_o)) < 1e-6
     assert rel_err(pm.posterior_variance_gradient(P.Xc), om.posterior_variance_gradient(P.Xc)) < 1e-6
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern52"])
+@pytest.mark.parametrize("noise", [1e-1, 1e-2, 1e-3, 1e-4, 1e-6])
+def test_auto_precision_holds_the_fp64_bar_across_conditioning(cuda_device, kind, noise):
+    # whatever AUTO picks (4, 5 or 6 digit planes, or the fp64 engine when L^-1 is too large for six planes), the
+    # variance must stay within the north-star fp64 bar of the oracle, element-wise
+    P = make_problem(m=2, d=4, n=220, H=1, kind=kind, N=512, S=4, noise=noise, seed=int(-np.log10(noise)))
+    om = oracle_model(P)
+    pm = product_model(P, cuda_device, precision="auto")
+    v, v_o = pm.posterior_variance(P.Xc), om.posterior_variance(P.Xc)
+    assert np.max(np.abs(v - v_o) / np.abs(v_o)) < 1e-6, (pm.active_slices(), noise)
+    dv, dv_o = pm.posterior_variance_gradient(P.Xc), om.posterior_variance_gradient(P.Xc)
+    assert rel_err(dv, dv_o) < 1e-6, (pm.active_slices(), noise)
+    if noise >= 1e-2:
+        assert pm.active_slices() in (4, 5)          # well conditioned: the tensor-core path is the one that runs
