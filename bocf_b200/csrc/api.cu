@@ -131,6 +131,13 @@ static int apply_precision(bocf_model* M, cudaStream_t st) {
   return split_prepare(M, S, st);
 }
 
+static int resolve_precision(bocf_model* M, cudaStream_t st) {
+  if (M->precision_resolved) return 0;
+  if (int rc = apply_precision(M, st)) return rc;
+  M->precision_resolved = true;
+  return 0;
+}
+
 static int check_ready(const bocf_model* M) {
   if (!M) {
     set_error("null model handle");
@@ -235,12 +242,20 @@ int bocf_model_set_precision(bocf_model* M, int mode, int slices, void* stream) 
   }
   M->precision = mode;
   if (mode == BOCF_PREC_SPLIT_I8) M->slices_req = slices;
+  M->precision_resolved = false;
   if (!M->factorized) return 0;
   DeviceGuard dg(M->device);
-  return apply_precision(M, static_cast<cudaStream_t>(stream));
+  return resolve_precision(M, static_cast<cudaStream_t>(stream));
 }
 
-int bocf_model_active_slices(const bocf_model* M) { return M ? M->S : -1; }
+int bocf_model_active_slices(bocf_model* M) {
+  if (!M) return -1;
+  if (M->factorized && !M->precision_resolved) {
+    DeviceGuard dg(M->device);
+    if (resolve_precision(M, nullptr)) return -1;
+  }
+  return M->S;
+}
 
 int bocf_debug_split_gemm(const double* A, const double* B, int R, int N, int K, int slices, int tri, double* out,
                           void* stream) {
@@ -388,8 +403,10 @@ int bocf_model_factorize(bocf_model* M, double* jitter_out, void* stream) {
   BOCF_CUDA_OK(cudaStreamSynchronize(st));
   if (jitter_out)
     for (int hj = 0; hj < Hm; ++hj) jitter_out[hj] = M->hyp_host[hj].jitter;
-  M->split_ready = false;                  // the digit planes belong to the previous factor
-  if (int rc = apply_precision(M, st)) return rc;
+  // the digit planes belong to the previous factor: rebuilt lazily by the first posterior / acquisition call, so
+  // likelihood-only users (ML-II, HMC: hundreds of factorisations per fit) never pay for them
+  M->split_ready = false;
+  M->precision_resolved = false;
   M->factorized = true;
   return 0;
 }
@@ -445,6 +462,7 @@ int bocf_posterior(bocf_model* M, int h, const double* Xc, int64_t N, int noisel
   if (N == 0) return 0;
   DeviceGuard dg(M->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = resolve_precision(M, st)) return rc;
   const bool grad = (dvar != nullptr) || (dmean != nullptr);
   const int64_t Nc = pick_chunk(M, N, grad, 0);
   if (int rc = ensure_scratch(M, chunk_bytes_per_candidate(M, grad) * Nc + (1 << 16))) return rc;
@@ -495,6 +513,7 @@ int bocf_acq_eval(bocf_model* M, int variant, int composite, const double* Xc, i
   if (N == 0) return 0;
   DeviceGuard dg(M->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = resolve_precision(M, st)) return rc;
   const bool grad = (dacq != nullptr);
 
   // small host-side parameters -> tail of the scratch buffer

@@ -62,6 +62,7 @@ struct bocf_model {
   double* aq = nullptr;       // H*m   2^(8S-2-eA): quantiser of K*   (K* <= sigma_f^2)
   double* vq = nullptr;       // H*m   2^(8S-2-eV): quantiser of V    (|V| <= sigma_f)
   bool split_ready = false;
+  bool precision_resolved = false;   // M->S and the digit planes match the current factor and requested mode
 };
 
 namespace bocf {

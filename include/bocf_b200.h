@@ -116,9 +116,10 @@ int bocf_model_H(const bocf_model* mdl);
 
 /* Select the contraction arithmetic (enum bocf_precision).  May be called before or after bocf_model_factorize; the
  * digit planes of L^-1 are (re)built when needed.  The environment variable BOCF_PRECISION (fp64 | auto | split3..6)
- * sets the initial mode of new handles.  bocf_model_active_slices: digit planes in use (0 = fp64 DMMA). */
+ * sets the initial mode of new handles.  The planes are built lazily by the first posterior / acquisition call after a
+ * factorisation (likelihood-only callers never pay for them).  bocf_model_active_slices: digit planes in use (0 = fp64). */
 int bocf_model_set_precision(bocf_model* mdl, int mode, int slices, void* stream);
-int bocf_model_active_slices(const bocf_model* mdl);
+int bocf_model_active_slices(bocf_model* mdl);
 
 /* Test hook of the split-integer tensor-core GEMM: out (R x N) = A (R x K) * B (N x K)^T, all [dev] fp64 row-major,
  * through the same digit-plane packing, tcgen05 kernel and Horner epilogue the posterior uses.
