@@ -10,7 +10,7 @@
 // quantisation 2^-(8S-2) (relative to the row scale) -- S = 5 carries 38-bit operands and reproduces the fp64 path
 // to ~1e-8 relative on the variance, S = 4 to ~1e-6 (tests/test_gpu_split.py measures both).
 //
-// Kernel structure (persistent, warp specialised, 192 threads, 1 CTA / SM):
+// Kernel structure (persistent, warp specialised, 320 threads, 1 CTA / SM):
 //   warp 0   producer: one lane streams 64-byte-wide K chunks of the packed, pre-swizzled digit planes of A
 //            (128 candidates) and B (NT factor rows) into a STAGES-deep shared-memory ring with bulk async copies
 //            (TMA engine, cp.async.bulk + mbarrier complete_tx).
@@ -18,11 +18,15 @@
 //            whose B operand STACKS the digit planes tb = S-1-ta .. S-1 along N, so every A plane is read from
 //            shared memory once per step while all S(S+1)/2 digit pairs are covered.  Accumulators live in TMEM,
 //            double buffered when 2*S*NT <= 512 columns so the epilogue of tile t overlaps the MMAs of tile t+1.
-//   warps 2-5 epilogue: tcgen05.ld the S int32 levels of a row (lane = candidate), Horner them into one fp64
-//            value, apply the column scale, and fuse the reductions of the reference:
+//   warps 2-9 epilogue (two warps per TMEM lane group, alternating 8-column groups): tcgen05.ld the S int32 levels of
+//            a row (lane = candidate), int32 -> fp64 by a magic-number add (no conversion-pipe instructions), Horner
+//            them into one fp64 value, apply the column scale, and fuse the reductions of the reference:
 //            VAR : sum_k V^2 per candidate (+ re-split V into digit planes = the A operand of the second GEMM)
-//            DVAR: sum_b Wt * G* * (xs_i - Xs_b)  -> per column-tile partial variance gradients.
-// Triangular structure of Linv is exploited per column tile at K-chunk granularity.
+//            DVAR: T = Wt * G*,  sum_b T and sum_b T Xs_b  (finalize_kernel forms xs_i sum T - sum T Xs_b).
+//            The sums live in registers across all column tiles of a work unit (see NP below).
+// Triangular structure of Linv is exploited per column tile: K chunks (64) for the loads, K steps (32) for the MMAs.
+// A cta_group::2 variant (CG = 2: CTA pairs, M = 256) is kept as a tested option; it measured slower on B200
+// (profiles/r1_split_experiments.md).
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
