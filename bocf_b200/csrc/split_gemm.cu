@@ -733,7 +733,9 @@ static int launch_s(int S, const GemmParams& P, cudaStream_t st) {
 }
 static int launch_dvar(int S, int d, const GemmParams& P, cudaStream_t st) {
   if (d <= 4) return launch_s<EPI_DVAR, 4>(S, P, st);
+  if (d <= 6) return launch_s<EPI_DVAR, 6>(S, P, st);
   if (d <= 8) return launch_s<EPI_DVAR, 8>(S, P, st);
+  if (d <= 10) return launch_s<EPI_DVAR, 10>(S, P, st);
   if (d <= 12) return launch_s<EPI_DVAR, 12>(S, P, st);
   return launch_s<EPI_DVAR, 16>(S, P, st);
 }
