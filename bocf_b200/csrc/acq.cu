@@ -83,6 +83,7 @@ __device__ __forceinline__ double comp_dphi(const CompCtx& c, double y) {
 
 // ---------------------------------------------------------------------------------------------------
 constexpr int MC_WARPS = 8;
+constexpr int MCU = 4;         // sample groups per trip (independent base-sample loads in flight per lane)
 
 // MODE: 0 = EI value only, 1 = EI value + gradient, 2 = PI value
 template <int COMP, int MODE>
@@ -112,23 +113,25 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
     double val_l = 0.0;
     for (int sb = 0; sb < S; sb += 1024) {
       unsigned mask = 0u;
-      // four sample groups per trip: their 4 x m base-sample loads are independent and issued together (the kernel
+      // MCU sample groups per trip: their MCU x m base-sample loads are independent and issued together (the kernel
       // was latency bound on one dependent load -> fma chain per sample, ncu: long_scoreboard)
 #pragma unroll 1
-      for (int k0 = 0; k0 < 32; k0 += 4) {
-        double U[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int k0 = 0; k0 < 32; k0 += MCU) {
+        double U[MCU];
+#pragma unroll
+        for (int u = 0; u < MCU; ++u) U[u] = 0.0;
         for (int j = 0; j < m; ++j) {
           const CompCtx c = comp_ctx<COMP>(th, j, m);
           const double muj = s_mu[warp][j], sgj = s_sig[warp][j];
           const double* zr = Zt + (int64_t)j * S + sb + lane;
-          double z[4];
+          double z[MCU];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) z[u] = (sb + (k0 + u) * 32 + lane < S) ? zr[(k0 + u) * 32] : 0.0;
+          for (int u = 0; u < MCU; ++u) z[u] = (sb + (k0 + u) * 32 + lane < S) ? zr[(k0 + u) * 32] : 0.0;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) U[u] += comp_phi<COMP>(c, muj + sgj * z[u]);
+          for (int u = 0; u < MCU; ++u) U[u] += comp_phi<COMP>(c, muj + sgj * z[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < MCU; ++u) {
           const int k = k0 + u;
           if (sb + k * 32 + lane < S) {
             if (MODE == 2) {
