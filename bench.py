@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 CONFIGS = {
     # BASELINE.json configs[2]: the configuration the metric is quoted on
     "cfg3": dict(m=16, d=10, n=1000, kind="matern52", composite="sumsq_target", S=1024, H=1, L=1, N=1000000),
+    # BASELINE.json configs[4] (large-n stress; 4M candidates over 8 GPUs = 500k per GPU -- pass --candidates to scale)
+    "cfg5": dict(m=32, d=10, n=4000, kind="matern52", composite="sumsq_target", S=512, H=1, L=1, N=500000),
     # BASELINE.json configs[1]
     "cfg2": dict(m=4, d=6, n=200, kind="rbf", composite="sumsq_target", S=256, H=1, L=1, N=100000),
 }
@@ -196,9 +198,10 @@ def run_reference(args, cfg):
 
 
 def workload_config(c, n_per_gpu):
-    return {"workload": "BASELINE.json configs[2]: synthetic independent multi-output GP m=%d d=%d n=%d %s-ARD, "
+    return {"workload": "BASELINE.json configs[%d]: synthetic independent multi-output GP m=%d d=%d n=%d %s-ARD, "
                         "%s composite, EI-CF with gradients, %d MC base samples, H=%d, L=%d"
-                        % (c["m"], c["d"], c["n"], c["kind"], c["composite"], c["S"], c["H"], c["L"]),
+                        % ({1000: 2, 200: 1, 4000: 4}.get(c["n"], 2), c["m"], c["d"], c["n"], c["kind"], c["composite"],
+                           c["S"], c["H"], c["L"]),
             "candidates_per_gpu_per_step": int(n_per_gpu), "mc_samples": c["S"], "top_k": K_TOP,
             "l2": "256 MiB flush between steps; per-step K*/V scratch (GiBs) far exceeds the 126 MB L2"}
 
