@@ -336,7 +336,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
               const uint64_t adesc = tc::smem_desc_sw64(a0 + ta * C::A_PLANE + ks * 32);
               const uint64_t bdesc = tc::smem_desc_sw64(b0 + C::b_off(ta) + ks * 32);
               const uint32_t acc = (first && ta == S - 1) ? 0u : 1u;
-              if (P.exp != 1) {
+              if (P.exp == 5 && CG == 1 && C::NBUF * C::ACC_COLS + 8 * S <= C::TMEM_COLS) {
+                // experiment (timing only, results invalid): A operand from spare tensor-memory columns
+                tc::mma_i8_ts(d_tmem, tmem_base + (uint32_t)(C::NBUF * C::ACC_COLS + 8 * ta), bdesc, tc::idesc_i8((ta + 1) * NT), acc);
+              } else if (P.exp != 1) {
                 if (CG == 2) tc::mma_i8_pair(d_tmem, adesc, bdesc, tc::idesc_i8_m256((ta + 1) * NT), acc);
                 else tc::mma_i8(d_tmem, adesc, bdesc, tc::idesc_i8((ta + 1) * NT), acc);
               }
@@ -992,7 +995,12 @@ int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int 
     P.raw_out = tmp;
     P.raw_rs = rs;
     P.ldo = N;
-    if ((rc = sg::launch_s<sg::EPI_RAW>(S, P, st))) break;
+    if (const char* env = std::getenv("BOCF_SPLIT_EXP")) P.exp = std::atoi(env);
+    {
+      ProfScope ps("split_raw_kernel", st);
+      rc = sg::launch_s<sg::EPI_RAW>(S, P, st);
+    }
+    if (rc) break;
     if (cudaMemcpyAsync(out, tmp, sizeof(double) * (size_t)R * N, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) {
       set_error(std::string("split_debug_gemm: ") + cudaGetErrorString(cudaGetLastError()));
