@@ -59,6 +59,27 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// Byte transpose for the digit planes: dg[e] holds the balanced base-256 digits of element e in its bytes 0..S-1;
+// out[t] packs digit t of the four elements (element e in byte e).  Two-stage PRMT butterfly: 8 permutes for digits
+// 0-3 and 3 more per digit above, instead of 4 shift/mask/or operations per byte.
+template <int S>
+__device__ __forceinline__ void digits_transpose4(const unsigned long long (&dg)[4], uint32_t (&out)[S]) {
+  const uint32_t l0 = (uint32_t)dg[0], l1 = (uint32_t)dg[1], l2 = (uint32_t)dg[2], l3 = (uint32_t)dg[3];
+  const uint32_t p0 = __byte_perm(l0, l1, 0x5140), p1 = __byte_perm(l0, l1, 0x7362);
+  const uint32_t q0 = __byte_perm(l2, l3, 0x5140), q1 = __byte_perm(l2, l3, 0x7362);
+  out[0] = __byte_perm(p0, q0, 0x5410);
+  if (S > 1) out[1] = __byte_perm(p0, q0, 0x7632);
+  if (S > 2) out[2] = __byte_perm(p1, q1, 0x5410);
+  if (S > 3) out[3] = __byte_perm(p1, q1, 0x7632);
+  if (S > 4) {
+    const uint32_t h0 = (uint32_t)(dg[0] >> 32), h1 = (uint32_t)(dg[1] >> 32), h2 = (uint32_t)(dg[2] >> 32),
+                   h3 = (uint32_t)(dg[3] >> 32);
+    const uint32_t r0 = __byte_perm(h0, h1, 0x5140), r1 = __byte_perm(h2, h3, 0x5140);
+    out[4] = __byte_perm(r0, r1, 0x5410);
+    if (S > 5) out[5] = __byte_perm(r0, r1, 0x7632);
+  }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

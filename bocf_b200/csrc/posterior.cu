@@ -32,6 +32,8 @@ constexpr int NT = PT::BN;                 // column tile
 struct SplitOut {
   uint8_t* A1;
   const double* aq;    // [H*m] quantiser 2^(8S-2-eA)
+  const double* gcs;   // [H*m][gcs_ld] power-of-two column scale of the second contraction, folded into G* here (exact)
+  int gcs_ld;
   int KCH, S;
 };
 
@@ -47,6 +49,7 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
   __shared__ double sX[128][DP];
   __shared__ double sxsq[128];
   __shared__ double salpha[128];
+  __shared__ double sgcs[128];
   const int tid = threadIdx.x;
   const int j = blockIdx.y;
   const int hj = h * m + j;
@@ -93,6 +96,7 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
       int b = b0 + tid;
       sxsq[tid] = (b < n) ? xsq[b] : 0.0;
       salpha[tid] = (b < n) ? alpha[b] : 0.0;
+      if (SPL > 0) sgcs[tid] = (b < n) ? so.gcs[(size_t)hj * so.gcs_ld + b] : 0.0;
     }
     __syncthreads();
     const int bmax = min(128, n16 - b0);
@@ -100,10 +104,7 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
     // independent chains interleave; padded points b >= n are evaluated like the others and masked at the end
     constexpr int UNR = SPLIT ? 16 : 4;
     for (int bb0 = 0; bb0 < bmax; bb0 += UNR) {
-      if (SPLIT) {
-#pragma unroll
-        for (int t = 0; t < MAXS; ++t) dv[t][0] = dv[t][1] = dv[t][2] = dv[t][3] = 0u;
-      }
+      unsigned long long dg4[4];
 #pragma unroll
       for (int e = 0; e < UNR; ++e) {
         const int bb = bb0 + e;
@@ -144,13 +145,17 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
             for (int q = 0; q < DP; ++q) gm[q] = fma(w, sX[bb][q], gm[q]);
           }
         }
-        if (GRAD) Gout[(int64_t)b * Nc + i] = gv;
+        if (GRAD) Gout[(int64_t)b * Nc + i] = SPLIT ? gv * sgcs[bb] : gv;
         if (!SPLIT) {
           Kout[(int64_t)b * Nc + i] = kv;
         } else {
-          const unsigned long long dg = ((unsigned long long)__double_as_longlong(fma(kv, aq, 6755399441055744.0)) + dbias) ^ dbias;
+          dg4[e & 3] = ((unsigned long long)__double_as_longlong(fma(kv, aq, 6755399441055744.0)) + dbias) ^ dbias;
+          if ((e & 3) == 3) {                                     // byte transpose of four points' digits
+            uint32_t o[MAXS];
+            digits_transpose4<MAXS>(dg4, o);
 #pragma unroll
-          for (int t = 0; t < MAXS; ++t) dv[t][e >> 2] |= (uint32_t)((dg >> (8 * t)) & 0xFFull) << (8 * (e & 3));
+            for (int t = 0; t < MAXS; ++t) dv[t][e >> 2] = o[t];
+          }
         }
       }
       if (SPLIT) {
@@ -427,6 +432,8 @@ static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid
   SplitOut so;
   so.A1 = cb.A1;
   so.aq = M->aq;
+  so.gcs = M->cs2;
+  so.gcs_ld = M->ncts * M->NTs;
   so.KCH = M->KCH;
   so.S = M->S;
   const int spl = (cb.A1 == nullptr) ? 0 : (M->S == 5 ? 5 : 6);

@@ -112,7 +112,8 @@ struct GemmParams {
   int d, n16, n_pad;
   int cg;                  // CTAs per tile group (1 or 2)
   int np;                  // parts per candidate tile
-  int exp;                 // experiment knob (BOCF_SPLIT_EXP): 1 = skip the MMAs, 2 = skip the bulk loads (results invalid)
+  int exp;                 // experiment knob (BOCF_SPLIT_EXP, results invalid): 1 skip the MMAs, 2 skip the bulk loads,
+                           // 5 A operand from spare TMEM columns, 6 skip the epilogue work
 };
 
 // Work decomposition.  A UNIT is (output j, candidate tile rt, part p of NP): the column tiles ct = p, p+NP, ... of one
@@ -200,6 +201,28 @@ __device__ __forceinline__ unsigned long long balanced_digits(long long Y) {
 __device__ __forceinline__ double i32_to_f64(uint32_t c) {
   return __hiloint2double(0x43300000, (int)(c ^ 0x80000000u)) - 4503601774854144.0;
 }
+// int64 (|x| < 2^51) -> double the same way: 64-bit integer add of the 1.5 * 2^52 bit pattern, one DADD.
+__device__ __forceinline__ double i64_to_f64(long long x) {
+  return __longlong_as_double(x + 0x4338000000000000LL) - 6755399441055744.0;
+}
+// sum_lb 256^lb c[lb]: adjacent levels are merged in 64-bit integer arithmetic first (c[lb] * 256 + c[lb-1] < 2^38), so
+// only ceil(S/2) conversions and floor(S/2) fused multiply-adds reach the fp64 pipe -- the epilogue's scarce resource
+// (ncu: math_pipe_throttle) -- instead of S and S-1.
+template <int S, int W>
+__device__ __forceinline__ double levels_to_f64(const uint32_t (&c)[S][W], int e) {
+  double v = 0.0;
+#pragma unroll
+  for (int lb = S - 1; lb >= 0; lb -= 2) {
+    if (lb >= 1) {
+      const long long t = (long long)(int)c[lb][e] * 256 + (long long)(int)c[lb - 1][e];
+      v = (lb == S - 1) ? i64_to_f64(t) : fma(v, 65536.0, i64_to_f64(t));
+    } else {
+      v = (lb == S - 1) ? i32_to_f64(c[0][e]) : fma(v, 256.0, i32_to_f64(c[0][e]));
+    }
+  }
+  return v;
+}
+
 // digits of rint(x) for |x| < 2^46 without F2I: adding 1.5 * 2^52 leaves rint(x) (two's complement) in the low mantissa bits
 template <int S>
 __device__ __forceinline__ unsigned long long balanced_digits_of(double x) {
@@ -442,31 +465,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
 
 #pragma unroll 1
       for (int cg = hw; cg < NCG; cg += PART_SPLIT) {
+        if (P.exp == 6) break;                                    // experiment: no epilogue work (timing only)
         uint32_t c[S][CGW];
 #pragma unroll
         for (int lb = 0; lb < S; ++lb) tc::tmem_ldw<CGW>(taddr + (uint32_t)(lb * NT + cg * CGW), c[lb]);
         tc::tmem_ld_wait();
         uint32_t vec[S][2];
-        if (EPI == EPI_VAR) {
-#pragma unroll
-          for (int tt = 0; tt < S; ++tt) vec[tt][0] = vec[tt][1] = 0u;
-        }
+        unsigned long long dgv[CGW];
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {
-          double v = i32_to_f64(c[S - 1][e]);
-#pragma unroll
-          for (int lb = S - 2; lb >= 0; --lb) v = fma(v, 256.0, i32_to_f64(c[lb][e]));
-          v *= s_cs[cg * CGW + e];
+          double v = levels_to_f64<S, CGW>(c, e);
+          if (EPI != EPI_DVAR) v *= s_cs[cg * CGW + e];             // DVAR: the column scale is folded into G* by the K* kernel
           if (EPI == EPI_RAW) {
             const int col = col0 + cg * CGW + e;
             const size_t grow = (size_t)(ti.j * P.RT + ti.rt) * TM + row;
             if (col < P.ldo) P.raw_out[grow * P.ldo + col] = v * P.raw_rs[grow];
           } else if (EPI == EPI_VAR) {
             sumsq = fma(v, v, sumsq);
-            const unsigned long long dg = balanced_digits_of<S>(v * vq);
-#pragma unroll
-            for (int tt = 0; tt < S; ++tt)
-              vec[tt][e >> 2] |= (uint32_t)((dg >> (8 * tt)) & 0xFFull) << (8 * (e & 3));
+            dgv[e] = balanced_digits_of<S>(v * vq);
           } else {
             const double w = v * gv[e];
             {                                                  // refill the slot with this warp's next column group's G*
@@ -484,6 +500,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
           }
         }
         if (EPI == EPI_VAR && P.A2 != nullptr) {
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {                          // byte transpose: digit t of 4 columns -> one word
+            const unsigned long long four[4] = {dgv[4 * w], dgv[4 * w + 1], dgv[4 * w + 2], dgv[4 * w + 3]};
+            uint32_t o[S];
+            digits_transpose4<S>(four, o);
+#pragma unroll
+            for (int tt = 0; tt < S; ++tt) vec[tt][w] = o[tt];
+          }
           const int k = col0 + cg * CGW;
           if (k < P.KCH * KC) {
             const int kc = k >> 6;
@@ -563,16 +587,18 @@ __global__ void pack_digits_kernel(const double* __restrict__ src, int64_t mat_s
     const double q = ldexp(1.0, 8 * S - 2 - e);
     uint32_t vec[S][4];
 #pragma unroll
-    for (int tt = 0; tt < S; ++tt)
+    for (int w = 0; w < 4; ++w) {
+      unsigned long long four[4];
 #pragma unroll
-      for (int w = 0; w < 4; ++w) vec[tt][w] = 0u;
+      for (int e4 = 0; e4 < 4; ++e4) {
+        const int k = kc * KC + piece * 16 + 4 * w + e4;
+        const double x = (row < R && k < K) ? src[mat * mat_stride + row * sr + k * sk] : 0.0;
+        four[e4] = balanced_digits_of<S>(x * q);
+      }
+      uint32_t o[S];
+      digits_transpose4<S>(four, o);
 #pragma unroll
-    for (int ee = 0; ee < 16; ++ee) {
-      const int k = kc * KC + piece * 16 + ee;
-      const double x = (row < R && k < K) ? src[mat * mat_stride + row * sr + k * sk] : 0.0;
-      const unsigned long long dg = balanced_digits_of<S>(x * q);
-#pragma unroll
-      for (int tt = 0; tt < S; ++tt) vec[tt][ee >> 2] |= (uint32_t)((dg >> (8 * tt)) & 0xFFull) << (8 * (ee & 3));
+      for (int tt = 0; tt < S; ++tt) vec[tt][w] = o[tt];
     }
 #pragma unroll
     for (int tt = 0; tt < S; ++tt)
