@@ -20,7 +20,7 @@ EXPORTS = [
     "bocf_model_factorize", "bocf_model_get_factor", "bocf_model_n", "bocf_model_H",
     "bocf_model_set_scratch_limit", "bocf_posterior", "bocf_acq_eval", "bocf_acq_eval_host",
     "bocf_utility_eval", "bocf_topk", "bocf_profile_enable", "bocf_profile_report",
-    "bocf_model_set_precision", "bocf_model_active_slices", "bocf_debug_split_gemm", "bocf_model_log_likelihood",
+    "bocf_model_set_precision", "bocf_model_active_slices", "bocf_debug_split_gemm", "bocf_model_log_likelihood", "bocf_model_append_point",
 ]
 PRECISIONS = {"fp64": (0, 0), "auto": (2, 0), "split3": (1, 3), "split4": (1, 4), "split5": (1, 5), "split6": (1, 6)}
 
@@ -76,6 +76,7 @@ def load_library():
     lib.bocf_model_active_slices.argtypes = [c_vp]
     lib.bocf_debug_split_gemm.argtypes = [c_dp, c_dp, i32, i32, i32, i32, i32, c_dp, c_vp]
     lib.bocf_model_log_likelihood.argtypes = [c_vp, c_dp, c_dp, c_dp, c_dp, c_vp]
+    lib.bocf_model_append_point.argtypes = [c_vp, c_dp, c_dp, c_vp]
     lib.bocf_profile_enable.argtypes = [i32]
     lib.bocf_profile_report.argtypes = [ctypes.c_char_p, i32]
     for name in EXPORTS:

@@ -411,6 +411,67 @@ int bocf_model_factorize(bocf_model* M, double* jitter_out, void* stream) {
   return 0;
 }
 
+int bocf_model_append_point(bocf_model* M, const double* x_new, const double* y_new, void* stream) {
+  if (int rc = check_ready(M)) return rc;
+  if (!x_new || !y_new) {
+    set_error("bocf_model_append_point: invalid arguments");
+    return BOCF_ERR_INVALID;
+  }
+  if (M->n + 1 > M->n_pad) {
+    set_error("bocf_model_append_point: factor buffers are full (n is a multiple of 128); call bocf_model_set_data + "
+              "bocf_model_factorize");
+    return BOCF_ERR_UNSUPPORTED;
+  }
+  DeviceGuard dg(M->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n_old = M->n, Hm = M->H * M->m;
+  double *Xn = nullptr, *Yn = nullptr, *work = nullptr;
+  if (int rc = dev_alloc(&Xn, (size_t)(n_old + 1) * M->d)) return rc;
+  if (int rc = dev_alloc(&Yn, (size_t)(n_old + 1) * M->m)) {
+    dev_free(Xn);
+    return rc;
+  }
+  if (int rc = dev_alloc(&work, (size_t)Hm * 2 * M->n_pad)) {
+    dev_free(Xn);
+    dev_free(Yn);
+    return rc;
+  }
+  int rc = launch_append_xy(M->X, M->Y, x_new, y_new, n_old, M->d, M->m, Xn, Yn, st);
+  if (!rc) {
+    cudaStreamSynchronize(st);
+    dev_free(M->X);
+    dev_free(M->Y);
+    M->X = Xn;
+    M->Y = Yn;
+    Xn = Yn = nullptr;
+    M->n = n_old + 1;
+    M->n16 = (int)round_up(M->n, 16);
+    rc = launch_append(M, n_old, work, st);
+  }
+  std::vector<int> info(Hm, 0);
+  if (!rc && (cudaMemcpyAsync(info.data(), M->info, sizeof(int) * Hm, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+              cudaStreamSynchronize(st) != cudaSuccess)) {
+    set_error("bocf_model_append_point: device error");
+    rc = BOCF_ERR_CUDA;
+  }
+  dev_free(Xn);
+  dev_free(Yn);
+  dev_free(work);
+  M->split_ready = false;                  // digit planes belong to the previous factor
+  M->precision_resolved = false;
+  if (rc) {
+    M->factorized = false;
+    return rc;
+  }
+  for (int hj = 0; hj < Hm; ++hj)
+    if (info[hj] != 0) {
+      M->factorized = false;               // data are in place: bocf_model_factorize (with its jitter schedule) recovers
+      set_error("bocf_model_append_point: bordered pivot not positive; refactorise with bocf_model_factorize");
+      return BOCF_ERR_UNSUPPORTED;
+    }
+  return 0;
+}
+
 int bocf_model_log_likelihood(bocf_model* M, double* lml, double* g_variance, double* g_lengthscale, double* g_noise,
                               void* stream) {
   if (int rc = check_ready(M)) return rc;

@@ -295,6 +295,92 @@ __global__ void linv_t_matvec_kernel(const double* __restrict__ Linv, const doub
   alpha[(int64_t)hj * n_pad + b] = s;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Appending ONE observation to a factorised model: O(n^2) per output instead of the O(n^3)
+// refactorisation.  With Ky' = [[Ky, k], [k^T, k** + noise + 1e-8 (+ jitter)]]:
+//   L' = [[L, 0], [l^T, l_nn]],  l = L^-1 k,  l_nn = sqrt(k_nn - l^T l)
+//   L'^-1 = [[L^-1, 0], [-(l^T L^-1) / l_nn, 1 / l_nn]]
+// (the bordering form of the Cholesky update; GPy ships the rank-1 variant in util/linalg_cython.pyx:24-37).
+__global__ void append_xy_kernel(const double* __restrict__ Xold, const double* __restrict__ Yold,
+                                 const double* __restrict__ xnew, const double* __restrict__ ynew, int n, int d, int m,
+                                 double* __restrict__ Xn, double* __restrict__ Yn) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (int64_t)(n + 1) * d) Xn[idx] = (idx < (int64_t)n * d) ? Xold[idx] : xnew[idx - (int64_t)n * d];
+  if (idx < (int64_t)m * (n + 1)) {
+    const int j = (int)(idx / (n + 1)), b = (int)(idx % (n + 1));
+    Yn[idx] = (b < n) ? Yold[(int64_t)j * n + b] : ynew[j];
+  }
+}
+
+// one CTA per (h, j); n = number of points BEFORE the append; Xs / xsq already hold the scaled new point in row n
+template <int KIND>
+__global__ void __launch_bounds__(256) append_factor_kernel(double* __restrict__ LmatAll, double* __restrict__ LinvAll,
+                                                            const double* __restrict__ XsAll,
+                                                            const double* __restrict__ xsqAll,
+                                                            const OutHyp* __restrict__ hyp, int n, int n_pad, int d,
+                                                            int* __restrict__ info, double* __restrict__ work) {
+  __shared__ double red[8];
+  __shared__ double s_lnn;
+  const int hj = blockIdx.x, tid = threadIdx.x;
+  const OutHyp& hp = hyp[hj];
+  double* L = LmatAll + (int64_t)hj * n_pad * n_pad;
+  double* Li = LinvAll + (int64_t)hj * n_pad * n_pad;
+  const double* Xs = XsAll + (int64_t)hj * n_pad * d;
+  const double* xsq = xsqAll + (int64_t)hj * n_pad;
+  double* kvec = work + (int64_t)hj * 2 * n_pad;
+  double* lvec = kvec + n_pad;
+  const double* xn = Xs + (int64_t)n * d;
+  for (int b = tid; b < n; b += 256) {                       // k = K(X, x_new)
+    double r2;
+    if (KIND == BOCF_KERN_SE) {
+      r2 = 0.0;
+      for (int q = 0; q < d; ++q) {
+        const double df = xn[q] - Xs[(int64_t)b * d + q];
+        r2 += df * df;
+      }
+    } else {
+      double dot = 0.0;
+      for (int q = 0; q < d; ++q) dot += xn[q] * Xs[(int64_t)b * d + q];
+      r2 = fmax(-2.0 * dot + (xsq[n] + xsq[b]), 0.0);
+    }
+    double kv, gdummy;
+    kern_eval<KIND, false>(r2, hp.variance, kv, gdummy);
+    kvec[b] = kv;
+  }
+  __syncthreads();
+  double ss = 0.0;
+  for (int k = tid; k < n; k += 256) {                       // l = L^-1 k  (row k of the lower-triangular inverse)
+    const double* row = Li + (int64_t)k * n_pad;
+    double acc = 0.0;
+    for (int b = 0; b <= k; ++b) acc += row[b] * kvec[b];
+    lvec[k] = acc;
+    L[(int64_t)n * n_pad + k] = acc;
+    ss += acc * acc;
+  }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    double d2 = (hp.variance + (hp.noise + 1e-8 + hp.jitter)) - tot;
+    if (!(d2 > 0.0)) {                                       // not positive definite: the caller refactorises (jitchol)
+      info[hj] = n + 1;
+      d2 = 1.0;
+    }
+    s_lnn = sqrt(d2);
+    L[(int64_t)n * n_pad + n] = s_lnn;
+    Li[(int64_t)n * n_pad + n] = 1.0 / s_lnn;
+  }
+  __syncthreads();
+  const double inv = 1.0 / s_lnn;
+  for (int b = tid; b < n; b += 256) {                       // new row of the inverse: -(l^T L^-1) / l_nn
+    double acc = 0.0;
+    for (int k = b; k < n; ++k) acc += lvec[k] * Li[(int64_t)k * n_pad + b];
+    Li[(int64_t)n * n_pad + b] = -acc * inv;
+  }
+}
+
 __global__ void copy_factor_kernel(const double* __restrict__ src, int n, int n_pad, int lower_only,
                                    double* __restrict__ dst) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,10 +459,38 @@ int launch_inverse_and_alpha(bocf_model* M, cudaStream_t st) {
     linv_row_kernel<2><<<dim3(I, Hm), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
     BOCF_LAUNCH_OK("linv_row_kernel<2>");
   }
+  return launch_alpha(M, st);
+}
+
+int launch_alpha(bocf_model* M, cudaStream_t st) {
+  const int Hm = M->H * M->m;
   linv_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 8), Hm), 256, 0, st>>>(M->Linv, M->yc, M->m, M->n_pad, M->tvec);
   BOCF_LAUNCH_OK("linv_matvec_kernel");
   linv_t_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 128), Hm), 128, 0, st>>>(M->Linv, M->tvec, M->n_pad, M->alpha);
   BOCF_LAUNCH_OK("linv_t_matvec_kernel");
+  return 0;
+}
+
+// n_old = points before the append; M->n, M->X, M->Y already describe the n_old + 1 points
+int launch_append(bocf_model* M, int n_old, double* work, cudaStream_t st) {
+  const int Hm = M->H * M->m;
+  BOCF_CUDA_OK(cudaMemsetAsync(M->info, 0, sizeof(int) * Hm, st));
+  if (int rc = launch_prepare(M, st)) return rc;             // ybar, centred y, scaled inputs incl. the new row
+  switch (M->kernel) {
+    case BOCF_KERN_SE: append_factor_kernel<BOCF_KERN_SE><<<Hm, 256, 0, st>>>(M->Lmat, M->Linv, M->Xs, M->xsq, M->hyp, n_old, M->n_pad, M->d, M->info, work); break;
+    case BOCF_KERN_RBF: append_factor_kernel<BOCF_KERN_RBF><<<Hm, 256, 0, st>>>(M->Lmat, M->Linv, M->Xs, M->xsq, M->hyp, n_old, M->n_pad, M->d, M->info, work); break;
+    case BOCF_KERN_MATERN52: append_factor_kernel<BOCF_KERN_MATERN52><<<Hm, 256, 0, st>>>(M->Lmat, M->Linv, M->Xs, M->xsq, M->hyp, n_old, M->n_pad, M->d, M->info, work); break;
+    default: append_factor_kernel<BOCF_KERN_MATERN32><<<Hm, 256, 0, st>>>(M->Lmat, M->Linv, M->Xs, M->xsq, M->hyp, n_old, M->n_pad, M->d, M->info, work); break;
+  }
+  BOCF_LAUNCH_OK("append_factor_kernel");
+  return launch_alpha(M, st);
+}
+
+int launch_append_xy(const double* Xold, const double* Yold, const double* xnew, const double* ynew, int n, int d, int m,
+                     double* Xn, double* Yn, cudaStream_t st) {
+  const int64_t work = (int64_t)(n + 1) * (d > m ? d : m);
+  append_xy_kernel<<<(unsigned)ceil_div(work, 256), 256, 0, st>>>(Xold, Yold, xnew, ynew, n, d, m, Xn, Yn);
+  BOCF_LAUNCH_OK("append_xy_kernel");
   return 0;
 }
 

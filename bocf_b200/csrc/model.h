@@ -73,6 +73,10 @@ int launch_gram(bocf_model* M, cudaStream_t st);                          // K +
 int launch_cholesky(bocf_model* M, cudaStream_t st);                      // blocked potrf, info flags
 int launch_inverse_and_alpha(bocf_model* M, cudaStream_t st);             // Linv, alpha
 int launch_copy_factor(bocf_model* M, int hj, double* L, double* Linv, double* alpha, cudaStream_t st);
+int launch_alpha(bocf_model* M, cudaStream_t st);                          // alpha = Linv^T (Linv yc)
+int launch_append_xy(const double* Xold, const double* Yold, const double* xnew, const double* ynew, int n, int d, int m,
+                     double* Xn, double* Yn, cudaStream_t st);
+int launch_append(bocf_model* M, int n_old, double* work, cudaStream_t st);   // bordered Cholesky / inverse update
 
 // ---- lml.cu -------------------------------------------------------------------------------------
 // out_host: H*m x (MAXD + 3) doubles [log p(y), d/dvariance, d/dnoise, d/dlengthscale[0..d)]

@@ -41,6 +41,8 @@ class multi_outputGP(object):
         # arithmetic of the two candidate-side contractions: None (library default / BOCF_PRECISION), "fp64",
         # "auto", or "split3".."split6" (tcgen05 int8 digit planes, include/bocf_b200.h: enum bocf_precision)
         self.precision = precision
+        self.incremental_updates = True     # one-point updateModel calls with unchanged hypers use the O(n^2) append
+        self.last_update = None
         self._handle = None
         self._handle_sig = None
         self._explicit_hyp = False
@@ -105,12 +107,37 @@ class multi_outputGP(object):
         X = np.ascontiguousarray(X_all, dtype=np.float64)
         Y = np.ascontiguousarray(np.stack([np.asarray(y, dtype=np.float64).reshape(-1) for y in Y_all], axis=0))
         assert Y.shape == (self.output_dim, X.shape[0])
+        old_X, old_Y, old_hyp = self.X, self.Y, self._hyp
         self.X = X
         self.Y = Y
         self.input_dim = X.shape[1]
         if self._hyp is None or not getattr(self, "_explicit_hyp", False):
             self._hyp = self._default_hypers(self.input_dim, Y_all)
+        if self._try_append(old_X, old_Y, old_hyp):
+            return
         self._upload_and_factorize()
+
+    def _try_append(self, old_X, old_Y, old_hyp):
+        """One new observation and unchanged hyper-parameters: O(n^2) bordered update on the device
+        (bocf_model_append_point) instead of a refactorisation.  Falls back (returns False) whenever it does not apply."""
+        if (not self.incremental_updates or self._handle is None or old_X is None or old_hyp is None or
+                self.X.shape[0] != old_X.shape[0] + 1 or self.X.shape[1] != old_X.shape[1] or
+                not np.array_equal(self.X[:-1], old_X) or not np.array_equal(self.Y[:, :-1], old_Y)):
+            return False
+        if old_hyp[0] != self._hyp[0] or any(not np.array_equal(a, b) for a, b in zip(old_hyp[1:], self._hyp[1:])):
+            return False
+        with torch.cuda.device(self.device):
+            xn = torch.from_numpy(np.ascontiguousarray(self.X[-1])).to(self.device)
+            yn = torch.from_numpy(np.ascontiguousarray(self.Y[:, -1])).to(self.device)
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            rc = self._lib.bocf_model_append_point(self._handle, _ptr(xn), _ptr(yn), st)
+            if rc == -5:                       # BOCF_ERR_UNSUPPORTED: buffers full / pivot not positive
+                return False
+            _lib.check(rc)
+            self._X_dev = torch.from_numpy(self.X).to(self.device)
+        self._current_h = 0
+        self.last_update = "append"
+        return True
 
     def _upload_and_factorize(self):
         kind, variance, lengthscale, noise = self._hyp
@@ -143,6 +170,7 @@ class multi_outputGP(object):
             self.jitter_added = jit
         self._X_dev = Xd
         self._current_h = 0
+        self.last_update = "factorize"
 
     def set_precision(self, precision):
         """Switch the contraction arithmetic ("fp64" | "auto" | "split3".."split6"); rebuilds the digit planes."""

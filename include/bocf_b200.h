@@ -99,6 +99,13 @@ int bocf_model_set_hypers(bocf_model* mdl, int H, const double* variance, const 
  * jitter jitchol had to add (0 if none).  Synchronises the stream (needs the device info flag). */
 int bocf_model_factorize(bocf_model* mdl, double* jitter_out, void* stream);
 
+/* Append ONE observation (x_new [dev] d, y_new [dev] m) to a factorised model with unchanged hyper-parameters: bordered
+ * update of L, L^-1 and alpha in O(n^2) per output instead of the O(n^3) refactorisation that multi_outputGP.updateModel
+ * (multi_outputGP.py:97-102) triggers every BO iteration (GPy's cholupdate, linalg_cython.pyx:24-37).
+ * Returns BOCF_ERR_UNSUPPORTED when the factor buffers are full (n a multiple of 128) or the new pivot is not positive:
+ * the data are in place then and bocf_model_factorize completes the update. */
+int bocf_model_append_point(bocf_model* mdl, const double* x_new, const double* y_new, void* stream);
+
 /* Log marginal likelihood of every (h, j) GP and its gradient w.r.t. the kernel variance, the ARD lengthscales and the
  * noise variance -- the objective / gradient pair of GPModel.updateModel's ML-II + HMC (gpmodel.py:117-119).  Replaces
  * ExactGaussianInference.inference's log_marginal and dL_dK (exact_gaussian_inference.py:53-63), Stationary /
