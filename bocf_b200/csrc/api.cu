@@ -109,9 +109,10 @@ static int64_t pick_chunk(const bocf_model* M, int64_t N, bool grad, uint64_t ex
 }
 
 // Resolve the requested contraction precision into the active number of digit planes (M->S; 0 = fp64 DMMA) and build
-// the split operands.  AUTO: predicted relative error of the variance ~ 400 * max|Linv|^2 * 256^-S (measured on the
-// synthetic models of tests/test_gpu_split.py); the smallest S in {4,5,6} that keeps it below 1e-7 is used, and
-// models too ill-conditioned for 6 planes stay on the fp64 tensor path.
+// the split operands.  AUTO: the relative error of the variance stays below ~2000 * max|Linv|^2 * 256^-S (measured
+// 240 ... 1350 across kernels, sizes and noise levels: tests/test_split_numerics.py, tests/test_gpu_split.py); the
+// smallest S in {4,5,6} with 400 * max|Linv|^2 * 256^-S <= 1e-7 (that bound <= 5e-7, half the north-star fp64 bar) is
+// used, and models too ill-conditioned for 6 planes stay on the fp64 tensor path.
 static int apply_precision(bocf_model* M, cudaStream_t st) {
   int S = 0;
   if (M->precision == BOCF_PREC_SPLIT_I8) {
