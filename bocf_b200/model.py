@@ -5,9 +5,10 @@ meaning and output shapes ((m,N) / (m,N,d) float64); numpy in -> numpy out, CUDA
 CUDA torch tensors out (no host round trip).  All arithmetic runs in libbocf_b200 (fp64, sm_100a);
 there is no CPU fallback.
 
-Hyper-parameter fitting (ML-II + HMC, GPyOpt/models/gpmodel.py:102-128) is out of scope for this
-path: hyper-samples are supplied with ``set_hyperparameter_samples`` (or default to
-the kernels' initial values, exactly what ``fixed_hyps=True`` does in the reference).
+Hyper-parameters: ``fixed_hyps=True`` keeps the kernels' initial values (gpmodel_fixed_hyps.py); explicit
+hyper-samples are loaded with ``set_hyperparameter_samples``; otherwise ``updateModel`` does what
+GPModel.updateModel does (gpmodel.py:102-128): ML-II, then an HMC chain whose sub-sampled states become
+the ``n_samples`` hyper-sample instances -- all outputs in lockstep on the device likelihood (hmc.py).
 """
 import ctypes
 
@@ -26,7 +27,8 @@ class multi_outputGP(object):
     analytical_gradient_prediction = True
 
     def __init__(self, output_dim, kernel=None, noise_var=None, exact_feval=None, n_samples=10, ARD=None,
-                 fixed_hyps=False, device=None, precision=None):
+                 fixed_hyps=False, device=None, precision=None, n_burnin=100, subsample_interval=10, step_size=1e-1,
+                 leapfrog_steps=20, max_iters=200, hyper_inference=None):
         self.output_dim = int(output_dim)
         self.kernel = [None] * output_dim if kernel is None else list(kernel)
         self.noise_var = [None] * output_dim if noise_var is None else list(noise_var)
@@ -41,6 +43,14 @@ class multi_outputGP(object):
         # arithmetic of the two candidate-side contractions: None (library default / BOCF_PRECISION), "fp64",
         # "auto", or "split3".."split6" (tcgen05 int8 digit planes, include/bocf_b200.h: enum bocf_precision)
         self.precision = precision
+        # GPModel's sampler settings (gpmodel.py:31: n_burnin=100, subsample_interval=10, step_size=1e-1, leapfrog_steps=20)
+        self.n_burnin, self.subsample_interval = n_burnin, subsample_interval
+        self.step_size, self.leapfrog_steps, self.max_iters = step_size, leapfrog_steps, max_iters
+        # "hmc": updateModel fits and samples the hyper-parameters like GPModel.updateModel; "none": keep the initial values
+        self.hyper_inference = ("none" if fixed_hyps else "hmc") if hyper_inference is None else hyper_inference
+        if self.hyper_inference not in ("hmc", "none"):
+            raise ValueError("hyper_inference must be 'hmc' or 'none'")
+        self._inference = None
         self.incremental_updates = True     # one-point updateModel calls with unchanged hypers use the O(n^2) append
         self.last_update = None
         self._handle = None
@@ -111,11 +121,56 @@ class multi_outputGP(object):
         self.X = X
         self.Y = Y
         self.input_dim = X.shape[1]
+        if not self._explicit_hyp and not self.fixed_hyps and self.hyper_inference == "hmc":
+            self._infer_hyperparameters(Y_all)
+            return
         if self._hyp is None or not getattr(self, "_explicit_hyp", False):
             self._hyp = self._default_hypers(self.input_dim, Y_all)
         if self._try_append(old_X, old_Y, old_hyp):
             return
         self._upload_and_factorize()
+
+    # ---- hyper-parameter inference (gpmodel.py:102-128, all outputs in lockstep) --------------------------------------
+    def _infer_hyperparameters(self, Y_all):
+        from . import hmc as _hmc
+        kind = self._kernel_kind()
+        d, m = self.input_dim, self.output_dim
+        if self._inference is None:
+            kernels, noises, fixes, inst = [], [], [], []
+            for j in range(m):
+                k = self.kernel[j]
+                if k is None:                               # gpmodel.py:57-58
+                    k = _kern.SE(d, variance=1., ARD=self.ARD[j])
+                kernels.append((float(k.variance[0]), np.array(k.lengthscale, dtype=float)))
+                if self.exact_feval[j]:                     # gpmodel.py:70-71
+                    noises.append(1e-6); fixes.append(True); inst.append(1e-6)
+                elif self.noise_var[j] is not None:         # gpmodel.py:72-73
+                    noises.append(float(self.noise_var[j])); fixes.append(True); inst.append(float(self.noise_var[j]))
+                else:                                       # gpmodel.py:64,74-75
+                    nv = float(np.var(Y_all[j])) * 0.01
+                    noises.append(nv); fixes.append(False); inst.append(nv)
+
+            def evaluate(variance, lengthscale, noise):
+                self._hyp = (kind, np.ascontiguousarray(variance[None, :]), np.ascontiguousarray(lengthscale[None, :, :]),
+                             np.ascontiguousarray(noise[None, :]))
+                self._upload_and_factorize(upload_data=self._fit_needs_data)
+                self._fit_needs_data = False
+                lml, gv, gl, gn = self.log_likelihood_and_gradients()
+                return lml[0], gv[0], gl[0], gn[0]
+
+            self._inference = _hmc.HyperInference(evaluate, d, kernels, noises, fixes, inst, n_samples=self.n_samples,
+                                                  n_burnin=self.n_burnin, subsample_interval=self.subsample_interval,
+                                                  step_size=self.step_size, leapfrog_steps=self.leapfrog_steps,
+                                                  max_iters=self.max_iters)
+        self._fit_needs_data = True
+        variance, lengthscale, noise = self._inference.update()
+        self._hyp = (kind, variance, lengthscale, noise)
+        self._upload_and_factorize()
+        self.last_update = "hmc"
+
+    def get_hyperparameters_samples(self):
+        """(variance (H,m), lengthscale (H,m,d), noise (H,m)) currently loaded (None before the first updateModel)."""
+        return None if self._hyp is None else tuple(np.array(a) for a in self._hyp[1:])
 
     def _try_append(self, old_X, old_Y, old_hyp):
         """One new observation and unchanged hyper-parameters: O(n^2) bordered update on the device
@@ -139,7 +194,7 @@ class multi_outputGP(object):
         self.last_update = "append"
         return True
 
-    def _upload_and_factorize(self):
+    def _upload_and_factorize(self, upload_data=True):
         kind, variance, lengthscale, noise = self._hyp
         lib = self._lib
         d = self.input_dim
@@ -153,14 +208,17 @@ class multi_outputGP(object):
                                              self.device.index or 0))
             self._handle = h
             self._handle_sig = (kind, d)
+            upload_data = True
             if self.precision is not None:
                 mode, slices = _lib.parse_precision(self.precision)
                 _lib.check(lib.bocf_model_set_precision(self._handle, mode, slices, None))
         with torch.cuda.device(self.device):
-            Xd = torch.from_numpy(self.X).to(self.device)
-            Yd = torch.from_numpy(self.Y).to(self.device)
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(lib.bocf_model_set_data(self._handle, self.X.shape[0], _ptr(Xd), _ptr(Yd), st))
+            if upload_data or getattr(self, "_X_dev", None) is None:
+                Xd = torch.from_numpy(self.X).to(self.device)
+                Yd = torch.from_numpy(self.Y).to(self.device)
+                _lib.check(lib.bocf_model_set_data(self._handle, self.X.shape[0], _ptr(Xd), _ptr(Yd), st))
+                self._X_dev = Xd
             _lib.check(lib.bocf_model_set_hypers(self._handle, variance.shape[0],
                                                  variance.ctypes.data_as(ctypes.c_void_p),
                                                  lengthscale.ctypes.data_as(ctypes.c_void_p),
@@ -168,7 +226,6 @@ class multi_outputGP(object):
             jit = np.zeros(variance.shape, dtype=np.float64)
             _lib.check(lib.bocf_model_factorize(self._handle, jit.ctypes.data_as(ctypes.c_void_p), st))
             self.jitter_added = jit
-        self._X_dev = Xd
         self._current_h = 0
         self.last_update = "factorize"
 

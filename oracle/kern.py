@@ -132,20 +132,26 @@ class Kern(object):
         """(d/d variance, d/d lengthscale) of an objective with derivative dL_dK wrt K(X, X).
 
         Stationary kinds: stationary.py:191-215 with the native loop of stationary_utils.c:34-48
-        (_lengthscale_grads); SE: se.py:169-185 (X2 is None branch).  ARD only (the fork's models are ARD)."""
-        assert self.ARD
+        (_lengthscale_grads); SE: se.py:169-185 (X2 is None branch).  Non-ARD: one shared lengthscale
+        (stationary.py:213-215, se.py:184-185)."""
         if self.kind == 'se':
             squared_dist = self._se_scaled_squared_dist(X)
             exp_squared_dist = np.exp(-0.5 * squared_dist)
             tmp = scipy.spatial.distance.squareform(exp_squared_dist, checks=False)
             np.fill_diagonal(tmp, 1.)
             g_var = np.sum(tmp * dL_dK)                                                  # se.py:181
+            if not self.ARD:                                                             # se.py:185
+                g_len = (self.variance / self.lengthscale) * np.sum(
+                    scipy.spatial.distance.squareform(exp_squared_dist * squared_dist) * dL_dK)
+                return float(g_var), np.asarray(g_len, dtype=float).reshape(-1)
             g_len = (self.variance * np.sum((tmp * dL_dK)[:, :, None] *
                                             np.square(X[:, None, :] - X[None, :, :]), axis=(0, 1))) / (self.lengthscale**3)
             return float(g_var), np.asarray(g_len, dtype=float)
         g_var = np.sum(self.K(X) * dL_dK) / self.variance                               # stationary.py:197
         r = self._scaled_dist(X)
         dL_dr = self.dK_dr(r) * dL_dK                                                    # :203 (dK_dr_via_X)
+        if not self.ARD:                                                                 # :213-215
+            return float(np.asarray(g_var).reshape(-1)[0]), np.asarray(-np.sum(dL_dr * r) / self.lengthscale).reshape(-1)
         tmp = dL_dr * self._inv_dist(X)                                                  # :206
         grads = np.array([np.sum(tmp * np.square(X[:, q:q + 1] - X[:, q:q + 1].T)) for q in range(self.input_dim)])
         return float(np.asarray(g_var).reshape(-1)[0]), -grads / self.lengthscale**3    # :232-240

@@ -1,0 +1,40 @@
+"""Wall time of one GPModel.updateModel-style hyper-parameter inference (ML-II + HMC with the reference's default sampler
+settings: 100 burn-in + 10 x 10 samples, 20 leap-frog steps) for all m outputs: device lockstep (bocf_b200) next to the
+sequential CPU oracle on a bounded number of samples.  Prints one JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bocf_b200 as B  # noqa: E402
+from tests.helpers import make_problem  # noqa: E402
+
+m, d, n = int(os.environ.get("HM", 4)), int(os.environ.get("HD", 6)), int(os.environ.get("HN", 200))
+kind = os.environ.get("HKIND", "rbf")
+cpu_samples = int(os.environ.get("HCPU_SAMPLES", 6))
+P = make_problem(m=m, d=d, n=n, kind=kind, N=8, S=8)
+K = B.kern.BY_KIND[kind]
+mod = B.multi_outputGP(m, kernel=[K(d, variance=1., ARD=True) for _ in range(m)], device="cuda:0")
+np.random.seed(0)
+t = time.perf_counter()
+mod.updateModel(P.X, P.Y)
+gpu_s = time.perf_counter() - t
+inf = mod._inference
+num = inf.n_burnin + inf.n_samples * inf.subsample_interval
+moves = [int(np.sum(np.any(np.diff(c, axis=0) != 0, axis=1))) for c in inf.chain]
+
+from oracle.hmc import GPModelHMC  # noqa: E402
+np.random.seed(0)
+t = time.perf_counter()
+for j in range(m):
+    g = GPModelHMC(kind=kind, ARD=True, n_samples=1, n_burnin=0, subsample_interval=cpu_samples, max_iters=200)
+    g.updateModel(P.X, P.Y[j])
+cpu_s = time.perf_counter() - t
+print(json.dumps({"what": "ML-II + HMC hyper-parameter inference, all outputs", "m": m, "d": d, "n": n, "kind": kind,
+                  "gpu_s": gpu_s, "device_passes": inf.device_passes, "ms_per_pass": 1e3 * gpu_s / inf.device_passes,
+                  "samples": num, "accepted_moves_per_output": moves,
+                  "cpu_oracle_s_for_%d_samples_plus_mlii" % cpu_samples: cpu_s,
+                  "cpu_oracle_s_extrapolated_to_%d_samples" % num: cpu_s * num / cpu_samples, "cores": os.cpu_count()}))
