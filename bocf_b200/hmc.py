@@ -145,7 +145,7 @@ class HyperInference(object):
         var, ls, nz = self._pack()
         good = getattr(self, "_last_good", None)
         if good is None:
-            raise
+            raise NotPositiveDefiniteError(-4, "not positive definite, even with jitter.")
         for j in which:
             v2, l2, n2 = good[0].copy(), good[1].copy(), good[2].copy()
             v2[j], l2[j], n2[j] = var[j], ls[j], nz[j]
@@ -184,9 +184,17 @@ class HyperInference(object):
 
         def flush_locked():
             keys = sorted(pending)
-            for j in keys:
-                self.out[j].set_optimizer_array(pending[j])
-            failed = self._infer(keys)
+            try:
+                for j in keys:
+                    self.out[j].set_optimizer_array(pending[j])
+                failed = self._infer(keys)
+            except BaseException as e:                       # no device / library error: wake every waiting run
+                errors.append(e)
+                for j in keys:
+                    results[j] = None
+                pending.clear()
+                cv.notify_all()
+                return
             if not failed:
                 self._remember_good()
             for j in keys:
