@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol_keep = tc::l2_policy_evict_last();
       for (int t = 0; t < num_tiles; ++t) {
         const TileInfo ti = decode_tile(P, NT, t);
         if (!ti.valid) continue;
@@ -301,8 +302,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
             tc::mbar_arrive(&full[stage]);
           } else {
             tc::mbar_arrive_expect_tx(&full[stage], C::STAGE);
-            tc::bulk_g2s(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage]);
-            tc::bulk_g2s(sB + stage * C::B_STAGE, gB + (size_t)kc * (C::B_STAGE * CG), C::B_STAGE, &full[stage]);
+            if (P.exp >= 10 && P.exp <= 12) {
+              // experiment: the unit's A tile (re-streamed once per column tile) and the factor planes stay in L2
+              tc::bulk_g2s_hint(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage], pol_keep);
+              if (P.exp == 12)
+                tc::bulk_g2s_hint(sB + stage * C::B_STAGE, gB + (size_t)kc * (C::B_STAGE * CG), C::B_STAGE, &full[stage], pol_keep);
+              else
+                tc::bulk_g2s(sB + stage * C::B_STAGE, gB + (size_t)kc * (C::B_STAGE * CG), C::B_STAGE, &full[stage]);
+            } else {
+              tc::bulk_g2s(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage]);
+              tc::bulk_g2s(sB + stage * C::B_STAGE, gB + (size_t)kc * (C::B_STAGE * CG), C::B_STAGE, &full[stage]);
+            }
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -451,12 +461,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       constexpr int NCG = NT / CGW;
       double gv[CGW];
       const double* Gcol = nullptr;
+      const bool g_stream = (P.exp == 11 || P.exp == 12);       // experiment: G* is read once -> streaming loads
       if (EPI == EPI_DVAR) {
         Gcol = P.GsT + (size_t)ti.j * P.n16 * P.Nc + i;
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {                      // first column group: in flight while the MMAs finish
           const int b = col0 + hw * CGW + e;
-          gv[e] = (b < P.n) ? __ldg(Gcol + (size_t)b * P.Nc) : 0.0;
+          gv[e] = (b < P.n) ? (g_stream ? __ldcs(Gcol + (size_t)b * P.Nc) : __ldg(Gcol + (size_t)b * P.Nc)) : 0.0;
         }
       }
 
@@ -497,7 +508,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
             const double w = v * gv[e];
             {                                                  // refill the slot with this warp's next column group's G*
               const int bn = col0 + (cg + PART_SPLIT) * CGW + e;
-              gv[e] = (cg + PART_SPLIT < NCG && bn < P.n) ? __ldg(Gcol + (size_t)bn * P.Nc) : 0.0;
+              gv[e] = (cg + PART_SPLIT < NCG && bn < P.n)
+                          ? (g_stream ? __ldcs(Gcol + (size_t)bn * P.Nc) : __ldg(Gcol + (size_t)bn * P.Nc)) : 0.0;
             }
             s0 += w;
             const double2* xb2 = reinterpret_cast<const double2*>(s_xb + (cg * CGW + e) * DPA);
@@ -524,7 +536,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
             uint8_t* dst = P.A2 + (((size_t)(ti.j * P.RT + ti.rt) * P.KCH + kc) * S) * C::A_PLANE + sw64(row, k & 63);
 #pragma unroll
             for (int tt = 0; tt < S; ++tt)
-              *reinterpret_cast<uint2*>(dst + (size_t)tt * C::A_PLANE) = make_uint2(vec[tt][0], vec[tt][1]);
+              if (P.exp == 11 || P.exp == 12) __stcs(reinterpret_cast<uint2*>(dst + (size_t)tt * C::A_PLANE), make_uint2(vec[tt][0], vec[tt][1]));
+              else *reinterpret_cast<uint2*>(dst + (size_t)tt * C::A_PLANE) = make_uint2(vec[tt][0], vec[tt][1]);
           }
         }
       }
