@@ -83,6 +83,8 @@ static void free_factor(bocf_model* M) {
   dev_free(M->alpha);
   dev_free(M->tvec);
   dev_free(M->info);
+  dev_free(M->lml_ws);
+  M->lml_ws_count = 0;
   M->factorized = false;
 }
 

@@ -97,13 +97,24 @@ __global__ void gram_kernel(const double* __restrict__ Xs, const double* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Diagonal block: unblocked Cholesky + in-place triangular inverse in shared memory (one CTA / matrix).
+// Diagonal block: Cholesky + in-place triangular inverse of one 128 x 128 block in shared memory (one CTA / matrix).
+// Both halves are blocked with 8-wide panels so the 128-step dependency chain of the unblocked algorithms (3 barriers
+// and a divide per column, a 8128-long serial dot-product chain in the inverse) shrinks to 16 panel steps:
+//   Cholesky (right-looking):  8 x 8 diagonal sub-block by one warp (lane = row, shuffles), rows below by forward
+//                              substitution (thread per row), rank-8 trailing update in 4 x 4 register tiles;
+//   inverse (dtrtri, lower):   from the last panel up,  A21 <- -X22 . A21 . D^-1  with X22 the already inverted trailing
+//                              block (two threads per row, eight accumulators each), D^-1 by one warp (lane = column).
+// The dpotrf failure convention is kept: the first non-positive pivot is reported in info[] (1-based), replaced by 1.
 constexpr int DLD = TILE + 1;
+constexpr int PW = 8;
+constexpr int POTRF_SMEM = (TILE * DLD + TILE * PW + PW * PW) * (int)sizeof(double);
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lmat, double* __restrict__ Dinv,
                                                          int* __restrict__ info, int n, int n_pad, int nb, int kb) {
-  extern __shared__ double T[];   // TILE x DLD
+  extern __shared__ __align__(16) double T[];   // TILE x DLD | Bt[TILE][PW] | Di[PW][PW]
+  double* Bt = T + TILE * DLD;
+  double* Di = Bt + TILE * PW;
   const int hj = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int k0 = kb * TILE;
   const int nrem = min(TILE, n - k0);
   double* Ablk = Lmat + (int64_t)hj * n_pad * n_pad + (int64_t)k0 * n_pad + k0;
@@ -113,23 +124,91 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
     T[r * DLD + c] = v;
   }
   __syncthreads();
-  for (int c = 0; c < TILE; ++c) {
-    double piv = T[c * DLD + c];
-    if (!(piv > 0.0)) {                       // dpotrf info != 0  -> jitchol retry on the host side
-      if (tid == 0 && info[hj] == 0) info[hj] = k0 + c + 1;
-      piv = 1.0;
+
+  // ---------------- Cholesky ----------------
+  for (int c0 = 0; c0 < TILE; c0 += PW) {
+    if (warp == 0) {
+      // lane k (< PW) owns row c0 + k of the diagonal sub-block
+      double a[PW];
+#pragma unroll
+      for (int q = 0; q < PW; ++q) a[q] = (lane < PW) ? T[(c0 + lane) * DLD + c0 + q] : 0.0;
+#pragma unroll
+      for (int k = 0; k < PW; ++k) {
+        double piv = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(piv > 0.0)) {                      // dpotrf info != 0  -> jitchol retry on the host side
+          if (lane == 0 && info[hj] == 0) info[hj] = k0 + c0 + k + 1;
+          piv = 1.0;
+        }
+        const double sq = sqrt(piv);
+        a[k] = (lane == k) ? sq : a[k] / sq;     // column k of L (meaningful for lanes >= k)
+#pragma unroll
+        for (int c2 = k + 1; c2 < PW; ++c2) {
+          const double lc2 = __shfl_sync(0xffffffffu, a[k], c2);
+          if (lane >= c2) a[c2] -= a[k] * lc2;
+        }
+      }
+      if (lane < PW) {
+#pragma unroll
+        for (int q = 0; q < PW; ++q)
+          if (q <= lane) T[(c0 + lane) * DLD + c0 + q] = a[q];
+      }
     }
-    const double s = sqrt(piv);
     __syncthreads();
-    if (tid == 0) T[c * DLD + c] = s;
-    for (int r = c + 1 + tid; r < TILE; r += 256) T[r * DLD + c] /= s;
+    {
+      // rows below the sub-block:  L[r][c0+k] = (A[r][c0+k] - sum_{t<k} L[r][c0+t] L[c0+k][c0+t]) / L[c0+k][c0+k]
+      const int r = c0 + PW + tid;
+      if (r < TILE) {
+        double a[PW];
+#pragma unroll
+        for (int q = 0; q < PW; ++q) a[q] = T[r * DLD + c0 + q];
+#pragma unroll
+        for (int k = 0; k < PW; ++k) {
+          double acc = a[k];
+#pragma unroll
+          for (int t = 0; t < k; ++t) acc -= a[t] * T[(c0 + k) * DLD + c0 + t];
+          a[k] = acc / T[(c0 + k) * DLD + c0 + k];
+        }
+#pragma unroll
+        for (int q = 0; q < PW; ++q) T[r * DLD + c0 + q] = a[q];
+      }
+    }
     __syncthreads();
-    const int w = TILE - 1 - c;
-    for (int idx = tid; idx < w * w; idx += 256) {
-      int rr = idx / w, cc = idx - rr * w;
-      if (cc <= rr) {
-        int r = c + 1 + rr, c2 = c + 1 + cc;
-        T[r * DLD + c2] -= T[r * DLD + c] * T[c2 * DLD + c];
+    {
+      // trailing update  A[r][c] -= sum_k L[r][c0+k] L[c][c0+k]  on the lower triangle of [w0, TILE)^2, 4 x 4 tiles
+      const int w0 = c0 + PW;
+      const int nt = (TILE - w0) >> 2;
+      const int nblk = nt * (nt + 1) / 2;
+      for (int b = tid; b < nblk; b += 256) {
+        int bi = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+        while (bi * (bi + 1) / 2 > b) --bi;
+        const int bj = b - bi * (bi + 1) / 2;
+        const double* Lr = T + (w0 + 4 * bi) * DLD + c0;
+        const double* Lc = T + (w0 + 4 * bj) * DLD + c0;
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll
+        for (int k = 0; k < PW; ++k) {
+          double lr[4], lc[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            lr[i] = Lr[i * DLD + k];
+            lc[i] = Lc[i * DLD + k];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(lr[i], lc[j], acc[i][j]);
+        }
+        double* Tt = T + (w0 + 4 * bi) * DLD + w0 + 4 * bj;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (bi != bj || j <= i) Tt[i * DLD + j] -= acc[i][j];
       }
     }
     __syncthreads();
@@ -140,17 +219,68 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
     Ablk[(int64_t)r * n_pad + c] = (r < nrem && c <= r) ? T[r * DLD + c] : 0.0;
   }
   __syncthreads();
-  // in-place inverse of the lower-triangular block, last column first (dtrti2, lower, non-unit)
-  for (int j = TILE - 1; j >= 0; --j) {
-    const double ajj = 1.0 / T[j * DLD + j];
-    double acc = 0.0;
-    const int r = j + 1 + tid;
-    if (r < TILE) {
-      for (int t = j + 1; t <= r; ++t) acc += T[r * DLD + t] * T[t * DLD + j];
+
+  // ---------------- in-place inverse of the lower-triangular block, last panel first ----------------
+  for (int jb = TILE - PW; jb >= 0; jb -= PW) {
+    const int w0 = jb + PW;                      // first row / column of the already inverted trailing block X22
+    // copy the panel below the diagonal sub-block (rows >= w0, columns jb .. jb+PW-1)
+    for (int idx = tid; idx < (TILE - w0) * PW; idx += 256) {
+      const int rr = idx / PW, q = idx - rr * PW;
+      Bt[rr * PW + q] = T[(w0 + rr) * DLD + jb + q];
+    }
+    if (warp == 0) {
+      // D^-1 of the PW x PW sub-block: lane k (< PW) owns column k of the inverse (forward substitution)
+      double x[PW];
+#pragma unroll
+      for (int r = 0; r < PW; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < r; ++t) acc += (t >= lane) ? T[(jb + r) * DLD + jb + t] * x[t] : 0.0;
+        const double drr = T[(jb + r) * DLD + jb + r];
+        x[r] = (r == lane) ? 1.0 / drr : ((r > lane) ? -acc / drr : 0.0);
+      }
+      __syncwarp();
+      if (lane < PW) {
+#pragma unroll
+        for (int r = 0; r < PW; ++r) {
+          Di[r * PW + lane] = x[r];
+          if (r >= lane) T[(jb + r) * DLD + jb + lane] = x[r];
+        }
+      }
     }
     __syncthreads();
-    if (r < TILE) T[r * DLD + j] = -acc * ajj;
-    if (tid == 0) T[j * DLD + j] = ajj;
+    {
+      // row r of the panel:  tmp[k] = sum_{t = w0..r} X22[r][t] Bt[t][k] ;  out[k] = -sum_{q >= k} tmp[q] Di[q][k]
+      const int r = w0 + (tid >> 1), half = tid & 1;
+      double tmp[PW];
+#pragma unroll
+      for (int q = 0; q < PW; ++q) tmp[q] = 0.0;
+      if (r < TILE) {
+        const double* Xr = T + r * DLD;
+        for (int t = w0 + half; t <= r; t += 2) {
+          const double xv = Xr[t];
+          const double2* b2 = reinterpret_cast<const double2*>(Bt + (t - w0) * PW);
+#pragma unroll
+          for (int q2 = 0; q2 < PW / 2; ++q2) {
+            const double2 bv = b2[q2];
+            tmp[2 * q2] = fma(xv, bv.x, tmp[2 * q2]);
+            tmp[2 * q2 + 1] = fma(xv, bv.y, tmp[2 * q2 + 1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < PW; ++q) tmp[q] += __shfl_xor_sync(0xffffffffu, tmp[q], 1);
+      if (r < TILE) {
+#pragma unroll
+        for (int kk = 0; kk < PW / 2; ++kk) {
+          const int k = half * (PW / 2) + kk;
+          double o = 0.0;
+#pragma unroll
+          for (int q = 0; q < PW; ++q) o += (q >= k) ? tmp[q] * Di[q * PW + k] : 0.0;
+          T[r * DLD + jb + k] = -o;
+        }
+      }
+    }
     __syncthreads();
   }
   double* Dblk = Dinv + ((int64_t)hj * nb + kb) * TILE * TILE;
@@ -419,8 +549,7 @@ int launch_gram(bocf_model* M, cudaStream_t st) {
 static int set_smem_attrs() {
   static bool done = false;
   if (done) return 0;
-  BOCF_CUDA_OK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    TILE * DLD * (int)sizeof(double)));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
   BOCF_CUDA_OK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
   BOCF_CUDA_OK(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
   BOCF_CUDA_OK(cudaFuncSetAttribute(linv_row_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
@@ -434,7 +563,7 @@ int launch_cholesky(bocf_model* M, cudaStream_t st) {
   const int Hm = M->H * M->m, nb = M->nb;
   BOCF_CUDA_OK(cudaMemsetAsync(M->info, 0, sizeof(int) * Hm, st));
   for (int kb = 0; kb < nb; ++kb) {
-    potrf_diag_kernel<<<Hm, 256, TILE * DLD * sizeof(double), st>>>(M->Lmat, M->Dinv, M->info, M->n, M->n_pad, nb, kb);
+    potrf_diag_kernel<<<Hm, 256, POTRF_SMEM, st>>>(M->Lmat, M->Dinv, M->info, M->n, M->n_pad, nb, kb);
     BOCF_LAUNCH_OK("potrf_diag_kernel");
     const int rem = nb - 1 - kb;
     if (rem > 0) {

@@ -179,13 +179,19 @@ int launch_log_likelihood(bocf_model* M, double* out_host, cudaStream_t st) {
   static_assert(2 * TILE * MAXD + 4 * TILE + 8 * (MAXD + 2) <= LT::SMEM_BYTES / (int)sizeof(double), "epilogue staging fits");
   const int Hm = M->H * M->m;
   const int ntiles = M->nb * (M->nb + 1) / 2;
-  double *part = nullptr, *out = nullptr;
-  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&part), sizeof(double) * Hm * ntiles * (MAXD + 2)));
-  if (cudaMalloc(reinterpret_cast<void**>(&out), sizeof(double) * Hm * (MAXD + 3)) != cudaSuccess) {
-    cudaFree(part);
-    set_error("bocf_model_log_likelihood: out of device memory");
-    return BOCF_ERR_CUDA;
+  const size_t n_part = (size_t)Hm * ntiles * (MAXD + 2), n_out = (size_t)Hm * (MAXD + 3);
+  if (M->lml_ws_count < n_part + n_out) {
+    if (M->lml_ws) cudaFree(M->lml_ws);
+    M->lml_ws = nullptr;
+    M->lml_ws_count = 0;
+    if (cudaMalloc(reinterpret_cast<void**>(&M->lml_ws), sizeof(double) * (n_part + n_out)) != cudaSuccess) {
+      set_error("bocf_model_log_likelihood: out of device memory");
+      return BOCF_ERR_CUDA;
+    }
+    M->lml_ws_count = n_part + n_out;
   }
+  double* part = M->lml_ws;
+  double* out = M->lml_ws + n_part;
   int rc = 0;
   switch (M->kernel) {
     case BOCF_KERN_SE: rc = launch_tiles<BOCF_KERN_SE>(M, ntiles, part, st); break;
@@ -204,8 +210,6 @@ int launch_log_likelihood(bocf_model* M, double* out_host, cudaStream_t st) {
       rc = BOCF_ERR_CUDA;
     }
   }
-  cudaFree(part);
-  cudaFree(out);
   return rc;
 }
 

@@ -61,6 +61,8 @@ struct bocf_model {
   double* cs2 = nullptr;      //                  ... of the second
   double* aq = nullptr;       // H*m   2^(8S-2-eA): quantiser of K*   (K* <= sigma_f^2)
   double* vq = nullptr;       // H*m   2^(8S-2-eV): quantiser of V    (|V| <= sigma_f)
+  double* lml_ws = nullptr;   // workspace of the likelihood pass (per-tile partials + results), kept across calls: the
+  size_t lml_ws_count = 0;    // fit loops call it thousands of times and cudaMalloc / cudaFree cost milliseconds each
   bool split_ready = false;
   bool precision_resolved = false;   // M->S and the digit planes match the current factor and requested mode
 };
