@@ -75,36 +75,37 @@ class GammaPrior(object):
         return (self.a - 1.) / x - self.b
 
 
-class _Output(object):
-    """Parameter bookkeeping of one output: param_array = [variance, lengthscale(s), noise] and its un-fixed mask."""
-
-    def __init__(self, variance, lengthscale, noise, fix_noise, instance_noise):
-        self.n_len = int(np.asarray(lengthscale).size)
-        self.param_array = np.concatenate([[float(variance)], np.asarray(lengthscale, dtype=float).reshape(-1), [float(noise)]])
-        self.free = np.ones(self.param_array.size, dtype=bool)
-        self.free[-1] = not fix_noise
-        self.fix_noise = bool(fix_noise)
-        self.instance_noise = float(instance_noise)
-        self.lml = None                 # likelihood terms of the LAST inference (may be stale w.r.t. param_array)
-        self.dlml = None
-        self.fail_count = 0
-
-    @property
-    def optimizer_array(self):
-        return logexp_finv(self.param_array[self.free])
-
-    def set_optimizer_array(self, x):
-        self.param_array[self.free] = logexp_f(np.asarray(x, dtype=float))
-
-
 class HyperInference(object):
+    """State of all outputs in one padded table: column 0 = kernel variance, columns 1..d = lengthscales (only column 1 for a
+    shared lengthscale), column d+1 = noise variance; `valid` marks the entries an output has, `free` the un-fixed ones.
+    The compact per-output param_array of the reference is PA[j, valid[j]] (same order)."""
+
     def __init__(self, evaluate, input_dim, kernels, noises, fix_noise, instance_noise, n_samples=10, n_burnin=100,
                  subsample_interval=10, step_size=1e-1, leapfrog_steps=20, max_iters=200):
         """kernels: per output (variance, lengthscale array of size 1 (shared) or d); noises: initial noise variances."""
         self.evaluate = evaluate
-        self.d = int(input_dim)
-        self.out = [_Output(k[0], k[1], nz, fx, inz) for k, nz, fx, inz in zip(kernels, noises, fix_noise, instance_noise)]
-        self.m = len(self.out)
+        self.d = d = int(input_dim)
+        self.m = m = len(kernels)
+        self.PA = np.ones((m, d + 2))
+        self.valid = np.zeros((m, d + 2), dtype=bool)
+        self.shared = np.zeros(m, dtype=bool)
+        for j, (k, nz) in enumerate(zip(kernels, noises)):
+            ls = np.asarray(k[1], dtype=float).reshape(-1)
+            assert ls.size in (1, d)
+            self.shared[j] = (ls.size == 1 and d > 1)
+            self.PA[j, 0] = float(k[0])
+            self.PA[j, 1:1 + ls.size] = ls
+            self.PA[j, d + 1] = float(nz)
+            self.valid[j, 0] = self.valid[j, d + 1] = True
+            self.valid[j, 1:1 + ls.size] = True
+        self.fix_noise = np.array([bool(f) for f in fix_noise])
+        self.instance_noise = np.array([float(v) for v in instance_noise])
+        self.free = self.valid.copy()
+        self.free[self.fix_noise, d + 1] = False
+        self.nfree = self.free.sum(1)
+        self.lml = np.zeros(m)                   # likelihood terms of the LAST inference (may be stale w.r.t. PA)
+        self.dlml = np.zeros((m, d + 2))
+        self.fail_count = [0] * m
         self.n_samples, self.n_burnin, self.subsample_interval = int(n_samples), int(n_burnin), int(subsample_interval)
         self.step_size, self.leapfrog_steps, self.max_iters = float(step_size), int(leapfrog_steps), int(max_iters)
         self.prior = GammaPrior(2., 4.)
@@ -113,29 +114,55 @@ class HyperInference(object):
         self.chain = None
         self.optimum = None
 
+    # ---- parameter views ------------------------------------------------------------------------------------------------
+    def param_array(self, j):
+        return self.PA[j, self.valid[j]]
+
+    def _free_compact(self, j):
+        return self.free[j, self.valid[j]]
+
+    def optimizer_array(self, j):
+        return logexp_finv(self.PA[j, self.free[j]])
+
+    def set_optimizer_array(self, j, x):
+        self.PA[j, self.free[j]] = logexp_f(np.asarray(x, dtype=float))
+
+    def _optimizer_table(self):
+        return np.where(self.free, logexp_finv(self.PA), 0.0)
+
+    def _set_optimizer_table(self, X, rows=None):
+        new = np.where(self.free, logexp_f(X), self.PA)
+        if rows is None:
+            self.PA = new
+        else:
+            self.PA[rows] = new[rows]
+
     # ---- one device pass for all outputs ------------------------------------------------------------------------------
     def _pack(self):
-        var = np.array([o.param_array[0] for o in self.out])
-        ls = np.stack([np.broadcast_to(o.param_array[1:1 + o.n_len], (self.d,)) if o.n_len == 1
-                       else o.param_array[1:1 + o.n_len] for o in self.out])
-        nz = np.array([o.param_array[-1] for o in self.out])
-        return var, np.ascontiguousarray(ls, dtype=np.float64), nz
+        d = self.d
+        ls = np.where(self.shared[:, None], self.PA[:, 1:2], self.PA[:, 1:1 + d])
+        return self.PA[:, 0].copy(), np.ascontiguousarray(ls, dtype=np.float64), self.PA[:, d + 1].copy()
 
-    def _store(self, j, lml, gv, gl, gn):
-        o = self.out[j]
-        o.lml = float(lml[j])
-        g_len = [gl[j].sum()] if o.n_len == 1 else gl[j]         # shared lengthscale: stationary.py:213-215, se.py:185
-        o.dlml = np.concatenate([[gv[j]], np.asarray(g_len, dtype=float), [gn[j]]])
+    def _store(self, rows, lml, gv, gl, gn):
+        d = self.d
+        rows = np.asarray(list(rows), dtype=int)
+        self.lml[rows] = np.asarray(lml)[rows]
+        self.dlml[rows, 0] = np.asarray(gv)[rows]
+        g = np.asarray(gl)[rows]
+        sh = self.shared[rows]
+        g = np.where(sh[:, None], 0.0, g)
+        g[:, 0] = np.where(sh, np.asarray(gl)[rows].sum(1), g[:, 0])   # shared lengthscale: stationary.py:213-215, se.py:185
+        self.dlml[rows, 1:1 + d] = g
+        self.dlml[rows, d + 1] = np.asarray(gn)[rows]
 
     def _infer(self, which=None):
-        """Re-run the inference at the current param_array of every output; returns the set of outputs whose covariance
-        was not positive definite even with jitter (their likelihood terms stay stale, like a failed paramz update)."""
+        """Re-run the inference at the current parameters of every output; returns the set of outputs whose covariance was
+        not positive definite even with jitter (their likelihood terms stay stale, like a failed paramz update)."""
         which = range(self.m) if which is None else which
         try:
             self.device_passes += 1
             res = self.evaluate(*self._pack())
-            for j in which:
-                self._store(j, *res)
+            self._store(which, *res)
             return set()
         except NotPositiveDefiniteError:
             if self.m == 1:
@@ -152,7 +179,7 @@ class HyperInference(object):
             try:
                 self.device_passes += 1
                 res = self.evaluate(v2, l2, n2)
-                self._store(j, *res)
+                self._store([j], *res)
             except NotPositiveDefiniteError:
                 failed.add(j)
         return failed
@@ -160,19 +187,32 @@ class HyperInference(object):
     def _remember_good(self):
         self._last_good = self._pack()
 
-    # ---- objective pieces (per output, host) ---------------------------------------------------------------------------
-    def _objective(self, o):
-        x = o.param_array
-        log_prior = float(np.sum(self.prior.lnpdf(x)) + np.sum(logexp_log_jacobian(x[o.free])))
-        return -o.lml - log_prior
+    # ---- objective pieces ---------------------------------------------------------------------------------------------------
+    def _objective(self, j):
+        """-log likelihood - log prior of output j (priorizable.py:49-65: Gamma prior on every entry, log-Jacobian of the
+        transform on the un-fixed ones)."""
+        x = self.param_array(j)
+        log_prior = float(np.sum(self.prior.lnpdf(x)) + np.sum(logexp_log_jacobian(x[self._free_compact(j)])))
+        return -self.lml[j] - log_prior
 
-    def _objective_gradient_t(self, o):
-        """_transform_gradients(objective_function_gradients()): gradient w.r.t. the optimizer array."""
-        x = o.param_array
+    def _objective_gradient_t(self, j):
+        """_transform_gradients(objective_function_gradients()) of output j: gradient w.r.t. its optimizer array."""
+        x = self.param_array(j)
+        fc = self._free_compact(j)
         dprior = self.prior.lnpdf_grad(x) * np.ones(x.size)
-        dprior[o.free] += logexp_log_jacobian_grad(x[o.free])
-        g = -(o.dlml + dprior)
-        return logexp_gradfactor(x[o.free], g[o.free])
+        dprior[fc] += logexp_log_jacobian_grad(x[fc])
+        g = -(self.dlml[j, self.valid[j]] + dprior)
+        return logexp_gradfactor(x[fc], g[fc])
+
+    def _objective_all(self):
+        x = self.PA
+        lp = np.where(self.valid, self.prior.lnpdf(x), 0.0).sum(1) + np.where(self.free, logexp_log_jacobian(x), 0.0).sum(1)
+        return -self.lml - lp
+
+    def _objective_gradient_t_all(self):
+        x = self.PA
+        dprior = self.prior.lnpdf_grad(x) + np.where(self.free, logexp_log_jacobian_grad(x), 0.0)
+        return np.where(self.free, logexp_gradfactor(x, -(self.dlml + dprior)), 0.0)
 
     # ---- ML-II: one L-BFGS-B run per output, objective calls batched -------------------------------------------------
     def optimize(self):
@@ -186,7 +226,7 @@ class HyperInference(object):
             keys = sorted(pending)
             try:
                 for j in keys:
-                    self.out[j].set_optimizer_array(pending[j])
+                    self.set_optimizer_array(j, pending[j])
                 failed = self._infer(keys)
             except BaseException as e:                       # no device / library error: wake every waiting run
                 errors.append(e)
@@ -198,15 +238,14 @@ class HyperInference(object):
             if not failed:
                 self._remember_good()
             for j in keys:
-                o = self.out[j]
                 if j in failed:                              # paramz Model._objective_grads, except branch
-                    if o.fail_count >= self.allowed_failures:
+                    if self.fail_count[j] >= self.allowed_failures:
                         errors.append(NotPositiveDefiniteError(-4, "not positive definite, even with jitter."))
-                    o.fail_count += 1
-                    results[j] = (np.inf, np.clip(self._objective_gradient_t(o), -1e10, 1e10))
+                    self.fail_count[j] += 1
+                    results[j] = (np.inf, np.clip(self._objective_gradient_t(j), -1e10, 1e10))
                 else:
-                    o.fail_count = 0
-                    results[j] = (self._objective(o), self._objective_gradient_t(o))
+                    self.fail_count[j] = 0
+                    results[j] = (self._objective(j), self._objective_gradient_t(j))
             pending.clear()
             cv.notify_all()
 
@@ -226,11 +265,10 @@ class HyperInference(object):
 
         def run(j):
             try:
-                o = self.out[j]
-                if not np.any(o.free):
-                    x_opt[j] = o.optimizer_array
+                if self.nfree[j] == 0:
+                    x_opt[j] = self.optimizer_array(j)
                 else:
-                    res = scipy.optimize.fmin_l_bfgs_b(lambda x: call(j, x), o.optimizer_array, maxfun=self.max_iters,
+                    res = scipy.optimize.fmin_l_bfgs_b(lambda x: call(j, x), self.optimizer_array(j), maxfun=self.max_iters,
                                                        maxiter=self.max_iters)
                     x_opt[j] = res[0]
             except BaseException as e:                       # pragma: no cover
@@ -249,54 +287,52 @@ class HyperInference(object):
         if errors:
             raise errors[0]
         for j in range(m):                                   # Model.optimize: self.optimizer_array = opt.x_opt
-            self.out[j].set_optimizer_array(x_opt[j])
+            self.set_optimizer_array(j, x_opt[j])
         if self._infer():
             raise NotPositiveDefiniteError(-4, "not positive definite, even with jitter.")
         self._remember_good()
-        self.optimum = [o.param_array.copy() for o in self.out]
+        self.optimum = [self.param_array(j).copy() for j in range(m)]
 
-    # ---- HMC, all outputs with the same leap-frog index ---------------------------------------------------------------
+    # ---- HMC, all outputs with the same leap-frog index (hmc.py:30-66) -------------------------------------------------
     def sample(self, momenta, uniforms):
         """momenta[j]: (num_samples, P_j); uniforms[j]: (num_samples,).  Returns chain[j] (num_samples, P_j)."""
         num = len(uniforms[0])
-        outs = self.out
-        chain = [np.empty((num, int(o.free.sum()))) for o in outs]
-        eps = self.step_size
+        m, eps = self.m, self.step_size
+        MOM = np.zeros((num, m, self.d + 2))
+        for j in range(m):
+            MOM[:, j, self.free[j]] = momenta[j]
+        U = np.stack([np.asarray(u, dtype=float) for u in uniforms], axis=1)         # (num, m)
+        rec = np.empty((num, m, self.d + 2))
+        const = self.nfree * np.log(2 * np.pi) / 2.
         for i in range(num):
-            p = [momenta[j][i].copy() for j in range(self.m)]
-            H_old, theta_old = [], []
-            for j, o in enumerate(outs):
-                H_old.append(self._objective(o) + p[j].size * np.log(2 * np.pi) / 2. + np.dot(p[j], p[j]) / 2.)
-                theta_old.append(o.optimizer_array.copy())
-                chain[j][i] = o.param_array[o.free]
+            p = MOM[i].copy()
+            H_old = self._objective_all() + const + (p * p).sum(1) / 2.
+            theta_old = self._optimizer_table()
+            rec[i] = self.PA
             for _ in range(self.leapfrog_steps):             # hmc.py:58-62
-                for j, o in enumerate(outs):
-                    p[j] += -eps / 2. * self._objective_gradient_t(o)
-                    o.set_optimizer_array(o.optimizer_array + eps * p[j])
+                p += -eps / 2. * self._objective_gradient_t_all()
+                self._set_optimizer_table(self._optimizer_table() + eps * p)
                 if self._infer():
                     raise NotPositiveDefiniteError(-4, "not positive definite, even with jitter.")
-                for j, o in enumerate(outs):
-                    p[j] += -eps / 2. * self._objective_gradient_t(o)
-            rejected = False
-            for j, o in enumerate(outs):
-                H_new = self._objective(o) + p[j].size * np.log(2 * np.pi) / 2. + np.dot(p[j], p[j]) / 2.
-                k = 1. if H_old[j] > H_new else np.exp(H_old[j] - H_new)
-                if uniforms[j][i] < k:
-                    chain[j][i] = o.param_array[o.free]
-                else:
-                    o.set_optimizer_array(theta_old[j])      # hmc.py:56
-                    rejected = True
-            if rejected and self._infer():
-                raise NotPositiveDefiniteError(-4, "not positive definite, even with jitter.")
-        return chain
+                p += -eps / 2. * self._objective_gradient_t_all()
+            H_new = self._objective_all() + const + (p * p).sum(1) / 2.
+            with np.errstate(over="ignore", invalid="ignore"):
+                k = np.where(H_old > H_new, 1., np.exp(H_old - H_new))
+            accept = U[i] < k
+            rec[i][accept] = self.PA[accept]
+            if not np.all(accept):
+                self._set_optimizer_table(theta_old, rows=~accept)                   # hmc.py:56
+                if self._infer():
+                    raise NotPositiveDefiniteError(-4, "not positive definite, even with jitter.")
+        return [rec[:, j, self.free[j]] for j in range(m)]
 
     def draw_randomness(self, num_samples):
         """numpy global-generator draws in the reference's order: for each output, the perturbation of the whole
         param_array (gpmodel.py:118), then per sample one momentum vector (hmc.py:43) and one uniform (hmc.py:53)."""
         perturb, momenta, uniforms = [], [], []
-        for o in self.out:
-            P = int(o.free.sum())
-            perturb.append(np.random.randn(o.param_array.size))
+        for j in range(self.m):
+            P = int(self.nfree[j])
+            perturb.append(np.random.randn(int(self.valid[j].sum())))
             mom = np.empty((num_samples, P))
             uni = np.empty(num_samples)
             for i in range(num_samples):
@@ -312,18 +348,19 @@ class HyperInference(object):
         self.optimize()
         num = self.n_burnin + self.n_samples * self.subsample_interval
         perturb, momenta, uniforms = self.draw_randomness(num)
-        for o, e in zip(self.out, perturb):
-            o.param_array[:] = o.param_array * (1. + e * 0.01)
+        for j, e in enumerate(perturb):
+            self.PA[j, self.valid[j]] = self.param_array(j) * (1. + e * 0.01)
         self.chain = self.sample(momenta, uniforms)
-        H = self.n_samples
+        H, d = self.n_samples, self.d
         var = np.empty((H, self.m))
-        ls = np.empty((H, self.m, self.d))
+        ls = np.empty((H, self.m, d))
         nz = np.empty((H, self.m))
         self.hmc_samples = []
-        for j, o in enumerate(self.out):
+        for j in range(self.m):
             s = self.chain[j][self.n_burnin::self.subsample_interval][:H]
             self.hmc_samples.append(s)
+            n_len = 1 if (self.shared[j] or d == 1) else d
             var[:, j] = s[:, 0]
-            ls[:, j, :] = s[:, 1:2] if o.n_len == 1 else s[:, 1:1 + o.n_len]
-            nz[:, j] = o.instance_noise if o.fix_noise else s[:, -1]
+            ls[:, j, :] = s[:, 1:2] if n_len == 1 else s[:, 1:1 + n_len]
+            nz[:, j] = self.instance_noise[j] if self.fix_noise[j] else s[:, -1]
         return var, ls, nz
