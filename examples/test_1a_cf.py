@@ -4,10 +4,12 @@ the CBO loop with EI-CF (uEI_noiseless, selected at test_1a.py:151), on the CUDA
 
 Problem (test_1a.py:19-33): d = 4, m = 5 attributes, each a GP sample on the 6^4 grid (SE kernel, variance 2,
 lengthscale 0.3, seeds j+7); the objective is the posterior mean of those GPs; utility -sum_j (y_j - theta_j)^2
-with theta = f(x_opt of attribute 0) (:60-96); model = multi_outputGP with fixed hyper-parameters.
-The two dead imports of the script (uKG_SGA, uKG_cf) are dropped; `fixed_hyps=True` keeps the run deterministic.
+with theta = f(x_opt of attribute 0) (:60-96); model = multi_outputGP(output_dim=m, exact_feval=[False]*m,
+fixed_hyps=False) as at test_1a.py:53, i.e. every iteration refits the hyper-parameters (ML-II) and draws 10 HMC
+hyper-samples per output -- all outputs in lockstep on the device likelihood.  `--fixed-hyps` switches to the
+deterministic GPModelFixedHyps variant.  The two dead imports of the script (uKG_SGA, uKG_cf) are dropped.
 
-    python examples/test_1a_cf.py [--iters 10] [--seed 0]
+    python examples/test_1a_cf.py [--iters 10] [--seed 0] [--fixed-hyps]
 """
 import argparse
 import os
@@ -20,7 +22,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bocf_b200 as B  # noqa: E402
 
 
-def build(seed=0, n_starting=400):
+def build(seed=0, n_starting=400, fixed_hyps=False):
     np.random.seed(seed)
     d, m = 4, 5
     I = np.linspace(0., 1., 6)
@@ -38,7 +40,7 @@ def build(seed=0, n_starting=400):
 
     objective = B.MultiObjective(f, as_list=False, output_dim=m)
     space = B.Design_space(space=[{'name': 'var', 'type': 'continuous', 'domain': (0, 1), 'dimensionality': d}])
-    model = B.multi_outputGP(output_dim=m, fixed_hyps=True)
+    model = B.multi_outputGP(output_dim=m, exact_feval=[False] * m, fixed_hyps=fixed_hyps)
     acq_opt = B.AcquisitionOptimizer(optimizer='lbfgs2', inner_optimizer='lbfgs2', space=space, n_starting=n_starting)
     X_init = B.initial_design('random', space, 2 * (d + 1))
     # theta: attribute values at the maximiser of attribute 0 (test_1a.py:60-81)
@@ -62,8 +64,9 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--fixed-hyps", action="store_true")
     a = ap.parse_args()
-    bo = build(a.seed)
+    bo = build(a.seed, fixed_hyps=a.fixed_hyps)
     bo.run_optimization(max_iter=a.iters, verbosity=True)
     print("suggested points:\n", np.vstack(bo.suggested_points))
     print("best-value trace:", np.array(bo.historical_optimal_values))

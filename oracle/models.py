@@ -5,8 +5,8 @@ instance per hyper-sample, selected with set_hyperparameters(i); variance
 clipped at 1e-10), GPyOpt/models/gpmodel_fixed_hyps.py:42-112,187-199 and
 multi_outputGP.py:97-306.
 
-Hyper-parameter fitting (ML-II + HMC, gpmodel.py:102-128) is out of scope; the
-hyper-samples are supplied explicitly.
+Hyper-samples are either supplied explicitly (from_hyper_samples) or inferred like
+GPModel.updateModel does (ML-II + HMC, gpmodel.py:102-128: GPModelInferred on top of oracle/hmc.py).
 """
 import numpy as np
 
@@ -79,6 +79,31 @@ class GPModel(object):
         return self.current_model.posterior_variance_gradient(X)
 
 
+class GPModelInferred(GPModel):
+    """GPModel with its own hyper-parameter inference (gpmodel.py:50-128): every updateModel runs ML-II + HMC on `model`
+    and copies the sub-sampled chain states into the n_samples instances (un-fixed entries only, :121-126)."""
+
+    def __init__(self, kind='se', kernel=None, noise_var=None, exact_feval=False, n_samples=10, ARD=False, **sampler):
+        from .hmc import GPModelHMC
+        self.inference = GPModelHMC(kind=kind, kernel=kernel, noise_var=noise_var, exact_feval=exact_feval,
+                                    n_samples=n_samples, ARD=ARD, **sampler)
+        self.kind = kind
+        self.n_samples = n_samples
+        self.model_instances = [None] * n_samples
+        self.model = None
+        self.current_model = None
+
+    def updateModel(self, X_all, Y_all, X_new=None, Y_new=None):
+        self.inference.updateModel(X_all, Y_all)
+        d = X_all.shape[1]
+        var, ls, noise = self.inference.hyper_samples(d)
+        for i in range(self.n_samples):
+            kern = Kern(self.kind, d, var[i], ls[i], ARD=True)
+            self.model_instances[i] = GPRegression(X_all, Y_all, kern, noise[i])
+        self.model = self.model_instances[0]
+        self.set_hyperparameters(0)
+
+
 class GPModelFixedHyps(GPModel):
     """gpmodel_fixed_hyps.py: one model, set_hyperparameters is a no-op (:76-77)."""
 
@@ -115,6 +140,14 @@ class multi_outputGP(object):
             kerns = [Kern(kind, d, variance[h, j], lengthscale[h, j], ARD=ARD) for h in range(H)]
             outs.append(GPModel(kerns, [noise[h, j] for h in range(H)]))
         return cls(m, outs, H if n_samples is None else n_samples)
+
+    @classmethod
+    def inferred(cls, output_dim, kind='se', noise_var=None, exact_feval=None, n_samples=10, ARD=None, **sampler):
+        # multi_outputGP.py:23-58 with fixed_hyps=False: one GPModel per output, each with its own ML-II + HMC
+        outs = [GPModelInferred(kind=kind, noise_var=None if noise_var is None else noise_var[j],
+                                exact_feval=False if exact_feval is None else exact_feval[j], n_samples=n_samples,
+                                ARD=True if ARD is None else ARD[j], **sampler) for j in range(output_dim)]
+        return cls(output_dim, outs, n_samples)
 
     @classmethod
     def fixed_hyps(cls, output_dim, input_dim, kernel=None, noise_var=None, n_samples=10):

@@ -75,3 +75,45 @@ def test_batched_multistart_equals_sequential(cuda_device):
         res.append(acq.optimize(x_baseline=P.X[:1]))
     np.testing.assert_allclose(res[0][0], res[1][0], atol=1e-9)
     np.testing.assert_allclose(np.asarray(res[0][1]).reshape(-1), np.asarray(res[1][1]).reshape(-1), atol=1e-12)
+
+
+def _run_inferred(side, cuda_device, iters=2, seed=3):
+    """The reference scripts' own configuration (test_1a.py:53, test_2a.py:49): fixed_hyps=False, so every updateModel
+    runs ML-II + HMC and the acquisition averages over the n_samples hyper-sample instances."""
+    import bocf_b200 as B
+    d, m, f, theta = _problem(5)
+    sampler = dict(n_burnin=4, subsample_interval=2, step_size=1e-1, leapfrog_steps=5, max_iters=200)
+    np.random.seed(seed)
+    space = B.Design_space(space=[{'name': 'var', 'type': 'continuous', 'domain': (0, 1), 'dimensionality': d}])
+    objective = B.MultiObjective(f, as_list=False, output_dim=m)
+    acq_opt = B.AcquisitionOptimizer(optimizer='lbfgs2', inner_optimizer='lbfgs2', space=space, n_starting=64, n_anchor=4)
+    X_init = B.initial_design('random', space, 4 * (d + 1))
+    if side == "cuda":
+        model = B.multi_outputGP(m, exact_feval=[True] * m, n_samples=3, fixed_hyps=False, device=cuda_device, **sampler)
+        pd = B.ParameterDistribution(support=theta, prob_dist=np.ones(1))
+        U = B.Utility(parameter_dist=pd, composite="sumsq_target")
+        acq = B.uEI_noiseless(model, space, optimizer=acq_opt, utility=U)
+    else:
+        from oracle.models import multi_outputGP
+        from oracle.utility import make_utility, ParameterDistribution
+        from oracle.acquisitions import uEI_noiseless
+        model = multi_outputGP.inferred(m, kind="se", exact_feval=[True] * m, n_samples=3, **sampler)
+        U = make_utility("sumsq_target", ParameterDistribution(support=theta, prob_dist=np.ones(1)))
+        acq = uEI_noiseless(model, space, optimizer=acq_opt, utility=U, vectorised=True)
+    expU = B.ExpectationUtility(
+        lambda th, mu, v: -np.sum(np.square((mu.T - th).T), axis=0) - np.sum(v, axis=0),
+        lambda th, mu, v: -np.concatenate((2 * (np.squeeze(mu) - th), np.ones((len(np.squeeze(v)),)))))
+    bo = B.CBO(model, space, objective, acq, B.Sequential(acq), X_init, expectation_utility=expU)
+    bo.run_optimization(max_iter=iters)
+    return bo, model
+
+
+def test_cbo_loop_with_inferred_hyperparameters(cuda_device):
+    bo_g, mod_g = _run_inferred("cuda", cuda_device)
+    bo_c, mod_c = _run_inferred("cpu", cuda_device)
+    assert mod_g.last_update == "hmc" and mod_g.n_hyper_samples_loaded() == 3
+    assert len(bo_g.suggested_points) == 2 and np.all(np.isfinite(bo_g.historical_optimal_values))
+    # first iteration: same random numbers, same chains (up to fp64 rounding amplified by the leap-frog dynamics), same
+    # hyper-samples -> same selected point
+    np.testing.assert_allclose(bo_g.suggested_points[0], bo_c.suggested_points[0], atol=1e-3)
+    np.testing.assert_allclose(bo_g.historical_optimal_values[0], bo_c.historical_optimal_values[0], rtol=1e-3, atol=1e-5)
