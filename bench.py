@@ -240,7 +240,13 @@ def run_ours(args, cfg):
     model = product_model(P, str(dev), precision=args.precision)
     torch.cuda.synchronize()
     slices = model.active_slices()
-    t_factor = time.perf_counter() - t_setup
+    t_factor = time.perf_counter() - t_setup          # cold: library load, context, allocations, first launches
+    t0 = time.perf_counter()
+    model._upload_and_factorize(upload_data=False)      # warm: Gram + blocked Cholesky + L^-1 + alpha of all m outputs
+    torch.cuda.synchronize()
+    t_factor_warm = time.perf_counter() - t0
+    # n^3/3 (Cholesky) + n^3/3 (triangular inverse) + 2 n^2 (alpha) per output, SURVEY.md 8a row a15
+    factor_flops = c["H"] * c["m"] * (2.0 * c["n"] ** 3 / 3.0 + 2.0 * c["n"] ** 2)
     acq = bocf_b200.uEI_noiseless(model, None, utility=product_utility(P))
     acq.W_samples = P.Z
     # this rank's shard of the global candidate set (weak scaling: N per rank), seeded per rank
@@ -459,7 +465,8 @@ def run_ours(args, cfg):
                 "d2h_bytes_per_step": int(N * 8 + N * c["d"] * 8), "ms_per_step": ms_e2e / args.steps,
                 "api": "uEI_noiseless.acquisition_function_withGradients(numpy (N,d)) -> numpy (N,1),(N,d)"},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "mixed_precision_mode": mixed,
-        "cand_x_samples_per_s": value * c["S"], "factorize_s": t_factor, "step_ms": value_step_ms,
+        "cand_x_samples_per_s": value * c["S"], "factorize_s": t_factor, "factorize_warm_s": t_factor_warm,
+        "factorize_warm_tflops": factor_flops / t_factor_warm / 1e12, "step_ms": value_step_ms,
     }
     print(json.dumps(line))
     if world > 1:
