@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbocf_b200.so")
+LIB_PATH = os.environ.get("BOCF_LIB_PATH") or os.path.join(_HERE, "csrc", "libbocf_b200.so")   # override: kernel-variant experiments
 _lib = None
 
 KERNELS = {"se": 0, "rbf": 1, "matern52": 2, "matern32": 3}

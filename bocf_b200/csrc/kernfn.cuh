@@ -17,11 +17,27 @@
 // results, far inside the 1e-6 / 1e-9 parity bars.
 #pragma once
 #include "model.h"
+// Compile-time switches of the K* arithmetic (defaults = fastest measured, profiles/r1_split_experiments.md section 10):
+//   KV_EXPSEL   1: exp clamps at -700 without the final flush-to-zero select      KV_SQRTBIAS 1: sqrt biased by 1e-300, no select
+//   KV_CONST    1: sqrt(5), 5/3 ... from constant memory instead of literals       KV_LB: min CTAs/SM in kstar's launch bounds
+#ifndef KV_EXPSEL
+#define KV_EXPSEL 1
+#endif
+#ifndef KV_SQRTBIAS
+#define KV_SQRTBIAS 1
+#endif
+#ifndef KV_CONST
+#define KV_CONST 1
+#endif
+#ifndef KV_LB
+#define KV_LB 1
+#endif
 
 namespace bocf {
 
 // exp(x) for x <= 0.  Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor/Horner (remainder < 4e-18),
-// scaling by 2^k through the exponent field.  x < -700 (result < 1e-304) flushes to 0.
+// scaling by 2^k through the exponent field.  The argument is clamped at -700: anything below returns e^-700 ~ 1e-304
+// (the reference underflows to 0 below -745; the difference is invisible at any tolerance and saves a compare + select).
 // Coefficients live in constant memory so every DFMA takes them as a constant-bank operand: as immediates each 64-bit
 // literal costs two extra move instructions per use (the K* kernel was issue-bound on exactly those moves).
 static __constant__ double EXPC[16] = {
@@ -41,6 +57,14 @@ static __constant__ double EXPC[16] = {
     6.93147180369123816490e-01,  // [13] ln2 high
     1.90821492927058770002e-10,  // [14] ln2 low
     -700.0};
+// Kernel-family constants with a non-zero low word: as literals each use costs two register moves (see EXPC).
+static __constant__ double KERC[8] = {
+    2.23606797749978969641,      // [0] sqrt(5)
+    5.0 / 3.0,                   // [1]
+    -5.0 / 3.0,                  // [2]
+    1.73205080756887729353,      // [3] sqrt(3)
+    1e-300,                      // [4] keeps sqrt's seed finite at r2 == 0
+    0.0, 0.0, 0.0};
 __device__ __forceinline__ double exp_nonpos(double x) {
   const double xc = fmax(x, EXPC[15]);
   // round-to-nearest integer of xc * log2(e) through the 1.5 * 2^52 shift: no FRND / F2I conversion instructions,
@@ -56,17 +80,40 @@ __device__ __forceinline__ double exp_nonpos(double x) {
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   const int k = __double2loint(sh);
+#if KV_EXPSEL
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
   const double scaled = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
   return (x < EXPC[15]) ? 0.0 : scaled;
+#endif
 }
 
-// sqrt(a) for a >= 0 (finite): one Newton step on a * rsqrt(a).
-__device__ __forceinline__ double sqrt_nonneg(double a) {
-  const double y = rsqrt(a);
+// sqrt(a) for a >= 0 (finite).  libdevice's rsqrt(double) wraps the hardware seed (MUFU.RSQ64H, ~22 bits) in a range check
+// with an out-of-line slow path; that branch (BSSY / CALL / BSYNC per evaluation) keeps ptxas from interleaving the
+// independent distance -> kernel chains of an unrolled trip.  Here the seed is taken directly (rsqrt.approx.ftz.f64) and
+// refined branch-free: y <- y (1 + e/2 + 3 e^2/8) with e = 1 - a y^2 (cubic, error ~e^3 ~ 1e-20), then one Newton step on
+// s = a y.  The argument is biased by 1e-300 (a no-op for a > 1e-284) so the seed stays finite at a == 0: sqrt(0) comes
+// out as 1e-150 instead of 0, which no kernel value can see (1 + sqrt5 * 1e-150 == 1) -- one add instead of a compare and
+// two selects.
+__device__ __forceinline__ double sqrt_nonneg(double a0) {
+#if KV_SQRTBIAS
+  const double a = a0 + KERC[4];
+#else
+  const double a = a0;
+#endif
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double e = fma(-a * y, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  y = fma(y * e, p, y);
   double s = a * y;
-  const double e = fma(-s, s, a);
-  s = fma(e, 0.5 * y, s);
-  return (a > 0.0) ? s : 0.0;
+  const double r = fma(-s, s, a);
+#if KV_SQRTBIAS
+  return fma(r, 0.5 * y, s);
+#else
+  s = fma(r, 0.5 * y, s);
+  return (a > 1e-300) ? s : 0.0;
+#endif
 }
 
 template <int KIND, bool GRAD>
@@ -82,17 +129,25 @@ __device__ __forceinline__ void kern_eval(double r2, double variance, double& k,
   } else if (KIND == BOCF_KERN_MATERN52) {
     // stationary.py:529-533
     const double r = sqrt_nonneg(r2);
+#if KV_CONST
+    const double t = KERC[0] * r;               // sqrt(5) r
+    const double e = variance * exp_nonpos(-t);
+    const double lin = 1.0 + t;
+    k = fma(KERC[1], r2, lin) * e;
+    if (GRAD) g = (r2 != 0.0) ? KERC[2] * (lin * e) : 0.0;
+#else
     const double s5 = 2.23606797749978969641;   // sqrt(5)
     const double e = variance * exp_nonpos(-s5 * r);
     const double lin = 1.0 + s5 * r;
     k = (lin + 5.0 / 3.0 * r2) * e;
     if (GRAD) g = (r2 != 0.0) ? (-5.0 / 3.0) * (lin * e) : 0.0;
+#endif
   } else {
     // Matern32, stationary.py:440-444
     const double r = sqrt_nonneg(r2);
-    const double s3 = 1.73205080756887729353;   // sqrt(3)
-    const double e = variance * exp_nonpos(-s3 * r);
-    k = (1.0 + s3 * r) * e;
+    const double t = KERC[3] * r;               // sqrt(3) r
+    const double e = variance * exp_nonpos(-t);
+    k = (1.0 + t) * e;
     if (GRAD) g = (r2 != 0.0) ? -3.0 * e : 0.0;
   }
 }

@@ -39,7 +39,7 @@ struct SplitOut {
 
 // SPL: 0 = fp64 K* output; 5 = exactly five digit planes (the common case, fewer registers); 6 = up to six (so.S)
 template <int KIND, int DP, bool GRAD, int SPL>
-__global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ Xc, int64_t Nvalid, int64_t Nc, int d,
+__global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restrict__ Xc, int64_t Nvalid, int64_t Nc, int d,
                                                     int n, int n16, int n_pad, int m, int h,
                                                     const OutHyp* __restrict__ hyp, const double* __restrict__ XsAll,
                                                     const double* __restrict__ xsqAll,
@@ -125,17 +125,18 @@ __global__ void __launch_bounds__(128) kstar_kernel(const double* __restrict__ X
             }
             r2 = r2a + r2b;
           } else {
-            double dot = 0.0;
+            double dot0 = 0.0, dot1 = 0.0;               // two chains: half the dependent-DFMA depth
 #pragma unroll
-            for (int q = 0; q < DP; ++q) dot += xs[q] * sX[bb][q];
-            r2 = -2.0 * dot + (xsq_i + sxsq[bb]);
+            for (int q = 0; q < DP; q += 2) {
+              dot0 = fma(xs[q], sX[bb][q], dot0);
+              if (q + 1 < DP) dot1 = fma(xs[q + 1], sX[bb][q + 1], dot1);
+            }
+            r2 = -2.0 * (dot0 + dot1) + (xsq_i + sxsq[bb]);
             r2 = fmax(r2, 0.0);
           }
           kern_eval<KIND, GRAD>(r2, variance, kv, gv);
-          if (b >= n) {
-            kv = 0.0;
-            gv = 0.0;
-          }
+          // padded points b >= n need no mask: their alpha, column scale and factor rows / columns are zero, so whatever
+          // finite K*, G* they produce is multiplied by an exact zero downstream (mean, both contractions, epilogues)
           const double a = salpha[bb];
           mu += kv * a;
           if (GRAD) {
