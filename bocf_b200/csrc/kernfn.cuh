@@ -32,6 +32,12 @@
 #ifndef KV_LB
 #define KV_LB 1
 #endif
+#ifndef KV_SQRTSHORT
+#define KV_SQRTSHORT 1
+#endif
+#ifndef KV_EXPTAB
+#define KV_EXPTAB 1
+#endif
 
 namespace bocf {
 
@@ -88,6 +94,39 @@ __device__ __forceinline__ double exp_nonpos(double x) {
 #endif
 }
 
+// Table variant for the K* kernel: x = (32 k + j) ln2/32 + r, |r| <= ln2/64, exp(x) = 2^k * 2^(j/32) * p(r) with a degree-6
+// polynomial (remainder r^7/5040 < 4e-18) -- 11 fp64 instructions instead of 17; `tab` = 2^(j/32), j = 0..31, in SHARED
+// memory (lanes index it independently).  Same clamp at -700.
+static __constant__ double EXPT[8] = {
+    46.166241308446828384,       // [0] 32 log2(e)
+    0.021660849392446835,  // [1] ln2/32 high (low 17 mantissa bits zero: n*hi is exact for |n| < 2^17)
+    5.145609244655338e-14,     // [2] ln2/32 low
+    1.3888888888888889e-03,      // [3] 1/720
+    8.333333333333333e-03,       // [4] 1/120
+    4.1666666666666664e-02,      // [5] 1/24
+    1.6666666666666666e-01,      // [6] 1/6
+    0.0};
+__device__ __forceinline__ double exp_nonpos_tab(double x, const double* __restrict__ tab) {
+  const double xc = fmax(x, EXPC[15]);
+  const double sh = fma(xc, EXPT[0], EXPC[12]);
+  const double kf = sh - EXPC[12];
+  double r = fma(-kf, EXPT[1], xc);
+  r = fma(-kf, EXPT[2], r);
+  const int n = __double2loint(sh);
+  const double t = tab[n & 31];
+  double p = fma(EXPT[3], r, EXPT[4]);
+  p = fma(p, r, EXPT[5]);
+  p = fma(p, r, EXPT[6]);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  p *= t;
+  return __hiloint2double(__double2hiint(p) + ((n >> 5) << 20), __double2loint(p));
+}
+__device__ __forceinline__ void exp_table_fill(double* tab, int tid) {   // 2^(j/32) to < 1 ulp via the Horner exp
+  if (tid < 32) tab[tid] = exp2((double)tid * 0.03125);
+}
+
 // sqrt(a) for a >= 0 (finite).  libdevice's rsqrt(double) wraps the hardware seed (MUFU.RSQ64H, ~22 bits) in a range check
 // with an out-of-line slow path; that branch (BSSY / CALL / BSYNC per evaluation) keeps ptxas from interleaving the
 // independent distance -> kernel chains of an unrolled trip.  Here the seed is taken directly (rsqrt.approx.ftz.f64) and
@@ -107,8 +146,15 @@ __device__ __forceinline__ double sqrt_nonneg(double a0) {
   const double p = fma(0.375, e, 0.5);
   y = fma(y * e, p, y);
   double s = a * y;
+#if KV_SQRTBIAS && KV_SQRTSHORT
+  const double r = 0.0;
+#else
   const double r = fma(-s, s, a);
-#if KV_SQRTBIAS
+#endif
+#if KV_SQRTBIAS && KV_SQRTSHORT
+  (void)r;
+  return s;                        // y carries ~1e-20 after the cubic step: a*y is within 1.5 ulp of sqrt(a)
+#elif KV_SQRTBIAS
   return fma(r, 0.5 * y, s);
 #else
   s = fma(r, 0.5 * y, s);
@@ -116,28 +162,29 @@ __device__ __forceinline__ double sqrt_nonneg(double a0) {
 #endif
 }
 
-template <int KIND, bool GRAD>
-__device__ __forceinline__ void kern_eval(double r2, double variance, double& k, double& g) {
+#define BOCF_EXP(x) (TAB ? exp_nonpos_tab((x), tab) : exp_nonpos(x))
+template <int KIND, bool GRAD, bool TAB = false>
+__device__ __forceinline__ void kern_eval(double r2, double variance, double& k, double& g, const double* tab = nullptr) {
   if (KIND == BOCF_KERN_SE) {
     // se.py:60  variance * exp(-0.5 * sqdist)
-    k = variance * exp_nonpos(-0.5 * r2);
+    k = variance * BOCF_EXP(-0.5 * r2);
     if (GRAD) g = -k;
   } else if (KIND == BOCF_KERN_RBF) {
     // rbf.py:42-46 (r*r of the rounded sqrt differs from r2 by <= 1 ulp)
-    k = variance * exp_nonpos(-0.5 * r2);
+    k = variance * BOCF_EXP(-0.5 * r2);
     if (GRAD) g = (r2 != 0.0) ? -k : 0.0;
   } else if (KIND == BOCF_KERN_MATERN52) {
     // stationary.py:529-533
     const double r = sqrt_nonneg(r2);
 #if KV_CONST
     const double t = KERC[0] * r;               // sqrt(5) r
-    const double e = variance * exp_nonpos(-t);
+    const double e = variance * BOCF_EXP(-t);
     const double lin = 1.0 + t;
     k = fma(KERC[1], r2, lin) * e;
     if (GRAD) g = (r2 != 0.0) ? KERC[2] * (lin * e) : 0.0;
 #else
     const double s5 = 2.23606797749978969641;   // sqrt(5)
-    const double e = variance * exp_nonpos(-s5 * r);
+    const double e = variance * BOCF_EXP(-s5 * r);
     const double lin = 1.0 + s5 * r;
     k = (lin + 5.0 / 3.0 * r2) * e;
     if (GRAD) g = (r2 != 0.0) ? (-5.0 / 3.0) * (lin * e) : 0.0;
@@ -146,7 +193,7 @@ __device__ __forceinline__ void kern_eval(double r2, double variance, double& k,
     // Matern32, stationary.py:440-444
     const double r = sqrt_nonneg(r2);
     const double t = KERC[3] * r;               // sqrt(3) r
-    const double e = variance * exp_nonpos(-t);
+    const double e = variance * BOCF_EXP(-t);
     k = (1.0 + t) * e;
     if (GRAD) g = (r2 != 0.0) ? -3.0 * e : 0.0;
   }

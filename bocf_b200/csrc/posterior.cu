@@ -50,7 +50,9 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
   __shared__ double sxsq[128];
   __shared__ double salpha[128];
   __shared__ double sgcs[128];
+  __shared__ double sexp[32];
   const int tid = threadIdx.x;
+  if (KV_EXPTAB) exp_table_fill(sexp, tid);     // visible after the first __syncthreads of the tile loop
   const int j = blockIdx.y;
   const int hj = h * m + j;
   const int64_t i = (int64_t)blockIdx.x * 128 + tid;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
             r2 = -2.0 * (dot0 + dot1) + (xsq_i + sxsq[bb]);
             r2 = fmax(r2, 0.0);
           }
-          kern_eval<KIND, GRAD>(r2, variance, kv, gv);
+          kern_eval<KIND, GRAD, (KV_EXPTAB != 0)>(r2, variance, kv, gv, sexp);
           // padded points b >= n need no mask: their alpha, column scale and factor rows / columns are zero, so whatever
           // finite K*, G* they produce is multiplied by an exact zero downstream (mean, both contractions, epilogues)
           const double a = salpha[bb];
