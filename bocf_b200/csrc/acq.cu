@@ -84,6 +84,8 @@ __device__ __forceinline__ double comp_dphi(const CompCtx& c, double y) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int MC_WARPS = 8;
 constexpr int MCU = 4;         // sample groups per trip (independent base-sample loads in flight per lane)
+constexpr int MCB = 4;         // candidates per warp: every base sample loaded is applied to MCB candidates (the kernel
+                               // was bound by its loads: one z + mu + sigma + theta fetch per 3 fp64 operations)
 
 // MODE: 0 = EI value only, 1 = EI value + gradient, 2 = PI value
 template <int COMP, int MODE>
@@ -93,70 +95,88 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
     const double* __restrict__ theta, int L, int p, const double* __restrict__ weight,
     const double* __restrict__ fstar, double scale, int accumulate, double* __restrict__ acq,
     double* __restrict__ dacq) {
-  __shared__ double s_mu[MC_WARPS][MAXM];
-  __shared__ double s_sig[MC_WARPS][MAXM];
+  __shared__ double2 s_ms[MC_WARPS][MAXM][MCB];            // (mu, sigma) of the warp's MCB candidates, output-major
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * MC_WARPS + warp;
-  if (i >= Nvalid) return;
-  for (int j = lane; j < m; j += 32) {
-    s_mu[warp][j] = mean[(int64_t)j * Nc + i];
-    s_sig[warp][j] = sqrt(var[(int64_t)j * Nc + i]);       // uEI_noiseless.py:74,151
+  const int64_t i0 = ((int64_t)blockIdx.x * MC_WARPS + warp) * MCB;
+  if (i0 >= Nvalid) return;
+  const int nc = (int)min((int64_t)MCB, Nvalid - i0);       // valid candidates of this warp
+  for (int idx = lane; idx < m * MCB; idx += 32) {
+    const int j = idx / MCB, c = idx - j * MCB;
+    const int64_t i = i0 + min(c, nc - 1);                  // ragged tail: replicate the last valid candidate
+    s_ms[warp][j][c] = make_double2(mean[(int64_t)j * Nc + i], sqrt(var[(int64_t)j * Nc + i]));   // uEI_noiseless.py:74,151
   }
   __syncwarp();
 
-  double val_total = 0.0;   // sum_l w_l sum_s improvement
-  double grad_q = 0.0;      // lane q < d
+  double val_total[MCB];     // sum_l w_l sum_s improvement
+  double grad_q[MCB];        // lane q < d
+#pragma unroll
+  for (int c = 0; c < MCB; ++c) val_total[c] = grad_q[c] = 0.0;
   for (int l = 0; l < L; ++l) {
     const double* th = theta + (int64_t)l * p;
     const double wl = weight[l];
     const double fs = (MODE == 2) ? fstar[l] + 1e-6 : fstar[l];       // uPI.py:83 jitter
-    double val_l = 0.0;
+    double val_l[MCB];
+#pragma unroll
+    for (int c = 0; c < MCB; ++c) val_l[c] = 0.0;
     for (int sb = 0; sb < S; sb += 1024) {
-      unsigned mask = 0u;
-      // MCU sample groups per trip: their MCU x m base-sample loads are independent and issued together (the kernel
-      // was latency bound on one dependent load -> fma chain per sample, ncu: long_scoreboard)
+      unsigned mask[MCB];
+#pragma unroll
+      for (int c = 0; c < MCB; ++c) mask[c] = 0u;
 #pragma unroll 1
       for (int k0 = 0; k0 < 32; k0 += MCU) {
-        double U[MCU];
+        double U[MCB][MCU];
 #pragma unroll
-        for (int u = 0; u < MCU; ++u) U[u] = 0.0;
+        for (int c = 0; c < MCB; ++c)
+#pragma unroll
+          for (int u = 0; u < MCU; ++u) U[c][u] = 0.0;
         for (int j = 0; j < m; ++j) {
-          const CompCtx c = comp_ctx<COMP>(th, j, m);
-          const double muj = s_mu[warp][j], sgj = s_sig[warp][j];
+          const CompCtx cx = comp_ctx<COMP>(th, j, m);
           const double* zr = Zt + (int64_t)j * S + sb + lane;
           double z[MCU];
 #pragma unroll
           for (int u = 0; u < MCU; ++u) z[u] = (sb + (k0 + u) * 32 + lane < S) ? zr[(k0 + u) * 32] : 0.0;
 #pragma unroll
-          for (int u = 0; u < MCU; ++u) U[u] += comp_phi<COMP>(c, muj + sgj * z[u]);
+          for (int c = 0; c < MCB; ++c) {
+            const double2 ms = s_ms[warp][j][c];
+#pragma unroll
+            for (int u = 0; u < MCU; ++u) U[c][u] += comp_phi<COMP>(cx, ms.x + ms.y * z[u]);
+          }
         }
 #pragma unroll
         for (int u = 0; u < MCU; ++u) {
           const int k = k0 + u;
           if (sb + k * 32 + lane < S) {
-            if (MODE == 2) {
-              val_l += ((U[u] - fs) > 0.0) ? 1.0 : 0.0;
-            } else {
-              val_l += fmax(U[u] - fs, 0.0);                              // uEI_noiseless.py:80,161
-              if (U[u] > fs) mask |= (1u << k);                           // :162 strict >
+#pragma unroll
+            for (int c = 0; c < MCB; ++c) {
+              if (MODE == 2) {
+                val_l[c] += ((U[c][u] - fs) > 0.0) ? 1.0 : 0.0;
+              } else {
+                val_l[c] += fmax(U[c][u] - fs, 0.0);                          // uEI_noiseless.py:80,161
+                if (U[c][u] > fs) mask[c] |= (1u << k);                       // :162 strict >
+              }
             }
           }
         }
       }
       if (MODE == 1) {
-        if (__any_sync(0xffffffffu, mask != 0u)) {
+#pragma unroll
+        for (int c = 0; c < MCB; ++c) {
+          if (c >= nc) break;
+          const unsigned mk = mask[c];
+          if (!__any_sync(0xffffffffu, mk != 0u)) continue;
+          const int64_t i = i0 + c;
           for (int j = 0; j < m; ++j) {
-            const CompCtx c = comp_ctx<COMP>(th, j, m);
-            const double muj = s_mu[warp][j], sgj = s_sig[warp][j];
+            const CompCtx cx = comp_ctx<COMP>(th, j, m);
+            const double2 ms = s_ms[warp][j][c];
             double Aj = 0.0, Bj = 0.0;
 #pragma unroll 1
             for (int k = 0; k < 32; ++k) {
-              const bool on = (mask >> k) & 1u;
+              const bool on = (mk >> k) & 1u;
               if (__ballot_sync(0xffffffffu, on) == 0u) continue;
               if (on) {
-                const int s = sb + k * 32 + lane;
-                const double z = Zt[(int64_t)j * S + s];
-                const double dp = comp_dphi<COMP>(c, muj + sgj * z);
+                const int sidx = sb + k * 32 + lane;
+                const double z = Zt[(int64_t)j * S + sidx];
+                const double dp = comp_dphi<COMP>(cx, ms.x + ms.y * z);
                 Aj += dp;
                 Bj += dp * z;
               }
@@ -165,21 +185,27 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
             Bj = warp_sum(Bj);
             if (lane < d) {
               const int64_t o = ((int64_t)j * Nc + i) * d + lane;
-              grad_q += wl * (Aj * dmean[o] + Bj * (0.5 / sgj) * dvar[o]);   // :163-166
+              grad_q[c] += wl * (Aj * dmean[o] + Bj * (0.5 / ms.y) * dvar[o]);   // :163-166
             }
           }
         }
       }
     }
-    val_total += wl * warp_sum(val_l);
+#pragma unroll
+    for (int c = 0; c < MCB; ++c) val_total[c] += wl * warp_sum(val_l[c]);
   }
-  if (lane == 0) {
-    const double v = val_total * scale;
-    acq[i] = accumulate ? acq[i] + v : v;
-  }
-  if (MODE == 1 && lane < d) {
-    const double gq = grad_q * scale;
-    dacq[i * d + lane] = accumulate ? dacq[i * d + lane] + gq : gq;
+#pragma unroll
+  for (int c = 0; c < MCB; ++c) {
+    if (c >= nc) break;
+    const int64_t i = i0 + c;
+    if (lane == 0) {
+      const double v = val_total[c] * scale;
+      acq[i] = accumulate ? acq[i] + v : v;
+    }
+    if (MODE == 1 && lane < d) {
+      const double gq = grad_q[c] * scale;
+      dacq[i * d + lane] = accumulate ? dacq[i * d + lane] + gq : gq;
+    }
   }
 }
 
@@ -367,7 +393,7 @@ __global__ void topk_gather_kernel(const double* __restrict__ val, const int64_t
 template <int COMP>
 static int launch_mc_t(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvalid, double* acq, double* dacq,
                        cudaStream_t st) {
-  const unsigned grid = (unsigned)ceil_div(Nvalid, MC_WARPS);
+  const unsigned grid = (unsigned)ceil_div(Nvalid, (int64_t)MC_WARPS * MCB);
   const int mode = (P.variant == BOCF_ACQ_PI_CF) ? 2 : (dacq ? 1 : 0);
 #define BOCF_MC_ARGS                                                                                              \
   cb.mean, cb.var, cb.dmean, cb.dvar, cb.Nc, Nvalid, P.m, P.d, P.Zt, P.S, P.theta, P.L, P.p, P.weight, P.fstar, \
