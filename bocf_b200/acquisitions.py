@@ -47,11 +47,26 @@ class AcquisitionBase(object):
         self.cost_withGradients = cost_withGradients
 
     def acquisition_function(self, x):
-        return -self._compute_acq(x)
+        # base.py:33-44: the optimiser minimises, so the sign is flipped
+        return self._negated(self._compute_acq, x)
 
     def acquisition_function_withGradients(self, x):
-        f_acqu, df_acqu = self._compute_acq_withGradients(x)
-        return -f_acqu, -df_acqu
+        # base.py:47-56
+        return self._negated(self._compute_acq_withGradients, x)
+
+    def _negated(self, fn, x):
+        """-fn(x).  The flip is applied on the device, before the results leave it (`_run` honours `_sign`): negating a
+        (1M, d) gradient on the host costs more than the whole D2H copy.  Results that did not come out of `_run` are
+        negated here."""
+        self._sign, self._sign_applied = -1.0, False
+        try:
+            out = fn(x)
+        finally:
+            applied = self._sign_applied
+            self._sign, self._sign_applied = 1.0, False
+        if applied:
+            return out
+        return tuple(-o for o in out) if isinstance(out, tuple) else -out
 
     def optimize(self, duplicate_manager=None, x_baseline=None):
         if not self.analytical_gradient_acq:
@@ -73,12 +88,30 @@ class AcquisitionBase(object):
         H_loaded = self.model.n_hyper_samples_loaded()
         return 1 if (self.model.fixed_hyps or H_loaded == 1) else min(self.n_hyps_samples, H_loaded)
 
+    PIPELINE_MIN = 1 << 17      # numpy inputs at least this long are streamed through the device in slabs
+    PIPELINE_SLABS = 4
+    _sign = 1.0
+    _sign_applied = False
+
     def _run(self, variant, X, theta, weight, fstar, grad, Zt=None, S=0, form=0):
         model = self.model
-        lib = model._lib
-        Xd, is_t = model._dev_in(X)
-        N, d = Xd.shape
         theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        if not isinstance(X, torch.Tensor):
+            Xn = np.atleast_2d(np.asarray(X, dtype=np.float64))
+            if Xn.shape[0] >= self.PIPELINE_MIN:
+                return self._run_pipelined(variant, np.ascontiguousarray(Xn), theta, weight, fstar, grad, Zt, S, form)
+        Xd, is_t = model._dev_in(X)
+        acq, dacq = self._eval_device(variant, Xd, theta, weight, fstar, grad, Zt, S, form)
+        acq = acq.reshape(-1, 1)
+        if not is_t:
+            acq = self._to_host(acq)
+            dacq = None if dacq is None else self._to_host(dacq)
+        return (acq, dacq) if grad else acq
+
+    def _eval_device(self, variant, Xd, theta, weight, fstar, grad, Zt, S, form):
+        """One bocf_acq_eval call on device-resident candidates; applies the pending sign flip on the device."""
+        model = self.model
+        N, d = Xd.shape
         L = theta.shape[0]
         th_h, th_p = _host(theta)
         w_h, w_p = _host(weight)
@@ -88,14 +121,57 @@ class AcquisitionBase(object):
             acq = torch.empty((N,), dtype=torch.float64, device=model.device)
             dacq = torch.empty((N, d), dtype=torch.float64, device=model.device) if grad else None
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(lib.bocf_acq_eval(model._handle, _lib.VARIANTS[variant], _lib.COMPOSITES[self.utility.composite],
-                                         _ptr(Xd), N, _ptr(Zt), S, th_p, L, theta.shape[1], w_p, f_p, H_use, form,
-                                         _ptr(acq), _ptr(dacq), st))
-        acq = acq.reshape(N, 1)
-        if not is_t:
-            acq = self._to_host(acq)
-            dacq = None if dacq is None else self._to_host(dacq)
-        return (acq, dacq) if grad else acq
+            _lib.check(model._lib.bocf_acq_eval(model._handle, _lib.VARIANTS[variant],
+                                                _lib.COMPOSITES[self.utility.composite], _ptr(Xd), N, _ptr(Zt), S, th_p, L,
+                                                theta.shape[1], w_p, f_p, H_use, form, _ptr(acq), _ptr(dacq), st))
+            if self._sign < 0:
+                acq.neg_()
+                if dacq is not None:
+                    dacq.neg_()
+        self._sign_applied = True
+        return acq, dacq
+
+    def _run_pipelined(self, variant, Xn, theta, weight, fstar, grad, Zt, S, form):
+        """Host candidates in, host results out, in slabs: the H2D copy of slab k+1 and the D2H copy of slab k-1 run on a
+        side stream while slab k is evaluated (candidates are independent, so slab results equal the one-shot ones)."""
+        model = self.model
+        dev = model.device
+        N, d = Xn.shape
+        step = -(-N // self.PIPELINE_SLABS)
+        step = ((step + 127) // 128) * 128
+        bounds = [(a, min(a + step, N)) for a in range(0, N, step)]
+        Xh = torch.from_numpy(Xn)
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            side = self._copy_stream
+            acq_h = torch.empty((N, 1), dtype=torch.float64, device="cpu", pin_memory=True)
+            dacq_h = torch.empty((N, d), dtype=torch.float64, device="cpu", pin_memory=True) if grad else None
+            side.wait_stream(main)
+            slabs, ready = [], []
+            with torch.cuda.stream(side):
+                for a, b in bounds:
+                    slabs.append(Xh[a:b].to(dev, non_blocking=True))
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    ready.append(ev)
+            keep = []
+            for (a, b), Xd, ev in zip(bounds, slabs, ready):
+                main.wait_event(ev)
+                acq, dacq = self._eval_device(variant, Xd, theta, weight, fstar, grad, Zt, S, form)
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(done)
+                    acq_h[a:b, 0].copy_(acq, non_blocking=True)
+                    if grad:
+                        dacq_h[a:b].copy_(dacq, non_blocking=True)
+                keep.append((Xd, acq, dacq))
+            side.synchronize()
+            main.wait_stream(side)
+        del keep
+        return (acq_h.numpy(), dacq_h.numpy()) if grad else acq_h.numpy()
 
     @staticmethod
     def _to_host(t):

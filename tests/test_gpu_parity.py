@@ -210,3 +210,36 @@ def test_acq_eval_host_entry(cuda_device):
     _lib.check(pm._lib.bocf_acq_eval_host(pm._handle, 0, 0, vp(Xh), P.N, ctypes.c_void_p(Zt.data_ptr()), P.S, vp(th), 1,
                                           P.m, vp(w), vp(fs), 1, 0, vp(out_a), vp(out_g), st))
     assert np.array_equal(out_a, a) and np.array_equal(out_g, g)
+
+
+def test_negated_and_pipelined_host_path(cuda_device):
+    """acquisition_function[_withGradients] flip the sign on the device and, for long numpy inputs, stream the candidates
+    through in slabs (H2D / D2H on a side stream): both must equal the plain one-shot evaluation bit for bit."""
+    import torch
+    import bocf_b200
+    from tests.helpers import make_problem, product_model, product_utility
+    P = make_problem(m=3, d=5, n=70, H=2, kind="matern52", composite="sumsq_target", N=1500, S=64, seed=21)
+    model = product_model(P, cuda_device)
+    acq = bocf_b200.uEI_noiseless(model, None, utility=product_utility(P))
+    acq.W_samples = P.Z
+    model.set_hyperparameters(0)
+    a0, g0 = acq._compute_acq_withGradients(P.Xc)                       # one shot, no sign
+    model.set_hyperparameters(0)
+    a1, g1 = acq.acquisition_function_withGradients(P.Xc)                # sign on device
+    assert np.array_equal(a1, -a0) and np.array_equal(g1, -g0)
+    acq.PIPELINE_MIN = 256                                               # force the slab pipeline (4 ragged slabs of 384)
+    model.set_hyperparameters(0)
+    a2, g2 = acq.acquisition_function_withGradients(P.Xc)
+    assert a2.shape == (1500, 1) and g2.shape == (1500, 5)
+    assert np.array_equal(a2, a1) and np.array_equal(g2, g1)
+    model.set_hyperparameters(0)
+    v2 = acq.acquisition_function(P.Xc)
+    model.set_hyperparameters(0)
+    acq.PIPELINE_MIN = 1 << 30
+    v1 = acq.acquisition_function(P.Xc)
+    assert np.array_equal(v2, v1) and np.all(v1 <= 0)
+    # device tensors in -> device tensors out, same values
+    model.set_hyperparameters(0)
+    at, gt = acq.acquisition_function_withGradients(torch.from_numpy(P.Xc).to(cuda_device))
+    assert at.is_cuda and np.array_equal(at.cpu().numpy().reshape(-1, 1), a1) and np.array_equal(gt.cpu().numpy(), g1)
+    assert acq._sign == 1.0
