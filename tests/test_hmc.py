@@ -199,3 +199,40 @@ def test_hyper_inference_none_keeps_initial_values(cuda_device):
     var, ls, nz = mod.get_hyperparameters_samples()
     assert var.shape == (1, 2) and np.all(var == 1.0) and np.all(ls == 1.0)
     np.testing.assert_allclose(nz[0], [0.01 * np.var(Y[0]), 0.01 * np.var(Y[1])])
+
+
+def test_failed_factorisation_is_isolated_per_output():
+    """One output's covariance not positive definite: the other outputs of the shared device pass keep their fresh
+    likelihood terms, the failing one reports failure (ML-II then sees +inf there, like paramz's _objective_grads)."""
+    from bocf_b200 import NotPositiveDefiniteError
+    from bocf_b200.hmc import HyperInference
+    m, d = 3, 2
+    calls = []
+
+    def evaluate(var, ls, nz):
+        calls.append(var.copy())
+        if var[1] > 5.0:                                     # output 1 "fails" for large variances
+            raise NotPositiveDefiniteError(-4, "not positive definite, even with jitter.")
+        return -var, 0.5 * np.ones(m), -0.1 * np.ones((m, d)), 0.2 * np.ones(m)
+
+    hi = HyperInference(evaluate, d, [(1.0, np.ones(d))] * m, [0.01] * m, [False] * m, [0.01] * m)
+    assert hi._infer() == set()
+    hi._remember_good()
+    np.testing.assert_array_equal(hi.lml, [-1.0, -1.0, -1.0])
+    hi.PA[:, 0] = [2.0, 9.0, 3.0]
+    failed = hi._infer()
+    assert failed == {1}
+    np.testing.assert_array_equal(hi.lml, [-2.0, -1.0, -3.0])   # output 1 keeps its stale value
+    # with nothing known-good to stand in for the other outputs the failure propagates
+    hi2 = HyperInference(evaluate, d, [(9.0, np.ones(d))] * m, [0.01] * m, [False] * m, [0.01] * m)
+    with pytest.raises(NotPositiveDefiniteError):
+        hi2._infer()
+    # ML-II survives a failing trial point: L-BFGS-B backs off from the +inf objective
+    def evaluate2(var, ls, nz):
+        if np.any(var > 50.0):
+            raise NotPositiveDefiniteError(-4, "not positive definite, even with jitter.")
+        lml = -(np.log(var) - 1.0) ** 2 - ((np.log(ls) - 0.5) ** 2).sum(1) - (np.log(nz) + 3.0) ** 2
+        return (lml, -2 * (np.log(var) - 1.0) / var, -2 * (np.log(ls) - 0.5) / ls, -2 * (np.log(nz) + 3.0) / nz)
+    hi3 = HyperInference(evaluate2, d, [(40.0, np.ones(d))] * m, [0.01] * m, [False] * m, [0.01] * m, max_iters=100)
+    hi3.optimize()
+    assert all(np.all(np.isfinite(o)) and o[0] < 50.0 for o in hi3.optimum)
