@@ -240,6 +240,7 @@ def run_ours(args, cfg):
     model = product_model(P, str(dev), precision=args.precision)
     torch.cuda.synchronize()
     slices = model.active_slices()
+    sch_var, sch_dvar = model.active_scheme()
     t_factor = time.perf_counter() - t_setup          # cold: library load, context, allocations, first launches
     t0 = time.perf_counter()
     model._upload_and_factorize(upload_data=False)      # warm: Gram + blocked Cholesky + L^-1 + alpha of all m outputs
@@ -395,20 +396,25 @@ def run_ours(args, cfg):
         except Exception:
             pass
         bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        passes = slices * (slices + 1) // 2
+        def scheme_pairs(code):                      # digit pairs (= int8 GEMM passes) of scheme 100 SA + 10 SB + LMIN
+            sa, sb, lmin = code // 100, (code // 10) % 10, code % 10
+            return sum(1 for ta in range(sa) for tb in range(sb) if ta + tb >= lmin)
+        dom_scheme = sch_dvar if dom == "split_dvar_kernel" else sch_var
+        passes = scheme_pairs(dom_scheme)
         traffic = None
         try:     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"][dom]
-            if slices == 5 and c["n"] == 1000 and c["m"] == 16:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["kernels"][dom]
+            if tj.get("scheme") == dom_scheme and c["n"] == 1000 and c["m"] == 16:
                 traffic = tj["traffic_GB_per_launch"] * 1e9 * cand_per_launch / tj["candidates_per_launch"]
         except Exception:
             traffic = None
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": bf16_peak, "unit": "TFLOP/s",
                     "frac": achieved_tf / bf16_peak, "traffic": traffic,
-                    "traffic_note": "bytes per launch, scaled from the ncu capture summarised in profiles/r1c_ncu_final_summary.md",
+                    "traffic_note": "bytes per launch, scaled from the ncu --set full capture recorded in profiles/r2_traffic.json",
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16 cuBLAS, measured)" if peaks else
                                     "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md); MEASURED_PEAKS.json absent"),
-                    "digit_planes": slices, "int8_passes": passes,
+                    "digit_planes": dom_scheme // 100, "scheme": dom_scheme, "int8_passes": passes,
+                    "schemes": {"split_var_kernel": sch_var, "split_dvar_kernel": sch_dvar},
                     "issued_int8_tops": achieved_tf * passes,
                     "issued_frac_of_nominal_int8_4500": achieved_tf * passes / 4500.0,
                     "int8_gemm_tops_measured": int8_tops,
@@ -440,14 +446,15 @@ def run_ours(args, cfg):
     # digit planes (tests/test_gpu_split.py: split4); reported next to the headline, which runs the fp64-grade setting
     mixed = None
     if world == 1 and slices > 4 and not args.no_mixed:
-        model.set_precision("split4")
+        model.set_precision("mixed")
         for _ in range(2):
             step_device()
         ms4, _, _, _ = timed(step_device, args.steps)
-        mixed = {"digit_planes": 4, "value": args.steps * N / (ms4 * 1e-3), "unit": "evals/s",
+        mixed = {"schemes": list(model.active_scheme()), "value": args.steps * N / (ms4 * 1e-3), "unit": "evals/s",
                  "ms_per_step": ms4 / args.steps,
-                 "note": "same sweep with 4 digit planes: meets the mixed-precision bar (<=1e-4 on acq / grad), "
-                         "~2e-6 relative on the variance"}
+                 "note": "same sweep in the library's mixed mode (variance 4 digit planes / 13 pairs, variance gradient "
+                         "3 planes / 8 pairs): meets the north star's mixed-precision bar (<=1e-4 on acq / grad acq, "
+                         "tests/test_gpu_split.py::test_auto_and_mixed_pick_their_schemes)"}
         model.set_precision(args.precision)
 
     cpu = None
@@ -468,6 +475,7 @@ def run_ours(args, cfg):
         "dtype": ("f64 (kernel, mean, MC, Cholesky) + tcgen05 int8 digit planes x%d with exact int32 accumulation for "
                   "the two factor contractions (fp64-level: <=1e-6 rel. on mean/variance, tests/test_gpu_split.py)"
                   % slices) if slices else "f64",
+        "schemes": [sch_var, sch_dvar],
         "data": "synthetic", "precision_mode": args.precision, "digit_planes": slices,
         "config": workload_config(c, N), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(N * c["d"] * 8),
@@ -495,7 +503,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=16.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mixed", action="store_true", help="skip the extra 4-digit-plane measurement")
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp64", "split3", "split4", "split5", "split6"],
+    ap.add_argument("--precision", default="auto", choices=["auto", "mixed", "fp64", "split3", "split4", "split5", "split6", "split54", "split43", "split53", "split44"],
                     help="arithmetic of the factor contractions (include/bocf_b200.h: enum bocf_precision)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

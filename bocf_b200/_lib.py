@@ -20,9 +20,15 @@ EXPORTS = [
     "bocf_model_factorize", "bocf_model_get_factor", "bocf_model_n", "bocf_model_H",
     "bocf_model_set_scratch_limit", "bocf_posterior", "bocf_acq_eval", "bocf_acq_eval_host",
     "bocf_utility_eval", "bocf_topk", "bocf_profile_enable", "bocf_profile_report",
-    "bocf_model_set_precision", "bocf_model_active_slices", "bocf_debug_split_gemm", "bocf_model_log_likelihood", "bocf_model_append_point",
+    "bocf_model_set_precision", "bocf_model_active_slices", "bocf_model_active_scheme", "bocf_debug_split_gemm", "bocf_model_log_likelihood", "bocf_model_append_point",
 ]
-PRECISIONS = {"fp64": (0, 0), "auto": (2, 0), "split3": (1, 3), "split4": (1, 4), "split5": (1, 5), "split6": (1, 6)}
+# name -> (enum bocf_precision, slices).  "splitN": both contractions on the N-plane scheme; "splitNM": variance on N,
+# variance gradient on M <= N planes (include/bocf_b200.h).
+PRECISIONS = {"fp64": (0, 0), "auto": (2, 0), "mixed": (3, 0)}
+for _s1 in range(3, 7):
+    PRECISIONS["split%d" % _s1] = (1, _s1)
+    for _s2 in range(3, _s1 + 1):
+        PRECISIONS["split%d%d" % (_s1, _s2)] = (1, 10 * _s1 + _s2)
 
 
 def parse_precision(name):
@@ -74,6 +80,7 @@ def load_library():
     lib.bocf_topk.argtypes = [c_dp, c_dp, i64, i32, i32, i64, c_dp, c_vp]
     lib.bocf_model_set_precision.argtypes = [c_vp, i32, i32, c_vp]
     lib.bocf_model_active_slices.argtypes = [c_vp]
+    lib.bocf_model_active_scheme.argtypes = [c_vp]
     lib.bocf_debug_split_gemm.argtypes = [c_dp, c_dp, i32, i32, i32, i32, i32, c_dp, c_vp]
     lib.bocf_model_log_likelihood.argtypes = [c_vp, c_dp, c_dp, c_dp, c_dp, c_vp]
     lib.bocf_model_append_point.argtypes = [c_vp, c_dp, c_dp, c_vp]

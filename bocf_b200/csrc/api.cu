@@ -74,7 +74,7 @@ static void free_data(bocf_model* M) {
 }
 static void free_factor(bocf_model* M) {
   split_release(M);
-  M->S = 0;
+  M->S = M->S2 = M->sch1 = M->sch2 = 0;
   dev_free(M->Xs);
   dev_free(M->xsq);
   dev_free(M->Lmat);
@@ -110,28 +110,36 @@ static int64_t pick_chunk(const bocf_model* M, int64_t N, bool grad, uint64_t ex
   return nc;
 }
 
-// Resolve the requested contraction precision into the active number of digit planes (M->S; 0 = fp64 DMMA) and build
-// the split operands.  AUTO: the relative error of the variance stays below ~2000 * max|Linv|^2 * 256^-S (measured
-// 240 ... 1350 across kernels, sizes and noise levels: tests/test_split_numerics.py, tests/test_gpu_split.py); the
-// smallest S in {4,5,6} with 400 * max|Linv|^2 * 256^-S <= 1e-7 (that bound <= 5e-7, half the north-star fp64 bar) is
-// used, and models too ill-conditioned for 6 planes stay on the fp64 tensor path.
+// Resolve the requested contraction precision into the active digit-pair schemes (M->sch1 / M->sch2; M->S = 0 means
+// fp64 DMMA) and build the split operands.  Error model (tests/test_split_numerics.py, tests/test_gpu_split.py): the
+// relative error of the variance stays below ~2000 * a^2 * 256^-5 for scheme 554 (15 digit pairs), ~2000 * a^2 * 256^-6
+// for 665 and ~150 * a^2 * 256^-4 for 442 (13 pairs), a = max|Linv|.  AUTO accepts a scheme when a fifth of that bound
+// is <= 1e-7 (bound <= 5e-7, half the north-star fp64 bar); the variance gradient runs one scheme below the variance
+// (442 under 554: ~1e-7 relative, norm-wise).  MIXED targets the 1e-4 bar on acq / grad acq instead: variance bound
+// <= 2e-5, gradient two schemes down to 331 (8 pairs, ~1e-5).  Models too ill-conditioned for 665 stay on fp64.
 static int apply_precision(bocf_model* M, cudaStream_t st) {
-  int S = 0;
+  int s1 = 0, s2 = 0;
   if (M->precision == BOCF_PREC_SPLIT_I8) {
-    S = M->slices_req;
-  } else if (M->precision == BOCF_PREC_AUTO) {
+    s1 = M->slices_req;
+    s2 = M->slices2_req > 0 ? M->slices2_req : s1;
+  } else if (M->precision == BOCF_PREC_AUTO || M->precision == BOCF_PREC_MIXED) {
     if (int rc = split_linv_absmax(M, &M->linv_absmax, st)) return rc;
     const double a2 = M->linv_absmax * M->linv_absmax;
-    for (int s = 4; s <= 6 && S == 0; ++s)
-      if (400.0 * a2 * std::pow(256.0, -s) <= 1e-7) S = s;
+    const double bound[7] = {0, 0, 0, 0, 150.0 * a2 * std::pow(256.0, -4), 2000.0 * a2 * std::pow(256.0, -5),
+                             2000.0 * a2 * std::pow(256.0, -6)};
+    const double target = (M->precision == BOCF_PREC_MIXED) ? 2e-5 : 5e-7;
+    for (int s = 4; s <= 6 && s1 == 0; ++s)
+      if (bound[s] <= target) s1 = s;
+    if (s1 > 0) s2 = (M->precision == BOCF_PREC_MIXED) ? (s1 == 4 ? 3 : s1 - 1) : (s1 > 4 ? s1 - 1 : 4);
   }
-  if (S == 0) {
+  if (s1 == 0) {
     split_release(M);
-    M->S = 0;
+    M->S = M->S2 = M->sch1 = M->sch2 = 0;
     return 0;
   }
-  if (M->split_ready && M->S == S) return 0;
-  return split_prepare(M, S, st);
+  const int sch1 = split_scheme_for_slices(s1), sch2 = split_scheme_for_slices(s2);
+  if (M->split_ready && M->sch1 == sch1 && M->sch2 == sch2) return 0;
+  return split_prepare(M, sch1, sch2, st);
 }
 
 static int resolve_precision(bocf_model* M, cudaStream_t st) {
@@ -159,7 +167,7 @@ using namespace bocf;
 extern "C" {
 
 const char* bocf_last_error(void) { return g_err.c_str(); }
-const char* bocf_version(void) { return "bocf_b200 0.2 sm_100a fp64-dmma + tcgen05-i8-split"; }
+const char* bocf_version(void) { return "bocf_b200 0.3 sm_100a fp64-dmma + tcgen05-i8-split"; }
 uint64_t bocf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int bocf_profile_enable(int on) {
@@ -225,13 +233,15 @@ int bocf_model_create(bocf_model** out, int m, int d, int kernel, int device) {
   M->kernel = kernel;
   M->device = device;
   M->precision = BOCF_PREC_AUTO;                                // library default
-  if (const char* env = std::getenv("BOCF_PRECISION")) {      // fp64 | auto | split3 .. split6
+  if (const char* env = std::getenv("BOCF_PRECISION")) {      // fp64 | auto | mixed | split3 .. split6 | split<s1><s2>
     const std::string v(env);
     if (v == "auto") M->precision = BOCF_PREC_AUTO;
+    else if (v == "mixed") M->precision = BOCF_PREC_MIXED;
     else if (v == "fp64") M->precision = BOCF_PREC_FP64_DMMA;
-    else if (v.rfind("split", 0) == 0 && v.size() == 6 && v[5] >= '3' && v[5] <= '6') {
+    else if (v.rfind("split", 0) == 0 && (v.size() == 6 || v.size() == 7) && v[5] >= '3' && v[5] <= '6') {
       M->precision = BOCF_PREC_SPLIT_I8;
       M->slices_req = v[5] - '0';
+      M->slices2_req = (v.size() == 7 && v[6] >= '3' && v[6] <= v[5]) ? v[6] - '0' : 0;
     }
   }
   *out = M;
@@ -239,12 +249,22 @@ int bocf_model_create(bocf_model** out, int m, int d, int kernel, int device) {
 }
 
 int bocf_model_set_precision(bocf_model* M, int mode, int slices, void* stream) {
-  if (!M || mode < BOCF_PREC_FP64_DMMA || mode > BOCF_PREC_AUTO || (mode == BOCF_PREC_SPLIT_I8 && (slices < 3 || slices > 6))) {
-    set_error("bocf_model_set_precision: mode must be 0 (fp64), 1 (split int8, 3..6 digit planes) or 2 (auto)");
+  int s1 = slices, s2 = 0;
+  if (slices >= 10) {
+    s1 = slices / 10;
+    s2 = slices % 10;
+  }
+  if (!M || mode < BOCF_PREC_FP64_DMMA || mode > BOCF_PREC_MIXED ||
+      (mode == BOCF_PREC_SPLIT_I8 && (s1 < 3 || s1 > 6 || (s2 != 0 && (s2 < 3 || s2 > s1))))) {
+    set_error("bocf_model_set_precision: mode must be 0 (fp64), 1 (split int8: slices = 3..6, or 10 s1 + s2 with "
+              "3 <= s2 <= s1 <= 6), 2 (auto) or 3 (mixed)");
     return BOCF_ERR_INVALID;
   }
   M->precision = mode;
-  if (mode == BOCF_PREC_SPLIT_I8) M->slices_req = slices;
+  if (mode == BOCF_PREC_SPLIT_I8) {
+    M->slices_req = s1;
+    M->slices2_req = s2;
+  }
   M->precision_resolved = false;
   if (!M->factorized) return 0;
   DeviceGuard dg(M->device);
@@ -260,9 +280,14 @@ int bocf_model_active_slices(bocf_model* M) {
   return M->S;
 }
 
+int bocf_model_active_scheme(bocf_model* M) {
+  if (bocf_model_active_slices(M) < 0) return -1;
+  return M->S > 0 ? M->sch1 * 1000 + M->sch2 : 0;
+}
+
 int bocf_debug_split_gemm(const double* A, const double* B, int R, int N, int K, int slices, int tri, double* out,
                           void* stream) {
-  return split_debug_gemm(A, B, R, N, K, slices, tri, out, static_cast<cudaStream_t>(stream));
+  return split_debug_gemm(A, B, R, N, K, split_scheme_for_slices(slices), tri, out, static_cast<cudaStream_t>(stream));
 }
 
 int bocf_model_destroy(bocf_model* M) {

@@ -547,7 +547,15 @@ int launch_gram(bocf_model* M, cudaStream_t st) {
 }
 
 static int set_smem_attrs() {
-  static bool done = false;
+  // per device: function attributes belong to the device's context (one process may drive several GPUs)
+  static bool done_dev[64] = {false};
+  int dev = 0;
+  BOCF_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) {
+    set_error("unsupported device ordinal");
+    return BOCF_ERR_INVALID;
+  }
+  bool& done = done_dev[dev];
   if (done) return 0;
   BOCF_CUDA_OK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
   BOCF_CUDA_OK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));

@@ -163,10 +163,10 @@ __global__ void lml_finish_kernel(const double* __restrict__ part, const double*
 
 template <int KIND>
 static int launch_tiles(bocf_model* M, int ntiles, double* part, cudaStream_t st) {
-  static bool done = false;
-  if (!done) {
+  static bool done[64] = {false};              // per device: function attributes belong to the device's context
+  if (M->device >= 0 && M->device < 64 && !done[M->device]) {
     BOCF_CUDA_OK(cudaFuncSetAttribute(lml_tile_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::SMEM_BYTES));
-    done = true;
+    done[M->device] = true;
   }
   lml_tile_kernel<KIND><<<dim3((unsigned)ntiles, (unsigned)(M->H * M->m)), LT::NTHREADS, LT::SMEM_BYTES, st>>>(
       M->Linv, M->alpha, M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, ntiles, part);

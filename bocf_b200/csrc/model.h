@@ -51,16 +51,19 @@ struct bocf_model {
   // ---- split-integer tensor-core contraction (split_gemm.cu) ---------------------------------------
   int precision = 2;          // requested mode (bocf_precision); default BOCF_PREC_AUTO
   int slices_req = 5;         // requested digit planes for BOCF_PREC_SPLIT_I8
-  int S = 0;                  // ACTIVE digit planes; 0 = fp64 DMMA contractions
-  int NTs = 0, ncts = 0, KCH = 0;   // column tile, number of column tiles, 64-wide K chunks
-  int split_cg = 1;           // CTAs per tile group of the split contraction: 1 = single CTAs (default), 2 = cta_group::2 pairs
+  int slices2_req = 0;        // ... of the second contraction (0: same as the first)
+  int S = 0;                  // ACTIVE digit planes of K* (first contraction); 0 = fp64 DMMA contractions
+  int S2 = 0;                 // ACTIVE digit planes of V  (second contraction)
+  int sch1 = 0, sch2 = 0;     // digit-pair schemes (SA*100 + SB*10 + LMIN) of the two contractions
+  int NTs = 0, ncts = 0, KCH = 0;   // first contraction: column tile, number of column tiles; 64-wide K chunks
+  int NT2 = 0, nct2 = 0;      // second contraction: column tile, number of column tiles
   double linv_absmax = 0.0;   // max |Linv| over all (h, j), measured at factorisation
-  uint8_t* B1 = nullptr;      // H*m x ncts x KCH x S x NTs x 64   digit planes of Linv rows   (V  = K* Linv^T)
-  uint8_t* B2 = nullptr;      // same layout, digit planes of Linv columns                      (Wt = V Linv)
+  uint8_t* B1 = nullptr;      // H*m x ncts x KCH x SB1 x NTs x 64  digit planes of Linv rows   (V  = K* Linv^T)
+  uint8_t* B2 = nullptr;      // H*m x nct2 x KCH x SB2 x NT2 x 64  digit planes of Linv columns (Wt = V Linv)
   double* cs1 = nullptr;      // H*m x ncts*NTs   power-of-two output scale per column of the first contraction
-  double* cs2 = nullptr;      //                  ... of the second
-  double* aq = nullptr;       // H*m   2^(8S-2-eA): quantiser of K*   (K* <= sigma_f^2)
-  double* vq = nullptr;       // H*m   2^(8S-2-eV): quantiser of V    (|V| <= sigma_f)
+  double* cs2 = nullptr;      // H*m x nct2*NT2   ... of the second
+  double* aq = nullptr;       // H*m   2^(8 S  - 2 - eA): quantiser of K*   (K* <= sigma_f^2)
+  double* vq = nullptr;       // H*m   2^(8 S2 - 2 - eV): quantiser of V    (|V| <= sigma_f)
   double* lml_ws = nullptr;   // workspace of the likelihood pass (per-tile partials + results), kept across calls: the
   size_t lml_ws_count = 0;    // fit loops call it thousands of times and cudaMalloc / cudaFree cost milliseconds each
   bool split_ready = false;
@@ -108,16 +111,19 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
                            const ChunkBuffers& cb, cudaStream_t st, bool need_var = true, bool need_dvar = true);
 
 // ---- split_gemm.cu ------------------------------------------------------------------------------
-int split_column_tile(int S);
-int split_partials_per_tile();   // partial sums the split epilogue writes per column tile
-int split_prepare(bocf_model* M, int S, cudaStream_t st);          // digit planes of Linv + scales
+int split_scheme_for_slices(int S);                 // 3..6 digit planes -> scheme code (331, 442, 554, 665)
+int split_scheme_pairs(int sch);                     // int8 GEMM passes of a scheme
+int split_parts(const bocf_model* M, int64_t Nc);    // parts per candidate tile for a chunk of Nc candidates (<= 0: upper bound)
+int split_partials_var(const bocf_model* M, int64_t Nc);    // partial sums per candidate the VAR / DVAR epilogues write
+int split_partials_dvar(const bocf_model* M, int64_t Nc);
+int split_prepare(bocf_model* M, int sch1, int sch2, cudaStream_t st);   // digit planes of Linv + scales
 void split_release(bocf_model* M);
 int split_linv_absmax(bocf_model* M, double* out_host, cudaStream_t st);
 uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad);
 void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* out);
 int launch_split_var(bocf_model* M, int h, const ChunkBuffers& cb, bool need_dvar, cudaStream_t st);
 int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, const ChunkBuffers& cb, cudaStream_t st);
-int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int S, int tri, double* out, cudaStream_t st);
+int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int sch, int tri, double* out, cudaStream_t st);
 
 // ---- acq.cu -------------------------------------------------------------------------------------
 struct AcqParams {

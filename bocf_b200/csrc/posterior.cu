@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(PT::NTHREADS, PT_MINBLOCKS) dvar_gemm_kernel(
 // split mode: part_dvar holds sum_b T_b Xs_bq and part_s0 holds sum_b T_b (T = Wt * G*), so that
 //   sum_b T_b (xs_iq - Xs_bq) = xs_iq * S0 - ACC_q   with xs_i = x_i / l formed here, once per candidate.
 __global__ void finalize_kernel(const double* __restrict__ part_var, const double* __restrict__ part_dvar,
-                                const OutHyp* __restrict__ hyp, int64_t Nc, int nct, int m, int d, int h, int grad,
+                                const OutHyp* __restrict__ hyp, int64_t Nc, int nct, int nct_g, int m, int d, int h, int grad,
                                 int noiseless, double* __restrict__ var, double* __restrict__ dvar,
                                 const double* __restrict__ part_s0, const double* __restrict__ Xc, int64_t Nvalid) {
   // thread idx covers candidate idx (variance) and flat element idx = i*d + q (gradient): both coalesced
@@ -368,11 +368,11 @@ __global__ void finalize_kernel(const double* __restrict__ part_var, const doubl
   if (grad && idx < Nc * d) {
     const int q = (int)(idx % d);
     double gsum = 0.0;
-    for (int tI = 0; tI < nct; ++tI) gsum += part_dvar[((int64_t)j * nct + tI) * Nc * d + idx];
+    for (int tI = 0; tI < nct_g; ++tI) gsum += part_dvar[((int64_t)j * nct_g + tI) * Nc * d + idx];
     if (part_s0 != nullptr) {
       const int64_t i = idx / d;
       double s0 = 0.0;
-      for (int tI = 0; tI < nct; ++tI) s0 += part_s0[((int64_t)j * nct + tI) * Nc + i];
+      for (int tI = 0; tI < nct_g; ++tI) s0 += part_s0[((int64_t)j * nct_g + tI) * Nc + i];
       const double xs = (i < Nvalid) ? Xc[i * d + q] / hp.ls[q] : 0.0;
       gsum = xs * s0 - gsum;
     }
@@ -436,7 +436,7 @@ static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid
   so.A1 = cb.A1;
   so.aq = M->aq;
   so.gcs = M->cs2;
-  so.gcs_ld = M->ncts * M->NTs;
+  so.gcs_ld = M->nct2 * M->NT2;
   so.KCH = M->KCH;
   so.S = M->S;
   const int spl = (cb.A1 == nullptr) ? 0 : (M->S == 5 ? 5 : 6);
@@ -468,11 +468,11 @@ static int launch_kstar_k(bocf_model* M, int h, const double* Xc, int64_t Nvalid
 
 int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, bool noiseless,
                            const ChunkBuffers& cb, cudaStream_t st, bool need_var, bool need_dvar) {
-  static bool attrs = false;
-  if (!attrs) {
+  static bool attrs[64] = {false};               // per device: function attributes belong to the device's context
+  if (M->device >= 0 && M->device < 64 && !attrs[M->device]) {
     BOCF_CUDA_OK(cudaFuncSetAttribute(var_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT::SMEM_BYTES));
     BOCF_CUDA_OK(cudaFuncSetAttribute(dvar_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT::SMEM_BYTES));
-    attrs = true;
+    attrs[M->device] = true;
   }
   need_dvar = need_dvar && grad;
   need_var = need_var || need_dvar;
@@ -490,7 +490,8 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
   if (rc) return rc;
   if (!need_var) return 0;      // mean (and mean gradient) only: no contraction against the factor
   const bool split = (cb.A1 != nullptr);
-  const int nct = split ? split_partials_per_tile() : M->n_pad / NT;   // partial sums per candidate
+  const int nct = split ? split_partials_var(M, cb.Nc) : M->n_pad / NT;       // partial sums per candidate: variance
+  const int nct_g = split ? split_partials_dvar(M, cb.Nc) : M->n_pad / NT;    //                             variance gradient
   const unsigned tiles = (unsigned)((cb.Nc / CT) * nct * M->m);
   if (split) {
     // tcgen05 kind::i8 digit-plane contractions (split_gemm.cu); same partial-sum layout, same finalize
@@ -515,7 +516,7 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
   dim3 fgrid((unsigned)ceil_div(need_dvar ? cb.Nc * M->d : cb.Nc, 256), (unsigned)M->m);
   {
     ProfScope ps("finalize_kernel", st);
-    finalize_kernel<<<fgrid, 256, 0, st>>>(cb.part_var, cb.part_dvar, M->hyp, cb.Nc, nct, M->m, M->d, h,
+    finalize_kernel<<<fgrid, 256, 0, st>>>(cb.part_var, cb.part_dvar, M->hyp, cb.Nc, nct, nct_g, M->m, M->d, h,
                                            need_dvar ? 1 : 0, noiseless ? 1 : 0, cb.var, cb.dvar,
                                            split ? cb.part_s0 : nullptr, Xc, Nvalid);
   }

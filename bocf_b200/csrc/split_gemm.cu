@@ -3,30 +3,39 @@
 //   V  = K* Linv^T   (posterior.py:312, the reference's dtrtrs route)      var  = k** - sum_k V^2
 //   Wt = V  Linv     (= K* W^-1, gp.py:474)                                 dvar = gradients_X(-2 Wt, x*, X)
 //
-// Blackwell's tcgen05 has no fp64 kind, so the fp64 operands are split into S signed 8-bit digits (balanced
-// base-256 expansion of round(x * 2^(8S-2-e)), e a per-row power-of-two scale) and the product is assembled from
-// S(S+1)/2 exact integer GEMMs on `tcgen05.mma.kind::i8` (SASS UTCIMMA): int8 x int8 products accumulated EXACTLY
-// in int32 tensor memory, one accumulator per digit weight 256^(ta+tb).  The only error is the operand
-// quantisation 2^-(8S-2) (relative to the row scale) -- S = 5 carries 38-bit operands and reproduces the fp64 path
-// to ~1e-8 relative on the variance, S = 4 to ~1e-6 (tests/test_gpu_split.py measures both).
+// Blackwell's tcgen05 has no fp64 kind, so the fp64 operands are split into signed 8-bit digits (balanced base-256
+// expansion of round(x * 2^(8S-2-e)), e a per-row power-of-two scale; SA digits on the candidate side, SB on the
+// factor side) and the product is assembled from exact integer GEMMs on `tcgen05.mma.kind::i8` (SASS UTCIMMA):
+// int8 x int8 products accumulated EXACTLY in int32 tensor memory, one accumulator per digit weight 256^(ta+tb).
+// A SCHEME (SA, SB, LMIN) keeps the digit pairs with ta + tb >= LMIN.  Which pairs are kept matters more than the
+// number of digits: the low digits of an operand are full-size even where the operand is small, so a dropped pair
+// costs the same absolute error everywhere, while the quantisation error is multiplied by the (usually small) other
+// operand (tests/test_split_numerics.py; profiles/r2_pair_selection.md):
+//     554  (15 pairs)  variance to ~3e-8 relative            -- first contraction of the default mode
+//     442  (13 pairs)  variance ~3e-7, variance gradient ~4e-8 -- second contraction of the default mode
+//     331  ( 8 pairs)  variance gradient ~1e-5               -- second contraction of the mixed mode
+//     665  (21 pairs)  ill-conditioned factors
 //
-// Kernel structure (persistent, warp specialised, 320 threads, 1 CTA / SM):
+// Kernel structure (persistent, warp specialised, 1 CTA / SM):
 //   warp 0   producer: one lane streams 64-byte-wide K chunks of the packed, pre-swizzled digit planes of A
 //            (128 candidates) and B (NT factor rows) into a STAGES-deep shared-memory ring with bulk async copies
 //            (TMA engine, cp.async.bulk + mbarrier complete_tx).
-//   warp 1   MMA issuer: one lane issues, per 32-byte K step, S instructions  D[128 x (ta+1)NT] += A_ta * [B_tb]^T
-//            whose B operand STACKS the digit planes tb = S-1-ta .. S-1 along N, so every A plane is read from
-//            shared memory once per step while all S(S+1)/2 digit pairs are covered.  Accumulators live in TMEM,
-//            double buffered when 2*S*NT <= 512 columns so the epilogue of tile t overlaps the MMAs of tile t+1.
-//   warps 2-9 epilogue (two warps per TMEM lane group, alternating 8-column groups): tcgen05.ld the S int32 levels of
-//            a row (lane = candidate), int32 -> fp64 by a magic-number add (no conversion-pipe instructions), Horner
-//            them into one fp64 value, apply the column scale, and fuse the reductions of the reference:
-//            VAR : sum_k V^2 per candidate (+ re-split V into digit planes = the A operand of the second GEMM)
+//   warp 1   MMA issuer: the WHOLE warp walks the tile / stage loop with warp-uniform control flow (the warp index
+//            comes from a shuffle, so the compiler keeps descriptors and loop state on the uniform datapath) and one
+//            elected lane issues, per 32-byte K step, one instruction per A digit plane
+//                 D[128 x np NT] += A_ta * [B_tbmin .. B_{SB-1}]^T
+//            whose B operand STACKS the kept digit planes along N, so every A plane is read from shared memory once
+//            per step and each weight level lands in its own TMEM column block.  (Round 1 issued from one divergent
+//            lane and rebuilt both descriptors per instruction: ~137 clocks per MMA against 24-120 clocks of tensor
+//            work -- profiles/r2_mma_probe.log shows the same stream at 95 % of the tensor pipe when issued lean.)
+//            Accumulators are double buffered so the epilogue of tile t overlaps the MMAs of tile t+1.
+//   warps 2+ epilogue (EW / 4 warps per TMEM lane group, alternating 8-column groups): tcgen05.ld the int32 levels
+//            of a row (lane = candidate), int32 -> fp64 by a magic-number add (no conversion-pipe instructions),
+//            Horner them into one fp64 value, apply the column scale, and fuse the reductions of the reference:
+//            VAR : sum_k V^2 per candidate (+ re-split V into S2 digit planes = the A operand of the second GEMM)
 //            DVAR: T = Wt * G*,  sum_b T and sum_b T Xs_b  (finalize_kernel forms xs_i sum T - sum T Xs_b).
 //            The sums live in registers across all column tiles of a work unit (see NP below).
 // Triangular structure of Linv is exploited per column tile: K chunks (64) for the loads, K steps (32) for the MMAs.
-// A cta_group::2 variant (CG = 2: CTA pairs, M = 256) is kept as a tested option; it measured slower on B200
-// (profiles/r1_split_experiments.md).
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -41,10 +50,6 @@ namespace sg {
 
 constexpr int KC = 64;        // bytes (= int8 elements) of K per shared-memory row: one SWIZZLE_64B span
 constexpr int TM = 128;       // candidate rows per tile (= TMEM lanes)
-constexpr int EPI_WARPS = 8;     // two warps per TMEM lane group: latency hiding on the fp64 epilogue math
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int NTHREADS = 64 + EPI_THREADS;
-constexpr int PART_SPLIT = EPI_WARPS / 4;   // partial sums per column tile (one per warp of a lane group)
 constexpr int SMEM_MAX = 232448;
 
 __host__ __device__ __forceinline__ uint32_t sw64(int r, int c) {   // byte offset of (row r, byte c) in a packed plane
@@ -52,25 +57,47 @@ __host__ __device__ __forceinline__ uint32_t sw64(int r, int c) {   // byte offs
 }
 __host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-// CG = 1: one CTA per tile (M = 128).  CG = 2: the two CTAs of a cluster form an M = 256 tile (cta_group::2): each CTA
-// brings its own 128 candidates (A planes, accumulators, epilogue) and HALF of the rows of every stacked B operand, so
-// the shared-memory operand traffic per SM -- the measured limiter of the 1-CTA stream -- drops from 42.5 to 31 KB per
-// K step.  Because the stacked operand of instruction ta starts at a different plane for every ta, its halves cannot
-// alias one natural plane layout: the pair layout stores, per CTA rank, one region per instruction
-// (rows [rank N_ta/2, (rank+1) N_ta/2) of the stack), S(S+1)/2 * NT/2 rows in total.
-template <int S, int NT, int DP = 0, int CG = 1>
-struct Cfg {
-  static constexpr int A_PLANE = TM * KC, B_PLANE = NT * KC;
-  static constexpr int B_ROWS = (CG == 1) ? S * NT : (S * (S + 1) / 2) * (NT / 2);
-  static constexpr int A_STAGE = S * A_PLANE, B_STAGE = B_ROWS * KC, STAGE = A_STAGE + B_STAGE;
-  // byte offset of the B operand of instruction ta (A plane ta against planes S-1-ta .. S-1) inside a stage
-  __host__ __device__ static constexpr int b_off(int ta) {
-    if (CG == 1) return (S - 1 - ta) * B_PLANE;
-    int rows = 0;                                        // regions ordered ta = S-1 (largest) first
-    for (int t = S - 1; t > ta; --t) rows += (t + 1) * (NT / 2);
-    return rows * KC;
+// A digit-pair scheme: SA digit planes of the candidate-side operand, SB of the factor side, pairs with
+// ta + tb >= LMIN kept; NT = factor rows (output columns) per tile; EW = epilogue warps.
+template <int SA_, int SB_, int LMIN_, int NT_, int EW_>
+struct Scheme {
+  static constexpr int SA = SA_, SB = SB_, LMIN = LMIN_, NT = NT_, EW = EW_;
+  static constexpr int NL = SA + SB - 1 - LMIN;        // weight levels = TMEM accumulators per output column
+  static constexpr int CODE = SA * 100 + SB * 10 + LMIN;
+};
+using P331 = Scheme<3, 3, 1, 64, 8>;
+using P442 = Scheme<4, 4, 2, 48, 12>;
+using P554 = Scheme<5, 5, 4, 48, 12>;
+using P665 = Scheme<6, 6, 5, 32, 8>;
+
+struct SchemeInfo {
+  int code, SA, SB, LMIN, NT, EW, NL, pairs;
+};
+inline bool scheme_info(int code, SchemeInfo* o) {
+  auto fill = [&](int SA, int SB, int LMIN, int NT, int EW) {
+    int pairs = 0;
+    for (int ta = 0; ta < SA; ++ta)
+      for (int tb = 0; tb < SB; ++tb)
+        if (ta + tb >= LMIN) ++pairs;
+    *o = SchemeInfo{SA * 100 + SB * 10 + LMIN, SA, SB, LMIN, NT, EW, SA + SB - 1 - LMIN, pairs};
+  };
+  switch (code) {
+    case 331: fill(3, 3, 1, 64, 8); return true;
+    case 442: fill(4, 4, 2, 48, 12); return true;
+    case 554: fill(5, 5, 4, 48, 12); return true;
+    case 665: fill(6, 6, 5, 32, 8); return true;
   }
-  static constexpr int ACC_COLS = S * NT;
+  return false;
+}
+
+template <class SCH, int DP = 0>
+struct Cfg {
+  static constexpr int SA = SCH::SA, SB = SCH::SB, LMIN = SCH::LMIN, NT = SCH::NT, NL = SCH::NL;
+  static constexpr int EPI_WARPS = SCH::EW, EPI_THREADS = EPI_WARPS * 32, NTHREADS = 64 + EPI_THREADS;
+  static constexpr int PART_SPLIT = EPI_WARPS / 4;       // partial sums per unit (one per warp of a lane group)
+  static constexpr int A_PLANE = TM * KC, B_PLANE = NT * KC;
+  static constexpr int A_STAGE = SA * A_PLANE, B_STAGE = SB * B_PLANE, STAGE = A_STAGE + B_STAGE;
+  static constexpr int ACC_COLS = NL * NT;
   static constexpr int NBUF = (2 * ACC_COLS <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = pow2_cols(NBUF * ACC_COLS);
   static constexpr int XB_BYTES = NT * DP * 8;                       // DVAR: scaled training inputs of the column tile
@@ -78,19 +105,25 @@ struct Cfg {
   static constexpr int STAGES_FIT = (SMEM_MAX - HEAD - 512) / STAGE;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int SMEM_BYTES = HEAD + 512 + STAGES * STAGE;
-  static_assert(S >= 2 && S <= 6 && NT % 16 == 0 && S * NT <= 256, "stacked B operand must fit one MMA (N <= 256)");
+  // kept digit planes of B for A plane ta: tb = tbmin(ta) .. SB-1, landing on levels lev0(ta) .. lev0 + np - 1
+  __host__ __device__ static constexpr int tbmin(int ta) { return LMIN - ta > 0 ? LMIN - ta : 0; }
+  __host__ __device__ static constexpr int np(int ta) { return SB - tbmin(ta); }
+  __host__ __device__ static constexpr int lev0(int ta) { return ta + tbmin(ta) - LMIN; }
+  static_assert(SA >= 2 && SA <= 6 && SB >= 2 && SB <= 6 && NT % 16 == 0 && SB * NT <= 256,
+                "stacked B operand must fit one MMA (N <= 256)");
+  static_assert(LMIN <= SA - 1 + SB - 1 && LMIN >= 0 && LMIN <= SB - 1, "every A plane needs at least one partner");
   static_assert(STAGES >= 2, "need at least a double-buffered ring");
   static_assert(B_STAGE % 512 == 0 && A_STAGE % 512 == 0, "planes must keep the 512-byte swizzle period");
-  static_assert(NT * 8 <= 512 && (3 * STAGES + 3 * NBUF) * 8 + 16 <= 512, "head area too small");
-  static_assert(CG == 1 || (NT / 2) % 8 == 0, "half operands must be whole 8-row groups");
+  static_assert(NT * 8 <= 512 && (2 * STAGES + 2 * NBUF) * 8 + 16 <= 512, "head area too small");
+  static_assert(EPI_WARPS % 4 == 0 && (NT / 8) % PART_SPLIT == 0, "column groups must divide evenly over the warps");
 };
 
 enum { EPI_RAW = 0, EPI_VAR = 1, EPI_DVAR = 2 };
 enum { TRI_FULL = 0, TRI_K_LE_N = 1, TRI_K_GE_N = 2 };
 
 struct GemmParams {
-  const uint8_t* A;        // [m][RT][KCH][S][128][64]   packed digit planes of the candidate-side operand
-  const uint8_t* B;        // [Hm][nct][KCH][S][NT][64]  packed digit planes of the factor-side operand
+  const uint8_t* A;        // [m][RT][KCH][SA][128][64]  packed digit planes of the candidate-side operand
+  const uint8_t* B;        // [Hm][nct][KCH][SB][NT][64] packed digit planes of the factor-side operand
   const double* cs;        // [Hm][nct*NT]               column scale (power of two)
   int m, h, RT, nct, KCH, n, tri;
   int64_t Nc, Nvalid;
@@ -99,30 +132,28 @@ struct GemmParams {
   const double* raw_rs;    // [m*RT*128] row scale
   int ldo;
   // VAR
-  double* part_var;        // [m][nct][Nc]
-  uint8_t* A2;             // [m][RT][KCH][S][128][64]   digit planes of V (nullptr: not needed)
-  const double* vq;        // [Hm] 2^(8S-2-eV)
+  double* part_var;        // [m][np*PART_SPLIT][Nc]
+  uint8_t* A2;             // [m][RT][KCH][S2][128][64]  digit planes of V (nullptr: not needed)
+  const double* vq;        // [Hm] 2^(8 S2 - 2 - eV)
   // DVAR
-  double* part_dvar;       // [m][nct*PART_SPLIT][Nc][d]   sum_b T_b Xs_bq
-  double* part_s0;         // [m][nct*PART_SPLIT][Nc]      sum_b T_b
+  double* part_dvar;       // [m][np*PART_SPLIT][Nc][d]   sum_b T_b Xs_bq
+  double* part_s0;         // [m][np*PART_SPLIT][Nc]      sum_b T_b
   const double* GsT;       // [m][n16][Nc]
   const double* Xc;        // [Nvalid][d]
   const double* Xs;        // [Hm][n_pad][d]
   const OutHyp* hyp;
   int d, n16, n_pad;
-  int cg;                  // CTAs per tile group (1 or 2)
   int np;                  // parts per candidate tile
-  int exp;                 // experiment knob (BOCF_SPLIT_EXP, results invalid): 1 skip the MMAs, 2 skip the bulk loads,
-                           // 5 A operand from spare TMEM columns, 6 skip the epilogue work, 8 epilogue = TMEM loads only,
-                           // 9 epilogue only (no loads, no MMAs)
+  int l2_keep_a;           // 1: A planes loaded with an L2 evict_last policy (BOCF_SPLIT_L2KEEP)
 };
 
 // Work decomposition.  A UNIT is (output j, candidate tile rt, part p of NP): the column tiles ct = p, p+NP, ... of one
 // 128-candidate tile.  A persistent CTA owns whole units and walks their column tiles back to back, so the epilogue
 // keeps its per-candidate reductions in registers across the unit and writes ONE partial per (unit, epilogue warp)
-// instead of one per column tile; the NP parts of a candidate tile run on neighbouring CTAs at the same time, which
-// keeps the digit planes of the tile (re-read by every column tile) L2 resident.
-constexpr int NP_DEFAULT = 2;   // parts per candidate tile (BOCF_SPLIT_NP overrides: 1, 2 or 4)
+// instead of one per column tile.  NP = 1 (a CTA owns the whole row of column tiles of its candidate tile) measured
+// best on B200: 354 vs 371 (NP = 2) vs 390 ms (NP = 4) per 1M-candidate step at cfg 3 -- fewer partial sums, and the
+// tile's digit planes are re-read by one SM back to back.  More parts only pay when there are fewer units than SMs.
+constexpr int NP_DEFAULT = 1;   // parts per candidate tile (BOCF_SPLIT_NP overrides: 1, 2 or 4)
 inline int parts_per_tile() {
   static int np = 0;
   if (np == 0) {
@@ -134,6 +165,15 @@ inline int parts_per_tile() {
   }
   return np;
 }
+// small batches (the L-BFGS rounds of the acquisition optimiser: tens of candidates = one candidate tile per output)
+// have fewer units than SMs: split the column tiles of a candidate tile over up to 4 CTAs then
+inline int parts_for(int units_at_np1, int sms) {
+  const int np = parts_per_tile();
+  if (std::getenv("BOCF_SPLIT_NP")) return np;
+  if (units_at_np1 * 4 <= sms) return 4;
+  if (units_at_np1 * 2 <= sms) return 2;
+  return np;
+}
 
 struct TileInfo {
   int j, rt, p, ct, kb, ke;
@@ -141,51 +181,59 @@ struct TileInfo {
   bool valid, first, last;      // first / last column tile of the unit
 };
 
-__device__ __forceinline__ int tiles_per_unit(const GemmParams& P) { return (P.nct + P.np - 1) / P.np; }
-// With CTA pairs (P.cg == 2) the pair is the scheduling entity: both CTAs walk the same (output, part, column tile)
-// sequence and CTA rank r of the pair owns candidate tile 2 * (pair's tile index) + r  (RT is even).
-__device__ __forceinline__ int local_tile_count(const GemmParams& P) {      // slots this CTA walks (some may be empty)
-  const int units = P.m * (P.RT / P.cg) * P.np;
-  const int me = (int)blockIdx.x / P.cg, groups = (int)gridDim.x / P.cg;
-  const int mine = (units > me) ? (units - 1 - me) / groups + 1 : 0;
-  return mine * tiles_per_unit(P);
-}
-
-// slot l of this CTA: unit = group + (l / TPU) * groups, position l % TPU inside the unit
-__device__ __forceinline__ TileInfo decode_tile(const GemmParams& P, int NT, int l) {
-  TileInfo ti;
-  const int tpu = tiles_per_unit(P);
-  const int k = l / tpu, pos = l - k * tpu;
-  const int me = (int)blockIdx.x / P.cg, groups = (int)gridDim.x / P.cg;
-  const int u = me + k * groups;
-  const int rtg = P.RT / P.cg;
-  ti.j = u / (rtg * P.np);
-  const int r = u - ti.j * (rtg * P.np);
-  ti.rt = (r / P.np) * P.cg + ((int)blockIdx.x % P.cg);
-  ti.p = r - (r / P.np) * P.np;
-  ti.ct = ti.p + pos * P.np;
-  ti.valid = ti.ct < P.nct;
-  ti.first = (pos == 0);
-  ti.last = (ti.ct + P.np >= P.nct);
-  const int kch_used = (P.n + KC - 1) / KC;
-  if (P.tri == TRI_K_LE_N) {                              // K index <= column index
-    ti.kb = 0;
-    ti.ke = min(kch_used, (min((ti.ct + 1) * NT, P.n) + KC - 1) / KC);
-    ti.sb = 0;
-    ti.se = min(ti.ke * (KC / 32), (min((ti.ct + 1) * NT, P.n) + 31) / 32);
-  } else if (P.tri == TRI_K_GE_N) {                       // K index >= column index
-    ti.kb = (ti.ct * NT) / KC;
-    ti.ke = kch_used;
-    ti.sb = (ti.ct * NT) / 32;
-    ti.se = ti.ke * (KC / 32);
-  } else {
-    ti.kb = 0;
-    ti.ke = kch_used;
-    ti.sb = 0;
-    ti.se = ti.ke * (KC / 32);
+// Walks the column tiles this CTA owns: units cta, cta + grid, ... and inside a unit the tiles ct = p, p + NP, ...
+// The (output, candidate tile, part) decode costs integer divisions, so it is done once per unit; advancing inside a
+// unit is additions only (every role of the kernel walks the same sequence, the epilogue one tile ahead as well).
+template <int NT>
+struct TileWalk {
+  int u, units, j, rt, p, ct;
+  __device__ __forceinline__ void start(const GemmParams& P) {
+    units = P.m * P.RT * P.np;
+    u = (int)blockIdx.x - (int)gridDim.x;
+    ct = P.nct;                                            // forces the first next() to open a unit
+    j = rt = p = 0;
   }
-  return ti;
-}
+  __device__ __forceinline__ bool next(const GemmParams& P, TileInfo& ti) {
+    bool first = false;
+    ct += P.np;
+    while (ct >= P.nct) {                                  // open the next unit that has at least one column tile
+      u += (int)gridDim.x;
+      if (u >= units) return false;
+      j = u / (P.RT * P.np);
+      const int r = u - j * (P.RT * P.np);
+      rt = r / P.np;
+      p = r - rt * P.np;
+      ct = p;
+      first = true;
+    }
+    ti.j = j;
+    ti.rt = rt;
+    ti.p = p;
+    ti.ct = ct;
+    ti.valid = true;
+    ti.first = first;
+    ti.last = (ct + P.np >= P.nct);
+    const int kch_used = (P.n + KC - 1) / KC;
+    if (P.tri == TRI_K_LE_N) {                              // K index <= column index
+      const int cend = min((ct + 1) * NT, P.n);
+      ti.kb = 0;
+      ti.ke = min(kch_used, (cend + KC - 1) / KC);
+      ti.sb = 0;
+      ti.se = min(ti.ke * (KC / 32), (cend + 31) / 32);
+    } else if (P.tri == TRI_K_GE_N) {                       // K index >= column index
+      ti.kb = (ct * NT) / KC;
+      ti.ke = kch_used;
+      ti.sb = (ct * NT) / 32;
+      ti.se = ti.ke * (KC / 32);
+    } else {
+      ti.kb = 0;
+      ti.ke = kch_used;
+      ti.sb = 0;
+      ti.se = ti.ke * (KC / 32);
+    }
+    return true;
+  }
+};
 
 // digits of a 64-bit integer |Y| < 2^(8S-2): byte t of the result is the balanced base-256 digit of weight 256^t
 template <int S>
@@ -206,19 +254,21 @@ __device__ __forceinline__ double i32_to_f64(uint32_t c) {
 __device__ __forceinline__ double i64_to_f64(long long x) {
   return __longlong_as_double(x + 0x4338000000000000LL) - 6755399441055744.0;
 }
-// sum_lb 256^lb c[lb]: adjacent levels are merged in 64-bit integer arithmetic first (c[lb] * 256 + c[lb-1] < 2^38), so
-// only ceil(S/2) conversions and floor(S/2) fused multiply-adds reach the fp64 pipe -- the epilogue's scarce resource
-// (ncu: math_pipe_throttle) -- instead of S and S-1.
-template <int S, int W>
-__device__ __forceinline__ double levels_to_f64(const uint32_t (&c)[S][W], int e) {
+// sum_lb 256^lb c[lb]: adjacent levels are merged in 64-bit integer arithmetic first (|c[lb]| < 2^29, so
+// c[lb] * 256 + c[lb-1] < 2^38), so only ceil(NL/2) conversions and floor(NL/2) fused multiply-adds reach the fp64
+// pipe instead of NL and NL-1.  The 1.5 * 2^52 bit pattern of the int64 -> fp64 trick rides in the addend of the
+// widening multiply-add (one IMAD.WIDE per pair, no separate 64-bit add).
+template <int NL, int W>
+__device__ __forceinline__ double levels_to_f64(const uint32_t (&c)[NL][W], int e) {
   double v = 0.0;
 #pragma unroll
-  for (int lb = S - 1; lb >= 0; lb -= 2) {
+  for (int lb = NL - 1; lb >= 0; lb -= 2) {
     if (lb >= 1) {
-      const long long t = (long long)(int)c[lb][e] * 256 + (long long)(int)c[lb - 1][e];
-      v = (lb == S - 1) ? i64_to_f64(t) : fma(v, 65536.0, i64_to_f64(t));
+      const long long addend = (long long)(int)c[lb - 1][e] + 0x4338000000000000LL;
+      const double t = __longlong_as_double((long long)(int)c[lb][e] * 256 + addend) - 6755399441055744.0;
+      v = (lb == NL - 1) ? t : fma(v, 65536.0, t);
     } else {
-      v = (lb == S - 1) ? i32_to_f64(c[0][e]) : fma(v, 256.0, i32_to_f64(c[0][e]));
+      v = (lb == NL - 1) ? i32_to_f64(c[0][e]) : fma(v, 256.0, i32_to_f64(c[0][e]));
     }
   }
   return v;
@@ -230,9 +280,36 @@ __device__ __forceinline__ unsigned long long balanced_digits_of(double x) {
   return balanced_digits<S>(__double_as_longlong(x + 6755399441055744.0));
 }
 
-template <int S, int NT, int EPI, int DP, int CG>
-__global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParams P) {
-  using C = Cfg<S, NT, DP, CG>;
+// One 32-byte K step of the digit-pair scheme: one instruction per A plane, B planes stacked along N.  FIRST: the
+// accumulators hold the previous tile -- every level is overwritten (accumulate = 0) by the first instruction that
+// touches it; an instruction that reaches one level below the initialised range is split in two.
+template <class C, bool FIRST>
+__device__ __forceinline__ void issue_kstep(uint32_t a_lo, uint32_t b_lo, uint32_t d_tmem) {
+  int init_lo = C::NL;                                   // levels >= init_lo are initialised (compile-time folded)
+#pragma unroll
+  for (int ta = C::SA - 1; ta >= 0; --ta) {
+    const int tb0 = C::tbmin(ta), np = C::np(ta), l0 = C::lev0(ta);
+    const uint64_t adesc = tc::desc_from_lo(a_lo + (uint32_t)(ta * (C::A_PLANE >> 4)));
+    if (!FIRST || l0 >= init_lo) {
+      tc::mma_i8(d_tmem + (uint32_t)(l0 * C::NT), adesc, tc::desc_from_lo(b_lo + (uint32_t)(tb0 * (C::B_PLANE >> 4))),
+                 tc::idesc_i8(np * C::NT), 1u);
+    } else {
+      const int fresh = (init_lo - l0 < np) ? init_lo - l0 : np;      // levels l0 .. l0 + fresh - 1 are new
+      tc::mma_i8(d_tmem + (uint32_t)(l0 * C::NT), adesc, tc::desc_from_lo(b_lo + (uint32_t)(tb0 * (C::B_PLANE >> 4))),
+                 tc::idesc_i8(fresh * C::NT), 0u);
+      if (fresh < np)
+        tc::mma_i8(d_tmem + (uint32_t)((l0 + fresh) * C::NT), adesc,
+                   tc::desc_from_lo(b_lo + (uint32_t)((tb0 + fresh) * (C::B_PLANE >> 4))),
+                   tc::idesc_i8((np - fresh) * C::NT), 1u);
+      init_lo = l0;
+    }
+  }
+}
+
+template <class SCH, int EPI, int DP, int S2>
+__global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(const GemmParams P) {
+  using C = Cfg<SCH, DP>;
+  constexpr int NT = C::NT, NL = C::NL, EPI_THREADS = C::EPI_THREADS, PART_SPLIT = C::PART_SPLIT;
   extern __shared__ uint8_t smem_raw[];
   // head: [0,512) barriers + tmem slot, [512, 1024) column scales; stages start at the next 512-byte boundary
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -240,9 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
   uint64_t* empty = bars + C::STAGES;
   uint64_t* tfull = bars + 2 * C::STAGES;
   uint64_t* tempty = tfull + C::NBUF;
-  uint64_t* pfull = tempty + C::NBUF;          // CG = 2, leader only: the peer CTA's stage has landed (relayed)
-  uint64_t* ptempty = pfull + C::STAGES;       // CG = 2, leader only: the peer CTA's epilogue has drained the buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ptempty + C::NBUF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::NBUF);
   double* s_cs = reinterpret_cast<double*>(smem_raw + 512);
   double* s_xb = reinterpret_cast<double*>(smem_raw + 1024);      // [NT][DP]
   const uint32_t raw_addr = tc::smem_u32(smem_raw);
@@ -250,7 +325,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
   uint8_t* sA = smem_raw + stage_off;
   uint8_t* sB = sA + C::STAGES * C::A_STAGE;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform branches and the
+  // MMA warp's loop state / descriptors stay on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       tc::mbar_init(&full[s], 1);
@@ -259,22 +336,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
     for (int b = 0; b < C::NBUF; ++b) {
       tc::mbar_init(&tfull[b], 1);
       tc::mbar_init(&tempty[b], EPI_THREADS);
-      tc::mbar_init(&ptempty[b], 1);
     }
-    for (int s = 0; s < C::STAGES; ++s) tc::mbar_init(&pfull[s], 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) {
-    if (CG == 2) tc::tmem_alloc2<C::TMEM_COLS>(tmem_slot);
-    else tc::tmem_alloc<C::TMEM_COLS>(tmem_slot);
-  }
+  if (warp == 1) tc::tmem_alloc<C::TMEM_COLS>(tmem_slot);
   tc::fence_before_sync();
-  if (CG == 2) tc::cluster_sync_all();         // peer barriers are initialised before any remote arrive / multicast commit
-  else __syncthreads();
+  __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t crank = (CG == 2) ? tc::cluster_ctarank() : 0u;
-  const int num_tiles = local_tile_count(P);   // slots of THIS CTA
 
   if (warp == 0) {
     // ================================ producer =================================================
@@ -282,13 +351,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       int stage = 0;
       uint32_t phase = 0;
       const uint64_t pol_keep = tc::l2_policy_evict_last();
-      for (int t = 0; t < num_tiles; ++t) {
-        const TileInfo ti = decode_tile(P, NT, t);
-        if (!ti.valid) continue;
+      TileWalk<NT> walk;
+      walk.start(P);
+      TileInfo ti;
+      while (walk.next(P, ti)) {
         const uint8_t* gA = P.A + ((size_t)(ti.j * P.RT + ti.rt) * P.KCH) * C::A_STAGE;
-        // CG = 2: [..][kc][rank][regions]  -- this CTA streams its own half-operand block
-        const uint8_t* gB = P.B + ((size_t)((P.h * P.m + ti.j) * P.nct + ti.ct) * P.KCH) * (C::B_STAGE * CG) +
-                            (size_t)crank * C::B_STAGE;
+        const uint8_t* gB = P.B + ((size_t)((P.h * P.m + ti.j) * P.nct + ti.ct) * P.KCH) * C::B_STAGE;
         if (EPI == EPI_DVAR) {
           // the epilogue of this tile (one tile later in time) reads 128 G* values of each of its NT columns:
           // pull those 1 KB rows into L2 now so its loads do not pay HBM latency
@@ -298,22 +366,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
         }
         for (int kc = ti.kb; kc < ti.ke; ++kc) {
           tc::mbar_wait(&empty[stage], phase ^ 1u);
-          if (P.exp == 2 || P.exp == 9) {
-            tc::mbar_arrive(&full[stage]);
-          } else {
-            tc::mbar_arrive_expect_tx(&full[stage], C::STAGE);
-            if (P.exp >= 10 && P.exp <= 12) {
-              // experiment: the unit's A tile (re-streamed once per column tile) and the factor planes stay in L2
-              tc::bulk_g2s_hint(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage], pol_keep);
-              if (P.exp == 12)
-                tc::bulk_g2s_hint(sB + stage * C::B_STAGE, gB + (size_t)kc * (C::B_STAGE * CG), C::B_STAGE, &full[stage], pol_keep);
-              else
-                tc::bulk_g2s(sB + stage * C::B_STAGE, gB + (size_t)kc * (C::B_STAGE * CG), C::B_STAGE, &full[stage]);
-            } else {
-              tc::bulk_g2s(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage]);
-              tc::bulk_g2s(sB + stage * C::B_STAGE, gB + (size_t)kc * (C::B_STAGE * CG), C::B_STAGE, &full[stage]);
-            }
-          }
+          tc::mbar_arrive_expect_tx(&full[stage], C::STAGE);
+          // the unit's A tile is re-streamed once per column tile: ask L2 to keep it (P.l2_keep_a)
+          if (P.l2_keep_a) tc::bulk_g2s_hint(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage], pol_keep);
+          else tc::bulk_g2s(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage]);
+          tc::bulk_g2s(sB + stage * C::B_STAGE, gB + (size_t)kc * C::B_STAGE, C::B_STAGE, &full[stage]);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -322,78 +379,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       }
     }
   } else if (warp == 1) {
-#define WAITFN(bar, par) tc::mbar_wait(bar, par)
-    // ================================ MMA issuer ===============================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = 0; t < num_tiles; ++t) {
-        const TileInfo ti = decode_tile(P, NT, t);
-        if (!ti.valid) continue;
-        const int buf = it % C::NBUF;
-        const uint32_t use = (uint32_t)(it / C::NBUF);
-        ++it;
-        if (CG == 2 && crank != 0) {
-          // follower of the pair: issues nothing; relays "my epilogue drained the buffer" and "my stage landed" to the
-          // leader, whose MMAs read this CTA's shared memory and write this CTA's tensor memory
-          WAITFN(&tempty[buf], (use & 1u) ^ 1u);
-          tc::mbar_arrive_remote(&ptempty[buf], 0);
-          for (int kc = ti.kb; kc < ti.ke; ++kc) {
-            WAITFN(&full[stage], phase);
-            tc::mbar_arrive_remote(&pfull[stage], 0);
-            if (++stage == C::STAGES) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-          continue;
-        }
-        WAITFN(&tempty[buf], (use & 1u) ^ 1u);          // epilogue has drained this accumulator buffer
-        if (CG == 2) WAITFN(&ptempty[buf], use & 1u);   // ... in the peer CTA too
+    // ================================ MMA issuer (whole warp, one elected lane issues) ==========
+    const uint32_t a_lo0 = tc::desc_lo_sw64(tc::smem_u32(sA)), b_lo0 = tc::desc_lo_sw64(tc::smem_u32(sB));
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    TileWalk<NT> walk;
+    walk.start(P);
+    TileInfo ti;
+    while (walk.next(P, ti)) {
+      const int buf = it % C::NBUF;
+      const uint32_t use = (uint32_t)(it / C::NBUF);
+      ++it;
+      tc::mbar_wait(&tempty[buf], (use & 1u) ^ 1u);          // epilogue has drained this accumulator buffer
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::ACC_COLS);
+      bool first = true;
+      for (int kc = ti.kb; kc < ti.ke; ++kc) {
+        tc::mbar_wait(&full[stage], phase);
         tc::fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::ACC_COLS);
-        bool first = true;
-        for (int kc = ti.kb; kc < ti.ke; ++kc) {
-          WAITFN(&full[stage], phase);
-          if (CG == 2) WAITFN(&pfull[stage], phase);
-          tc::fence_after_sync();
-          const uint32_t a0 = tc::smem_u32(sA + stage * C::A_STAGE);
-          const uint32_t b0 = tc::smem_u32(sB + stage * C::B_STAGE);
+        const uint32_t a_lo = a_lo0 + (uint32_t)(stage * (C::A_STAGE >> 4));
+        const uint32_t b_lo = b_lo0 + (uint32_t)(stage * (C::B_STAGE >> 4));
 #pragma unroll
-          for (int ks = 0; ks < KC / 32; ++ks) {
-            const int kstep = kc * (KC / 32) + ks;            // K steps wholly outside the triangle multiply zeros: skip
-            if (kstep < ti.sb || kstep >= ti.se) continue;
-#pragma unroll
-            for (int ta = S - 1; ta >= 0; --ta) {
-              // A digit plane ta against the stacked B planes tb = S-1-ta .. S-1  ->  levels 0 .. ta
-              const uint64_t adesc = tc::smem_desc_sw64(a0 + ta * C::A_PLANE + ks * 32);
-              const uint64_t bdesc = tc::smem_desc_sw64(b0 + C::b_off(ta) + ks * 32);
-              const uint32_t acc = (first && ta == S - 1) ? 0u : 1u;
-              if (P.exp == 5 && CG == 1 && C::NBUF * C::ACC_COLS + 8 * S <= C::TMEM_COLS) {
-                // experiment (timing only, results invalid): A operand from spare tensor-memory columns
-                tc::mma_i8_ts(d_tmem, tmem_base + (uint32_t)(C::NBUF * C::ACC_COLS + 8 * ta), bdesc, tc::idesc_i8((ta + 1) * NT), acc);
-              } else if (P.exp != 1 && P.exp != 9) {
-                if (CG == 2) tc::mma_i8_pair(d_tmem, adesc, bdesc, tc::idesc_i8_m256((ta + 1) * NT), acc);
-                else tc::mma_i8(d_tmem, adesc, bdesc, tc::idesc_i8((ta + 1) * NT), acc);
-              }
-            }
-            first = false;
+        for (int ks = 0; ks < KC / 32; ++ks) {
+          const int kstep = kc * (KC / 32) + ks;            // K steps wholly outside the triangle multiply zeros: skip
+          if (kstep < ti.sb || kstep >= ti.se) continue;
+          if (first) {
+            if (tc::elect_one()) issue_kstep<C, true>(a_lo + ks * 2, b_lo + ks * 2, d_tmem);
+          } else {
+            if (tc::elect_one()) issue_kstep<C, false>(a_lo + ks * 2, b_lo + ks * 2, d_tmem);
           }
-          // stage reusable once these MMAs have read it (both CTAs' stages for a pair)
-          if (CG == 2) tc::mma_commit_pair(&empty[stage]);
-          else tc::mma_commit(&empty[stage]);
-          if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          first = false;
         }
-        // accumulators of this tile complete (in both CTAs' tensor memory for a pair)
-        if (CG == 2) tc::mma_commit_pair(&tfull[buf]);
-        else tc::mma_commit(&tfull[buf]);
+        if (tc::elect_one()) tc::mma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
+        __syncwarp();
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
+      if (tc::elect_one()) tc::mma_commit(&tfull[buf]);      // accumulators of this tile complete
+      __syncwarp();
     }
-#undef WAITFN
   } else {
     // ================================ epilogue (EPI_WARPS warps) ===============================
     const int et = threadIdx.x - 64;
@@ -406,11 +433,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
     constexpr int DPA0 = DP > 0 ? DP : 1;
     constexpr int XPT = (EPI == EPI_DVAR) ? (NT * DPA0 + EPI_THREADS - 1) / EPI_THREADS : 1;
     double pre_cs = 0.0, pre_vq = 0.0, pre_xb[XPT];
-    auto prefetch_tile_consts = [&](int tnext) {
-      TileInfo tn;
-      tn.valid = false;
-      while (tnext < num_tiles && !(tn = decode_tile(P, NT, tnext)).valid) ++tnext;
-      if (!tn.valid) return;
+    auto prefetch_tile_consts = [&](const TileInfo& tn) {
       const int hjn = P.h * P.m + tn.j;
       if (et < NT) pre_cs = __ldg(P.cs + (size_t)hjn * P.nct * NT + tn.ct * NT + et);
       if (EPI == EPI_VAR) pre_vq = __ldg(P.vq + hjn);
@@ -425,13 +448,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
         }
       }
     };
-    prefetch_tile_consts(0);
+    TileWalk<NT> walk;
+    walk.start(P);
+    TileInfo ti, tnext;
+    bool have = walk.next(P, tnext);
+    if (have) prefetch_tile_consts(tnext);
     // reductions over the column tiles of a unit live in registers
     constexpr int DPA = DP > 0 ? DP : 2;
     double sumsq = 0.0, s0 = 0.0, acc[DPA];
-    for (int t = 0; t < num_tiles; ++t) {
-      const TileInfo ti = decode_tile(P, NT, t);
-      if (!ti.valid) continue;
+    while (have) {
+      ti = tnext;
+      have = walk.next(P, tnext);
       const int buf = it % C::NBUF;
       const uint32_t use = (uint32_t)(it / C::NBUF);
       ++it;
@@ -453,21 +480,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       }
       const double vq = pre_vq;
       tc::named_bar_sync(1, EPI_THREADS);
-      prefetch_tile_consts(t + 1);
+      if (have) prefetch_tile_consts(tnext);
       const int64_t i = (int64_t)ti.rt * TM + row;              // chunk-local candidate
 
       // per-tile thread state
       constexpr int CGW = 8;                                    // columns per TMEM load group
       constexpr int NCG = NT / CGW;
+      constexpr int NGW = NCG / PART_SPLIT;                     // column groups per warp
       double gv[CGW];
+      // G* of this warp's column groups: rows b of GsT, one candidate per lane (coalesced).  Columns b >= n of the last
+      // tile carry an exactly zero Wt (zero factor planes), so their G* is read from row n-1 instead of being masked.
       const double* Gcol = nullptr;
-      const bool g_stream = (P.exp == 11 || P.exp == 12);       // experiment: G* is read once -> streaming loads
+      const int64_t gstride = P.Nc;
+      const bool tile_full = (col0 + NT <= P.n);
       if (EPI == EPI_DVAR) {
         Gcol = P.GsT + (size_t)ti.j * P.n16 * P.Nc + i;
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {                      // first column group: in flight while the MMAs finish
           const int b = col0 + hw * CGW + e;
-          gv[e] = (b < P.n) ? (g_stream ? __ldcs(Gcol + (size_t)b * P.Nc) : __ldg(Gcol + (size_t)b * P.Nc)) : 0.0;
+          gv[e] = __ldg(Gcol + (size_t)(tile_full ? b : min(b, P.n - 1)) * gstride);
         }
       }
 
@@ -475,27 +506,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
       tc::fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
 
-#pragma unroll 1
-      for (int cg = hw; cg < NCG; cg += PART_SPLIT) {
-        if (P.exp == 6) break;                                    // experiment: no epilogue work (timing only)
-        uint32_t c[S][CGW];
+      // VAR / RAW: the levels of the NEXT column group are requested from tensor memory before the current group is
+      // processed (two register buffers), so the TMEM round trip overlaps the fp64 work.  DVAR keeps one buffer: its
+      // 2 d + 2 accumulators leave no registers for a second one.
+      constexpr bool PREF = (EPI != EPI_DVAR);
+      uint32_t c[PREF ? 2 : 1][NL][CGW];
+      if (PREF) {
 #pragma unroll
-        for (int lb = 0; lb < S; ++lb) tc::tmem_ldw<CGW>(taddr + (uint32_t)(lb * NT + cg * CGW), c[lb]);
-        tc::tmem_ld_wait();
-        if (P.exp == 8) {                                         // experiment: TMEM loads only, no epilogue math
-          uint32_t x = 0;
+        for (int lb = 0; lb < NL; ++lb) tc::tmem_ldw<CGW>(taddr + (uint32_t)(lb * NT + hw * CGW), c[0][lb]);
+      }
 #pragma unroll
-          for (int lb = 0; lb < S; ++lb)
+      for (int gi = 0; gi < NGW; ++gi) {
+        const int cg = hw + gi * PART_SPLIT;
+        constexpr int dummy = 0;
+        (void)dummy;
+        if (PREF) {
+          tc::tmem_ld_wait();
+          if (gi + 1 < NGW) {
 #pragma unroll
-            for (int e = 0; e < CGW; ++e) x ^= c[lb][e];
-          if (x == 0x9e3779b9u) sumsq += 1.0;                     // keeps the loads alive
-          continue;
+            for (int lb = 0; lb < NL; ++lb)
+              tc::tmem_ldw<CGW>(taddr + (uint32_t)(lb * NT + (cg + PART_SPLIT) * CGW), c[(gi + 1) & 1][lb]);
+          }
+        } else {
+#pragma unroll
+          for (int lb = 0; lb < NL; ++lb) tc::tmem_ldw<CGW>(taddr + (uint32_t)(lb * NT + cg * CGW), c[0][lb]);
+          tc::tmem_ld_wait();
         }
-        uint32_t vec[S][2];
+        const uint32_t (&cc)[NL][CGW] = c[PREF ? (gi & 1) : 0];
+        uint32_t vec[S2][2];
         unsigned long long dgv[CGW];
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {
-          double v = levels_to_f64<S, CGW>(c, e);
+          double v = levels_to_f64<NL, CGW>(cc, e);
           if (EPI != EPI_DVAR) v *= s_cs[cg * CGW + e];             // DVAR: the column scale is folded into G* by the K* kernel
           if (EPI == EPI_RAW) {
             const int col = col0 + cg * CGW + e;
@@ -503,13 +545,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
             if (col < P.ldo) P.raw_out[grow * P.ldo + col] = v * P.raw_rs[grow];
           } else if (EPI == EPI_VAR) {
             sumsq = fma(v, v, sumsq);
-            dgv[e] = balanced_digits_of<S>(v * vq);
+            dgv[e] = balanced_digits_of<S2>(v * vq);
           } else {
             const double w = v * gv[e];
-            {                                                  // refill the slot with this warp's next column group's G*
+            if (gi + 1 < NGW) {                                // refill the slot with this warp's next column group's G*
               const int bn = col0 + (cg + PART_SPLIT) * CGW + e;
-              gv[e] = (cg + PART_SPLIT < NCG && bn < P.n)
-                          ? (g_stream ? __ldcs(Gcol + (size_t)bn * P.Nc) : __ldg(Gcol + (size_t)bn * P.Nc)) : 0.0;
+              gv[e] = __ldg(Gcol + (size_t)(tile_full ? bn : min(bn, P.n - 1)) * gstride);
             }
             s0 += w;
             const double2* xb2 = reinterpret_cast<const double2*>(s_xb + (cg * CGW + e) * DPA);
@@ -525,19 +566,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
 #pragma unroll
           for (int w = 0; w < 2; ++w) {                          // byte transpose: digit t of 4 columns -> one word
             const unsigned long long four[4] = {dgv[4 * w], dgv[4 * w + 1], dgv[4 * w + 2], dgv[4 * w + 3]};
-            uint32_t o[S];
-            digits_transpose4<S>(four, o);
+            uint32_t o[S2];
+            digits_transpose4<S2>(four, o);
 #pragma unroll
-            for (int tt = 0; tt < S; ++tt) vec[tt][w] = o[tt];
+            for (int tt = 0; tt < S2; ++tt) vec[tt][w] = o[tt];
           }
           const int k = col0 + cg * CGW;
           if (k < P.KCH * KC) {
             const int kc = k >> 6;
-            uint8_t* dst = P.A2 + (((size_t)(ti.j * P.RT + ti.rt) * P.KCH + kc) * S) * C::A_PLANE + sw64(row, k & 63);
+            uint8_t* dst = P.A2 + (((size_t)(ti.j * P.RT + ti.rt) * P.KCH + kc) * S2) * C::A_PLANE + sw64(row, k & 63);
 #pragma unroll
-            for (int tt = 0; tt < S; ++tt)
-              if (P.exp == 11 || P.exp == 12) __stcs(reinterpret_cast<uint2*>(dst + (size_t)tt * C::A_PLANE), make_uint2(vec[tt][0], vec[tt][1]));
-              else *reinterpret_cast<uint2*>(dst + (size_t)tt * C::A_PLANE) = make_uint2(vec[tt][0], vec[tt][1]);
+            for (int tt = 0; tt < S2; ++tt)
+              *reinterpret_cast<uint2*>(dst + (size_t)tt * C::A_PLANE) = make_uint2(vec[tt][0], vec[tt][1]);
           }
         }
       }
@@ -558,13 +598,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) split_gemm_kernel(const GemmParam
     }
   }
   tc::fence_before_sync();
-  if (CG == 2) tc::cluster_sync_all();         // no CTA leaves while its peer may still signal it / use its memories
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc::fence_after_sync();
-    if (CG == 2) tc::tmem_dealloc2<C::TMEM_COLS>(tmem_base);
-    else tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -630,52 +668,6 @@ __global__ void pack_digits_kernel(const double* __restrict__ src, int64_t mat_s
   }
 }
 
-// Pair layout of the factor-side operand (cta_group::2, see Cfg): per (tile, K chunk) two blocks (CTA rank 0 / 1), each
-// holding for every instruction ta = S-1 .. 0 the rows [rank N_ta/2, (rank+1) N_ta/2) of the stack of planes S-1-ta .. S-1.
-template <int S>
-__global__ void pack_digits_pair_kernel(const double* __restrict__ src, int64_t mat_stride, int64_t sr, int64_t sk,
-                                        int R, int K, const int* __restrict__ exps, int Rpad, int NTr, int ntile,
-                                        int KCH, uint8_t* __restrict__ out) {
-  const int kc = blockIdx.x, tile = blockIdx.y, mat = blockIdx.z;
-  const int half = NTr / 2;
-  const int rows_per_rank = (S * (S + 1) / 2) * half;
-  uint8_t* obase = out + ((size_t)(mat * ntile + tile) * KCH + kc) * (size_t)(2 * rows_per_rank * KC);
-  for (int idx = threadIdx.x; idx < 2 * rows_per_rank * 4; idx += blockDim.x) {
-    int piece, rr_all;
-    if (sk == 1) {
-      rr_all = idx >> 2;
-      piece = idx & 3;
-    } else {
-      rr_all = idx % (2 * rows_per_rank);
-      piece = idx / (2 * rows_per_rank);
-    }
-    const int rank = rr_all / rows_per_rank;
-    int rem = rr_all - rank * rows_per_rank;
-    int ta = S - 1, off_rows = 0;
-    while (rem >= (ta + 1) * half) {                     // regions ordered ta = S-1 first
-      rem -= (ta + 1) * half;
-      off_rows += (ta + 1) * half;
-      --ta;
-    }
-    const int sidx = rank * (ta + 1) * half + rem;       // row inside the stack of instruction ta
-    const int tb = (S - 1 - ta) + sidx / NTr;
-    const int r = sidx % NTr;
-    const int row = tile * NTr + r;
-    const int e = exps[(size_t)mat * Rpad + row];
-    const double q = ldexp(1.0, 8 * S - 2 - e);
-    uint32_t vec[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int ee = 0; ee < 16; ++ee) {
-      const int k = kc * KC + piece * 16 + ee;
-      const double x = (row < R && k < K) ? src[mat * mat_stride + row * sr + k * sk] : 0.0;
-      const unsigned long long dg = balanced_digits_of<S>(x * q);
-      vec[ee >> 2] |= (uint32_t)((dg >> (8 * tb)) & 0xFFull) << (8 * (ee & 3));
-    }
-    *reinterpret_cast<uint4*>(obase + (size_t)rank * rows_per_rank * KC + (size_t)off_rows * KC + sw64(rem, piece * 16)) =
-        make_uint4(vec[0], vec[1], vec[2], vec[3]);
-  }
-}
-
 __global__ void absmax_kernel(const double* __restrict__ src, size_t count, double* __restrict__ out) {
   double a = 0.0;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += (size_t)gridDim.x * blockDim.x)
@@ -692,20 +684,6 @@ static int pack_t(const double* src, int64_t mat_stride, int64_t sr, int64_t sk,
   dim3 grid((unsigned)KCH, (unsigned)ntile, (unsigned)mats);
   pack_digits_kernel<S><<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, exps, Rpad, TR, ntile, KCH, out);
   BOCF_LAUNCH_OK("pack_digits_kernel");
-  return 0;
-}
-static int pack_digits_pair(int S, const double* src, int64_t mat_stride, int64_t sr, int64_t sk, int R, int K,
-                            const int* exps, int Rpad, int NTr, int ntile, int KCH, int mats, uint8_t* out,
-                            cudaStream_t st) {
-  dim3 grid((unsigned)KCH, (unsigned)ntile, (unsigned)mats);
-  switch (S) {
-    case 3: pack_digits_pair_kernel<3><<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, exps, Rpad, NTr, ntile, KCH, out); break;
-    case 4: pack_digits_pair_kernel<4><<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, exps, Rpad, NTr, ntile, KCH, out); break;
-    case 5: pack_digits_pair_kernel<5><<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, exps, Rpad, NTr, ntile, KCH, out); break;
-    case 6: pack_digits_pair_kernel<6><<<grid, 256, 0, st>>>(src, mat_stride, sr, sk, R, K, exps, Rpad, NTr, ntile, KCH, out); break;
-    default: set_error("split contraction supports 3..6 digit planes"); return BOCF_ERR_INVALID;
-  }
-  BOCF_LAUNCH_OK("pack_digits_pair_kernel");
   return 0;
 }
 static int pack_digits(int S, const double* src, int64_t mat_stride, int64_t sr, int64_t sk, int R, int K,
@@ -727,75 +705,96 @@ static int row_exps(const double* src, int64_t mat_stride, int64_t sr, int64_t s
   return 0;
 }
 
-template <int S, int NT, int EPI, int DP, int CG>
-static int launch_cg(const GemmParams& P, cudaStream_t st) {
-  using C = Cfg<S, NT, DP, CG>;
+template <class SCH, int EPI, int DP, int S2>
+static int launch_k(const GemmParams& P, cudaStream_t st) {
+  using C = Cfg<SCH, DP>;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   static bool attr_done[64] = {false};          // per device: function attributes belong to the device's context
   if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    BOCF_CUDA_OK(cudaFuncSetAttribute(split_gemm_kernel<S, NT, EPI, DP, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    BOCF_CUDA_OK(cudaFuncSetAttribute(split_gemm_kernel<SCH, EPI, DP, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       C::SMEM_BYTES));
     attr_done[dev] = true;
   }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int units = P.m * (P.RT / CG) * P.np;     // scheduling entities (CTAs, or CTA pairs)
-  if (const char* env = std::getenv("BOCF_SPLIT_GRID")) {          // experiment knob: persistent CTAs launched
-    const int g = std::atoi(env);
-    if (g > 0 && g < sms) sms = g;
-  }
-  int groups = sms / CG;
-  if (units < groups) groups = units;
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(groups * CG));
-  cfg.blockDim = dim3(NTHREADS);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, split_gemm_kernel<S, NT, EPI, DP, CG>, P);
-  count_launch();
-  if (e != cudaSuccess) {
-    set_error(std::string("launch split_gemm_kernel: ") + cudaGetErrorString(e));
-    return -2;
-  }
+  const int units = P.m * P.RT * P.np;            // scheduling entities
+  const int grid = units < sms ? units : sms;
+  split_gemm_kernel<SCH, EPI, DP, S2><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(P);
+  BOCF_LAUNCH_OK("split_gemm_kernel");
   return 0;
 }
-template <int S, int NT, int EPI, int DP = 0>
-static int launch_t(const GemmParams& P, cudaStream_t st) {
-  if (P.cg == 2) return launch_cg<S, NT, EPI, DP, 2>(P, st);
-  return launch_cg<S, NT, EPI, DP, 1>(P, st);
-}
-template <int EPI, int DP = 0>
-static int launch_s(int S, const GemmParams& P, cudaStream_t st) {
-  switch (S) {
-    case 3: return launch_t<3, 64, EPI, DP>(P, st);
-    case 4: return launch_t<4, 64, EPI, DP>(P, st);
-    case 5: return launch_t<5, 48, EPI, DP>(P, st);
-    case 6: return launch_t<6, 32, EPI, DP>(P, st);
-  }
-  set_error("split contraction supports 3..6 digit planes");
+
+static int bad_scheme() {
+  set_error("split contraction: unsupported digit-pair scheme (331, 442, 554, 665)");
   return BOCF_ERR_INVALID;
 }
-static int launch_dvar(int S, int d, const GemmParams& P, cudaStream_t st) {
-  if (d <= 4) return launch_s<EPI_DVAR, 4>(S, P, st);
-  if (d <= 6) return launch_s<EPI_DVAR, 6>(S, P, st);
-  if (d <= 8) return launch_s<EPI_DVAR, 8>(S, P, st);
-  if (d <= 10) return launch_s<EPI_DVAR, 10>(S, P, st);
-  if (d <= 12) return launch_s<EPI_DVAR, 12>(S, P, st);
-  return launch_s<EPI_DVAR, 16>(S, P, st);
+static int launch_raw(int sch, const GemmParams& P, cudaStream_t st) {
+  switch (sch) {
+    case 331: return launch_k<P331, EPI_RAW, 0, 3>(P, st);
+    case 442: return launch_k<P442, EPI_RAW, 0, 4>(P, st);
+    case 554: return launch_k<P554, EPI_RAW, 0, 5>(P, st);
+    case 665: return launch_k<P665, EPI_RAW, 0, 6>(P, st);
+  }
+  return bad_scheme();
+}
+// first contraction with scheme `sch`, re-splitting V into the s2 digit planes the second contraction's scheme reads
+static int launch_var(int sch, int s2, const GemmParams& P, cudaStream_t st) {
+  switch (sch * 10 + s2) {
+    case 3313: return launch_k<P331, EPI_VAR, 0, 3>(P, st);
+    case 4423: return launch_k<P442, EPI_VAR, 0, 3>(P, st);
+    case 4424: return launch_k<P442, EPI_VAR, 0, 4>(P, st);
+    case 5544: return launch_k<P554, EPI_VAR, 0, 4>(P, st);
+    case 5545: return launch_k<P554, EPI_VAR, 0, 5>(P, st);
+    case 6655: return launch_k<P665, EPI_VAR, 0, 5>(P, st);
+    case 6656: return launch_k<P665, EPI_VAR, 0, 6>(P, st);
+  }
+  return bad_scheme();
+}
+template <int DP>
+static int launch_dvar_d(int sch, const GemmParams& P, cudaStream_t st) {
+  switch (sch) {
+    case 331: return launch_k<P331, EPI_DVAR, DP, 3>(P, st);
+    case 442: return launch_k<P442, EPI_DVAR, DP, 4>(P, st);
+    case 554: return launch_k<P554, EPI_DVAR, DP, 5>(P, st);
+    case 665: return launch_k<P665, EPI_DVAR, DP, 6>(P, st);
+  }
+  return bad_scheme();
+}
+static int launch_dvar(int sch, int d, const GemmParams& P, cudaStream_t st) {
+  if (d <= 4) return launch_dvar_d<4>(sch, P, st);
+  if (d <= 6) return launch_dvar_d<6>(sch, P, st);
+  if (d <= 8) return launch_dvar_d<8>(sch, P, st);
+  if (d <= 10) return launch_dvar_d<10>(sch, P, st);
+  if (d <= 12) return launch_dvar_d<12>(sch, P, st);
+  return launch_dvar_d<16>(sch, P, st);
 }
 
 }  // namespace sg
 
-int split_column_tile(int S) { return S == 5 ? 48 : (S == 6 ? 32 : 64); }
-int split_partials_per_tile() { return sg::PART_SPLIT * sg::parts_per_tile(); }   // partial sums per candidate and output
+// scheme of a symmetric "N digit planes" request (bocf_model_set_precision slices = 3..6)
+int split_scheme_for_slices(int S) { return S == 3 ? 331 : S == 4 ? 442 : S == 5 ? 554 : S == 6 ? 665 : 0; }
+int split_scheme_pairs(int sch) {
+  sg::SchemeInfo si;
+  return sg::scheme_info(sch, &si) ? si.pairs : 0;
+}
+// parts per candidate tile for a chunk of Nc candidates (Nc <= 0: the upper bound, for sizing the scratch)
+int split_parts(const bocf_model* M, int64_t Nc) {
+  if (Nc <= 0) return 4;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sg::parts_for((int)(M->m * (Nc / sg::TM)), sms);
+}
+int split_partials_var(const bocf_model* M, int64_t Nc) {      // partial sums per candidate and output written by the epilogues
+  sg::SchemeInfo si;
+  sg::scheme_info(M->sch1, &si);
+  return si.EW / 4 * split_parts(M, Nc);
+}
+int split_partials_dvar(const bocf_model* M, int64_t Nc) {
+  sg::SchemeInfo si;
+  sg::scheme_info(M->sch2, &si);
+  return si.EW / 4 * split_parts(M, Nc);
+}
 
 static void free_split(bocf_model* M) {
   auto fr = [](auto*& p) {
@@ -812,7 +811,7 @@ static void free_split(bocf_model* M) {
 }
 void split_release(bocf_model* M) { free_split(M); }
 
-// Largest |Linv| entry over all (h, j): drives the automatic choice of the number of digit planes.
+// Largest |Linv| entry over all (h, j): drives the automatic choice of the digit-pair schemes.
 int split_linv_absmax(bocf_model* M, double* out_host, cudaStream_t st) {
   double* d = nullptr;
   BOCF_CUDA_OK(cudaMalloc(&d, sizeof(double)));
@@ -827,30 +826,31 @@ int split_linv_absmax(bocf_model* M, double* out_host, cudaStream_t st) {
 }
 
 // Digit planes of Linv for both contractions + all power-of-two scales.  Called after the factorisation.
-int split_prepare(bocf_model* M, int S, cudaStream_t st) {
+// sch1: scheme of V = K* Linv^T;  sch2: scheme of Wt = V Linv (its SA is the number of planes V is re-split into).
+int split_prepare(bocf_model* M, int sch1, int sch2, cudaStream_t st) {
   free_split(M);
+  sg::SchemeInfo s1, s2;
+  if (!sg::scheme_info(sch1, &s1) || !sg::scheme_info(sch2, &s2)) return sg::bad_scheme();
   const int Hm = M->H * M->m;
-  const int NT = split_column_tile(S);
-  M->S = S;
-  M->NTs = NT;
-  M->ncts = (int)ceil_div(M->n, NT);
+  M->sch1 = sch1;
+  M->sch2 = sch2;
+  M->S = s1.SA;
+  M->S2 = s2.SA;
+  M->NTs = s1.NT;
+  M->NT2 = s2.NT;
+  M->ncts = (int)ceil_div(M->n, s1.NT);
+  M->nct2 = (int)ceil_div(M->n, s2.NT);
   M->KCH = (int)ceil_div(M->n, sg::KC);
-  const int Rpad = M->ncts * NT;
-  // CTA pairs (cta_group::2, BOCF_SPLIT_CG=2) are implemented and bit-exact but measured SLOWER on B200 (first
-  // contraction 26.6 vs 15.6 ms per 131072 candidates, profiles/r1_split_experiments.md): single CTAs are the default.
-  M->split_cg = 1;
-  if (const char* env = std::getenv("BOCF_SPLIT_CG"))
-    if (std::atoi(env) == 2) M->split_cg = 2;
-  const size_t rows_per_tile = (M->split_cg == 2) ? (size_t)S * (S + 1) / 2 * NT : (size_t)S * NT;   // both ranks
-  const size_t plane_bytes = (size_t)Hm * M->ncts * M->KCH * rows_per_tile * sg::KC;
-  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->B1), plane_bytes));
-  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->B2), plane_bytes));
-  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->cs1), sizeof(double) * Hm * Rpad));
-  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->cs2), sizeof(double) * Hm * Rpad));
+  const int Rpad1 = M->ncts * s1.NT, Rpad2 = M->nct2 * s2.NT;
+  const int Rmax = Rpad1 > Rpad2 ? Rpad1 : Rpad2;
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->B1), (size_t)Hm * M->ncts * M->KCH * s1.SB * s1.NT * sg::KC));
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->B2), (size_t)Hm * M->nct2 * M->KCH * s2.SB * s2.NT * sg::KC));
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->cs1), sizeof(double) * Hm * Rpad1));
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->cs2), sizeof(double) * Hm * Rpad2));
   BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->aq), sizeof(double) * Hm));
   BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->vq), sizeof(double) * Hm));
   int *exps = nullptr, *extra = nullptr;
-  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&exps), sizeof(int) * Hm * Rpad));
+  BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&exps), sizeof(int) * Hm * Rmax));
   BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&extra), sizeof(int) * 2 * Hm));
   // candidate-side scales: K* <= sigma_f^2 (stationary kernels), |V_k| <= sqrt(k**) = sigma_f
   std::vector<int> ex(2 * Hm);
@@ -861,27 +861,23 @@ int split_prepare(bocf_model* M, int S, cudaStream_t st) {
     std::frexp(std::sqrt(M->hyp_host[hj].variance) * 1.02, &eV);
     ex[hj] = eA;
     ex[Hm + hj] = eV;
-    aq[hj] = std::ldexp(1.0, 8 * S - 2 - eA);
-    vq[hj] = std::ldexp(1.0, 8 * S - 2 - eV);
+    aq[hj] = std::ldexp(1.0, 8 * s1.SA - 2 - eA);
+    vq[hj] = std::ldexp(1.0, 8 * s2.SA - 2 - eV);
   }
   BOCF_CUDA_OK(cudaMemcpyAsync(extra, ex.data(), sizeof(int) * 2 * Hm, cudaMemcpyHostToDevice, st));
   BOCF_CUDA_OK(cudaMemcpyAsync(M->aq, aq.data(), sizeof(double) * Hm, cudaMemcpyHostToDevice, st));
   BOCF_CUDA_OK(cudaMemcpyAsync(M->vq, vq.data(), sizeof(double) * Hm, cudaMemcpyHostToDevice, st));
-  const int base = -2 * (8 * S - 2) + 8 * (S - 1);
+  // output scale of a scheme: 2^(eA + eB) * 256^LMIN / (2^(8 SA - 2) 2^(8 SB - 2))
+  const int base1 = -(8 * s1.SA - 2) - (8 * s1.SB - 2) + 8 * s1.LMIN;
+  const int base2 = -(8 * s2.SA - 2) - (8 * s2.SB - 2) + 8 * s2.LMIN;
   const int64_t nn = (int64_t)M->n_pad * M->n_pad;
   int rc = 0;
   // first contraction: rows = factor row k, K = b      (element Linv[k][b])
-  if (!rc) rc = sg::row_exps(M->Linv, nn, M->n_pad, 1, M->n, M->n, Rpad, Hm, exps, M->cs1, extra, base, st);
-  if (!rc)
-    rc = (M->split_cg == 2)
-             ? sg::pack_digits_pair(S, M->Linv, nn, M->n_pad, 1, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B1, st)
-             : sg::pack_digits(S, M->Linv, nn, M->n_pad, 1, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B1, st);
+  if (!rc) rc = sg::row_exps(M->Linv, nn, M->n_pad, 1, M->n, M->n, Rpad1, Hm, exps, M->cs1, extra, base1, st);
+  if (!rc) rc = sg::pack_digits(s1.SB, M->Linv, nn, M->n_pad, 1, M->n, M->n, exps, Rpad1, s1.NT, M->ncts, M->KCH, Hm, M->B1, st);
   // second contraction: rows = factor column b, K = k  (element Linv[k][b])
-  if (!rc) rc = sg::row_exps(M->Linv, nn, 1, M->n_pad, M->n, M->n, Rpad, Hm, exps, M->cs2, extra + Hm, base, st);
-  if (!rc)
-    rc = (M->split_cg == 2)
-             ? sg::pack_digits_pair(S, M->Linv, nn, 1, M->n_pad, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B2, st)
-             : sg::pack_digits(S, M->Linv, nn, 1, M->n_pad, M->n, M->n, exps, Rpad, NT, M->ncts, M->KCH, Hm, M->B2, st);
+  if (!rc) rc = sg::row_exps(M->Linv, nn, 1, M->n_pad, M->n, M->n, Rpad2, Hm, exps, M->cs2, extra + Hm, base2, st);
+  if (!rc) rc = sg::pack_digits(s2.SB, M->Linv, nn, 1, M->n_pad, M->n, M->n, exps, Rpad2, s2.NT, M->nct2, M->KCH, Hm, M->B2, st);
   cudaError_t e = cudaStreamSynchronize(st);      // ex/aq/vq are host vectors going out of scope
   cudaFree(exps);
   cudaFree(extra);
@@ -897,12 +893,12 @@ int split_prepare(bocf_model* M, int S, cudaStream_t st) {
 uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
   uint64_t per = 0;
   per += (uint64_t)M->m * M->KCH * sg::KC * M->S;       // A1 digit planes of K*
-  per += (uint64_t)M->m * sg::parts_per_tile() * sg::PART_SPLIT * 8;  // part_var
+  per += (uint64_t)M->m * split_partials_var(M, 0) * 8; // part_var (upper bound on the parts)
   per += 2ull * M->m * 8;                               // mean, var
   if (grad) {
     per += (uint64_t)M->m * M->n16 * 8;                 // GsT
-    per += (uint64_t)M->m * M->KCH * sg::KC * M->S;     // A2 digit planes of V
-    per += (uint64_t)M->m * sg::parts_per_tile() * sg::PART_SPLIT * (M->d + 1) * 8;   // part_dvar, part_s0
+    per += (uint64_t)M->m * M->KCH * sg::KC * M->S2;    // A2 digit planes of V
+    per += (uint64_t)M->m * split_partials_dvar(M, 0) * (M->d + 1) * 8;   // part_dvar, part_s0
     per += 2ull * M->m * M->d * 8;                      // dmean, dvar
   }
   return per;
@@ -915,18 +911,18 @@ void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, C
     p += round_up((int64_t)bytes, 1024);
     return r;
   };
-  const uint64_t planes = (uint64_t)M->m * Nc * M->KCH * sg::KC * M->S;
+  const uint64_t plane = (uint64_t)M->m * Nc * M->KCH * sg::KC;
   cb->Nc = Nc;
   cb->KsT = cb->V = nullptr;
-  cb->A1 = take(planes);
-  cb->part_var = reinterpret_cast<double*>(take((uint64_t)M->m * sg::parts_per_tile() * sg::PART_SPLIT * Nc * 8));
+  cb->A1 = take(plane * M->S);
+  cb->part_var = reinterpret_cast<double*>(take((uint64_t)M->m * split_partials_var(M, 0) * Nc * 8));
   cb->mean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
   cb->var = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
   if (grad) {
     cb->GsT = reinterpret_cast<double*>(take((uint64_t)M->m * M->n16 * Nc * 8));
-    cb->A2 = take(planes);
-    cb->part_dvar = reinterpret_cast<double*>(take((uint64_t)M->m * sg::parts_per_tile() * sg::PART_SPLIT * Nc * M->d * 8));
-    cb->part_s0 = reinterpret_cast<double*>(take((uint64_t)M->m * sg::parts_per_tile() * sg::PART_SPLIT * Nc * 8));
+    cb->A2 = take(plane * M->S2);
+    cb->part_dvar = reinterpret_cast<double*>(take((uint64_t)M->m * split_partials_dvar(M, 0) * Nc * M->d * 8));
+    cb->part_s0 = reinterpret_cast<double*>(take((uint64_t)M->m * split_partials_dvar(M, 0) * Nc * 8));
     cb->dmean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
     cb->dvar = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
   } else {
@@ -941,7 +937,6 @@ static sg::GemmParams base_params(const bocf_model* M, int h, const ChunkBuffers
   P.m = M->m;
   P.h = h;
   P.RT = (int)(cb.Nc / sg::TM);
-  P.nct = M->ncts;
   P.KCH = M->KCH;
   P.n = M->n;
   P.Nc = cb.Nc;
@@ -949,9 +944,13 @@ static sg::GemmParams base_params(const bocf_model* M, int h, const ChunkBuffers
   P.n16 = M->n16;
   P.n_pad = M->n_pad;
   P.hyp = M->hyp;
-  P.cg = M->split_cg;
-  P.np = sg::parts_per_tile();
-  if (const char* env = std::getenv("BOCF_SPLIT_EXP")) P.exp = std::atoi(env);
+  P.np = split_parts(M, cb.Nc);
+  static int keep = -1;
+  if (keep < 0) {
+    const char* env = std::getenv("BOCF_SPLIT_L2KEEP");
+    keep = (env && std::atoi(env) != 0) ? 1 : 0;
+  }
+  P.l2_keep_a = keep;
   return P;
 }
 
@@ -960,14 +959,15 @@ int launch_split_var(bocf_model* M, int h, const ChunkBuffers& cb, bool need_dva
   P.A = cb.A1;
   P.B = M->B1;
   P.cs = M->cs1;
+  P.nct = M->ncts;
   P.tri = sg::TRI_K_LE_N;
   P.part_var = cb.part_var;
   P.A2 = need_dvar ? cb.A2 : nullptr;
   P.vq = M->vq;
-  if (M->ncts < sg::parts_per_tile())      // parts without a column tile never write their partial
-    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_var, 0, sizeof(double) * M->m * sg::parts_per_tile() * sg::PART_SPLIT * cb.Nc, st));
+  if (M->ncts < P.np)                      // parts without a column tile never write their partial
+    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_var, 0, sizeof(double) * M->m * split_partials_var(M, cb.Nc) * cb.Nc, st));
   ProfScope ps("split_var_kernel", st);
-  return sg::launch_s<sg::EPI_VAR>(M->S, P, st);
+  return sg::launch_var(M->sch1, M->S2, P, st);
 }
 
 int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, const ChunkBuffers& cb, cudaStream_t st) {
@@ -975,6 +975,7 @@ int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, co
   P.A = cb.A2;
   P.B = M->B2;
   P.cs = M->cs2;
+  P.nct = M->nct2;
   P.tri = sg::TRI_K_GE_N;
   P.part_dvar = cb.part_dvar;
   P.part_s0 = cb.part_s0;
@@ -982,30 +983,31 @@ int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, co
   P.Xc = Xc;
   P.Nvalid = Nvalid;
   P.Xs = M->Xs;
-  if (M->ncts < sg::parts_per_tile()) {
-    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_dvar, 0, sizeof(double) * M->m * sg::parts_per_tile() * sg::PART_SPLIT * cb.Nc * M->d, st));
-    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_s0, 0, sizeof(double) * M->m * sg::parts_per_tile() * sg::PART_SPLIT * cb.Nc, st));
+  if (M->nct2 < P.np) {
+    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_dvar, 0, sizeof(double) * M->m * split_partials_dvar(M, cb.Nc) * cb.Nc * M->d, st));
+    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_s0, 0, sizeof(double) * M->m * split_partials_dvar(M, cb.Nc) * cb.Nc, st));
   }
   ProfScope ps("split_dvar_kernel", st);
-  return sg::launch_dvar(M->S, M->d, P, st);
+  return sg::launch_dvar(M->sch2, M->d, P, st);
 }
 
 // Test entry: out (R x N) = A (R x K) * B (N x K)^T through the digit-plane machinery.  All pointers [dev] fp64 row-major.
-int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int S, int tri, double* out, cudaStream_t st) {
-  if (S < 3 || S > 6 || R < 1 || N < 1 || K < 1) {
+int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int sch, int tri, double* out, cudaStream_t st) {
+  sg::SchemeInfo si;
+  if (!sg::scheme_info(sch, &si) || R < 1 || N < 1 || K < 1) {
     set_error("split_debug_gemm: invalid arguments");
     return BOCF_ERR_INVALID;
   }
-  const int NT = split_column_tile(S);
-  const int RT = (int)round_up(ceil_div(R, sg::TM), 2), nct = (int)ceil_div(N, NT), KCH = (int)ceil_div(K, sg::KC);
+  const int NT = si.NT;
+  const int RT = (int)ceil_div(R, sg::TM), nct = (int)ceil_div(N, NT), KCH = (int)ceil_div(K, sg::KC);
   const int RpadA = RT * sg::TM, RpadB = nct * NT;
   uint8_t *pa = nullptr, *pb = nullptr;
   int *ea = nullptr, *eb = nullptr;
   double *rs = nullptr, *cs = nullptr, *tmp = nullptr;
   int rc = 0;
   do {
-    if (cudaMalloc(reinterpret_cast<void**>(&pa), (size_t)RT * KCH * S * sg::TM * sg::KC) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&pb), (size_t)nct * KCH * (S * (S + 1) / 2) * NT * sg::KC) != cudaSuccess ||
+    if (cudaMalloc(reinterpret_cast<void**>(&pa), (size_t)RT * KCH * si.SA * sg::TM * sg::KC) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&pb), (size_t)nct * KCH * si.SB * NT * sg::KC) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&ea), sizeof(int) * RpadA) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&eb), sizeof(int) * RpadB) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&rs), sizeof(double) * RpadA) != cudaSuccess ||
@@ -1015,16 +1017,11 @@ int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int 
       rc = BOCF_ERR_CUDA;
       break;
     }
-    const int base = -2 * (8 * S - 2) + 8 * (S - 1);
+    const int base = -(8 * si.SA - 2) - (8 * si.SB - 2) + 8 * si.LMIN;
     if ((rc = sg::row_exps(A, 0, K, 1, R, K, RpadA, 1, ea, rs, nullptr, 0, st))) break;
     if ((rc = sg::row_exps(B, 0, K, 1, N, K, RpadB, 1, eb, cs, nullptr, base, st))) break;
-    if ((rc = sg::pack_digits(S, A, 0, K, 1, R, K, ea, RpadA, sg::TM, RT, KCH, 1, pa, st))) break;
-    int cg = 1;
-    if (const char* env = std::getenv("BOCF_SPLIT_CG"))
-      if (std::atoi(env) == 2) cg = 2;
-    if (cg == 2) {
-      if ((rc = sg::pack_digits_pair(S, B, 0, K, 1, N, K, eb, RpadB, NT, nct, KCH, 1, pb, st))) break;
-    } else if ((rc = sg::pack_digits(S, B, 0, K, 1, N, K, eb, RpadB, NT, nct, KCH, 1, pb, st))) break;
+    if ((rc = sg::pack_digits(si.SA, A, 0, K, 1, R, K, ea, RpadA, sg::TM, RT, KCH, 1, pa, st))) break;
+    if ((rc = sg::pack_digits(si.SB, B, 0, K, 1, N, K, eb, RpadB, NT, nct, KCH, 1, pb, st))) break;
     sg::GemmParams P;
     std::memset(&P, 0, sizeof(P));
     P.A = pa;
@@ -1032,22 +1029,19 @@ int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int 
     P.cs = cs;
     P.m = 1;
     P.h = 0;
-    P.cg = cg;
     P.np = sg::parts_per_tile();
     P.RT = RT;
     P.nct = nct;
     P.KCH = KCH;
-    P.n = (tri == sg::TRI_FULL) ? K : (K < N ? K : N);
-    if (tri != sg::TRI_FULL) P.n = K;
+    P.n = K;
     P.tri = tri;
     P.Nc = RpadA;
     P.raw_out = tmp;
     P.raw_rs = rs;
     P.ldo = N;
-    if (const char* env = std::getenv("BOCF_SPLIT_EXP")) P.exp = std::atoi(env);
     {
       ProfScope ps("split_raw_kernel", st);
-      rc = sg::launch_s<sg::EPI_RAW>(S, P, st);
+      rc = sg::launch_raw(sch, P, st);
     }
     if (rc) break;
     if (cudaMemcpyAsync(out, tmp, sizeof(double) * (size_t)R * N, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||

@@ -133,6 +133,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
+// The same descriptor split into its two words: only the low word (address field) changes between instructions, so the
+// issue loop keeps one base per operand and adds byte offsets >> 4 (shared memory is < 256 KB: no carry out of [0,14)).
+constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint32_t desc_lo_sw64(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return ((uint64_t)DESC_HI_SW64 << 32) | (uint64_t)lo; }
+// One lane of a converged warp (the lowest): the MMA warp walks its loop as a whole and only this lane issues.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n .reg .pred px;\n elect.sync _|px, 0xffffffff;\n selp.u32 %0, 1, 0, px;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 // Instruction descriptor for kind::i8: s8 x s8 -> s32, both operands K-major, M = 128.
 //   [4,6) D format = 2 (S32) | [7,10) A = 1 (signed) | [10,13) B = 1 (signed) | [17,23) N>>3 | [24,29) M>>4
 __host__ __device__ constexpr uint32_t idesc_i8(int N) {

@@ -242,6 +242,12 @@ class multi_outputGP(object):
         """Digit planes the tensor-core contraction currently uses (0 = fp64 DMMA)."""
         return int(self._lib.bocf_model_active_slices(self._handle)) if self._handle is not None else 0
 
+    def active_scheme(self):
+        """(scheme of the variance contraction, scheme of the variance-gradient contraction), a scheme being
+        100 SA + 10 SB + LMIN (include/bocf_b200.h); (0, 0) = fp64 DMMA."""
+        code = int(self._lib.bocf_model_active_scheme(self._handle)) if self._handle is not None else 0
+        return (code // 1000, code % 1000) if code > 0 else (0, 0)
+
     def _destroy(self):
         if getattr(self, "_handle", None) is not None:
             self._lib.bocf_model_destroy(self._handle)

@@ -65,11 +65,16 @@ enum bocf_acq_variant {
  * Everything else (kernel evaluation, mean, MC acquisition, Cholesky) is always IEEE fp64. */
 enum bocf_precision {
   BOCF_PREC_FP64_DMMA = 0,  /* fp64 tensor-core MMA (mma.sync m8n8k4.f64)                                          */
-  BOCF_PREC_SPLIT_I8 = 1,   /* tcgen05.mma kind::i8: operands split into `slices` signed 8-bit digit planes,
-                               exact int32 accumulation in tensor memory; slices = 5 matches fp64 to ~1e-8 on the
-                               variance of a well-conditioned model, slices = 4 to ~1e-6                           */
-  BOCF_PREC_AUTO = 2        /* pick slices in {4,5,6} from max|L^-1| so the predicted variance error stays below
-                               1e-7 relative; fall back to fp64 DMMA for ill-conditioned factors                   */
+  BOCF_PREC_SPLIT_I8 = 1,   /* tcgen05.mma kind::i8: operands split into signed 8-bit digit planes, exact int32
+                               accumulation in tensor memory.  `slices` = s (3..6): both contractions use the scheme of
+                               s planes (3: 8 digit pairs, 4: 13, 5: 15, 6: 21);  `slices` = 10 s1 + s2: the first
+                               contraction (variance) uses s1, the second (variance gradient) s2 <= s1               */
+  BOCF_PREC_AUTO = 2,       /* default: variance scheme from max|L^-1| so its predicted relative error stays below
+                               1e-7 (5 planes / 15 pairs for well-conditioned models), variance gradient one scheme
+                               below (4 planes / 13 pairs: ~1e-7 on the gradient); fp64 DMMA for ill-conditioned factors */
+  BOCF_PREC_MIXED = 3       /* the north star's mixed mode (1e-4 on acq / grad acq): variance 4 planes / 13 pairs
+                               (~1e-6), variance gradient 3 planes / 8 pairs (~1e-5); falls back towards AUTO when
+                               max|L^-1| is large                                                                   */
 };
 
 const char* bocf_last_error(void);
@@ -122,11 +127,15 @@ int bocf_model_n(const bocf_model* mdl);
 int bocf_model_H(const bocf_model* mdl);
 
 /* Select the contraction arithmetic (enum bocf_precision).  May be called before or after bocf_model_factorize; the
- * digit planes of L^-1 are (re)built when needed.  The environment variable BOCF_PRECISION (fp64 | auto | split3..6)
+ * digit planes of L^-1 are (re)built when needed.  The environment variable BOCF_PRECISION (fp64 | auto | mixed | split3..6 | split<s1><s2>)
  * sets the initial mode of new handles.  The planes are built lazily by the first posterior / acquisition call after a
- * factorisation (likelihood-only callers never pay for them).  bocf_model_active_slices: digit planes in use (0 = fp64). */
+ * factorisation (likelihood-only callers never pay for them).  bocf_model_active_slices: digit planes of the first contraction in use (0 = fp64);
+ * bocf_model_active_scheme: 1000 * scheme of the first contraction + scheme of the second, a scheme being
+ * 100 SA + 10 SB + LMIN (digit planes of the candidate side, of the factor side, lowest digit-pair weight kept);
+ * 0 = fp64. */
 int bocf_model_set_precision(bocf_model* mdl, int mode, int slices, void* stream);
 int bocf_model_active_slices(bocf_model* mdl);
+int bocf_model_active_scheme(bocf_model* mdl);
 
 /* Test hook of the split-integer tensor-core GEMM: out (R x N) = A (R x K) * B (N x K)^T, all [dev] fp64 row-major,
  * through the same digit-plane packing, tcgen05 kernel and Horner epilogue the posterior uses.

@@ -1,11 +1,12 @@
 """GPU tests of the tcgen05 split-integer contraction mode (bocf_b200/csrc/split_gemm.cu).
 
 The two candidate-side contractions of the posterior variance (posterior.py:312, gp.py:474) run on
-`tcgen05.mma.kind::i8` with the fp64 operands split into S signed 8-bit digit planes and EXACT int32
-accumulation in tensor memory.  Bars (BASELINE.json north_star):
-  * S = 5 ("split5", what "auto" picks for well-conditioned models) must meet the FP64-mode bar:
-    1e-6 relative on posterior mean and variance -- and the same selected next point;
-  * S = 4 must meet the mixed-precision bar: 1e-4 relative on the EI-CF value and gradient.
+`tcgen05.mma.kind::i8` with the fp64 operands split into signed 8-bit digit planes and EXACT int32
+accumulation in tensor memory.  A scheme (SA, SB, LMIN) keeps the digit pairs with ta + tb >= LMIN; "splitN" selects
+331 / 442 / 554 / 665.  Bars (BASELINE.json north_star):
+  * "auto" (554 for the variance, 442 for its gradient on well-conditioned models) and "split5" must meet the
+    FP64-mode bar: 1e-6 relative on posterior mean and variance, element-wise -- and the same selected next point;
+  * "mixed" (442 / 331) must meet the mixed-precision bar: 1e-4 relative on the EI-CF value and gradient.
 The integer GEMM itself must be exact whenever the operands are exactly representable.
 """
 import ctypes
@@ -138,20 +139,22 @@ def test_auto_precision_follows_conditioning(cuda_device):
     assert np.max(np.abs(pm.posterior_variance(ill.Xc) - om.posterior_variance(ill.Xc))) < 1e-7
 
 
-def test_cta_pair_variant_is_exact_too(cuda_device, monkeypatch):
-    # cta_group::2 (M = 256 across a cluster of two CTAs, BOCF_SPLIT_CG=2): experimental, slower on B200, but it must
-    # produce the same exact integer products -- through the raw GEMM and through the posterior
-    monkeypatch.setenv("BOCF_SPLIT_CG", "2")
-    rng = np.random.default_rng(5)
-    A = rng.integers(-100, 101, size=(300, 500)).astype(np.float64)
-    B = rng.integers(-100, 101, size=(500, 500)).astype(np.float64)
-    assert np.array_equal(_split_gemm(A, B, 5), A @ B.T)
-    P = make_problem(m=2, d=5, n=257, H=1, kind="matern52", N=700, S=4, seed=3)
+def test_auto_and_mixed_pick_their_schemes(cuda_device):
+    # auto: 15 digit pairs for the variance, 13 for its gradient; mixed: 13 / 8 (include/bocf_b200.h)
+    P = make_problem(m=3, d=6, n=300, H=1, kind="matern52", composite="sumsq_target", N=1024, S=64, seed=6)
     om = oracle_model(P)
-    pm = product_model(P, cuda_device, precision="split5")
-    v, v_o = pm.posterior_variance(P.Xc), om.posterior_variance(P.Xc)
-    assert np.max(np.abs(v - v_o) / np.abs(v_o)) < 1e-6
-    assert rel_err(pm.posterior_variance_gradient(P.Xc), om.posterior_variance_gradient(P.Xc)) < 1e-6
+    v_o, dv_o = om.posterior_variance(P.Xc), om.posterior_variance_gradient(P.Xc)
+    a_o, g_o = oracle_acq(P, grad=True)
+    for prec, schemes, tol_v, tol_dv, tol_a in [("auto", (554, 442), 1e-6, 1e-6, 1e-6), ("split54", (554, 442), 1e-6, 1e-6, 1e-6),
+                                               ("mixed", (442, 331), 2e-5, 1e-4, 1e-4), ("split43", (442, 331), 2e-5, 1e-4, 1e-4)]:
+        pm = product_model(P, cuda_device, precision=prec)
+        v, dv = pm.posterior_variance(P.Xc), pm.posterior_variance_gradient(P.Xc)
+        assert pm.active_scheme() == schemes, (prec, pm.active_scheme())
+        assert np.max(np.abs(v - v_o) / np.abs(v_o)) < tol_v, (prec, np.max(np.abs(v - v_o) / np.abs(v_o)))
+        assert rel_err(dv, dv_o) < tol_dv, (prec, rel_err(dv, dv_o))
+        a, g = product_acq(P, grad=True, device=cuda_device, model=pm)
+        assert rel_err(a, a_o) < tol_a and rel_err(g, g_o) < tol_a, (prec, rel_err(a, a_o), rel_err(g, g_o))
+        assert int(np.argmax(a)) == int(np.argmax(a_o))
 
 
 @pytest.mark.parametrize("kind", ["rbf", "matern52"])
