@@ -12,7 +12,7 @@ _lib = None
 
 KERNELS = {"se": 0, "rbf": 1, "matern52": 2, "matern32": 3}
 COMPOSITES = {"sumsq_target": 0, "neg_sum_exp": 1, "exp_cos": 2, "rosen_composite": 3, "linear": 4}
-VARIANTS = {"ei_cf": 0, "pi_cf": 1, "ma_ei": 2, "ma_pi": 3}
+VARIANTS = {"ei_cf": 0, "pi_cf": 1, "ma_ei": 2, "ma_pi": 3, "mean_utility": 4, "psi": 5}
 
 EXPORTS = [
     "bocf_last_error", "bocf_version", "bocf_launch_count",
@@ -20,7 +20,7 @@ EXPORTS = [
     "bocf_model_factorize", "bocf_model_get_factor", "bocf_model_n", "bocf_model_H",
     "bocf_model_set_scratch_limit", "bocf_posterior", "bocf_acq_eval", "bocf_acq_eval_host",
     "bocf_utility_eval", "bocf_topk", "bocf_profile_enable", "bocf_profile_report",
-    "bocf_model_set_precision", "bocf_model_active_slices", "bocf_model_active_scheme", "bocf_debug_split_gemm", "bocf_model_log_likelihood", "bocf_model_append_point",
+    "bocf_model_set_precision", "bocf_model_active_slices", "bocf_model_active_scheme", "bocf_model_chunk_candidates", "bocf_debug_split_gemm", "bocf_model_log_likelihood", "bocf_model_append_point",
 ]
 # name -> (enum bocf_precision, slices).  "splitN": both contractions on the N-plane scheme; "splitNM": variance on N,
 # variance gradient on M <= N planes (include/bocf_b200.h).
@@ -81,6 +81,8 @@ def load_library():
     lib.bocf_model_set_precision.argtypes = [c_vp, i32, i32, c_vp]
     lib.bocf_model_active_slices.argtypes = [c_vp]
     lib.bocf_model_active_scheme.argtypes = [c_vp]
+    lib.bocf_model_chunk_candidates.argtypes = [c_vp, i64, i32]
+    lib.bocf_model_chunk_candidates.restype = i64
     lib.bocf_debug_split_gemm.argtypes = [c_dp, c_dp, i32, i32, i32, i32, i32, c_dp, c_vp]
     lib.bocf_model_log_likelihood.argtypes = [c_vp, c_dp, c_dp, c_dp, c_dp, c_vp]
     lib.bocf_model_append_point.argtypes = [c_vp, c_dp, c_dp, c_vp]

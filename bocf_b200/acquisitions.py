@@ -19,11 +19,13 @@ One deviation: with ``fixed_hyps=True`` the reference averages 10 identical pass
 identical passes are evaluated once.
 """
 import ctypes
+import threading
 
 import numpy as np
 import torch
 
 from . import _lib
+from .utility import theta_matrix
 
 
 def _ptr(t):
@@ -57,16 +59,32 @@ class AcquisitionBase(object):
     def _negated(self, fn, x):
         """-fn(x).  The flip is applied on the device, before the results leave it (`_run` honours `_sign`): negating a
         (1M, d) gradient on the host costs more than the whole D2H copy.  Results that did not come out of `_run` are
-        negated here."""
-        self._sign, self._sign_applied = -1.0, False
+        negated here.  The pending flip is per THREAD (the batched multistart optimiser runs one scipy L-BFGS state
+        machine per thread, optimization.py), and every call into the model handle is serialised by the model's lock."""
+        tls = self._tls
+        tls.sign, tls.applied = -1.0, False
         try:
             out = fn(x)
         finally:
-            applied = self._sign_applied
-            self._sign, self._sign_applied = 1.0, False
+            applied = tls.applied
+            tls.sign, tls.applied = 1.0, False
         if applied:
             return out
         return tuple(-o for o in out) if isinstance(out, tuple) else -out
+
+    @property
+    def _tls(self):
+        t = self.__dict__.get("_tls_obj")
+        if t is None:
+            t = self.__dict__.setdefault("_tls_obj", threading.local())
+        return t
+
+    @property
+    def _sign(self):
+        return getattr(self._tls, "sign", 1.0)
+
+    def _mark_sign_applied(self):
+        self._tls.applied = True
 
     def optimize(self, duplicate_manager=None, x_baseline=None):
         if not self.analytical_gradient_acq:
@@ -90,8 +108,6 @@ class AcquisitionBase(object):
 
     PIPELINE_MIN = 1 << 17      # numpy inputs at least this long are streamed through the device in slabs
     PIPELINE_SLABS = 4
-    _sign = 1.0
-    _sign_applied = False
 
     def _run(self, variant, X, theta, weight, fstar, grad, Zt=None, S=0, form=0):
         model = self.model
@@ -116,8 +132,11 @@ class AcquisitionBase(object):
         th_h, th_p = _host(theta)
         w_h, w_p = _host(weight)
         f_h, f_p = _host(fstar)
+        if w_h.size != L or f_h.ndim != 2 or f_h.shape[1] != L:
+            raise ValueError("need one weight and one incumbent column per utility parameter: L=%d, %d weights, f* %s"
+                             % (L, w_h.size, f_h.shape))
         H_use = f_h.shape[0]
-        with torch.cuda.device(model.device):
+        with model._lock, torch.cuda.device(model.device):
             acq = torch.empty((N,), dtype=torch.float64, device=model.device)
             dacq = torch.empty((N, d), dtype=torch.float64, device=model.device) if grad else None
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -128,7 +147,7 @@ class AcquisitionBase(object):
                 acq.neg_()
                 if dacq is not None:
                     dacq.neg_()
-        self._sign_applied = True
+        self._mark_sign_applied()
         return acq, dacq
 
     def _run_pipelined(self, variant, Xn, theta, weight, fstar, grad, Zt, S, form):
@@ -257,7 +276,7 @@ class uEI_noiseless(AcquisitionBase):
 
     def _compute_acq(self, X, parallel=True):
         # uEI_noiseless.py:40-61 (+ :63-83 / :85-116)
-        theta = np.atleast_2d(self.utility_params_samples)
+        theta = theta_matrix(self.utility, self.utility_params_samples)
         n_cand = X.shape[0] if hasattr(X, "shape") and len(X.shape) == 2 else len(np.atleast_2d(X))
         fstar = self._fstar(theta, per_hyper_sample=bool(parallel and n_cand > 1))     # :43-46
         Zt = self._Zt()
@@ -271,7 +290,7 @@ class uEI_noiseless(AcquisitionBase):
             theta = self.utility.parameter_dist.support
         else:
             theta = self.utility.parameter_dist.sample(1)                     # :126 (quirk q4)
-        theta = np.atleast_2d(theta)
+        theta = theta_matrix(self.utility, theta)
         fstar = self._fstar(theta)
         Zt = self._Zt()
         out = self._run(self._variant, X, theta, self._weights(len(theta)), fstar, True, Zt, Zt.shape[1])
@@ -318,7 +337,7 @@ class maEI(AcquisitionBase):
         else:
             self.utility_params_samples = self.utility.parameter_dist.sample(k)
             w = np.full(len(self.utility_params_samples), 1.0 / len(self.utility_params_samples))
-        return np.atleast_2d(np.asarray(self.utility_params_samples, dtype=np.float64)), w
+        return theta_matrix(self.utility, self.utility_params_samples), w
 
     def _best(self, theta):
         """best_l = max_n theta_l^T mu_h(X_n), recomputed per hyper-sample (maEI.py:88,129-136): (H_use, L)."""

@@ -104,90 +104,59 @@ class CBO(object):
         return float(np.squeeze(val))
 
     def _current_marginal_argmax(self, parameter):
+        """argmax_x E_n[U(theta, f(x))] (cbo.py:121-235).  The three objectives the reference evaluates candidate by
+        candidate in Python -- posterior-mean utility (linear U), closed-form psi, 50-sample MC utility -- are one
+        device call per L-BFGS round each (multi_outputGP.expected_utility -> psi_acq_kernel / mc_acq_kernel<_,3|4>)."""
         model = self.model
+        if not hasattr(model, "expected_utility"):
+            raise TypeError("CBO needs a bocf_b200.multi_outputGP (CUDA) model: there is no CPU path "
+                            "(CPU models are driven through oracle.cbo.CBO in the tests)")
         n_h = self._n_hyps()
-        if self.utility.linear:
-            def val_func(X):
-                X = np.atleast_2d(X)
-                valX = np.zeros((X.shape[0], 1))
-                for h in range(n_h):
-                    model.set_hyperparameters(h)
-                    muX = model.posterior_mean(X)
-                    valX += np.reshape(np.matmul(np.atleast_1d(parameter), muX), (X.shape[0], 1))
-                return -valX
+        comp = self.utility.composite
+        if self.utility.linear:                                           # cbo.py:126-168
+            if comp != "linear":
+                raise ValueError("Utility(linear=True) needs composite='linear'")
+            Z = None
+        elif self.expectation_utility is not None:                        # cbo.py:170-198
+            self._check_expectation_utility(parameter)
+            Z = None
+        else:                                                             # cbo.py:203-231
+            Z = np.random.normal(size=(50, self.n_attributes))
 
-            def val_func_with_gradient(X):
-                X = np.atleast_2d(X)
-                valX = np.zeros((X.shape[0], 1))
-                dval_dX = np.zeros(X.shape)
-                for h in range(n_h):
-                    model.set_hyperparameters(h)
-                    muX = model.posterior_mean(X)
-                    dmu_dX = model.posterior_mean_gradient(X)
-                    valX += np.reshape(np.matmul(np.atleast_1d(parameter), muX), (X.shape[0], 1))
-                    dval_dX += np.tensordot(np.atleast_1d(parameter), dmu_dX, axes=1)
-                return -valX, -dval_dX
-        elif self.expectation_utility is not None:
-            def val_func(X):
-                X = np.atleast_2d(X)
-                func_val = np.zeros((X.shape[0], 1))
-                for h in range(n_h):
-                    model.set_hyperparameters(h)
-                    mean, var = model.predict_noiseless(X)
-                    for i in range(X.shape[0]):
-                        func_val[i, 0] += self.expectation_utility.func(parameter, mean[:, i], var[:, i])
-                return -func_val
+        def val_func(X):
+            val, _ = model.expected_utility(np.atleast_2d(X), comp, parameter, n_h, Z=Z, grad=False)
+            return -val.reshape(-1, 1)
 
-            def val_func_with_gradient(X):
-                X = np.atleast_2d(X)
-                func_val = np.zeros((X.shape[0], 1))
-                func_gradient = np.zeros(X.shape)
-                for h in range(n_h):
-                    model.set_hyperparameters(h)
-                    mean, var = model.predict_noiseless(X)
-                    dmean_dX = model.posterior_mean_gradient(X)
-                    dvar_dX = model.posterior_variance_gradient(X)
-                    aux = np.concatenate((dmean_dX, dvar_dX))
-                    for i in range(X.shape[0]):
-                        func_val[i, 0] += self.expectation_utility.func(parameter, mean[:, i], var[:, i])
-                        func_gradient[i, :] += np.matmul(self.expectation_utility.gradient(parameter, mean[:, i], var[:, i]),
-                                                         aux[:, i])
-                return -func_val, -func_gradient
-        else:
-            Z_samples = np.random.normal(size=(50, self.n_attributes))
-
-            def val_func(X):
-                X = np.atleast_2d(X)
-                func_val = np.zeros((X.shape[0], 1))
-                for h in range(n_h):
-                    model.set_hyperparameters(h)
-                    mean, var = model.predict_noiseless(X)
-                    std = np.sqrt(var)
-                    for Z in Z_samples:
-                        func_val[:, 0] += np.asarray(self.utility.eval_func(parameter, mean + std * Z[:, None])).reshape(-1)
-                return -func_val
-
-            def val_func_with_gradient(X):
-                X = np.atleast_2d(X)
-                func_val = np.zeros((X.shape[0], 1))
-                func_gradient = np.zeros(X.shape)
-                for h in range(n_h):
-                    model.set_hyperparameters(h)
-                    mean, var = model.predict_noiseless(X)
-                    std = np.sqrt(var)
-                    dmean_dX = model.posterior_mean_gradient(X)
-                    dstd_dX = model.posterior_variance_gradient(X) / (2 * std[:, :, None])
-                    for i in range(X.shape[0]):
-                        for Z in Z_samples:
-                            aux1 = mean[:, i] + np.multiply(Z, std[:, i])
-                            func_val[i, 0] += self.utility.eval_func(parameter, aux1)
-                            aux2 = dmean_dX[:, i, :] + np.multiply(dstd_dX[:, i, :].T, Z).T
-                            func_gradient[i, :] += np.matmul(self.utility.eval_gradient(parameter, aux1), aux2)
-                return -func_val, -func_gradient
+        def val_func_with_gradient(X):
+            val, g = model.expected_utility(np.atleast_2d(X), comp, parameter, n_h, Z=Z, grad=True)
+            return -val.reshape(-1, 1), -g
 
         argmax = self.evaluation_optimizer.optimize(f=val_func, f_df=val_func_with_gradient, parallel=False)[0]
+        model.set_hyperparameters(n_h - 1)          # the reference's h loop leaves the model on its last hyper-sample
         self.current_argmax = argmax
         return argmax
+
+    def _check_expectation_utility(self, parameter):
+        """The ExpectationUtility callables of the reference's interface cannot run in a kernel: the device evaluates
+        the closed form catalogued for the composite.  Checked once against the callables the user passed."""
+        if getattr(self, "_psi_checked", False):
+            return
+        from .utility import _host_psi
+        pair = _host_psi(self.utility.composite)
+        if pair is None:
+            raise ValueError("no closed-form expectation is catalogued for composite %r: pass expectation_utility=None "
+                             "(MC branch)" % (self.utility.composite,))
+        rng = np.random.default_rng(0)
+        m = self.n_attributes
+        mu, v = rng.standard_normal(m), rng.uniform(0.1, 1.0, m)
+        th = np.asarray(parameter, dtype=float)
+        ok = np.allclose(self.expectation_utility.func(th, mu, v), pair[0](th, mu, v), rtol=1e-9, atol=1e-12) and \
+            np.allclose(np.asarray(self.expectation_utility.gradient(th, mu, v), dtype=float).reshape(-1),
+                        np.asarray(pair[1](th, mu, v), dtype=float).reshape(-1), rtol=1e-9, atol=1e-12)
+        if not ok:
+            raise ValueError("expectation_utility disagrees with the closed form of composite %r"
+                             % (self.utility.composite,))
+        self._psi_checked = True
 
     # ---- main loop (cbo.py:238-329) ---------------------------------------------------------------------------
     def run_optimization(self, max_iter=1, parallel=False, plot=False, results_file=None, max_time=np.inf, eps=1e-8,

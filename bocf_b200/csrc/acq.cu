@@ -5,7 +5,11 @@
 //   improvement max(U - f*, 0) (or the PI indicator), warp-shuffle reduction over samples, and the
 //   pathwise gradient  sum_s 1[U>f*] dU(h)^T (dmu + (Z/(2 sigma)) * dvar)  folded into per-output
 //   sums A_j = sum_s 1 dphi_j, B_j = sum_s 1 dphi_j Z_sj  (uEI_noiseless.py:71-80,148-166; uPI.py:74-83).
+//   MODE 3 / 4 drop the improvement: plain sum_s U(theta, mu + sigma Z_s) and its pathwise gradient, the 50-sample MC
+//   branch of cbo._current_marginal_argmax (cbo.py:203-231).
 // ma_acq_kernel : analytic EI / PI of theta^T y (maEI.py:81-126, maPI.py, EI.py, PI.py).
+// psi_acq_kernel: closed-form E[U(theta, y)] under the posterior (the psi / psi_gradient pairs of test_1a.py:100-113,
+//   test_2a.py:70-83, test_5a.py:64-77) and the posterior-mean branch for linear utilities (cbo.py:126-168,170-198).
 // topk kernels  : local top-k of the acquisition (anchor_points_generator.py:59-64), deterministic ties.
 #include <math_constants.h>
 
@@ -87,7 +91,8 @@ constexpr int MCU = 4;         // sample groups per trip (independent base-sampl
 constexpr int MCB = 4;         // candidates per warp: every base sample loaded is applied to MCB candidates (the kernel
                                // was bound by its loads: one z + mu + sigma + theta fetch per 3 fp64 operations)
 
-// MODE: 0 = EI value only, 1 = EI value + gradient, 2 = PI value
+// MODE: 0 = EI value only, 1 = EI value + gradient, 2 = PI value, 3 = mean utility (no improvement) value,
+//       4 = mean utility value + gradient
 template <int COMP, int MODE>
 __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
     const double* __restrict__ mean, const double* __restrict__ var, const double* __restrict__ dmean,
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
   for (int l = 0; l < L; ++l) {
     const double* th = theta + (int64_t)l * p;
     const double wl = weight[l];
-    const double fs = (MODE == 2) ? fstar[l] + 1e-6 : fstar[l];       // uPI.py:83 jitter
+    const double fs = (MODE >= 3) ? 0.0 : ((MODE == 2) ? fstar[l] + 1e-6 : fstar[l]);       // uPI.py:83 jitter
     double val_l[MCB];
 #pragma unroll
     for (int c = 0; c < MCB; ++c) val_l[c] = 0.0;
@@ -150,6 +155,9 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
             for (int c = 0; c < MCB; ++c) {
               if (MODE == 2) {
                 val_l[c] += ((U[c][u] - fs) > 0.0) ? 1.0 : 0.0;
+              } else if (MODE >= 3) {
+                val_l[c] += U[c][u];                                          // cbo.py:213,227: no max, no indicator
+                mask[c] |= (1u << k);
               } else {
                 val_l[c] += fmax(U[c][u] - fs, 0.0);                          // uEI_noiseless.py:80,161
                 if (U[c][u] > fs) mask[c] |= (1u << k);                       // :162 strict >
@@ -158,7 +166,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
           }
         }
       }
-      if (MODE == 1) {
+      if (MODE == 1 || MODE == 4) {
 #pragma unroll
         for (int c = 0; c < MCB; ++c) {
           if (c >= nc) break;
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
       const double v = val_total[c] * scale;
       acq[i] = accumulate ? acq[i] + v : v;
     }
-    if (MODE == 1 && lane < d) {
+    if ((MODE == 1 || MODE == 4) && lane < d) {
       const double gq = grad_q[c] * scale;
       dacq[i * d + lane] = accumulate ? dacq[i * d + lane] + gq : gq;
     }
@@ -278,6 +286,105 @@ __global__ void ma_acq_kernel(const double* __restrict__ mean, const double* __r
         dacq[i * d + q] = accumulate ? dacq[i * d + q] + gq : gq;
       }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// closed-form expectation of a separable composite under y_j ~ N(mu_j, v_j):  psi = sum_j psi_j(mu_j, v_j).
+//   SUMSQ_TARGET  -(mu - th)^2 - v            test_1a.py:100-113, test_4a.py:96-107
+//   NEG_SUM_EXP   -exp(mu + v / 2)            test_2a.py:70-83
+//   ROSEN         -(a - mu)^2 - v  |  -100 mu^2 - 100 v      test_5a.py:64-77
+//   LINEAR        th mu                        cbo.py:126-168 (posterior-mean branch; var / dvar are not read)
+// One thread per candidate.  val = sum_l w_l psi(theta_l, .),  grad = sum_j dpsi/dmu_j dmu_j + dpsi/dv_j dv_j (cbo.py:196).
+template <int COMP>
+__device__ __forceinline__ void comp_psi(const CompCtx& c, double mu, double v, double& val, double& dmu, double& dv) {
+  if (COMP == BOCF_U_SUMSQ_TARGET) {
+    const double a = mu - c.th;
+    val = -(a * a) - v;
+    dmu = -2.0 * a;
+    dv = -1.0;
+  } else if (COMP == BOCF_U_NEG_SUM_EXP) {
+    const double e = exp(mu + 0.5 * v);
+    val = -e;
+    dmu = -e;
+    dv = -0.5 * e;
+  } else if (COMP == BOCF_U_ROSEN_COMPOSITE) {
+    if (c.lower == 1) {
+      const double a = c.th - mu;
+      val = -(a * a) - v;
+      dmu = 2.0 * a;
+      dv = -1.0;
+    } else if (c.lower == 0) {
+      val = -(100.0 * (mu * mu)) - 100.0 * v;
+      dmu = -200.0 * mu;
+      dv = -100.0;
+    } else {
+      val = dmu = dv = 0.0;
+    }
+  } else {
+    val = c.th * mu;
+    dmu = c.th;
+    dv = 0.0;
+  }
+}
+
+template <int COMP, int GRAD>
+__global__ void psi_acq_kernel(const double* __restrict__ mean, const double* __restrict__ var,
+                               const double* __restrict__ dmean, const double* __restrict__ dvar, int64_t Nc,
+                               int64_t Nvalid, int m, int d, const double* __restrict__ theta, int L, int p,
+                               const double* __restrict__ weight, double scale, int accumulate,
+                               double* __restrict__ acq, double* __restrict__ dacq) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nvalid) return;
+  double val = 0.0;
+  double g[MAXD];
+#pragma unroll
+  for (int q = 0; q < MAXD; ++q) g[q] = 0.0;
+  for (int l = 0; l < L; ++l) {
+    const double* th = theta + (int64_t)l * p;
+    const double wl = weight[l];
+    for (int j = 0; j < m; ++j) {
+      const CompCtx cx = comp_ctx<COMP>(th, j, m);
+      const double mu = mean[(int64_t)j * Nc + i];
+      const double v = (COMP == BOCF_U_LINEAR) ? 0.0 : var[(int64_t)j * Nc + i];
+      double pj, dm, dvv;
+      comp_psi<COMP>(cx, mu, v, pj, dm, dvv);
+      val += wl * pj;
+      if (GRAD) {
+        const int64_t o = ((int64_t)j * Nc + i) * d;
+#pragma unroll
+        for (int q = 0; q < MAXD; ++q)
+          if (q < d) {
+            double t = dm * dmean[o + q];
+            if (COMP != BOCF_U_LINEAR) t += dvv * dvar[o + q];
+            g[q] += wl * t;
+          }
+      }
+    }
+  }
+  const double v = val * scale;
+  acq[i] = accumulate ? acq[i] + v : v;
+  if (GRAD) {
+#pragma unroll
+    for (int q = 0; q < MAXD; ++q)
+      if (q < d) {
+        const double gq = g[q] * scale;
+        dacq[i * d + q] = accumulate ? dacq[i * d + q] + gq : gq;
+      }
+  }
+}
+
+template <int COMP>
+static int launch_psi_t(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvalid, double* acq, double* dacq,
+                        cudaStream_t st) {
+  const unsigned grid = (unsigned)ceil_div(Nvalid, 128);
+  if (dacq)
+    psi_acq_kernel<COMP, 1><<<grid, 128, 0, st>>>(cb.mean, cb.var, cb.dmean, cb.dvar, cb.Nc, Nvalid, P.m, P.d, P.theta,
+                                                  P.L, P.p, P.weight, P.scale, P.accumulate, acq, dacq);
+  else
+    psi_acq_kernel<COMP, 0><<<grid, 128, 0, st>>>(cb.mean, cb.var, cb.dmean, cb.dvar, cb.Nc, Nvalid, P.m, P.d, P.theta,
+                                                  P.L, P.p, P.weight, P.scale, P.accumulate, acq, dacq);
+  BOCF_LAUNCH_OK("psi_acq_kernel");
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -394,7 +501,7 @@ template <int COMP>
 static int launch_mc_t(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvalid, double* acq, double* dacq,
                        cudaStream_t st) {
   const unsigned grid = (unsigned)ceil_div(Nvalid, (int64_t)MC_WARPS * MCB);
-  const int mode = (P.variant == BOCF_ACQ_PI_CF) ? 2 : (dacq ? 1 : 0);
+  const int mode = (P.variant == BOCF_ACQ_MEAN_UTILITY) ? (dacq ? 4 : 3) : (P.variant == BOCF_ACQ_PI_CF) ? 2 : (dacq ? 1 : 0);
 #define BOCF_MC_ARGS                                                                                              \
   cb.mean, cb.var, cb.dmean, cb.dvar, cb.Nc, Nvalid, P.m, P.d, P.Zt, P.S, P.theta, P.L, P.p, P.weight, P.fstar, \
       P.scale, P.accumulate, acq, dacq
@@ -402,7 +509,9 @@ static int launch_mc_t(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvali
   ProfScope ps("mc_acq_kernel", st);
   if (mode == 0) mc_acq_kernel<COMP, 0><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
   else if (mode == 1) mc_acq_kernel<COMP, 1><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
-  else mc_acq_kernel<COMP, 2><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
+  else if (mode == 2) mc_acq_kernel<COMP, 2><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
+  else if (mode == 3) mc_acq_kernel<COMP, 3><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
+  else mc_acq_kernel<COMP, 4><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);
   }
 #undef BOCF_MC_ARGS
   BOCF_LAUNCH_OK("mc_acq_kernel");
@@ -412,7 +521,19 @@ static int launch_mc_t(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvali
 int launch_acq_chunk(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvalid, double* acq, double* dacq,
                      cudaStream_t st) {
   if (Nvalid <= 0) return 0;
-  if (P.variant == BOCF_ACQ_EI_CF || P.variant == BOCF_ACQ_PI_CF) {
+  if (P.variant == BOCF_ACQ_PSI) {
+    switch (P.composite) {
+      case BOCF_U_SUMSQ_TARGET: return launch_psi_t<BOCF_U_SUMSQ_TARGET>(P, cb, Nvalid, acq, dacq, st);
+      case BOCF_U_NEG_SUM_EXP: return launch_psi_t<BOCF_U_NEG_SUM_EXP>(P, cb, Nvalid, acq, dacq, st);
+      case BOCF_U_ROSEN_COMPOSITE: return launch_psi_t<BOCF_U_ROSEN_COMPOSITE>(P, cb, Nvalid, acq, dacq, st);
+      case BOCF_U_LINEAR: return launch_psi_t<BOCF_U_LINEAR>(P, cb, Nvalid, acq, dacq, st);
+      default:
+        set_error("no closed-form expectation for this composite (the reference ships none for EXP_COS): use "
+                  "BOCF_ACQ_MEAN_UTILITY");
+        return BOCF_ERR_UNSUPPORTED;
+    }
+  }
+  if (P.variant == BOCF_ACQ_EI_CF || P.variant == BOCF_ACQ_PI_CF || P.variant == BOCF_ACQ_MEAN_UTILITY) {
     if (P.m > MAXM) {
       set_error("mc acquisition: m exceeds MAXM");
       return -5;

@@ -301,6 +301,13 @@ int bocf_model_destroy(bocf_model* M) {
   return 0;
 }
 
+int64_t bocf_model_chunk_candidates(bocf_model* M, int64_t N, int with_grad) {
+  if (check_ready(M) || N < 1) return -1;
+  DeviceGuard dg(M->device);
+  if (resolve_precision(M, nullptr)) return -1;
+  return pick_chunk(M, N, with_grad != 0, 0);
+}
+
 int bocf_model_n(const bocf_model* M) { return M ? M->n : -1; }
 int bocf_model_H(const bocf_model* M) { return M ? M->H : -1; }
 
@@ -577,9 +584,10 @@ int bocf_acq_eval(bocf_model* M, int variant, int composite, const double* Xc, i
                   const double* theta, int L, int p, const double* weight, const double* fstar, int H_use,
                   int with_grad_formula, double* acq, double* dacq, void* stream) {
   if (int rc = check_ready(M)) return rc;
-  const bool mc = (variant == BOCF_ACQ_EI_CF || variant == BOCF_ACQ_PI_CF);
+  const bool mc = (variant == BOCF_ACQ_EI_CF || variant == BOCF_ACQ_PI_CF || variant == BOCF_ACQ_MEAN_UTILITY);
+  const bool marginal = (variant == BOCF_ACQ_MEAN_UTILITY || variant == BOCF_ACQ_PSI);   // cbo._current_marginal_argmax
   if (!Xc || N < 0 || !acq || L < 1 || !weight || !fstar || H_use < 1 || H_use > M->H || variant < 0 ||
-      variant > BOCF_ACQ_MA_PI || (mc && (!Zt || S < 1)) || (p > 0 && !theta)) {
+      variant > BOCF_ACQ_PSI || (mc && (!Zt || S < 1)) || (p > 0 && !theta)) {
     set_error("bocf_acq_eval: invalid arguments");
     return BOCF_ERR_INVALID;
   }
@@ -587,11 +595,11 @@ int bocf_acq_eval(bocf_model* M, int variant, int composite, const double* Xc, i
     set_error("uPI has no analytical gradient (uPI.py:19 analytical_gradient_prediction = False)");
     return BOCF_ERR_UNSUPPORTED;
   }
-  if (!mc && p != M->m) {
+  if (!mc && !marginal && p != M->m) {
     set_error("maEI/maPI need theta of length m (linear scalarisation)");
     return BOCF_ERR_INVALID;
   }
-  if (mc) {
+  if (mc || marginal) {
     const int need_p = (composite == BOCF_U_SUMSQ_TARGET || composite == BOCF_U_LINEAR) ? M->m
                        : (composite == BOCF_U_ROSEN_COMPOSITE ? 1 : 0);
     if (p < need_p) {
@@ -633,12 +641,15 @@ int bocf_acq_eval(bocf_model* M, int variant, int composite, const double* Xc, i
   P.Zt = Zt;
   P.theta = par;
   P.weight = par + n_theta;
-  P.scale = mc ? 1.0 / ((double)H_use * (double)S) : 1.0 / (double)H_use;
+  // cbo.py:171 "the value of these functions is not normalized": plain sums over Z samples and hyper-samples
+  P.scale = marginal ? 1.0 : (mc ? 1.0 / ((double)H_use * (double)S) : 1.0 / (double)H_use);
+  const bool mean_only = (variant == BOCF_ACQ_PSI && composite == BOCF_U_LINEAR);   // posterior-mean branch: no contraction
 
   for (int64_t off = 0; off < N; off += Nc) {
     const int64_t cnt = (N - off < Nc) ? N - off : Nc;
     for (int h = 0; h < H_use; ++h) {
-      if (int rc = launch_posterior_chunk(M, h, Xc + off * M->d, cnt, grad, false, cb, st)) return rc;
+      if (int rc = launch_posterior_chunk(M, h, Xc + off * M->d, cnt, grad, marginal, cb, st, !mean_only, !mean_only))
+        return rc;
       P.fstar = par + n_theta + L + (size_t)h * L;
       P.accumulate = (h > 0) ? 1 : 0;
       if (int rc = launch_acq_chunk(P, cb, cnt, acq + off, grad ? dacq + off * M->d : nullptr, st)) return rc;

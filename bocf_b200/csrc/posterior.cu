@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
       int b = b0 + tid;
       sxsq[tid] = (b < n) ? xsq[b] : 0.0;
       salpha[tid] = (b < n) ? alpha[b] : 0.0;
-      if (SPL > 0) sgcs[tid] = (b < n) ? so.gcs[(size_t)hj * so.gcs_ld + b] : 0.0;
+      // column scale of the second contraction times the 256 its epilogue's merged Horner leaves out (split_gemm.cu)
+      if (SPL > 0) sgcs[tid] = (b < n) ? 256.0 * so.gcs[(size_t)hj * so.gcs_ld + b] : 0.0;
     }
     __syncthreads();
     const int bmax = min(128, n16 - b0);

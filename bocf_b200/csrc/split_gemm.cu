@@ -101,7 +101,9 @@ struct Cfg {
   static constexpr int NBUF = (2 * ACC_COLS <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = pow2_cols(NBUF * ACC_COLS);
   static constexpr int XB_BYTES = NT * DP * 8;                       // DVAR: scaled training inputs of the column tile
-  static constexpr int HEAD = 1024 + XB_BYTES;                        // barriers, tmem slot, column scales, xb tile
+  static constexpr int CS_OFF = 256, CS_BYTES = 2 * NT * 16;          // two buffers of {cs, cs * vq} pairs per column
+  static constexpr int XB_OFF = CS_OFF + CS_BYTES;
+  static constexpr int HEAD = XB_OFF + XB_BYTES;                      // barriers, tmem slot, column scales, xb tile
   static constexpr int STAGES_FIT = (SMEM_MAX - HEAD - 512) / STAGE;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int SMEM_BYTES = HEAD + 512 + STAGES * STAGE;
@@ -114,9 +116,18 @@ struct Cfg {
   static_assert(LMIN <= SA - 1 + SB - 1 && LMIN >= 0 && LMIN <= SB - 1, "every A plane needs at least one partner");
   static_assert(STAGES >= 2, "need at least a double-buffered ring");
   static_assert(B_STAGE % 512 == 0 && A_STAGE % 512 == 0, "planes must keep the 512-byte swizzle period");
-  static_assert(NT * 8 <= 512 && (2 * STAGES + 2 * NBUF) * 8 + 16 <= 512, "head area too small");
+  static_assert((2 * STAGES + 2 * NBUF) * 8 + 16 <= CS_OFF && XB_OFF % 16 == 0, "head area too small");
   static_assert(EPI_WARPS % 4 == 0 && (NT / 8) % PART_SPLIT == 0, "column groups must divide evenly over the warps");
 };
+
+// Knock-out build (-DBOCF_KNOCKOUT, never the shipped library): BOCF_SPLIT_EXP is a bit mask -- 1 skips the MMAs,
+// 2 the bulk loads, 4 the epilogue work, 8 only the V-digit stores, 16 only the epilogue arithmetic (TMEM loads stay).
+// Results are invalid; only time / energy are read (scripts/dev_knockout.sh).
+#ifdef BOCF_KNOCKOUT
+#define BOCF_KO(x) ((P.exp & (x)) != 0)
+#else
+#define BOCF_KO(x) false
+#endif
 
 enum { EPI_RAW = 0, EPI_VAR = 1, EPI_DVAR = 2 };
 enum { TRI_FULL = 0, TRI_K_LE_N = 1, TRI_K_GE_N = 2 };
@@ -145,6 +156,7 @@ struct GemmParams {
   int d, n16, n_pad;
   int np;                  // parts per candidate tile
   int l2_keep_a;           // 1: A planes loaded with an L2 evict_last policy (BOCF_SPLIT_L2KEEP)
+  int exp;                 // knock-out builds only
 };
 
 // Work decomposition.  A UNIT is (output j, candidate tile rt, part p of NP): the column tiles ct = p, p+NP, ... of one
@@ -274,6 +286,30 @@ __device__ __forceinline__ double levels_to_f64(const uint32_t (&c)[NL][W], int 
   return v;
 }
 
+// The same sum divided by 256, for the fused epilogues: level 0 is folded into level 1 first,
+//   t = c[1] + round(c[0] / 256)   (|t| < 2^29 + 2^21),
+// which drops at most half a unit of level 1 -- 2^7 in units of the full sum, against the ~2^10 those units already
+// carry from the digit pairs below LMIN -- and saves one conversion and one fused multiply-add per element.  The
+// factor 256 is folded into the (power-of-two) column scale by the caller.
+template <int NL, int W>
+__device__ __forceinline__ double levels_to_f64_merged(const uint32_t (&c)[NL][W], int e) {
+  static_assert(NL >= 2, "needs at least two levels");
+  const int t = (int)c[1][e] + (((int)c[0][e] + 128) >> 8);
+  double v = 0.0;
+#pragma unroll
+  for (int lb = NL - 1; lb >= 1; lb -= 2) {
+    if (lb >= 2) {
+      const int lo = (lb - 1 == 1) ? t : (int)c[lb - 1][e];
+      const long long addend = (long long)lo + 0x4338000000000000LL;
+      const double x = __longlong_as_double((long long)(int)c[lb][e] * 256 + addend) - 6755399441055744.0;
+      v = (lb == NL - 1) ? x : fma(v, 65536.0, x);
+    } else {                                                 // lb == 1: t alone
+      v = (lb == NL - 1) ? i32_to_f64((uint32_t)t) : fma(v, 256.0, i32_to_f64((uint32_t)t));
+    }
+  }
+  return v;
+}
+
 // digits of rint(x) for |x| < 2^46 without F2I: adding 1.5 * 2^52 leaves rint(x) (two's complement) in the low mantissa bits
 template <int S>
 __device__ __forceinline__ unsigned long long balanced_digits_of(double x) {
@@ -311,15 +347,16 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
   using C = Cfg<SCH, DP>;
   constexpr int NT = C::NT, NL = C::NL, EPI_THREADS = C::EPI_THREADS, PART_SPLIT = C::PART_SPLIT;
   extern __shared__ uint8_t smem_raw[];
-  // head: [0,512) barriers + tmem slot, [512, 1024) column scales; stages start at the next 512-byte boundary
+  // head: [0,256) barriers + tmem slot, then two buffers of per-column scale pairs, then the DVAR training-input
+  // tile; stages start at the next 512-byte boundary
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
   uint64_t* tfull = bars + 2 * C::STAGES;
   uint64_t* tempty = tfull + C::NBUF;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::NBUF);
-  double* s_cs = reinterpret_cast<double*>(smem_raw + 512);
-  double* s_xb = reinterpret_cast<double*>(smem_raw + 1024);      // [NT][DP]
+  double2* s_cs = reinterpret_cast<double2*>(smem_raw + C::CS_OFF);   // [2][NT] {256 cs, 256 cs vq}
+  double* s_xb = reinterpret_cast<double*>(smem_raw + C::XB_OFF);     // [NT][DP]
   const uint32_t raw_addr = tc::smem_u32(smem_raw);
   const uint32_t stage_off = ((raw_addr + C::HEAD + 511u) & ~511u) - raw_addr;
   uint8_t* sA = smem_raw + stage_off;
@@ -366,6 +403,14 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
         }
         for (int kc = ti.kb; kc < ti.ke; ++kc) {
           tc::mbar_wait(&empty[stage], phase ^ 1u);
+          if (BOCF_KO(2)) {
+            tc::mbar_arrive(&full[stage]);
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            continue;
+          }
           tc::mbar_arrive_expect_tx(&full[stage], C::STAGE);
           // the unit's A tile is re-streamed once per column tile: ask L2 to keep it (P.l2_keep_a)
           if (P.l2_keep_a) tc::bulk_g2s_hint(sA + stage * C::A_STAGE, gA + (size_t)kc * C::A_STAGE, C::A_STAGE, &full[stage], pol_keep);
@@ -404,6 +449,7 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
         for (int ks = 0; ks < KC / 32; ++ks) {
           const int kstep = kc * (KC / 32) + ks;            // K steps wholly outside the triangle multiply zeros: skip
           if (kstep < ti.sb || kstep >= ti.se) continue;
+          if (BOCF_KO(1)) continue;
           if (first) {
             if (tc::elect_one()) issue_kstep<C, true>(a_lo + ks * 2, b_lo + ks * 2, d_tmem);
           } else {
@@ -435,9 +481,10 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
     double pre_cs = 0.0, pre_vq = 0.0, pre_xb[XPT];
     auto prefetch_tile_consts = [&](const TileInfo& tn) {
       const int hjn = P.h * P.m + tn.j;
-      if (et < NT) pre_cs = __ldg(P.cs + (size_t)hjn * P.nct * NT + tn.ct * NT + et);
-      if (EPI == EPI_VAR) pre_vq = __ldg(P.vq + hjn);
-      if (EPI == EPI_DVAR) {
+      if (EPI != EPI_DVAR) {
+        if (et < NT) pre_cs = __ldg(P.cs + (size_t)hjn * P.nct * NT + tn.ct * NT + et);
+        if (EPI == EPI_VAR) pre_vq = __ldg(P.vq + hjn);
+      } else {
         const double* Xb = P.Xs + (size_t)hjn * P.n_pad * P.d;
 #pragma unroll
         for (int x = 0; x < XPT; ++x) {
@@ -461,7 +508,6 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
       have = walk.next(P, tnext);
       const int buf = it % C::NBUF;
       const uint32_t use = (uint32_t)(it / C::NBUF);
-      ++it;
       const int col0 = ti.ct * NT;
       if (ti.first) {
         sumsq = 0.0;
@@ -469,22 +515,31 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
 #pragma unroll
         for (int q = 0; q < DPA; ++q) acc[q] = 0.0;
       }
-      tc::named_bar_sync(1, EPI_THREADS);                       // previous tile's readers of s_cs / s_xb are done
-      if (et < NT) s_cs[et] = pre_cs;
-      if (EPI == EPI_DVAR) {
+      // per-tile constants into shared memory.  VAR / RAW: {scale, scale * quantiser} pairs, double buffered (buffer
+      // it & 1), so ONE barrier per tile suffices: a warp can be at most one tile ahead of the slowest one.
+      // DVAR: the training-input tile is single buffered (it would cost a pipeline stage): two barriers.
+      const double2* cs_t = s_cs + (it & 1) * NT;
+      if (EPI != EPI_DVAR) {
+        if (et < NT) s_cs[(it & 1) * NT + et] = make_double2(pre_cs * (EPI == EPI_RAW ? 1.0 : 256.0), pre_cs * 256.0 * pre_vq);
+      } else {
+        tc::named_bar_sync(1, EPI_THREADS);                     // previous tile's readers of s_xb are done
 #pragma unroll
         for (int x = 0; x < XPT; ++x) {
           const int idx = et + x * EPI_THREADS;
           if (idx < NT * DPA0) s_xb[idx] = pre_xb[x];
         }
       }
-      const double vq = pre_vq;
       tc::named_bar_sync(1, EPI_THREADS);
+      ++it;
       if (have) prefetch_tile_consts(tnext);
       const int64_t i = (int64_t)ti.rt * TM + row;              // chunk-local candidate
 
       // per-tile thread state
-      constexpr int CGW = 8;                                    // columns per TMEM load group
+      // columns per TMEM load group.  VAR: 16, so a thread's digits of one plane are ONE 16-byte piece of the swizzled
+      // 64-byte row -- half as many L2 write requests as 8-byte stores (knock-out: the V-digit stores cost 22 of the
+      // first contraction's 121 ms per 1M-candidate step as 8-byte pieces, profiles/r2_knockouts.md)
+      constexpr int CGW = (EPI == EPI_VAR) ? 16 : 8;
+      static_assert(NT % (CGW * PART_SPLIT) == 0, "column groups must divide evenly over the warps");
       constexpr int NCG = NT / CGW;
       constexpr int NGW = NCG / PART_SPLIT;                     // column groups per warp
       double gv[CGW];
@@ -517,6 +572,10 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
       }
 #pragma unroll
       for (int gi = 0; gi < NGW; ++gi) {
+        if (BOCF_KO(4)) {
+          if (PREF) tc::tmem_ld_wait();
+          break;
+        }
         const int cg = hw + gi * PART_SPLIT;
         constexpr int dummy = 0;
         (void)dummy;
@@ -533,21 +592,26 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
           tc::tmem_ld_wait();
         }
         const uint32_t (&cc)[NL][CGW] = c[PREF ? (gi & 1) : 0];
-        uint32_t vec[S2][2];
+        uint32_t vec[S2][CGW / 4];
         unsigned long long dgv[CGW];
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {
-          double v = levels_to_f64<NL, CGW>(cc, e);
-          if (EPI != EPI_DVAR) v *= s_cs[cg * CGW + e];             // DVAR: the column scale is folded into G* by the K* kernel
+          if (BOCF_KO(16)) break;
           if (EPI == EPI_RAW) {
+            const double v = levels_to_f64<NL, CGW>(cc, e) * cs_t[cg * CGW + e].x;
             const int col = col0 + cg * CGW + e;
             const size_t grow = (size_t)(ti.j * P.RT + ti.rt) * TM + row;
             if (col < P.ldo) P.raw_out[grow * P.ldo + col] = v * P.raw_rs[grow];
           } else if (EPI == EPI_VAR) {
+            const double y = levels_to_f64_merged<NL, CGW>(cc, e);    // V / (256 cs)
+            const double2 sc = cs_t[cg * CGW + e];
+            const double v = y * sc.x;
             sumsq = fma(v, v, sumsq);
-            dgv[e] = balanced_digits_of<S2>(v * vq);
+            // digits of rint(V vq): one fused multiply-add onto the 1.5 * 2^52 rounding constant
+            dgv[e] = balanced_digits<S2>(__double_as_longlong(fma(y, sc.y, 6755399441055744.0)));
           } else {
-            const double w = v * gv[e];
+            // the column scale (and the factor 256 of the merged Horner) is folded into G* by the K* kernel
+            const double w = levels_to_f64_merged<NL, CGW>(cc, e) * gv[e];
             if (gi + 1 < NGW) {                                // refill the slot with this warp's next column group's G*
               const int bn = col0 + (cg + PART_SPLIT) * CGW + e;
               gv[e] = __ldg(Gcol + (size_t)(tile_full ? bn : min(bn, P.n - 1)) * gstride);
@@ -562,9 +626,18 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
             }
           }
         }
-        if (EPI == EPI_VAR && P.A2 != nullptr) {
+        if (BOCF_KO(16)) {                                       // keep the loads alive, skip the arithmetic
+          uint32_t x = 0;
 #pragma unroll
-          for (int w = 0; w < 2; ++w) {                          // byte transpose: digit t of 4 columns -> one word
+          for (int lb = 0; lb < NL; ++lb)
+#pragma unroll
+            for (int e = 0; e < CGW; ++e) x ^= cc[lb][e];
+          if (x == 0x9e3779b9u) sumsq += 1.0;
+          continue;
+        }
+        if (EPI == EPI_VAR && P.A2 != nullptr && !BOCF_KO(8)) {
+#pragma unroll
+          for (int w = 0; w < CGW / 4; ++w) {                    // byte transpose: digit t of 4 columns -> one word
             const unsigned long long four[4] = {dgv[4 * w], dgv[4 * w + 1], dgv[4 * w + 2], dgv[4 * w + 3]};
             uint32_t o[S2];
             digits_transpose4<S2>(four, o);
@@ -576,8 +649,12 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
             const int kc = k >> 6;
             uint8_t* dst = P.A2 + (((size_t)(ti.j * P.RT + ti.rt) * P.KCH + kc) * S2) * C::A_PLANE + sw64(row, k & 63);
 #pragma unroll
-            for (int tt = 0; tt < S2; ++tt)
-              *reinterpret_cast<uint2*>(dst + (size_t)tt * C::A_PLANE) = make_uint2(vec[tt][0], vec[tt][1]);
+            for (int tt = 0; tt < S2; ++tt) {
+              if (CGW == 16)
+                *reinterpret_cast<uint4*>(dst + (size_t)tt * C::A_PLANE) = make_uint4(vec[tt][0], vec[tt][1], vec[tt][2], vec[tt][3]);
+              else
+                *reinterpret_cast<uint2*>(dst + (size_t)tt * C::A_PLANE) = make_uint2(vec[tt][0], vec[tt][1]);
+            }
           }
         }
       }
@@ -951,6 +1028,7 @@ static sg::GemmParams base_params(const bocf_model* M, int h, const ChunkBuffers
     keep = (env && std::atoi(env) != 0) ? 1 : 0;
   }
   P.l2_keep_a = keep;
+  if (const char* env = std::getenv("BOCF_SPLIT_EXP")) P.exp = std::atoi(env);
   return P;
 }
 

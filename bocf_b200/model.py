@@ -11,6 +11,7 @@ GPModel.updateModel does (gpmodel.py:102-128): ML-II, then an HMC chain whose su
 the ``n_samples`` hyper-sample instances -- all outputs in lockstep on the device likelihood (hmc.py).
 """
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -43,6 +44,9 @@ class multi_outputGP(object):
         # arithmetic of the two candidate-side contractions: None (library default / BOCF_PRECISION), "fp64",
         # "auto", or "split3".."split6" (tcgen05 int8 digit planes, include/bocf_b200.h: enum bocf_precision)
         self.precision = precision
+        # the C handle is stream-ordered and NOT thread-safe (shared scratch, selected hyper-sample): every call into it
+        # takes this lock (the batched multistart optimiser runs one L-BFGS state machine per thread)
+        self._lock = threading.RLock()
         # GPModel's sampler settings (gpmodel.py:31: n_burnin=100, subsample_interval=10, step_size=1e-1, leapfrog_steps=20)
         self.n_burnin, self.subsample_interval = n_burnin, subsample_interval
         self.step_size, self.leapfrog_steps, self.max_iters = step_size, leapfrog_steps, max_iters
@@ -242,6 +246,10 @@ class multi_outputGP(object):
         """Digit planes the tensor-core contraction currently uses (0 = fp64 DMMA)."""
         return int(self._lib.bocf_model_active_slices(self._handle)) if self._handle is not None else 0
 
+    def chunk_candidates(self, N, grad=True):
+        """Candidates per internal chunk of a call with N candidates (results never depend on it)."""
+        return int(self._lib.bocf_model_chunk_candidates(self._handle, int(N), 1 if grad else 0))
+
     def active_scheme(self):
         """(scheme of the variance contraction, scheme of the variance-gradient contraction), a scheme being
         100 SA + 10 SB + LMIN (include/bocf_b200.h); (0, 0) = fp64 DMMA."""
@@ -294,7 +302,7 @@ class multi_outputGP(object):
         N, d = Xd.shape
         assert d == self.input_dim
         m = self.output_dim
-        with torch.cuda.device(self.device):
+        with self._lock, torch.cuda.device(self.device):
             mean = torch.empty((m, N), dtype=torch.float64, device=self.device)
             var = torch.empty((m, N), dtype=torch.float64, device=self.device) if want_var else None
             dmean = torch.empty((m, N, d), dtype=torch.float64, device=self.device) if want_dmean else None
@@ -306,6 +314,35 @@ class multi_outputGP(object):
         if is_t:
             return outs
         return tuple(None if o is None else o.cpu().numpy() for o in outs)
+
+    def expected_utility(self, X, composite, parameter, n_hyps, Z=None, grad=False):
+        """sum over the first n_hyps hyper-samples of the expected composite utility at X under the NOISELESS posterior,
+        NOT normalised -- the objective cbo._current_marginal_argmax maximises (cbo.py:121-235):
+          Z is None : closed form psi(theta, mu, var) (cbo.py:170-198; LINEAR = the posterior-mean branch :126-168)
+          Z (S, m)  : sum_s U(theta, mu + sqrt(var) Z_s) with the pathwise gradient (cbo.py:203-231).
+        Returns (value (N,), gradient (N, d) or None) as numpy (CUDA tensors for tensor input)."""
+        Xd, is_t = self._dev_in(X)
+        N, d = Xd.shape
+        theta = np.ascontiguousarray(np.asarray(parameter, dtype=np.float64).reshape(1, -1))
+        ones = np.ones(1)
+        zeros = np.zeros((int(n_hyps), 1))
+        variant = "psi" if Z is None else "mean_utility"
+        with self._lock, torch.cuda.device(self.device):
+            Zt, S = None, 0
+            if Z is not None:
+                Z = np.ascontiguousarray(np.asarray(Z, dtype=np.float64))
+                Zt = torch.from_numpy(np.ascontiguousarray(Z.T)).to(self.device)
+                S = Z.shape[0]
+            val = torch.empty((N,), dtype=torch.float64, device=self.device)
+            g = torch.empty((N, d), dtype=torch.float64, device=self.device) if grad else None
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(self._lib.bocf_acq_eval(self._handle, _lib.VARIANTS[variant], _lib.COMPOSITES[composite], _ptr(Xd), N,
+                                               _ptr(Zt), S, theta.ctypes.data_as(ctypes.c_void_p), 1, theta.shape[1],
+                                               ones.ctypes.data_as(ctypes.c_void_p), zeros.ctypes.data_as(ctypes.c_void_p),
+                                               int(n_hyps), 0, _ptr(val), _ptr(g), st))
+            if is_t:
+                return val, g
+            return val.cpu().numpy(), (None if g is None else g.cpu().numpy())
 
     def predict(self, X, full_cov=False):
         """multi_outputGP.py:138-149: (mean (m,N), variance incl. noise, clipped at 1e-10 (gpmodel.py:147))."""

@@ -50,6 +50,55 @@ def _host_funcs(name):
     raise ValueError("unknown composite %r (known: %s)" % (name, sorted(COMPOSITES)))
 
 
+# length of one utility parameter: "m" = one entry per output, 1 = a scalar
+THETA_DIM = {"sumsq_target": "m", "linear": "m", "neg_sum_exp": 1, "exp_cos": 1, "rosen_composite": 1}
+
+
+def theta_matrix(utility, samples):
+    """Utility parameters as an (L, p) matrix.  A 1-D support is L scalar parameters for the composites that take a
+    scalar (test_5a.py:41: np.atleast_1d([1.]) -- the reference iterates len(support)), one vector otherwise."""
+    th = np.asarray(samples, dtype=np.float64)
+    if th.ndim == 0:
+        th = th.reshape(1, 1)
+    elif th.ndim == 1:
+        th = th.reshape(-1, 1) if THETA_DIM.get(utility.composite) == 1 else th.reshape(1, -1)
+    return np.ascontiguousarray(th)
+
+
+def _host_psi(name):
+    """Closed-form E[U(theta, y)], y_j ~ N(mu_j, v_j), as (psi, dpsi/d(mu, v)) -- the pairs the reference's scripts pass
+    as ExpectationUtility; the device enum of acq.cu (psi_acq_kernel) restates the same formulas."""
+    if name == "sumsq_target":       # test_1a.py:100-113
+        return (lambda th, mu, v: -np.sum(np.square((np.asarray(mu).T - th).T), axis=0) - np.sum(v, axis=0),
+                lambda th, mu, v: -np.concatenate((2 * (np.squeeze(mu) - th), np.ones(len(np.squeeze(v))))))
+    if name == "neg_sum_exp":        # test_2a.py:70-83
+        return (lambda th, mu, v: -np.sum(np.exp(np.squeeze(mu) + 0.5 * np.squeeze(v))),
+                lambda th, mu, v: -np.concatenate((np.exp(np.squeeze(mu) + 0.5 * np.squeeze(v)),
+                                                   0.5 * np.exp(np.squeeze(mu) + 0.5 * np.squeeze(v)))))
+    if name == "rosen_composite":    # test_5a.py:64-77
+        def psi(a, mu, v):
+            mu, v = np.squeeze(mu), np.squeeze(v)
+            h = len(mu) // 2
+            a = float(np.asarray(a).reshape(-1)[0])
+            return -np.sum((a - mu[:h]) ** 2 + 100 * mu[h:2 * h] ** 2 + v[:h] + 100 * v[h:2 * h])
+
+        def dpsi(a, mu, v):
+            mu = np.squeeze(mu)
+            m, h = len(mu), len(mu) // 2
+            a = float(np.asarray(a).reshape(-1)[0])
+            g = np.zeros(2 * m)
+            g[:h] = 2 * (a - mu[:h])
+            g[h:2 * h] = -200 * mu[h:2 * h]
+            g[m:m + h] = -1.0
+            g[m + h:m + 2 * h] = -100.0
+            return g
+        return psi, dpsi
+    if name == "linear":             # cbo.py:126-168: E[theta . y] = theta . mu
+        return (lambda th, mu, v: np.dot(th, np.squeeze(mu)),
+                lambda th, mu, v: np.concatenate((np.atleast_1d(th), np.zeros(len(np.squeeze(mu))))))
+    return None
+
+
 class Utility(object):
     """utility.py:6-48 plus ``composite``: the name of the device-side U(theta, y)."""
 
@@ -66,6 +115,25 @@ class Utility(object):
         self.dfunc = dfunc if dfunc is not None else hdf
         self.parameter_dist = parameter_dist
         self.linear = linear or composite == "linear"
+        if func is not None or dfunc is not None:
+            self._check_callables(hf, hdf)
+
+    def _check_callables(self, hf, hdf, m=4):
+        """A user-supplied func / dfunc must be the catalogued composite: the device evaluates the enum, the loop's
+        reporting path the callable -- two different utilities would silently optimise one and report the other."""
+        rng = np.random.default_rng(0)
+        y = rng.standard_normal(m)
+        th = rng.standard_normal(m) if THETA_DIM[self.composite] == "m" else np.array([0.7])
+        try:
+            ok = np.allclose(np.asarray(self.func(th, y), dtype=float), np.asarray(hf(th, y), dtype=float), rtol=1e-9, atol=1e-12)
+            if self.dfunc is not None:
+                ok = ok and np.allclose(np.asarray(self.dfunc(th, y), dtype=float).reshape(-1),
+                                        np.asarray(hdf(th, y), dtype=float).reshape(-1), rtol=1e-9, atol=1e-12)
+        except Exception:            # callables written for one fixed m (test_5a.py) cannot be probed at m = 4
+            return
+        if not ok:
+            raise ValueError("Utility: func / dfunc disagree with composite=%r (the CUDA kernels evaluate the composite)"
+                             % (self.composite,))
 
     def evaluate_w_gradient(self, parameter, y):
         return self.eval_func(parameter, y), self.eval_gradient(parameter, y)

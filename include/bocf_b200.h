@@ -58,7 +58,12 @@ enum bocf_acq_variant {
   BOCF_ACQ_EI_CF = 0,  /* uEI_noiseless.py:63-83,138-170  MC composite EI (+ pathwise gradient) */
   BOCF_ACQ_PI_CF = 1,  /* uPI.py:66-86                     MC composite PI, value only           */
   BOCF_ACQ_MA_EI = 2,  /* maEI.py:81-126 / EI.py:79-123    analytic EI of theta^T y              */
-  BOCF_ACQ_MA_PI = 3   /* maPI.py:80-120 / PI.py           analytic PI of theta^T y              */
+  BOCF_ACQ_MA_PI = 3,  /* maPI.py:80-120 / PI.py           analytic PI of theta^T y              */
+  /* the two consumers of cbo._current_marginal_argmax (cbo.py:121-235): NOISELESS posterior variance, sums over the
+   * hyper-samples and base samples NOT normalised (as in the reference), fstar ignored */
+  BOCF_ACQ_MEAN_UTILITY = 4, /* cbo.py:203-231  sum_h sum_s U(theta, mu_h + sigma_h Z_s) + pathwise gradient    */
+  BOCF_ACQ_PSI = 5     /* cbo.py:126-198  sum_h psi(theta, mu_h, var_h): closed-form E[U] of the composite (psi of
+                          test_1a.py:100-113, test_2a.py:70-83, test_5a.py:64-77); LINEAR = posterior-mean branch  */
 };
 
 /* Arithmetic of the two candidate-side contractions  V = K* Linv^T,  Wt = V Linv  (posterior.py:312, gp.py:474).
@@ -123,6 +128,9 @@ int bocf_model_log_likelihood(bocf_model* mdl, double* lml, double* g_variance, 
 /* Copy one factor out for inspection (tests): L, Linv n x n row-major, alpha n, [dev] or NULL. */
 int bocf_model_get_factor(bocf_model* mdl, int h, int j, double* L, double* Linv, double* alpha,
                           void* stream);
+/* Candidates the library evaluates per internal chunk for a call with N candidates (the K* / V scratch of one chunk
+ * must fit the scratch limit); results never depend on it -- exposed so tests can place spot checks on chunk borders. */
+int64_t bocf_model_chunk_candidates(bocf_model* mdl, int64_t N, int with_grad);
 int bocf_model_n(const bocf_model* mdl);
 int bocf_model_H(const bocf_model* mdl);
 

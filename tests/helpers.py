@@ -166,3 +166,20 @@ def rel_err(a, b):
     a = np.asarray(a)
     b = np.asarray(b)
     return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
+
+
+def elem_err(a, b, floor=1e-2):
+    """Element-wise error metric used next to the norm-wise `rel_err`:  max_k |a_k - b_k| / max(|b_k|, floor * max|b|).
+    Entries above floor * max|b| are held to a RELATIVE bar, smaller ones to an absolute bar `floor` times tighter
+    than the norm-wise one.  (A purely relative check has no meaning for EI values in the far tail, which are sums of
+    a handful of U(theta, a_s) - f* differences that cancel to nothing.)"""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.abs(b), floor * max(1e-300, np.max(np.abs(b))))
+    return float(np.max(np.abs(a - b) / scale))
+
+
+def assert_close(a, b, tol_, what="", floor=1e-2):
+    """Norm-wise AND element-wise agreement (see elem_err) within tol_."""
+    nw, ew = rel_err(a, b), elem_err(a, b, floor)
+    assert nw < tol_ and ew < 4 * tol_, "%s: norm-wise %.3e, element-wise %.3e, tol %.1e" % (what, nw, ew, tol_)

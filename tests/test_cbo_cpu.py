@@ -41,7 +41,8 @@ def _build(seed, fixed_hyps=True, sampler=None):
     expU = B.ExpectationUtility(
         lambda th, mu, v: -np.sum(np.square((mu.T - th).T), axis=0) - np.sum(v, axis=0),
         lambda th, mu, v: -np.concatenate((2 * (np.squeeze(mu) - th), np.ones((len(np.squeeze(v)),)))))
-    bo = B.CBO(model, space, objective, acq, B.Sequential(acq), X_init, expectation_utility=expU)
+    from oracle.cbo import CBO            # host loop of bocf_b200.cbo + the reference's literal marginal-argmax objectives
+    bo = CBO(model, space, objective, acq, B.Sequential(acq), X_init, expectation_utility=expU)
     return bo, acq_opt, d
 
 
@@ -98,4 +99,25 @@ def test_negated_wrapper_host_fallback():
         a.acquisition_function_withGradients(np.zeros((0, 3)))
     except ValueError:
         pass
-    assert a._sign == 1.0 and a._sign_applied is False
+    assert a._sign == 1.0 and getattr(a._tls, "applied", False) is False
+
+
+def test_product_cbo_refuses_cpu_models():
+    """No CPU fallback: the product's marginal-argmax objectives are device calls; CPU models go through oracle.cbo."""
+    import bocf_b200 as B
+    import pytest
+    bo, _, _ = _build(seed=0)
+    with pytest.raises(TypeError):
+        B.CBO._current_marginal_argmax(bo, np.zeros(4))
+
+
+def test_theta_matrix_and_utility_consistency():
+    import bocf_b200 as B
+    import pytest
+    from bocf_b200.utility import theta_matrix
+    pd = B.ParameterDistribution(support=np.array([0.5, 1.0, 2.0]), prob_dist=np.ones(3) / 3)
+    assert theta_matrix(B.Utility(parameter_dist=pd, composite="rosen_composite"), pd.support).shape == (3, 1)
+    assert theta_matrix(B.Utility(parameter_dist=pd, composite="sumsq_target"), pd.support).shape == (1, 3)
+    B.Utility(func=lambda th, y: -np.sum(np.square((y.T - th).T), axis=0), parameter_dist=pd, composite="sumsq_target")
+    with pytest.raises(ValueError):
+        B.Utility(func=lambda th, y: np.sum(y, axis=0), parameter_dist=pd, composite="sumsq_target")

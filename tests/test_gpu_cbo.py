@@ -43,7 +43,11 @@ def _run(side, cuda_device, iters=2, seed=0):
     expU = B.ExpectationUtility(
         lambda th, mu, v: -np.sum(np.square((mu.T - th).T), axis=0) - np.sum(v, axis=0),
         lambda th, mu, v: -np.concatenate((2 * (np.squeeze(mu) - th), np.ones((len(np.squeeze(v)),)))))
-    bo = B.CBO(model, space, objective, acq, B.Sequential(acq), X_init, expectation_utility=expU)
+    if side == "cuda":
+        bo = B.CBO(model, space, objective, acq, B.Sequential(acq), X_init, expectation_utility=expU)
+    else:
+        from oracle.cbo import CBO
+        bo = CBO(model, space, objective, acq, B.Sequential(acq), X_init, expectation_utility=expU)
     bo.run_optimization(max_iter=iters)
     return bo, acq_opt
 
@@ -103,7 +107,11 @@ def _run_inferred(side, cuda_device, iters=2, seed=3):
     expU = B.ExpectationUtility(
         lambda th, mu, v: -np.sum(np.square((mu.T - th).T), axis=0) - np.sum(v, axis=0),
         lambda th, mu, v: -np.concatenate((2 * (np.squeeze(mu) - th), np.ones((len(np.squeeze(v)),)))))
-    bo = B.CBO(model, space, objective, acq, B.Sequential(acq), X_init, expectation_utility=expU)
+    if side == "cuda":
+        bo = B.CBO(model, space, objective, acq, B.Sequential(acq), X_init, expectation_utility=expU)
+    else:
+        from oracle.cbo import CBO
+        bo = CBO(model, space, objective, acq, B.Sequential(acq), X_init, expectation_utility=expU)
     bo.run_optimization(max_iter=iters)
     return bo, model
 
@@ -117,3 +125,53 @@ def test_cbo_loop_with_inferred_hyperparameters(cuda_device):
     # hyper-samples -> same selected point
     np.testing.assert_allclose(bo_g.suggested_points[0], bo_c.suggested_points[0], atol=1e-3)
     np.testing.assert_allclose(bo_g.historical_optimal_values[0], bo_c.historical_optimal_values[0], rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("branch", ["psi", "mc", "linear"])
+@pytest.mark.parametrize("composite", ["sumsq_target", "neg_sum_exp", "rosen_composite", "exp_cos"])
+def test_marginal_argmax_objectives_match_literal_loops(cuda_device, branch, composite):
+    """cbo._current_marginal_argmax (cbo.py:121-235): the device objectives (psi_acq_kernel, mc_acq_kernel<_,3|4>) against
+    the reference's per-candidate Python loops (oracle/cbo.py) on the same model, parameter and base samples."""
+    import bocf_b200 as B
+    from bocf_b200.utility import _host_psi
+    from oracle.cbo import CBO as OracleCBO
+    from tests.helpers import make_problem, oracle_model, product_model, oracle_utility, product_utility, rel_err, tol
+    if branch == "linear":
+        if composite != "sumsq_target":
+            pytest.skip("one linear case")
+        composite = "linear"
+    if branch == "psi" and composite == "exp_cos":
+        pytest.skip("the reference ships no closed form for exp_cos")
+    m = 4
+    P = make_problem(m=m, d=3, n=60, H=2, kind="matern52", composite=composite, N=37, S=8, seed=13, noise=1e-3)
+    parameter = P.theta[0] if composite in ("sumsq_target", "linear") else np.array([0.8])
+    om, pm = oracle_model(P), product_model(P, cuda_device)
+    Uo, Up = oracle_utility(P), product_utility(P)
+    if composite == "linear":
+        Uo.linear = True
+    expU = None
+    if branch == "psi":
+        expU = B.ExpectationUtility(*_host_psi(composite))
+
+    class _Opt(object):                       # captures the objectives instead of optimising them
+        def optimize(self, f=None, f_df=None, parallel=False):
+            self.f, self.f_df = f, f_df
+            return np.zeros((1, 3)), 0.0
+
+    vals = {}
+    for side, model, U, cls in (("cpu", om, Uo, OracleCBO), ("cuda", pm, Up, B.CBO)):
+        bo = cls.__new__(cls)
+        bo.model, bo.utility, bo.expectation_utility = model, U, expU
+        bo.n_attributes, bo.n_hyps_samples = m, 2
+        bo.acquisition = None
+        bo._n_hyps = lambda: 2
+        bo.evaluation_optimizer = _Opt()
+        np.random.seed(5)                     # the MC branch draws its 50 base samples from numpy's global stream
+        bo._current_marginal_argmax(parameter)
+        f = bo.evaluation_optimizer.f(P.Xc)
+        f2, g = bo.evaluation_optimizer.f_df(P.Xc)
+        assert f.shape == (P.N, 1) and g.shape == (P.N, 3)
+        np.testing.assert_allclose(f, f2, rtol=1e-12, atol=0)
+        vals[side] = (f, g)
+    assert rel_err(vals["cuda"][0], vals["cpu"][0]) < tol(1e-8), rel_err(vals["cuda"][0], vals["cpu"][0])
+    assert rel_err(vals["cuda"][1], vals["cpu"][1]) < tol(1e-7), rel_err(vals["cuda"][1], vals["cpu"][1])

@@ -11,9 +11,22 @@ import ctypes
 import numpy as np
 import pytest
 
-from tests.helpers import tol, make_problem, oracle_model, oracle_acq, product_model, product_utility, rel_err
+from tests.helpers import (assert_close, tol, make_problem, oracle_model, oracle_acq, product_model, product_utility,
+                           rel_err)
 
 pytestmark = pytest.mark.gpu
+
+
+def _stratified(N, chunk, rng, n_random, extra=()):
+    """Spot-check indices: both sides of every few chunk borders (multiples of the library's internal chunk), the first
+    and the last candidates (ragged last chunk / last 128-tile), the caller's picks, and a random rest."""
+    idx = [np.arange(0, 96), np.arange(N - 200, N)]
+    borders = np.arange(chunk, N, chunk)
+    for b in borders[:: max(1, len(borders) // 6)]:
+        idx.append(np.arange(b - 48, b + 48))
+    idx.append(np.asarray(extra, dtype=np.int64))
+    idx.append(rng.choice(N, n_random, replace=False))
+    return np.unique(np.clip(np.concatenate(idx), 0, N - 1))
 
 
 def _sweep(P, model, variant="uEI_noiseless", grad=True, Xc=None):
@@ -42,12 +55,16 @@ def test_cfg3_million_candidates(cuda_device):
     assert np.all(np.isfinite(a)) and np.all(np.isfinite(g)) and np.all(a >= 0)
     assert np.all(g[a == 0] == 0)                       # no active sample -> no pathwise gradient
     assert np.mean(a > 0) > 1e-3
-    # (1) oracle spot-check on 48 candidates, half of them with non-zero EI
+    # (1) oracle spot-check on >= 2048 candidates: chunk borders, ragged tail, 400 with non-zero EI, random rest
     rng = np.random.default_rng(1)
     nz = np.nonzero(a > 0)[0]
-    idx = np.concatenate([rng.choice(nz, 24, replace=False), rng.choice(P.N, 24, replace=False)])
+    chunk = model.chunk_candidates(P.N, grad=True)
+    assert 0 < chunk < P.N and P.N % chunk != 0                      # several chunks and a ragged last one
+    idx = _stratified(P.N, chunk, rng, 900, extra=rng.choice(nz, 400, replace=False))
+    assert len(idx) >= 2048
     a_o, g_o = oracle_acq(P, grad=True, Xc=P.Xc[idx])
-    assert rel_err(a[idx], a_o) < tol(1e-8) and rel_err(g[idx], g_o) < tol(1e-7)
+    assert_close(a[idx], a_o, tol(1e-8), "acq")
+    assert_close(g[idx], g_o, tol(1e-7), "grad acq")
     # (2) independence / determinism: the same candidates alone (other chunk, other tile position) -> bitwise equal
     a_s, g_s, _ = _sweep(P, model, Xc=P.Xc[idx])
     assert np.array_equal(a_s, a[idx]) and np.array_equal(g_s, g[idx])
@@ -98,7 +115,8 @@ def test_cfg4_parameter_uncertain_maei_upi(cuda_device):
     import bocf_b200
     from oracle import acquisitions as OA
     from tests.helpers import oracle_utility
-    idx = rng.choice(P.N, 96, replace=False)
+    idx = _stratified(P.N, model.chunk_candidates(P.N, grad=True), rng, 1200)
+    assert len(idx) >= 2048
     # maEI with the 64 theta samples as an explicit sample set
     acq = bocf_b200.maEI(model, None, utility=product_utility(P))
     acq.use_full_support = False
@@ -107,7 +125,9 @@ def test_cfg4_parameter_uncertain_maei_upi(cuda_device):
     o = OA.maEI(om, utility=oracle_utility(P), utility_params_samples=P.theta)
     o.use_full_support = False
     a_o, g_o = o._compute_acq_withGradients(P.Xc[idx])
-    assert a.shape == (P.N, 1) and rel_err(a[idx], a_o) < tol(1e-8) and rel_err(g[idx], g_o) < tol(1e-7)
+    assert a.shape == (P.N, 1)
+    assert_close(a[idx], a_o, tol(1e-8), "maEI")
+    assert_close(g[idx], g_o, tol(1e-7), "grad maEI")
     # uPI with 64 sum-of-squares targets
     P2 = make_problem(m=8, d=8, n=500, H=1, kind="matern52", composite="sumsq_target", N=32768, S=256, L=64, seed=4,
                       focus=0.1)
@@ -121,7 +141,7 @@ def test_cfg4_parameter_uncertain_maei_upi(cuda_device):
                 vectorised=True)
     o2.use_full_support = False
     o2.utility_params_samples = P2.theta
-    idx2 = np.concatenate([np.argsort(-v)[:32], rng.choice(P2.N, 32, replace=False)])
+    idx2 = np.unique(np.concatenate([np.argsort(-v)[:256], rng.choice(P2.N, 768, replace=False), np.arange(P2.N - 300, P2.N)]))
     v_o = o2._compute_acq(P2.Xc[idx2])[:, 0]
     assert np.max(np.abs(v[idx2] - v_o)) < tol(1e-12) and v.max() > 0
 
@@ -131,13 +151,20 @@ def test_cfg5_large_n_cholesky_and_variance(cuda_device):
     triangular-solve variance and its gradient, 512 MC samples."""
     P = make_problem(m=4, d=10, n=4000, H=1, kind="matern52", composite="sumsq_target", N=4096, S=512, L=1, seed=5,
                      prior_draw=False, focus=0.2)
+    P.N = 4096 - 57                                                   # ragged last candidate tile
+    P.Xc = P.Xc[:P.N]
     model = product_model(P, cuda_device)
     assert np.all(model.jitter_added == 0)
     om = oracle_model(P)
     L, Linv, alpha = model.get_factor(0, 2)
     gp = om.output[2].model_instances[0]
     assert rel_err(L, gp.woodbury_chol) < 1e-9 and rel_err(alpha, gp.woodbury_vector[:, 0]) < 1e-7
-    idx = np.random.default_rng(6).choice(P.N, 96, replace=False)
+    from bocf_b200 import _lib
+    _lib.check(model._lib.bocf_model_set_scratch_limit(model._handle, ctypes.c_uint64(256 << 20)))   # several chunks
+    chunk = model.chunk_candidates(P.N, grad=True)
+    assert chunk < P.N
+    idx = _stratified(P.N, chunk, np.random.default_rng(6), 1500)
+    assert len(idx) >= 2048
     Xs = P.Xc[idx]
     assert rel_err(model.posterior_mean(P.Xc)[:, idx], om.posterior_mean(Xs)) < tol(1e-8)
     v, vo = model.posterior_variance(P.Xc)[:, idx], om.posterior_variance(Xs)
@@ -145,7 +172,8 @@ def test_cfg5_large_n_cholesky_and_variance(cuda_device):
     assert rel_err(model.posterior_variance_gradient(P.Xc)[:, idx], om.posterior_variance_gradient(Xs)) < tol(1e-6)
     a, g, _ = _sweep(P, model)
     a_o, g_o = oracle_acq(P, grad=True, Xc=Xs, model=om)
-    assert rel_err(a[idx], a_o) < tol(1e-7) and rel_err(g[idx], g_o) < tol(1e-6)
+    assert_close(a[idx], a_o, tol(1e-7), "acq")
+    assert_close(g[idx], g_o, tol(1e-6), "grad acq")
 
 
 def test_small_scratch_limit_gives_identical_results(cuda_device):

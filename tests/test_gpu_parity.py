@@ -8,7 +8,7 @@ the EI-CF value / gradient bar of 1e-4 is the mixed-precision bar and is trivial
 import numpy as np
 import pytest
 
-from tests.helpers import (tol, make_problem, oracle_model, oracle_acq, product_model, product_acq, product_utility,
+from tests.helpers import (assert_close, tol, make_problem, oracle_model, oracle_acq, product_model, product_acq, product_utility,
                            rel_err)
 
 pytestmark = pytest.mark.gpu
@@ -52,6 +52,9 @@ def test_posterior_matches_oracle(cuda_device, kind, shape):
         assert rel_err(mu, mu_o) < tol(TOL_MEANVAR) and rel_err(v, v_o) < tol(TOL_MEANVAR)
         assert rel_err(mu, mu_o) < tol(TOL_TIGHT) and np.max(np.abs(v - v_o) / np.abs(v_o)) < tol(1e-7)
         assert rel_err(dm, dm_o) < tol(TOL_TIGHT) and rel_err(dv, dv_o) < tol(1e-7)
+        # element-wise (entries above 1 % of the largest: relative; below: 100x tighter than the norm-wise bar)
+        assert_close(dm, dm_o, tol(TOL_TIGHT), "dmean")
+        assert_close(dv, dv_o, tol(1e-7), "dvar")
         mp, vp = pm.predict(P.Xc)
         mo, vo = om.predict(P.Xc)
         assert rel_err(mp, mo) < tol(TOL_TIGHT) and rel_err(vp, vo) < tol(1e-7)
@@ -81,6 +84,8 @@ def test_eicf_value_and_gradient(cuda_device, composite, kind):
     assert np.mean(a_o > 0) > 0.02, "degenerate test problem"
     assert rel_err(a, a_o) < tol(1e-8), rel_err(a, a_o)
     assert rel_err(g, g_o) < tol(1e-7), rel_err(g, g_o)
+    assert_close(a, a_o, tol(1e-8), "acq")                     # element-wise as well (tests/helpers.py: elem_err)
+    assert_close(g, g_o, tol(1e-7), "grad acq")
     assert np.argmax(a) == np.argmax(a_o)                      # same selected candidate
     av, _ = product_acq(P, grad=False, device=cuda_device)
     avo, _ = oracle_acq(P, grad=False)
@@ -119,6 +124,8 @@ def test_analytic_variants(cuda_device, variant):
     a_o, g_o = oracle_acq(P, grad=True, variant=variant)
     a, g = product_acq(P, grad=True, variant=variant, device=cuda_device)
     assert rel_err(a, a_o) < tol(1e-8) and rel_err(g, g_o) < tol(1e-7)
+    assert_close(a, a_o, tol(1e-8), "acq")
+    assert_close(g, g_o, tol(1e-7), "grad acq")
     av_o, _ = oracle_acq(P, grad=False, variant=variant)
     av, _ = product_acq(P, grad=False, variant=variant, device=cuda_device)
     assert rel_err(av, av_o) < tol(1e-8)
