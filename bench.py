@@ -37,14 +37,17 @@ CONFIGS = {
     "cfg5": dict(m=32, d=10, n=4000, kind="matern52", composite="sumsq_target", S=512, H=1, L=1, N=500000),
     # BASELINE.json configs[1]
     "cfg2": dict(m=4, d=6, n=200, kind="rbf", composite="sumsq_target", S=256, H=1, L=1, N=100000),
+    # BASELINE.json configs[3]: parameter-uncertain utility, 64 theta samples, analytic maEI of the linear scalarisation
+    "cfg4": dict(m=8, d=8, n=500, kind="matern52", composite="linear", S=256, H=1, L=64, N=262144, variant="maEI"),
 }
 K_TOP = 16
 
 
 def f_grad(c):
-    """Algorithmic flops per evaluation with gradients, SURVEY.md 8(d)."""
+    """Algorithmic flops per evaluation with gradients, SURVEY.md 8(d) (analytic variants: L (4m + 2md + 30))."""
     m, n, d, S, H, L = c["m"], c["n"], c["d"], c["S"], c["H"], c["L"]
-    return H * (m * (2 * n * n + n * (7 * d + 14)) + L * S * (12 * m + 2) + 4 * m * d)
+    acq = L * (4 * m + 2 * m * d + 30) if c.get("variant") in ("maEI", "maPI") else L * S * (12 * m + 2)
+    return H * (m * (2 * n * n + n * (7 * d + 14)) + acq + 4 * m * d)
 
 
 # ---- clocks ------------------------------------------------------------------------------------------------
@@ -200,10 +203,94 @@ def run_reference(args, cfg):
 def workload_config(c, n_per_gpu):
     return {"workload": "BASELINE.json configs[%d]: synthetic independent multi-output GP m=%d d=%d n=%d %s-ARD, "
                         "%s composite, EI-CF with gradients, %d MC base samples, H=%d, L=%d"
-                        % ({1000: 2, 200: 1, 4000: 4}.get(c["n"], 2), c["m"], c["d"], c["n"], c["kind"], c["composite"],
+                        % ({1000: 2, 200: 1, 4000: 4, 500: 3}.get(c["n"], 2), c["m"], c["d"], c["n"], c["kind"], c["composite"],
                            c["S"], c["H"], c["L"]),
             "candidates_per_gpu_per_step": int(n_per_gpu), "mc_samples": c["S"], "top_k": K_TOP,
             "l2": "256 MiB flush between steps; per-step K*/V scratch (GiBs) far exceeds the 126 MB L2"}
+
+
+def bf16_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1400.0)), True
+    except Exception:
+        return 1400.0, False
+
+
+def quick_sweep(cname, N, dev, precision, steps=2, warmup=2, e2e=True, seed=0):
+    """A short device-resident (+ end-to-end) sweep of another BASELINE.json configuration or contraction mode on this
+    rank's GPU: {value, ms_per_step, e2e, roofline of its dominant contraction}.  Same timing rules as the headline
+    (CUDA events, L2 flushed between steps, per-kernel events in a separate pass)."""
+    import torch
+    import bocf_b200
+    from bocf_b200 import _lib
+    from tests.helpers import make_problem, product_model, product_utility
+    c = dict(CONFIGS[cname])
+    variant = c.get("variant", "uEI_noiseless")
+    P = make_problem(m=c["m"], d=c["d"], n=c["n"], H=c["H"], kind=c["kind"], composite=c["composite"], N=4096,
+                     S=c["S"], L=c["L"], seed=seed, prior_draw=c["n"] <= 2500)
+    model = product_model(P, str(dev), precision=precision)
+    acq = getattr(bocf_b200, variant)(model, None, utility=product_utility(P))
+    if variant == "uEI_noiseless":
+        acq.W_samples = P.Z
+    else:                                  # the 64 theta samples as an explicit sample set (tests/test_gpu_fullsize.py)
+        acq.use_full_support = False
+        acq.utility.parameter_dist.sample = lambda k: P.theta
+    Xh = torch.from_numpy(np.random.default_rng(7).uniform(size=(N, c["d"]))).pin_memory()
+    Xd = Xh.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_dev():
+        model.set_hyperparameters(0)
+        a, g = acq._compute_acq_withGradients(Xd)
+        return a
+
+    def timed(fn, k, profile=False):
+        torch.cuda.synchronize()
+        if profile:
+            _lib.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(k):
+            fn()
+            flush.zero_()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        prof = _lib.profile_report() if profile else None
+        if profile:
+            _lib.profile_enable(False)
+        return e0.elapsed_time(e1), wall, prof
+
+    for _ in range(warmup):
+        step_dev()
+        flush.zero_()
+    ms, _, _ = timed(step_dev, steps)
+    _, _, prof = timed(step_dev, steps, profile=True)
+    out = {"config": workload_config(c, N), "precision_mode": precision, "schemes": list(model.active_scheme()),
+           "value": steps * N / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup}
+    gemms = [k for k in ("split_dvar_kernel", "split_var_kernel", "dvar_gemm_kernel", "var_gemm_kernel") if k in prof]
+    if gemms:
+        dom = max(gemms, key=lambda k: prof[k][1])
+        cnt, tot = prof[dom]
+        tf = c["m"] * float(c["n"]) ** 2 * (steps * N / cnt) / (tot / cnt * 1e-3) / 1e12
+        peak, measured = bf16_peak()
+        out["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": tf, "unit": "TFLOP/s",
+                           "peak": peak if model.active_slices() else None,
+                           "frac": tf / peak if model.active_slices() else None,
+                           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if measured else "fallback 1400",
+                           "kernel_ms_per_step": {k: v[1] / steps for k, v in prof.items()}}
+    if e2e:
+        def step_host():
+            model.set_hyperparameters(0)
+            return acq.acquisition_function_withGradients(Xh.numpy())
+        step_host()
+        _, wall, _ = timed(step_host, steps)
+        out["e2e"] = {"value": steps * N / (wall * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": int(N * c["d"] * 8),
+                      "d2h_bytes_per_step": int(N * 8 + N * c["d"] * 8), "ms_per_step": wall / steps}
+    del model, acq, Xd, flush
+    torch.cuda.empty_cache()
+    return out
 
 
 # ---- our arm -----------------------------------------------------------------------------------------------
@@ -329,6 +416,57 @@ def run_ours(args, cfg):
     ms_prof, _, _, prof = timed(step_device, args.steps, profile=True)
     step_host()                                                     # warm the host path (pinned staging, allocator)
     _, ms_e2e, _, _ = timed(step_host, args.steps)
+
+    # STRONG scaling next to the weak headline: BASELINE.json configs[2] as written -- 1M candidates in total, sharded
+    # over the ranks (bocf_b200.distributed.shard_bounds), same exchange step
+    strong = None
+    if world > 1 and not args.no_strong:
+        n_total = c["N"]
+        lo, hi = bd.shard_bounds(n_total, world, rank)
+        Xs = Xd[: hi - lo]
+
+        def step_strong():
+            model.set_hyperparameters(0)
+            a, g = acq._compute_acq_withGradients(Xs)
+            rec = bd.local_topk(a, Xs, K_TOP, index_offset=lo)
+            return bd.allgather_topk(rec, K_TOP)
+        for _ in range(2):
+            step_strong()
+            flush.zero_()
+        ms_s, _, _, _ = timed(step_strong, args.steps)
+        strong = {"scaling": "strong", "candidates_total_per_step": int(n_total), "candidates_per_gpu_per_step": int(hi - lo),
+                  "value": args.steps * n_total / (ms_s * 1e-3), "unit": "evals/s", "ms_per_step": ms_s / args.steps}
+    # BASELINE.json configs[4] on >= 4 GPUs: 4M candidates x 512 samples sharded over the ranks, m=32, n=4000 (the model
+    # is replicated: 32 factors of 4000^2 per GPU, factorised on every rank -- 79 ms, cheaper than sharding + all-gather)
+    cfg5 = None
+    if world >= 4 and not args.no_cfg5:
+        del Xd
+        torch.cuda.empty_cache()
+        c5 = dict(CONFIGS["cfg5"])
+        n5 = 4000000 // world
+        P5 = make_problem(m=c5["m"], d=c5["d"], n=c5["n"], H=1, kind=c5["kind"], composite=c5["composite"], N=4096,
+                          S=c5["S"], L=1, seed=0, prior_draw=False)
+        t0 = time.perf_counter()
+        model5 = product_model(P5, str(dev), precision=args.precision)
+        torch.cuda.synchronize()
+        t_fac5 = time.perf_counter() - t0
+        acq5 = bocf_b200.uEI_noiseless(model5, None, utility=product_utility(P5))
+        acq5.W_samples = P5.Z
+        X5 = torch.from_numpy(np.random.default_rng(7 + 1000 * rank).uniform(size=(n5, c5["d"]))).to(dev)
+
+        def step5():
+            model5.set_hyperparameters(0)
+            a, g = acq5._compute_acq_withGradients(X5)
+            rec = bd.local_topk(a, X5, K_TOP, index_offset=rank * n5)
+            return bd.allgather_topk(rec, K_TOP)
+        step5()
+        flush.zero_()
+        ms5, _, _, _ = timed(step5, 1)
+        cfg5 = {"config": workload_config(c5, n5), "candidates_total_per_step": int(n5 * world), "value": n5 * world / (ms5 * 1e-3),
+                "unit": "evals/s", "ms_per_step": ms5, "steps": 1, "warmup": 1, "schemes": list(model5.active_scheme()),
+                "factorize_cold_s": t_fac5}
+        del model5, acq5, X5
+        torch.cuda.empty_cache()
 
     # fp64 peak: cuBLAS DGEMM 8192^3, best of 5, measured here because MEASURED_PEAKS.json has no fp64 entry
     peak_tf = None
@@ -457,6 +595,21 @@ def run_ours(args, cfg):
                          "tests/test_gpu_split.py::test_auto_and_mixed_pick_their_schemes)"}
         model.set_precision(args.precision)
 
+    # the other BASELINE.json configurations and the fp64 DMMA mode, each as a short sweep on the same GPU
+    extras = None
+    if world == 1 and not args.no_extras:
+        del Xd
+        torch.cuda.empty_cache()
+        extras = {}
+        for key, cname, n_x, prec, kw in (("fp64_dmma_mode", args.config, 262144, "fp64", dict(steps=2, warmup=1)),
+                                          ("cfg2", "cfg2", 100000, args.precision, dict(steps=10, warmup=3)),
+                                          ("cfg4_maEI_L64", "cfg4", 262144, args.precision, dict(steps=3, warmup=2)),
+                                          ("cfg5_500k_share", "cfg5", 500000, args.precision, dict(steps=1, warmup=1, e2e=False))):
+            try:
+                extras[key] = quick_sweep(cname, n_x, dev, prec, **kw)
+            except Exception as exc:                       # an extra must never cost the headline line
+                extras[key] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate_l, done_l, el_l = cpu_literal_rate(P, args.cpu_budget)
@@ -484,6 +637,7 @@ def run_ours(args, cfg):
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "mixed_precision_mode": mixed,
         "cand_x_samples_per_s": value * c["S"], "factorize_s": t_factor, "factorize_warm_s": t_factor_warm,
         "factorize_warm_tflops": factor_flops / t_factor_warm / 1e12, "step_ms": value_step_ms,
+        "strong_scaling": strong, "cfg5_sharded": cfg5, "other_configs": extras,
     }
     print(json.dumps(line))
     if world > 1:
@@ -502,7 +656,10 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=96, help="candidates per step of the reference arm")
     ap.add_argument("--cpu-budget", type=float, default=16.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-mixed", action="store_true", help="skip the extra 4-digit-plane measurement")
+    ap.add_argument("--no-mixed", action="store_true", help="skip the extra mixed-precision measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short sweeps of the other configs / fp64 mode (N=1)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling pass (N>1)")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the sharded configs[4] pass (N>=4)")
     ap.add_argument("--precision", default="auto", choices=["auto", "mixed", "fp64", "split3", "split4", "split5", "split6", "split54", "split43", "split53", "split44"],
                     help="arithmetic of the factor contractions (include/bocf_b200.h: enum bocf_precision)")
     args = ap.parse_args()

@@ -18,7 +18,7 @@ EXPORTS = [
     "bocf_last_error", "bocf_version", "bocf_launch_count",
     "bocf_model_create", "bocf_model_destroy", "bocf_model_set_data", "bocf_model_set_hypers",
     "bocf_model_factorize", "bocf_model_get_factor", "bocf_model_n", "bocf_model_H",
-    "bocf_model_set_scratch_limit", "bocf_posterior", "bocf_acq_eval", "bocf_acq_eval_host",
+    "bocf_model_set_scratch_limit", "bocf_posterior", "bocf_posterior_cov_point", "bocf_acq_eval", "bocf_acq_eval_host",
     "bocf_utility_eval", "bocf_topk", "bocf_profile_enable", "bocf_profile_report",
     "bocf_model_set_precision", "bocf_model_active_slices", "bocf_model_active_scheme", "bocf_model_chunk_candidates", "bocf_debug_split_gemm", "bocf_model_log_likelihood", "bocf_model_append_point",
 ]
@@ -73,6 +73,7 @@ def load_library():
     lib.bocf_model_H.argtypes = [c_vp]
     lib.bocf_model_set_scratch_limit.argtypes = [c_vp, u64]
     lib.bocf_posterior.argtypes = [c_vp, i32, c_dp, i64, i32, c_dp, c_dp, c_dp, c_dp, c_vp]
+    lib.bocf_posterior_cov_point.argtypes = [c_vp, i32, c_dp, i64, c_dp, c_dp, c_dp, c_vp]
     lib.bocf_acq_eval.argtypes = [c_vp, i32, i32, c_dp, i64, c_dp, i32, c_dp, i32, i32, c_dp, c_dp, i32, i32,
                                   c_dp, c_dp, c_vp]
     lib.bocf_acq_eval_host.argtypes = lib.bocf_acq_eval.argtypes

@@ -106,6 +106,7 @@ class AcquisitionBase(object):
         H_loaded = self.model.n_hyper_samples_loaded()
         return 1 if (self.model.fixed_hyps or H_loaded == 1) else min(self.n_hyps_samples, H_loaded)
 
+    HOST_ENTRY_MAX = 4096       # numpy inputs up to this long go through ONE C call (bocf_acq_eval_host)
     PIPELINE_MIN = 1 << 17      # numpy inputs at least this long are streamed through the device in slabs
     PIPELINE_SLABS = 4
 
@@ -116,12 +117,41 @@ class AcquisitionBase(object):
             Xn = np.atleast_2d(np.asarray(X, dtype=np.float64))
             if Xn.shape[0] >= self.PIPELINE_MIN:
                 return self._run_pipelined(variant, np.ascontiguousarray(Xn), theta, weight, fstar, grad, Zt, S, form)
+            if Xn.shape[0] <= self.HOST_ENTRY_MAX:
+                return self._eval_host_small(variant, np.ascontiguousarray(Xn), theta, weight, fstar, grad, Zt, S, form)
         Xd, is_t = model._dev_in(X)
         acq, dacq = self._eval_device(variant, Xd, theta, weight, fstar, grad, Zt, S, form)
         acq = acq.reshape(-1, 1)
         if not is_t:
             acq = self._to_host(acq)
             dacq = None if dacq is None else self._to_host(dacq)
+        return (acq, dacq) if grad else acq
+
+    def _eval_host_small(self, variant, Xn, theta, weight, fstar, grad, Zt, S, form):
+        """Small numpy batches (the L-BFGS rounds of the acquisition optimiser): one C call does the H2D copy, the sweep
+        and the D2H copies with a single stream synchronisation (bocf_acq_eval_host), no torch tensors in between."""
+        model = self.model
+        N, d = Xn.shape
+        L = theta.shape[0]
+        th_h, th_p = _host(theta)
+        w_h, w_p = _host(weight)
+        f_h, f_p = _host(fstar)
+        if w_h.size != L or f_h.ndim != 2 or f_h.shape[1] != L:
+            raise ValueError("need one weight and one incumbent column per utility parameter: L=%d, %d weights, f* %s"
+                             % (L, w_h.size, f_h.shape))
+        acq = np.empty((N, 1))
+        dacq = np.empty((N, d)) if grad else None
+        with model._lock, torch.cuda.device(model.device):
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(model._lib.bocf_acq_eval_host(
+                model._handle, _lib.VARIANTS[variant], _lib.COMPOSITES[self.utility.composite],
+                Xn.ctypes.data_as(ctypes.c_void_p), N, _ptr(Zt), S, th_p, L, theta.shape[1], w_p, f_p, f_h.shape[0], form,
+                acq.ctypes.data_as(ctypes.c_void_p), None if dacq is None else dacq.ctypes.data_as(ctypes.c_void_p), st))
+        if self._sign < 0:
+            np.negative(acq, out=acq)
+            if dacq is not None:
+                np.negative(dacq, out=dacq)
+        self._mark_sign_applied()
         return (acq, dacq) if grad else acq
 
     def _eval_device(self, variant, Xd, theta, weight, fstar, grad, Zt, S, form):
@@ -235,7 +265,26 @@ class uEI_noiseless(AcquisitionBase):
         return Zt
 
     def _fstar_current(self, theta):
-        """max_n U(theta_l, mu(X_n)) under the CURRENTLY selected hyper-sample: (L,)."""
+        """max_n U(theta_l, mu(X_n)) under the CURRENTLY selected hyper-sample: (L,).
+
+        The reference recomputes it in every call (uEI_noiseless.py:66,76,141,155); it depends only on the factorised
+        model, the selected hyper-sample and theta, so it is cached on exactly those (the L-BFGS rounds of one
+        acquisition optimisation call this ~100 times with the same model: a 1000-candidate posterior mean, a utility
+        sweep and a device->host sync each)."""
+        model = self.model
+        theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        key = (id(model), model._version, model._current_h, self.utility.composite, theta.shape, theta.tobytes())
+        cache = self.__dict__.setdefault("_fstar_cache", {})
+        hit = cache.get(key)
+        if hit is not None:
+            return hit.copy()
+        if len(cache) > 64:
+            cache.clear()
+        val = self._fstar_compute(theta)
+        cache[key] = val
+        return val.copy()
+
+    def _fstar_compute(self, theta):
         model = self.model
         fX = model._posterior_mean_at_evaluated_points_dev()                  # (m, n) on device
         theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))

@@ -149,6 +149,42 @@ static int resolve_precision(bocf_model* M, cudaStream_t st) {
   return 0;
 }
 
+// Pinned / device parameter ring of the handle (see bocf_acq_eval).
+template <class Fill>
+static int stage_params(bocf_model* M, size_t doubles, double** dev_out, cudaStream_t st, Fill fill) {
+  const size_t bytes = doubles * sizeof(double);
+  if (bytes > M->par_slot_bytes) {                       // (re)allocate: rare, synchronises
+    cudaStreamSynchronize(st);
+    for (int s = 0; s < bocf_model::PAR_SLOTS; ++s)
+      if (M->par_event[s]) {
+        cudaEventDestroy(M->par_event[s]);
+        M->par_event[s] = nullptr;
+      }
+    if (M->par_host) cudaFreeHost(M->par_host);
+    if (M->par_dev) cudaFree(M->par_dev);
+    M->par_host = M->par_dev = nullptr;
+    size_t slot = 4096;
+    while (slot < bytes) slot *= 2;
+    BOCF_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&M->par_host), slot * bocf_model::PAR_SLOTS, cudaHostAllocDefault));
+    BOCF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->par_dev), slot * bocf_model::PAR_SLOTS));
+    M->par_slot_bytes = slot;
+    M->par_next = 0;
+  }
+  const int s = M->par_next;
+  M->par_next = (s + 1) % bocf_model::PAR_SLOTS;
+  if (M->par_event[s]) BOCF_CUDA_OK(cudaEventSynchronize(M->par_event[s]));     // normally long complete
+  else BOCF_CUDA_OK(cudaEventCreateWithFlags(&M->par_event[s], cudaEventDisableTiming));
+  double* host = reinterpret_cast<double*>(reinterpret_cast<char*>(M->par_host) + (size_t)s * M->par_slot_bytes);
+  double* dev = reinterpret_cast<double*>(reinterpret_cast<char*>(M->par_dev) + (size_t)s * M->par_slot_bytes);
+  fill(host);
+  BOCF_CUDA_OK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st));
+  // the DEVICE slot is read by kernels enqueued after this copy on the same stream; it is overwritten PAR_SLOTS calls
+  // later by a copy that the stream orders behind them.  The event guards the HOST slot.
+  BOCF_CUDA_OK(cudaEventRecord(M->par_event[s], st));
+  *dev_out = dev;
+  return 0;
+}
+
 static int check_ready(const bocf_model* M) {
   if (!M) {
     set_error("null model handle");
@@ -297,6 +333,11 @@ int bocf_model_destroy(bocf_model* M) {
   free_factor(M);
   dev_free(M->hyp);
   if (M->scratch) cudaFree(M->scratch);
+  for (int s = 0; s < bocf_model::PAR_SLOTS; ++s)
+    if (M->par_event[s]) cudaEventDestroy(M->par_event[s]);
+  if (M->par_host) cudaFreeHost(M->par_host);
+  if (M->par_dev) cudaFree(M->par_dev);
+  if (M->io_buf) cudaFree(M->io_buf);
   delete M;
   return 0;
 }
@@ -551,7 +592,7 @@ static int scatter_out(const double* src, int64_t Nc, double* dst, int64_t N, in
 int bocf_posterior(bocf_model* M, int h, const double* Xc, int64_t N, int noiseless, double* mean, double* var,
                    double* dmean, double* dvar, void* stream) {
   if (int rc = check_ready(M)) return rc;
-  if (h < 0 || h >= M->H || !Xc || N < 0) {
+  if (h < 0 || h >= M->H || !Xc || N < 0 || noiseless < 0 || noiseless > 2) {
     set_error("bocf_posterior: invalid arguments");
     return BOCF_ERR_INVALID;
   }
@@ -566,7 +607,7 @@ int bocf_posterior(bocf_model* M, int h, const double* Xc, int64_t N, int noisel
   carve_chunk(M, M->scratch, Nc, grad, &cb);
   for (int64_t off = 0; off < N; off += Nc) {
     const int64_t cnt = (N - off < Nc) ? N - off : Nc;
-    if (int rc = launch_posterior_chunk(M, h, Xc + off * M->d, cnt, grad, noiseless != 0, cb, st, var != nullptr,
+    if (int rc = launch_posterior_chunk(M, h, Xc + off * M->d, cnt, grad, noiseless, cb, st, var != nullptr,
                                         dvar != nullptr))
       return rc;
     if (int rc = scatter_out(cb.mean, Nc, mean, N, off, cnt, M->m, 1, st)) return rc;
@@ -578,6 +619,20 @@ int bocf_posterior(bocf_model* M, int h, const double* Xc, int64_t N, int noisel
       if (int rc = scatter_out(cb.dvar, Nc, dvar, N, off, cnt, M->m, M->d, st)) return rc;
   }
   return 0;
+}
+
+int bocf_posterior_cov_point(bocf_model* M, int h, const double* Xc, int64_t N, const double* x2, double* cov,
+                             double* dcov, void* stream) {
+  if (int rc = check_ready(M)) return rc;
+  if (h < 0 || h >= M->H || !Xc || !x2 || !cov || N < 0) {
+    set_error("bocf_posterior_cov_point: invalid arguments");
+    return BOCF_ERR_INVALID;
+  }
+  if (N == 0) return 0;
+  DeviceGuard dg(M->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = ensure_scratch(M, sizeof(double) * 3 * (size_t)M->m * M->n_pad + 256)) return rc;
+  return launch_cov_point(M, h, Xc, N, x2, cov, dcov, reinterpret_cast<double*>(M->scratch), st);
 }
 
 int bocf_acq_eval(bocf_model* M, int variant, int composite, const double* Xc, int64_t N, const double* Zt, int S,
@@ -613,21 +668,25 @@ int bocf_acq_eval(bocf_model* M, int variant, int composite, const double* Xc, i
   if (int rc = resolve_precision(M, st)) return rc;
   const bool grad = (dacq != nullptr);
 
-  // small host-side parameters -> tail of the scratch buffer
+  // small host-side parameters (theta, weights, f*): staged through a handle-owned ring of PINNED slots and copied
+  // to a matching ring of device slots, so the call never synchronises the stream (the L-BFGS rounds of the acquisition
+  // optimiser are latency-bound: ~100 calls of <= 17 candidates per BO iteration).  A slot is reused only after the copy
+  // that read it has completed (event per slot).
   const size_t n_theta = (size_t)L * (p > 0 ? p : 1);
   const size_t par_doubles = n_theta + (size_t)L + (size_t)H_use * L;
   const int64_t Nc = pick_chunk(M, N, grad, 0);
   const uint64_t chunk_bytes = chunk_bytes_per_candidate(M, grad) * Nc + (1 << 16);
-  if (int rc = ensure_scratch(M, chunk_bytes + par_doubles * sizeof(double) + 256)) return rc;
+  if (int rc = ensure_scratch(M, chunk_bytes + 256)) return rc;
   ChunkBuffers cb;
   carve_chunk(M, M->scratch, Nc, grad, &cb);
-  double* par = reinterpret_cast<double*>(reinterpret_cast<char*>(M->scratch) + (chunk_bytes / 256 + 1) * 256);
-  std::vector<double> hostpar(par_doubles, 0.0);
-  if (p > 0) std::memcpy(hostpar.data(), theta, sizeof(double) * L * p);
-  std::memcpy(hostpar.data() + n_theta, weight, sizeof(double) * L);
-  std::memcpy(hostpar.data() + n_theta + L, fstar, sizeof(double) * H_use * L);
-  BOCF_CUDA_OK(cudaMemcpyAsync(par, hostpar.data(), sizeof(double) * par_doubles, cudaMemcpyHostToDevice, st));
-  BOCF_CUDA_OK(cudaStreamSynchronize(st));   // hostpar is pageable and goes out of scope
+  double* par = nullptr;
+  if (int rc = stage_params(M, par_doubles, &par, st, [&](double* host) {
+        if (p > 0) std::memcpy(host, theta, sizeof(double) * L * p);
+        else host[0] = 0.0;
+        std::memcpy(host + n_theta, weight, sizeof(double) * L);
+        std::memcpy(host + n_theta + L, fstar, sizeof(double) * H_use * L);
+      }))
+    return rc;
 
   AcqParams P;
   P.variant = variant;
@@ -648,7 +707,7 @@ int bocf_acq_eval(bocf_model* M, int variant, int composite, const double* Xc, i
   for (int64_t off = 0; off < N; off += Nc) {
     const int64_t cnt = (N - off < Nc) ? N - off : Nc;
     for (int h = 0; h < H_use; ++h) {
-      if (int rc = launch_posterior_chunk(M, h, Xc + off * M->d, cnt, grad, marginal, cb, st, !mean_only, !mean_only))
+      if (int rc = launch_posterior_chunk(M, h, Xc + off * M->d, cnt, grad, marginal ? 1 : 0, cb, st, !mean_only, !mean_only))
         return rc;
       P.fstar = par + n_theta + L + (size_t)h * L;
       P.accumulate = (h > 0) ? 1 : 0;
@@ -670,12 +729,21 @@ int bocf_acq_eval_host(bocf_model* M, int variant, int composite, const double* 
   if (N == 0) return 0;
   DeviceGuard dg(M->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  double *dX = nullptr, *dA = nullptr, *dG = nullptr;
+  // grow-only device staging owned by the handle (cudaMalloc / cudaFree per call cost more than a small sweep)
+  const size_t need = (size_t)N * (2 * M->d + 1);
+  if (M->io_doubles < need) {
+    cudaStreamSynchronize(st);
+    if (M->io_buf) cudaFree(M->io_buf);
+    M->io_buf = nullptr;
+    M->io_doubles = 0;
+    if (int rc0 = dev_alloc(&M->io_buf, need)) return rc0;
+    M->io_doubles = need;
+  }
+  double* dX = M->io_buf;
+  double* dA = dX + (size_t)N * M->d;
+  double* dG = dacq_host ? dA + N : nullptr;
   int rc = 0;
   do {
-    if ((rc = dev_alloc(&dX, (size_t)N * M->d))) break;
-    if ((rc = dev_alloc(&dA, (size_t)N))) break;
-    if (dacq_host && (rc = dev_alloc(&dG, (size_t)N * M->d))) break;
     if (cudaMemcpyAsync(dX, Xc_host, sizeof(double) * N * M->d, cudaMemcpyHostToDevice, st) != cudaSuccess) {
       set_error("H2D copy of candidates failed");
       rc = BOCF_ERR_CUDA;
@@ -692,9 +760,6 @@ int bocf_acq_eval_host(bocf_model* M, int variant, int composite, const double* 
       break;
     }
   } while (0);
-  dev_free(dX);
-  dev_free(dA);
-  dev_free(dG);
   return rc;
 }
 

@@ -44,6 +44,16 @@ struct bocf_model {
   double* tvec = nullptr;     // H*m x n_pad           L^-1 (y - ybar)
   int* info = nullptr;        // H*m                   first failing pivot (1-based) or 0
 
+  // small per-call parameters (theta, weights, f*): ring of pinned host slots + device slots, one event per slot
+  static constexpr int PAR_SLOTS = 8;
+  void* par_host = nullptr;
+  void* par_dev = nullptr;
+  size_t par_slot_bytes = 0;
+  int par_next = 0;
+  cudaEvent_t par_event[PAR_SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double* io_buf = nullptr;   // grow-only staging of bocf_acq_eval_host (candidates in, acq / gradient out)
+  size_t io_doubles = 0;
+
   void* scratch = nullptr;
   uint64_t scratch_bytes = 0;
   uint64_t scratch_limit = 4ull << 30;
@@ -107,7 +117,8 @@ uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad);
 void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* out);
 // Posterior of hyper-sample h for candidates Xc[0..Nvalid) into the chunk buffers.
 // grad: also K*-side gradient quantities (dmean, G*); need_var / need_dvar select the two contractions.
-int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, bool noiseless,
+// noiseless: 0 = likelihood variance added, clipped at 1e-10; 1 = noiseless, clipped; 2 = noiseless, not clipped
+int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, int noiseless,
                            const ChunkBuffers& cb, cudaStream_t st, bool need_var = true, bool need_dvar = true);
 
 // ---- split_gemm.cu ------------------------------------------------------------------------------
@@ -124,6 +135,12 @@ void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, C
 int launch_split_var(bocf_model* M, int h, const ChunkBuffers& cb, bool need_dvar, cudaStream_t st);
 int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, const ChunkBuffers& cb, cudaStream_t st);
 int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int sch, int tri, double* out, cudaStream_t st);
+
+// ---- kg.cu --------------------------------------------------------------------------------------
+// cov (m x N), dcov (m x N x d, may be NULL): posterior covariance between each candidate and the point x2 [dev, d];
+// work [dev]: 3 * m * n_pad doubles
+int launch_cov_point(bocf_model* M, int h, const double* Xc, int64_t N, const double* x2, double* cov, double* dcov,
+                     double* work, cudaStream_t st);
 
 // ---- acq.cu -------------------------------------------------------------------------------------
 struct AcqParams {

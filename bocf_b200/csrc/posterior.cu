@@ -364,7 +364,7 @@ __global__ void finalize_kernel(const double* __restrict__ part_var, const doubl
     for (int tI = 0; tI < nct; ++tI) s += part_var[((int64_t)j * nct + tI) * Nc + idx];
     double v = hp.variance - s;
     if (!noiseless) v = hp.noise + v;
-    var[(int64_t)j * Nc + idx] = fmax(v, 1e-10);
+    var[(int64_t)j * Nc + idx] = (noiseless == 2) ? v : fmax(v, 1e-10);     // 2: the KG helpers' unclipped form (gp.py:543)
   }
   if (grad && idx < Nc * d) {
     const int q = (int)(idx % d);
@@ -467,7 +467,7 @@ static int launch_kstar_k(bocf_model* M, int h, const double* Xc, int64_t Nvalid
   return launch_kstar_t<KIND, MAXD>(M, h, Xc, Nvalid, grad, cb, st);
 }
 
-int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, bool noiseless,
+int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, int noiseless,
                            const ChunkBuffers& cb, cudaStream_t st, bool need_var, bool need_dvar) {
   static bool attrs[64] = {false};               // per device: function attributes belong to the device's context
   if (M->device >= 0 && M->device < 64 && !attrs[M->device]) {
@@ -518,7 +518,7 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
   {
     ProfScope ps("finalize_kernel", st);
     finalize_kernel<<<fgrid, 256, 0, st>>>(cb.part_var, cb.part_dvar, M->hyp, cb.Nc, nct, nct_g, M->m, M->d, h,
-                                           need_dvar ? 1 : 0, noiseless ? 1 : 0, cb.var, cb.dvar,
+                                           need_dvar ? 1 : 0, noiseless, cb.var, cb.dvar,
                                            split ? cb.part_s0 : nullptr, Xc, Nvalid);
   }
   BOCF_LAUNCH_OK("finalize_kernel");

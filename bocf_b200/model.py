@@ -47,6 +47,7 @@ class multi_outputGP(object):
         # the C handle is stream-ordered and NOT thread-safe (shared scratch, selected hyper-sample): every call into it
         # takes this lock (the batched multistart optimiser runs one L-BFGS state machine per thread)
         self._lock = threading.RLock()
+        self._version = 0           # bumped whenever the factorised state changes (data, hyper-samples, append): cache key
         # GPModel's sampler settings (gpmodel.py:31: n_burnin=100, subsample_interval=10, step_size=1e-1, leapfrog_steps=20)
         self.n_burnin, self.subsample_interval = n_burnin, subsample_interval
         self.step_size, self.leapfrog_steps, self.max_iters = step_size, leapfrog_steps, max_iters
@@ -189,6 +190,7 @@ class multi_outputGP(object):
             xn = torch.from_numpy(np.ascontiguousarray(self.X[-1])).to(self.device)
             yn = torch.from_numpy(np.ascontiguousarray(self.Y[:, -1])).to(self.device)
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            self._version += 1
             rc = self._lib.bocf_model_append_point(self._handle, _ptr(xn), _ptr(yn), st)
             if rc == -5:                       # BOCF_ERR_UNSUPPORTED: buffers full / pivot not positive
                 return False
@@ -199,6 +201,7 @@ class multi_outputGP(object):
         return True
 
     def _upload_and_factorize(self, upload_data=True):
+        self._version += 1
         kind, variance, lengthscale, noise = self._hyp
         lib = self._lib
         d = self.input_dim
@@ -295,7 +298,7 @@ class multi_outputGP(object):
         X = np.atleast_2d(np.asarray(X, dtype=np.float64))
         return torch.from_numpy(np.ascontiguousarray(X)).to(self.device), False
 
-    def _posterior(self, X, want_mean=True, want_var=False, want_dmean=False, want_dvar=False, noiseless=False):
+    def _posterior(self, X, want_mean=True, want_var=False, want_dmean=False, want_dvar=False, noiseless=False, clip=True):
         if self._handle is None:
             raise RuntimeError("model has no data: call updateModel first")
         Xd, is_t = self._dev_in(X)
@@ -308,7 +311,8 @@ class multi_outputGP(object):
             dmean = torch.empty((m, N, d), dtype=torch.float64, device=self.device) if want_dmean else None
             dvar = torch.empty((m, N, d), dtype=torch.float64, device=self.device) if want_dvar else None
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(self._lib.bocf_posterior(self._handle, self._current_h, _ptr(Xd), N, 1 if noiseless else 0,
+            _lib.check(self._lib.bocf_posterior(self._handle, self._current_h, _ptr(Xd), N,
+                                                (1 if clip else 2) if noiseless else 0,
                                                 _ptr(mean), _ptr(var), _ptr(dmean), _ptr(dvar), st))
         outs = (mean if want_mean else None, var, dmean, dvar)
         if is_t:
@@ -343,6 +347,78 @@ class multi_outputGP(object):
             if is_t:
                 return val, g
             return val.cpu().numpy(), (None if g is None else g.cpu().numpy())
+
+    # ---- knowledge-gradient helpers (multi_outputGP.py:203-281,309-331 -> GPModel -> GPy/core/gp.py:493-627) --------
+    def _cov_point(self, X, x2, grad=False):
+        """(cov (m,N), dcov (m,N,d) or None): posterior covariance of the latent functions between the rows of X and the
+        single point x2 under the current hyper-sample (bocf_posterior_cov_point)."""
+        Xd, is_t = self._dev_in(X)
+        N, d = Xd.shape
+        x2d, _ = self._dev_in(np.asarray(x2, dtype=np.float64).reshape(1, -1) if not isinstance(x2, torch.Tensor) else x2.reshape(1, -1))
+        m = self.output_dim
+        with self._lock, torch.cuda.device(self.device):
+            cov = torch.empty((m, N), dtype=torch.float64, device=self.device)
+            dcov = torch.empty((m, N, d), dtype=torch.float64, device=self.device) if grad else None
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(self._lib.bocf_posterior_cov_point(self._handle, self._current_h, _ptr(Xd), N, _ptr(x2d), _ptr(cov),
+                                                          _ptr(dcov), st))
+        if is_t:
+            return cov, dcov
+        return cov.cpu().numpy(), (None if dcov is None else dcov.cpu().numpy())
+
+    def posterior_covariance_between_points(self, X1, X2):
+        """multi_outputGP.py:257-266 -> gp.py:577-585: (m, N1, N2); one device sweep per column of X2."""
+        X2 = np.atleast_2d(np.asarray(X2, dtype=np.float64))
+        return np.stack([self._cov_point(X1, x2)[0] for x2 in X2], axis=2)
+
+    def partial_precomputation_for_covariance(self, X):
+        """multi_outputGP.py:203-210 -> gp.py:493-501.  The reference caches W^-1 K(X_train, X); here the per-column
+        vectors beta = W^-1 k(X_train, x2) are rebuilt inside the device call (two matrix-vector products on the
+        resident factor), so this only records the points."""
+        self._pp_cov_X = np.atleast_2d(np.asarray(X, dtype=np.float64)).copy()
+
+    def posterior_covariance_between_points_partially_precomputed(self, X1, X2):
+        """multi_outputGP.py:269-281 -> gp.py:588-599 (X2 must be the points of partial_precomputation_for_covariance)."""
+        return self.posterior_covariance_between_points(X1, X2)
+
+    def posterior_covariance_gradient(self, X, x2):
+        """multi_outputGP.py:309-318 -> gp.py:601-609: d cov(X_i, x2) / d X_i, (m, N, d), x2 a single point."""
+        return self._cov_point(X, np.asarray(x2, dtype=np.float64).reshape(-1), grad=True)[1]
+
+    def partial_precomputation_for_covariance_gradient(self, x):
+        """multi_outputGP.py:213-220 -> gp.py:504-512 (see partial_precomputation_for_covariance)."""
+        self._pp_dcov_x = np.asarray(x, dtype=np.float64).reshape(-1).copy()
+
+    def posterior_covariance_gradient_partially_precomputed(self, X, x2):
+        """multi_outputGP.py:321-330 -> gp.py:612-627."""
+        return self.posterior_covariance_gradient(X, x2)
+
+    def partial_precomputation_for_variance_conditioned_on_next_point(self, next_point):
+        """multi_outputGP.py:223-230 -> gp.py:515-530.  The reference refactorises K(X u {x_next}) + (noise + 1e-8) I; the
+        same conditional variance follows from the resident factor by the rank-one Schur complement
+            var(x | x_next) = var_nl(x) - cov(x, x_next)^2 / (var_nl(x_next) + noise + 1e-8),
+        so only x_next and its own noiseless variance are kept."""
+        xn = np.asarray(next_point, dtype=np.float64).reshape(1, -1)
+        self._next_point = xn.copy()
+        self._next_h = self._current_h
+        _, v, _, _ = self._posterior(xn, want_var=True, noiseless=True, clip=False)
+        noise = self._noise_of_current()                                      # (m,)
+        self._next_s = v[:, 0] + noise + 1e-8                                 # Schur complement pivot per output
+
+    def _noise_of_current(self):
+        return np.asarray(self._hyp[3][self._current_h], dtype=np.float64)
+
+    def posterior_variance_conditioned_on_next_point(self, X):
+        """multi_outputGP.py:233-242 -> gp.py:533-544: (m, N); noiseless, NOT clipped (the reference does not clip here)."""
+        cov, _ = self._cov_point(X, self._next_point[0])
+        _, v, _, _ = self._posterior(X, want_var=True, noiseless=True, clip=False)
+        return v - cov ** 2 / self._next_s[:, None]
+
+    def posterior_variance_gradient_conditioned_on_next_point(self, X):
+        """multi_outputGP.py:245-254 -> gp.py:547-575: (m, N, d)."""
+        cov, dcov = self._cov_point(X, self._next_point[0], grad=True)
+        dv = self._posterior(X, want_dvar=True)[3]
+        return dv - (2.0 * cov / self._next_s[:, None])[:, :, None] * dcov
 
     def predict(self, X, full_cov=False):
         """multi_outputGP.py:138-149: (mean (m,N), variance incl. noise, clipped at 1e-10 (gpmodel.py:147))."""

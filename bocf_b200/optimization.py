@@ -149,7 +149,11 @@ class BatchedEvaluations(object):
 
     Each run calls `f_df(x)` with a single point; the calls of all still-running anchors are collected and evaluated
     together as one (N_active, d) batch.  Every run sees exactly the values it would have seen alone (candidates are
-    independent), so the per-anchor trajectories are those of the sequential reference."""
+    independent), so the per-anchor trajectories are those of the sequential reference.
+    One deviation, only when the utility parameter is SAMPLED (more than 20 support points or a continuous sampler):
+    the gradient call draws one fresh theta per call (uEI_noiseless.py:126, quirk q4), so a batched round shares one
+    draw across its anchors where the reference would draw one per anchor; with full support (every shipped script)
+    there is no draw and the runs are identical."""
 
     def __init__(self, f_df, n_runs):
         self.f_df = f_df
@@ -213,7 +217,10 @@ def optimize_anchors_batched(optimizer, anchor_points, f, f_df):
     if errors:
         raise errors[0]
     X_opt = np.vstack(out)
-    F_opt = np.asarray(f(X_opt)).reshape(-1)          # optimizer.py:464, one batched call
+    # optimizer.py:464 re-evaluates f at ONE point per anchor: single-candidate semantics (uEI_noiseless._compute_acq
+    # takes its sequential branch -- f* of the current hyper-sample -- for one candidate and the pool branch for more,
+    # uEI_noiseless.py:43-46), so the optima are scored one by one, like x_baseline in AcquisitionOptimizer.optimize
+    F_opt = np.concatenate([np.asarray(f(X_opt[i:i + 1])).reshape(-1) for i in range(n)])
     return [(np.atleast_2d(X_opt[i]), np.atleast_2d(F_opt[i])) for i in range(n)], be.batches
 
 

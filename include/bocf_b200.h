@@ -158,12 +158,22 @@ int bocf_model_set_scratch_limit(bocf_model* mdl, uint64_t bytes);
  *   mean  m x N      GP.posterior_mean            gp.py:380-400 -> posterior.py:299-305
  *   var   m x N      GP.posterior_variance (+noise) gp.py:403-418 -> posterior.py:308-320, clipped at
  *                    1e-10 as GPModel.posterior_variance does (gpmodel.py:174); noiseless=1 omits the
- *                    likelihood variance (gp.py:421-435, gpmodel.py:183)
+ *                    likelihood variance (gp.py:421-435, gpmodel.py:183); noiseless=2 omits it and the clip
+ *                    (the form the knowledge-gradient helpers use, gp.py:533-544)
  *   dmean m x N x d  GP.posterior_mean_gradient     gp.py:438-461 (Stationary.gradients_X / _grad_X)
  *   dvar  m x N x d  GP.posterior_variance_gradient gp.py:464-490 (not clipped, no noise term)
  * Stacking order is multi_outputGP's (multi_outputGP.py:165-191,284-306). */
 int bocf_posterior(bocf_model* mdl, int h, const double* Xc, int64_t N, int noiseless, double* mean,
                    double* var, double* dmean, double* dvar, void* stream);
+
+/* Posterior covariance of the latent functions between each of N candidates Xc [dev] N x d and ONE point x2 [dev] d,
+ * under hyper-sample h:  cov [dev] m x N,  dcov [dev, may be NULL] m x N x d = its gradient w.r.t. the candidate.
+ * Replaces GP.posterior_covariance_between_points[_partially_precomputed] (GPy/core/gp.py:577-599) and
+ * GP.posterior_covariance_gradient[_partially_precomputed] (gp.py:601-627) for one column X2 = x2; the
+ * conditioned-on-next-point variance helpers of gp.py:518-575 are built from it on the host side
+ * (bocf_b200/model.py).  fp64 throughout (no digit planes). */
+int bocf_posterior_cov_point(bocf_model* mdl, int h, const double* Xc, int64_t N, const double* x2, double* cov,
+                             double* dcov, void* stream);
 
 /* ---- acquisition: replaces _compute_acq / _compute_acq_withGradients ------------------------------
  * Xc   [dev] N x d candidates

@@ -4,7 +4,7 @@ Follows GPy/models/gp_regression.py:29-36 (GPRegression: Gaussian likelihood,
 normalizer=True), GPy/util/normalizer.py:57-72 (fork: mean-centring only, std==1),
 GPy/inference/latent_function_inference/exact_gaussian_inference.py:29-65,
 GPy/inference/latent_function_inference/posterior.py:171-191,268-320 and the
-author-added GPy/core/gp.py:286-326,380-490.
+author-added GPy/core/gp.py:286-326,380-490 and the knowledge-gradient helpers gp.py:493-627.
 """
 import numpy as np
 
@@ -114,3 +114,54 @@ class GPRegression(object):
         alpha = -2. * np.dot(self.kern.K(X, self.X), self.woodbury_inv)
         dv_dX = dv_dX + self.kern.gradients_X(alpha, X, self.X)
         return dv_dX
+
+    # ---- knowledge-gradient helpers (author-added, gp.py:493-627) ----------------------------------------------
+    # gp.py:493-501
+    def partial_precomputation_for_covariance(self, X):
+        self.partial_precomp_cov = np.matmul(self.woodbury_inv, self.kern.K(self.X, X))
+
+    # gp.py:504-512
+    def partial_precomputation_for_covariance_gradient(self, x):
+        self.partial_precomp_dcov = np.matmul(self.kern.K(x, self.X), self.woodbury_inv)
+
+    # gp.py:515-530
+    def partial_precomputation_for_variance_conditioned_on_next_point(self, next_point):
+        self.X_next = np.append(self.X, next_point, axis=0)
+        K_aux = self.kern.K(self.X_next)
+        K_aux[np.diag_indices_from(K_aux)] += self.noise_var + 1e-8            # diag.add(K_aux, noise_var + 1e-8)
+        tmp = pdinv(K_aux)
+        self.woodbury_inv_conditioned_on_next_point = tmp[0]
+        self.woodbury_chol_conditioned_on_next_point = tmp[1]
+
+    # gp.py:533-544
+    def posterior_variance_conditioned_on_next_point(self, X):
+        Kx = self.kern.K(self.X_next, X)
+        Kxx = self.kern.Kdiag(X)
+        tmp = dtrtrs(self.woodbury_chol_conditioned_on_next_point, Kx)[0]
+        return (Kxx - np.square(tmp).sum(0))[:, None]
+
+    # gp.py:547-575
+    def posterior_variance_gradient_conditioned_on_next_point(self, X):
+        dv_dX = self.kern.gradients_X(np.eye(X.shape[0]), X)
+        alpha = -2. * np.dot(self.kern.K(X, self.X_next), self.woodbury_inv_conditioned_on_next_point)
+        dv_dX = dv_dX + self.kern.gradients_X(alpha, X, self.X_next)
+        return dv_dX
+
+    # gp.py:577-585 -> posterior.py covariance_between_points: K(X1, X2) - (L^-1 K(X, X1))^T (L^-1 K(X, X2))
+    def posterior_covariance_between_points(self, X1, X2):
+        tmp1 = dtrtrs(self.woodbury_chol, self.kern.K(self.X, X1))[0]
+        tmp2 = dtrtrs(self.woodbury_chol, self.kern.K(self.X, X2))[0]
+        return self.kern.K(X1, X2) - tmp1.T.dot(tmp2)
+
+    # gp.py:588-599
+    def posterior_covariance_between_points_partially_precomputed(self, X1, X2):
+        return self.kern.K(X1, X2) - np.matmul(self.kern.K(self.X, X1).T, self.partial_precomp_cov)
+
+    # gp.py:601-609 (kern.gradients_X(None, ...) returns the per-pair tensor (N, M, d): se.py:142-144)
+    def posterior_covariance_gradient(self, X, x2):
+        factor = np.matmul(self.kern.K(x2, self.X), self.woodbury_inv)
+        return self.kern.gradients_X(None, X, x2) - np.matmul(factor, self.kern.gradients_X(None, X, self.X))
+
+    # gp.py:612-627
+    def posterior_covariance_gradient_partially_precomputed(self, X, x2):
+        return self.kern.gradients_X(None, X, x2) - np.matmul(self.partial_precomp_dcov, self.kern.gradients_X(None, X, self.X))

@@ -170,6 +170,9 @@ class Kern(object):
                 X2 = X
             aux1 = X[:, None, :] - X2[None, :, :]
             aux2 = (-self.variance) / (self.lengthscale**2)
+            if dL_dK is None:                       # se.py:142-144: the per-pair gradient tensor (N, M, d)
+                aux3 = np.exp((-0.5) * self._se_scaled_squared_norm(aux1))
+                return (aux3[:, :, None] * aux1) * aux2
             aux3 = np.exp((-0.5) * self._se_scaled_squared_norm(aux1)) * dL_dK
             grad = np.sum(aux3[:, :, None] * aux1, axis=1) * aux2
             return grad

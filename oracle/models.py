@@ -78,6 +78,34 @@ class GPModel(object):
         # gpmodel.py:266-271
         return self.current_model.posterior_variance_gradient(X)
 
+    # knowledge-gradient helpers, gpmodel.py:187-250,273-287: plain dispatch to the current hyper-sample instance
+    def partial_precomputation_for_covariance(self, X):
+        self.current_model.partial_precomputation_for_covariance(X)
+
+    def partial_precomputation_for_covariance_gradient(self, x):
+        self.current_model.partial_precomputation_for_covariance_gradient(x)
+
+    def partial_precomputation_for_variance_conditioned_on_next_point(self, next_point):
+        self.current_model.partial_precomputation_for_variance_conditioned_on_next_point(next_point)
+
+    def posterior_variance_conditioned_on_next_point(self, X):
+        return self.current_model.posterior_variance_conditioned_on_next_point(X)
+
+    def posterior_variance_gradient_conditioned_on_next_point(self, X):
+        return self.current_model.posterior_variance_gradient_conditioned_on_next_point(X)
+
+    def posterior_covariance_between_points(self, X1, X2):
+        return self.current_model.posterior_covariance_between_points(X1, X2)
+
+    def posterior_covariance_between_points_partially_precomputed(self, X1, X2):
+        return self.current_model.posterior_covariance_between_points_partially_precomputed(X1, X2)
+
+    def posterior_covariance_gradient(self, X, X2):
+        return self.current_model.posterior_covariance_gradient(X, X2)
+
+    def posterior_covariance_gradient_partially_precomputed(self, X, x2):
+        return self.current_model.posterior_covariance_gradient_partially_precomputed(X, x2)
+
 
 class GPModelInferred(GPModel):
     """GPModel with its own hyper-parameter inference (gpmodel.py:50-128): every updateModel runs ML-II + HMC on `model`
@@ -224,3 +252,52 @@ class multi_outputGP(object):
         for j in range(self.output_dim):
             dvar_dX[j, :, :] = self.output[j].posterior_variance_gradient(X)
         return dvar_dX
+
+    # knowledge-gradient helpers, multi_outputGP.py:203-281,309-331: loop over outputs, stack
+    def partial_precomputation_for_covariance(self, X):
+        for j in range(self.output_dim):
+            self.output[j].partial_precomputation_for_covariance(X)
+
+    def partial_precomputation_for_covariance_gradient(self, x):
+        for j in range(self.output_dim):
+            self.output[j].partial_precomputation_for_covariance_gradient(x)
+
+    def partial_precomputation_for_variance_conditioned_on_next_point(self, next_point):
+        for j in range(self.output_dim):
+            self.output[j].partial_precomputation_for_variance_conditioned_on_next_point(next_point)
+
+    def posterior_variance_conditioned_on_next_point(self, X):
+        var = np.empty((self.output_dim, X.shape[0]))
+        for j in range(self.output_dim):
+            var[j, :] = self.output[j].posterior_variance_conditioned_on_next_point(X)[:, 0]
+        return var
+
+    def posterior_variance_gradient_conditioned_on_next_point(self, X):
+        dvar_dX = np.empty((self.output_dim, X.shape[0], X.shape[1]))
+        for j in range(self.output_dim):
+            dvar_dX[j, :, :] = self.output[j].posterior_variance_gradient_conditioned_on_next_point(X)
+        return dvar_dX
+
+    def posterior_covariance_between_points(self, X1, X2):
+        cov = np.empty((self.output_dim, X1.shape[0], X2.shape[0]))
+        for j in range(self.output_dim):
+            cov[j, :, :] = self.output[j].posterior_covariance_between_points(X1, X2)
+        return cov
+
+    def posterior_covariance_between_points_partially_precomputed(self, X1, X2):
+        cov = np.empty((self.output_dim, X1.shape[0], X2.shape[0]))
+        for j in range(self.output_dim):
+            cov[j, :, :] = self.output[j].posterior_covariance_between_points_partially_precomputed(X1, X2)
+        return cov
+
+    def posterior_covariance_gradient(self, X, x2):
+        dK_dX = np.empty((self.output_dim, X.shape[0], X.shape[1]))
+        for j in range(self.output_dim):
+            dK_dX[j, :, :] = self.output[j].posterior_covariance_gradient(X, x2)[:, 0, :]      # multi_outputGP.py:317
+        return dK_dX
+
+    def posterior_covariance_gradient_partially_precomputed(self, X, x2):
+        dK_dX = np.empty((self.output_dim, X.shape[0], X.shape[1]))
+        for j in range(self.output_dim):
+            dK_dX[j, :, :] = self.output[j].posterior_covariance_gradient_partially_precomputed(X, x2)[:, 0, :]
+        return dK_dX

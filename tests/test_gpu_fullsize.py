@@ -115,7 +115,7 @@ def test_cfg4_parameter_uncertain_maei_upi(cuda_device):
     import bocf_b200
     from oracle import acquisitions as OA
     from tests.helpers import oracle_utility
-    idx = _stratified(P.N, model.chunk_candidates(P.N, grad=True), rng, 1200)
+    idx = _stratified(P.N, model.chunk_candidates(P.N, grad=True), rng, 1700)
     assert len(idx) >= 2048
     # maEI with the 64 theta samples as an explicit sample set
     acq = bocf_b200.maEI(model, None, utility=product_utility(P))
@@ -163,7 +163,7 @@ def test_cfg5_large_n_cholesky_and_variance(cuda_device):
     _lib.check(model._lib.bocf_model_set_scratch_limit(model._handle, ctypes.c_uint64(256 << 20)))   # several chunks
     chunk = model.chunk_candidates(P.N, grad=True)
     assert chunk < P.N
-    idx = _stratified(P.N, chunk, np.random.default_rng(6), 1500)
+    idx = _stratified(P.N, chunk, np.random.default_rng(6), 2300)
     assert len(idx) >= 2048
     Xs = P.Xc[idx]
     assert rel_err(model.posterior_mean(P.Xc)[:, idx], om.posterior_mean(Xs)) < tol(1e-8)
