@@ -141,8 +141,11 @@ class AcquisitionBase(object):
                              % (L, w_h.size, f_h.shape))
         acq = np.empty((N, 1))
         dacq = np.empty((N, d)) if grad else None
-        with model._lock, torch.cuda.device(model.device):
-            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        with model._lock:
+            # self-contained call (copies in, sweep, copies out, one synchronisation) on the handle's own stream: no
+            # torch device / stream bookkeeping on this latency-bound path.  Everything it depends on (factor, digit
+            # planes, base samples) was synchronised when it was produced.
+            st = model._side_stream_ptr()
             _lib.check(model._lib.bocf_acq_eval_host(
                 model._handle, _lib.VARIANTS[variant], _lib.COMPOSITES[self.utility.composite],
                 Xn.ctypes.data_as(ctypes.c_void_p), N, _ptr(Zt), S, th_p, L, theta.shape[1], w_p, f_p, f_h.shape[0], form,

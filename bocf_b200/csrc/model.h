@@ -112,7 +112,10 @@ struct ChunkBuffers {          // scratch views for one candidate chunk (Nc rows
   double* part_s0 = nullptr;   // split mode: m x parts x Nc  per column-tile partial sums of Wt * G*
   uint8_t* A1 = nullptr;       // split mode: m x Nc/128 x KCH x S x 128 x 64  digit planes of K* (replaces KsT)
   uint8_t* A2 = nullptr;       // split mode: same layout, digit planes of V   (replaces V)
+  double* kpart = nullptr;     // K-split partial sums of mean / dmean for small chunks (posterior.cu: kstar_ksplit)
 };
+int kstar_ksplit(const bocf_model* M, int64_t Nc);
+uint64_t kstar_part_bytes(const bocf_model* M, int64_t Nc);
 uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad);
 void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* out);
 // Posterior of hyper-sample h for candidates Xc[0..Nvalid) into the chunk buffers.

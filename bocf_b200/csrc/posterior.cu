@@ -12,6 +12,8 @@
 // The two contractions run on the fp64 tensor-core tile engine (DMMA.8x8x4, 256 x 64 tiles) and skip the
 // zero blocks of the triangular factor; K*, G* and V live in a per-chunk HBM scratch, everything else
 // (n x n factor, training inputs) is L2-resident and shared by all candidate tiles of one output.
+#include <cstdlib>
+
 #include "gemm_f64.cuh"
 #include "kernfn.cuh"
 #include "model.h"
@@ -20,6 +22,15 @@ namespace bocf {
 
 using PT = gemm::TilePost;                 // 128 candidates x 64 factor columns, 128 threads, 2 CTAs / SM
 constexpr int PT_MINBLOCKS = 2;
+constexpr int64_t KSTAR_SPLIT_MAX = 1024;  // chunks up to this many candidates split the training points over blocks
+constexpr int KSTAR_SPLIT = 8;
+
+// K-split factor of the K* kernel for a chunk of Nc candidates (1 = none); also sizes the partial-sum scratch
+int kstar_ksplit(const bocf_model* M, int64_t Nc) {
+  if (Nc > KSTAR_SPLIT_MAX) return 1;
+  const int blocks = (M->n16 + 127) / 128;
+  return blocks < KSTAR_SPLIT ? (blocks < 1 ? 1 : blocks) : KSTAR_SPLIT;
+}
 constexpr int MI = PT::MI;                 // 8-row MMA tiles per warp (warp tile = 8*MI x 32)
 constexpr int CT = PT::BM;                 // candidate tile
 constexpr int NT = PT::BN;                 // column tile
@@ -46,6 +57,11 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
                                                     const double* __restrict__ alphaAll, double* __restrict__ KsT,
                                                     double* __restrict__ GsT, double* __restrict__ mean,
                                                     double* __restrict__ dmean, const SplitOut so) {
+  // gridDim.z > 1: K-SPLIT for small batches.  One thread walks its candidate's training points serially -- ~120 us of
+  // pure latency at n = 1000 however few candidates there are (the L-BFGS rounds of the acquisition optimiser evaluate
+  // tens).  Block z then takes the 128-point blocks z, z + gridDim.z, ... and writes ADDITIVE partial sums of the mean
+  // and its gradient (slab z of mean / dmean); kstar_reduce_kernel adds the slabs in fixed order.
+  const int ks = (int)gridDim.z, kz = (int)blockIdx.z;
   __shared__ double sX[128][DP];
   __shared__ double sxsq[128];
   __shared__ double salpha[128];
@@ -87,7 +103,7 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
   uint8_t* Aout = SPLIT ? so.A1 + ((size_t)((size_t)j * gridDim.x + blockIdx.x) * so.KCH) * so.S * (128 * 64) : nullptr;
   const uint32_t swz = (uint32_t)((tid >> 1) & 3);
 
-  for (int b0 = 0; b0 < n16; b0 += 128) {
+  for (int b0 = kz * 128; b0 < n16; b0 += 128 * ks) {
     __syncthreads();
     for (int idx = tid; idx < 128 * DP; idx += 128) {
       int bb = idx / DP, q = idx - bb * DP;
@@ -171,11 +187,31 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
       }
     }
   }
-  mean[(int64_t)j * Nc + i] = mu + hp.ybar;
+  const int64_t slab = (int64_t)kz * m * Nc;                   // 0 without the K-split
+  mean[slab + (int64_t)j * Nc + i] = (ks == 1) ? mu + hp.ybar : mu;
   if (GRAD) {
 #pragma unroll
     for (int q = 0; q < DP; ++q)
-      if (q < d) dmean[((int64_t)j * Nc + i) * d + q] = (xs[q] * wsum - gm[q]) / hp.ls[q];
+      if (q < d) dmean[(slab + (int64_t)j * Nc + i) * d + q] = (xs[q] * wsum - gm[q]) / hp.ls[q];
+  }
+}
+
+// mean = ybar + sum_z slab_z, dmean = sum_z slab_z  (K-split partials, fixed order)
+__global__ void kstar_reduce_kernel(const double* __restrict__ mean_part, const double* __restrict__ dmean_part, int ks,
+                                    int64_t Nc, int m, int d, int h, const OutHyp* __restrict__ hyp, int grad,
+                                    double* __restrict__ mean, double* __restrict__ dmean) {
+  const int j = blockIdx.y;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t slab = (int64_t)m * Nc;
+  if (idx < Nc) {
+    double s = hyp[h * m + j].ybar;
+    for (int z = 0; z < ks; ++z) s += mean_part[z * slab + (int64_t)j * Nc + idx];
+    mean[(int64_t)j * Nc + idx] = s;
+  }
+  if (grad && idx < Nc * d) {
+    double s = 0.0;
+    for (int z = 0; z < ks; ++z) s += dmean_part[(z * slab + (int64_t)j * Nc) * d + idx];
+    dmean[(int64_t)j * Nc * d + idx] = s;
   }
 }
 
@@ -383,6 +419,11 @@ __global__ void finalize_kernel(const double* __restrict__ part_var, const doubl
 
 // ===================================================================================================
 int candidate_tile() { return CT; }
+// scratch of the K-split partial sums (small chunks only; added on top of the per-candidate chunk bytes)
+uint64_t kstar_part_bytes(const bocf_model* M, int64_t Nc) {
+  const int ks = kstar_ksplit(M, Nc);
+  return ks > 1 ? (uint64_t)ks * M->m * Nc * (1 + M->d) * sizeof(double) + 1024 : 0;
+}
 
 uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
   if (M->S > 0) return split_chunk_bytes_per_candidate(M, grad);
@@ -427,12 +468,12 @@ void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBu
   } else {
     cb->GsT = cb->V = cb->part_dvar = cb->dmean = cb->dvar = nullptr;
   }
+  cb->kpart = (kstar_ksplit(M, Nc) > 1) ? take((uint64_t)kstar_ksplit(M, Nc) * M->m * Nc * (1 + M->d)) : nullptr;
 }
 
 template <int KIND, int DP>
 static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, const ChunkBuffers& cb,
                           cudaStream_t st) {
-  dim3 grid((unsigned)(cb.Nc / 128), (unsigned)M->m);
   SplitOut so;
   so.A1 = cb.A1;
   so.aq = M->aq;
@@ -441,9 +482,14 @@ static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid
   so.KCH = M->KCH;
   so.S = M->S;
   const int spl = (cb.A1 == nullptr) ? 0 : (M->S == 5 ? 5 : 6);
-#define BOCF_KSTAR(G, SP)                                                                                              \
-  kstar_kernel<KIND, DP, G, SP><<<grid, 128, 0, st>>>(Xc, Nvalid, cb.Nc, M->d, M->n, M->n16, M->n_pad, M->m, h, M->hyp, \
-                                                      M->Xs, M->xsq, M->alpha, cb.KsT, cb.GsT, cb.mean, cb.dmean, so)
+  // small batches: split the training points over gridDim.z blocks (latency), partial sums into cb.kpart
+  const int ks = kstar_ksplit(M, cb.Nc);
+  dim3 kgrid((unsigned)(cb.Nc / 128), (unsigned)M->m, (unsigned)ks);
+  double* mean_out = (ks > 1) ? cb.kpart : cb.mean;
+  double* dmean_out = (ks > 1) ? cb.kpart + (size_t)ks * M->m * cb.Nc : cb.dmean;
+#define BOCF_KSTAR(G, SP)                                                                                               \
+  kstar_kernel<KIND, DP, G, SP><<<kgrid, 128, 0, st>>>(Xc, Nvalid, cb.Nc, M->d, M->n, M->n16, M->n_pad, M->m, h, M->hyp, \
+                                                       M->Xs, M->xsq, M->alpha, cb.KsT, cb.GsT, mean_out, dmean_out, so)
   if (grad && spl == 5) BOCF_KSTAR(true, 5);
   else if (grad && spl == 6) BOCF_KSTAR(true, 6);
   else if (grad) BOCF_KSTAR(true, 0);
@@ -452,6 +498,12 @@ static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid
   else BOCF_KSTAR(false, 0);
 #undef BOCF_KSTAR
   BOCF_LAUNCH_OK("kstar_kernel");
+  if (ks > 1) {
+    dim3 rgrid((unsigned)ceil_div(grad ? cb.Nc * M->d : cb.Nc, 256), (unsigned)M->m);
+    kstar_reduce_kernel<<<rgrid, 256, 0, st>>>(mean_out, dmean_out, ks, cb.Nc, M->m, M->d, h, M->hyp, grad ? 1 : 0, cb.mean,
+                                               cb.dmean);
+    BOCF_LAUNCH_OK("kstar_reduce_kernel");
+  }
   return 0;
 }
 

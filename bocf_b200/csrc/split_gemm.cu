@@ -1006,6 +1006,7 @@ void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, C
     cb->GsT = cb->part_dvar = cb->dmean = cb->dvar = nullptr;
     cb->A2 = nullptr;
   }
+  cb->kpart = (kstar_ksplit(M, Nc) > 1) ? reinterpret_cast<double*>(take(kstar_part_bytes(M, Nc))) : nullptr;
 }
 
 static sg::GemmParams base_params(const bocf_model* M, int h, const ChunkBuffers& cb) {

@@ -249,6 +249,15 @@ class multi_outputGP(object):
         """Digit planes the tensor-core contraction currently uses (0 = fp64 DMMA)."""
         return int(self._lib.bocf_model_active_slices(self._handle)) if self._handle is not None else 0
 
+    def _side_stream_ptr(self):
+        """A non-blocking stream owned by this model for self-contained host-entry calls (created once)."""
+        st = getattr(self, "_side_stream", None)
+        if st is None:
+            with torch.cuda.device(self.device):
+                st = self._side_stream = torch.cuda.Stream(device=self.device)
+            self._side_stream_c = ctypes.c_void_p(st.cuda_stream)
+        return self._side_stream_c
+
     def chunk_candidates(self, N, grad=True):
         """Candidates per internal chunk of a call with N candidates (results never depend on it)."""
         return int(self._lib.bocf_model_chunk_candidates(self._handle, int(N), 1 if grad else 0))

@@ -24,8 +24,30 @@ space = B.Design_space(space=[{'name': 'var', 'type': 'continuous', 'domain': (0
 opt = B.AcquisitionOptimizer(space, optimizer='lbfgs2', inner_optimizer='lbfgs2')          # 400 starts, 16 anchors
 acq = B.uEI_noiseless(model, space, optimizer=opt, utility=product_utility(P))
 acq.W_samples = P.Z
-stats = {"rounds": 0, "t_fdf": 0.0, "cands": 0}
+stats = {"rounds": 0, "t_fdf": 0.0, "cands": 0, "t_c": 0.0, "c_calls": 0}
 orig = acq.acquisition_function_withGradients
+_c_entry = model._lib.bocf_acq_eval_host
+
+
+class _TimedEntry(object):                        # time spent inside the C call (copies + kernels + sync) vs Python
+    def __call__(self, *args):
+        t0 = time.perf_counter()
+        rc = _c_entry(*args)
+        stats["t_c"] += time.perf_counter() - t0
+        stats["c_calls"] += 1
+        return rc
+
+
+class _LibProxy(object):
+    def __init__(self, lib):
+        self._lib = lib
+        self.bocf_acq_eval_host = _TimedEntry()
+
+    def __getattr__(self, k):
+        return getattr(self._lib, k)
+
+
+model._lib = _LibProxy(model._lib)
 
 
 def timed_fdf(X):
@@ -41,7 +63,7 @@ acq.acquisition_function_withGradients = timed_fdf
 res = []
 for r in range(a.repeat + 1):
     np.random.seed(r)
-    stats.update(rounds=0, t_fdf=0.0, cands=0)
+    stats.update(rounds=0, t_fdf=0.0, cands=0, t_c=0.0, c_calls=0)
     torch.cuda.synchronize()
     l0, t0 = _lib.launch_count(), time.perf_counter()
     x, fx = acq.optimize(x_baseline=P.X[:1])
@@ -52,8 +74,18 @@ for r in range(a.repeat + 1):
     res.append({"wall_ms": 1e3 * wall, "rounds": stats["rounds"], "launches": int(_lib.launch_count() - l0),
                 "us_per_fdf_round": 1e6 * stats["t_fdf"] / max(1, stats["rounds"]),
                 "candidates_per_round": stats["cands"] / max(1, stats["rounds"]), "fdf_share": stats["t_fdf"] / wall,
+                "us_in_c_call_per_call": 1e6 * stats["t_c"] / max(1, stats["c_calls"]), "c_calls": stats["c_calls"],
                 "best_value": float(np.asarray(fx).reshape(-1)[0])})
-out = {"workload": "cfg3 model (m=16, d=10, n=1000, Matern-5/2), EI-CF with %d base samples, AcquisitionOptimizer default "
+# per-kernel device time of one small batch (library event scopes), separate pass
+_lib.profile_enable(True)
+Xs = np.random.default_rng(0).uniform(size=(17, P.d))
+for _ in range(20):
+    orig(Xs)
+torch.cuda.synchronize()
+prof = _lib.profile_report()
+_lib.profile_enable(False)
+kernel_us = {k: 1e3 * v[1] / v[0] for k, v in prof.items()}
+out = {"kernel_us_per_launch_at_17_candidates": kernel_us, "workload": "cfg3 model (m=16, d=10, n=1000, Matern-5/2), EI-CF with %d base samples, AcquisitionOptimizer default "
                    "(400 starts, 16 anchors + 1 baseline, lbfgs2, batched rounds)" % a.samples,
        "precision": a.precision, "schemes": list(model.active_scheme()), "runs": res,
        "median_wall_ms": float(np.median([r["wall_ms"] for r in res])),

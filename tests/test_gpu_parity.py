@@ -221,7 +221,8 @@ def test_acq_eval_host_entry(cuda_device):
 
 def test_negated_and_pipelined_host_path(cuda_device):
     """acquisition_function[_withGradients] flip the sign on the device and, for long numpy inputs, stream the candidates
-    through in slabs (H2D / D2H on a side stream): both must equal the plain one-shot evaluation bit for bit."""
+    through in slabs (H2D / D2H on a side stream).  The sign flip is exact; slabs of <= 1024 candidates take the K-split
+    form of the K* kernel (posterior.cu), whose mean / mean-gradient sums run in a different order: equal to 1e-13."""
     import torch
     import bocf_b200
     from tests.helpers import make_problem, product_model, product_utility
@@ -238,13 +239,13 @@ def test_negated_and_pipelined_host_path(cuda_device):
     model.set_hyperparameters(0)
     a2, g2 = acq.acquisition_function_withGradients(P.Xc)
     assert a2.shape == (1500, 1) and g2.shape == (1500, 5)
-    assert np.array_equal(a2, a1) and np.array_equal(g2, g1)
+    assert rel_err(a2, a1) < 1e-13 and rel_err(g2, g1) < 1e-13
     model.set_hyperparameters(0)
     v2 = acq.acquisition_function(P.Xc)
     model.set_hyperparameters(0)
     acq.PIPELINE_MIN = 1 << 30
     v1 = acq.acquisition_function(P.Xc)
-    assert np.array_equal(v2, v1) and np.all(v1 <= 0)
+    assert rel_err(v2, v1) < 1e-13 and np.all(v1 <= 0)
     # device tensors in -> device tensors out, same values
     model.set_hyperparameters(0)
     at, gt = acq.acquisition_function_withGradients(torch.from_numpy(P.Xc).to(cuda_device))
