@@ -93,14 +93,18 @@ constexpr int MCU = 4;         // sample groups per trip (independent base-sampl
 // the samples is pure latency (83 -> ~25 us at 17 candidates, S = 1024) -- sums are per candidate, so results are identical.
 
 // MODE: 0 = EI value only, 1 = EI value + gradient, 2 = PI value, 3 = mean utility (no improvement) value,
-//       4 = mean utility value + gradient
+//       4 = mean utility value + gradient, 5 / 6 = as 1 / 4 but the gradient is left as per-(candidate, output) WEIGHTS
+//       WA_j = scale sum_l w_l sum_s 1 dphi_j,  WB_j = scale sum_l w_l sum_s 1 dphi_j Z_sj / (2 sigma_j)
+//       for the fused gradient path (the second contraction's epilogue applies them, split_gemm.cu EPI_DACQ)
 template <int COMP, int MODE, int MCB>
 __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
     const double* __restrict__ mean, const double* __restrict__ var, const double* __restrict__ dmean,
     const double* __restrict__ dvar, int64_t Nc, int64_t Nvalid, int m, int d, const double* __restrict__ Zt, int S,
     const double* __restrict__ theta, int L, int p, const double* __restrict__ weight,
     const double* __restrict__ fstar, double scale, int accumulate, double* __restrict__ acq,
-    double* __restrict__ dacq) {
+    double* __restrict__ dacq, double* __restrict__ wa_out, double* __restrict__ wb_out) {
+  constexpr bool WITH_GRAD = (MODE == 1 || MODE == 4), WEIGHTS = (MODE == 5 || MODE == 6);
+  constexpr bool PLAIN_U = (MODE == 3 || MODE == 4 || MODE == 6);
   __shared__ double2 s_ms[MC_WARPS][MAXM][MCB];            // (mu, sigma) of the warp's MCB candidates, output-major
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i0 = ((int64_t)blockIdx.x * MC_WARPS + warp) * MCB;
@@ -115,12 +119,17 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
 
   double val_total[MCB];     // sum_l w_l sum_s improvement
   double grad_q[MCB];        // lane q < d
+  double wa[MCB][MAXM / 32], wb[MCB][MAXM / 32];   // WEIGHTS: lane (j & 31) keeps output j
 #pragma unroll
-  for (int c = 0; c < MCB; ++c) val_total[c] = grad_q[c] = 0.0;
+  for (int c = 0; c < MCB; ++c) {
+    val_total[c] = grad_q[c] = 0.0;
+#pragma unroll
+    for (int w = 0; w < MAXM / 32; ++w) wa[c][w] = wb[c][w] = 0.0;
+  }
   for (int l = 0; l < L; ++l) {
     const double* th = theta + (int64_t)l * p;
     const double wl = weight[l];
-    const double fs = (MODE >= 3) ? 0.0 : ((MODE == 2) ? fstar[l] + 1e-6 : fstar[l]);       // uPI.py:83 jitter
+    const double fs = PLAIN_U ? 0.0 : ((MODE == 2) ? fstar[l] + 1e-6 : fstar[l]);       // uPI.py:83 jitter
     double val_l[MCB];
 #pragma unroll
     for (int c = 0; c < MCB; ++c) val_l[c] = 0.0;
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
             for (int c = 0; c < MCB; ++c) {
               if (MODE == 2) {
                 val_l[c] += ((U[c][u] - fs) > 0.0) ? 1.0 : 0.0;
-              } else if (MODE >= 3) {
+              } else if (PLAIN_U) {
                 val_l[c] += U[c][u];                                          // cbo.py:213,227: no max, no indicator
                 mask[c] |= (1u << k);
               } else {
@@ -167,7 +176,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
           }
         }
       }
-      if (MODE == 1 || MODE == 4) {
+      if (WITH_GRAD || WEIGHTS) {
 #pragma unroll
         for (int c = 0; c < MCB; ++c) {
           if (c >= nc) break;
@@ -190,7 +199,16 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
             __syncwarp();
             Aj = warp_sum(Aj);
             Bj = warp_sum(Bj);
-            if (lane < d) {
+            if (WEIGHTS) {
+              if (lane == (j & 31)) {
+#pragma unroll
+                for (int w = 0; w < MAXM / 32; ++w)
+                  if (w == (j >> 5)) {
+                    wa[c][w] += wl * Aj;
+                    wb[c][w] += wl * (Bj * (0.5 / ms.y));
+                  }
+              }
+            } else if (lane < d) {
               const int64_t o = ((int64_t)j * Nc + i) * d + lane;
               grad_q[c] += wl * (Aj * dmean[o] + Bj * (0.5 / ms.y) * dvar[o]);   // :163-166
             }
@@ -209,9 +227,19 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
       const double v = val_total[c] * scale;
       acq[i] = accumulate ? acq[i] + v : v;
     }
-    if ((MODE == 1 || MODE == 4) && lane < d) {
+    if (WITH_GRAD && lane < d) {
       const double gq = grad_q[c] * scale;
       dacq[i * d + lane] = accumulate ? dacq[i * d + lane] + gq : gq;
+    }
+    if (WEIGHTS) {
+#pragma unroll
+      for (int w = 0; w < MAXM / 32; ++w) {
+        const int j = w * 32 + lane;
+        if (j < m) {
+          wa_out[(int64_t)j * Nc + i] = wa[c][w] * scale;
+          wb_out[(int64_t)j * Nc + i] = wb[c][w] * scale;
+        }
+      }
     }
   }
 }
@@ -501,10 +529,13 @@ static int launch_mc_t(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvali
                        cudaStream_t st) {
   const bool small = (Nvalid <= 1024);
   const unsigned grid = (unsigned)ceil_div(Nvalid, (int64_t)MC_WARPS * (small ? 1 : 4));
-  const int mode = (P.variant == BOCF_ACQ_MEAN_UTILITY) ? (dacq ? 4 : 3) : (P.variant == BOCF_ACQ_PI_CF) ? 2 : (dacq ? 1 : 0);
+  const bool weights = (P.wa != nullptr);
+  const int mode = (P.variant == BOCF_ACQ_MEAN_UTILITY) ? (weights ? 6 : dacq ? 4 : 3)
+                   : (P.variant == BOCF_ACQ_PI_CF)      ? 2
+                                                         : (weights ? 5 : dacq ? 1 : 0);
 #define BOCF_MC_ARGS                                                                                              \
   cb.mean, cb.var, cb.dmean, cb.dvar, cb.Nc, Nvalid, P.m, P.d, P.Zt, P.S, P.theta, P.L, P.p, P.weight, P.fstar, \
-      P.scale, P.accumulate, acq, dacq
+      P.scale, P.accumulate, acq, dacq, P.wa, P.wb
   {
   ProfScope ps("mc_acq_kernel", st);
 #define BOCF_MC_LAUNCH(MD)                                                                       \
@@ -516,7 +547,9 @@ static int launch_mc_t(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvali
   else if (mode == 1) BOCF_MC_LAUNCH(1);
   else if (mode == 2) BOCF_MC_LAUNCH(2);
   else if (mode == 3) BOCF_MC_LAUNCH(3);
-  else BOCF_MC_LAUNCH(4);
+  else if (mode == 4) BOCF_MC_LAUNCH(4);
+  else if (mode == 5) BOCF_MC_LAUNCH(5);
+  else BOCF_MC_LAUNCH(6);
 #undef BOCF_MC_LAUNCH
   }
 #undef BOCF_MC_ARGS

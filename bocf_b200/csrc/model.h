@@ -113,6 +113,8 @@ struct ChunkBuffers {          // scratch views for one candidate chunk (Nc rows
   uint8_t* A1 = nullptr;       // split mode: m x Nc/128 x KCH x S x 128 x 64  digit planes of K* (replaces KsT)
   uint8_t* A2 = nullptr;       // split mode: same layout, digit planes of V   (replaces V)
   double* kpart = nullptr;     // K-split partial sums of mean / dmean for small chunks (posterior.cu: kstar_ksplit)
+  double* wa = nullptr;        // split mode, fused gradient path: m x Nc weights of the mean gradient      (acq.cu)
+  double* wb = nullptr;        //                                  m x Nc weights of the variance gradient
 };
 int kstar_ksplit(const bocf_model* M, int64_t Nc);
 uint64_t kstar_part_bytes(const bocf_model* M, int64_t Nc);
@@ -137,6 +139,8 @@ uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad);
 void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* out);
 int launch_split_var(bocf_model* M, int h, const ChunkBuffers& cb, bool need_dvar, cudaStream_t st);
 int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, const ChunkBuffers& cb, cudaStream_t st);
+// second contraction with the fused acquisition-gradient epilogue (weights cb.wa / cb.wb, alpha of the model)
+int launch_split_dacq(bocf_model* M, int h, const double* Xc, int64_t Nvalid, const ChunkBuffers& cb, cudaStream_t st);
 int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int sch, int tri, double* out, cudaStream_t st);
 
 // ---- kg.cu --------------------------------------------------------------------------------------
@@ -154,7 +158,11 @@ struct AcqParams {
   const double* fstar;         // [dev] L    (already for this hyper-sample)
   double scale;                // 1 / (H * S)  or 1 / H
   int accumulate;              // 0: overwrite outputs, 1: add
+  double* wa = nullptr;        // MC variants, fused gradient path: write the gradient weights (m x Nc each) instead of
+  double* wb = nullptr;        // contracting them with dmean / dvar
 };
+int launch_fused_grad_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, int noiseless, const ChunkBuffers& cb,
+                            AcqParams P, double* acq, double* dacq, cudaStream_t st);
 int launch_acq_chunk(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvalid, double* acq, double* dacq,
                      cudaStream_t st);
 int launch_utility_eval(int composite, int m, const double* Y, int64_t N, const double* theta, int L, int p,

@@ -49,7 +49,10 @@ struct SplitOut {
 };
 
 // SPL: 0 = fp64 K* output; 5 = exactly five digit planes (the common case, fewer registers); 6 = up to six (so.S)
-template <int KIND, int DP, bool GRAD, int SPL>
+// GRAD: 0 = value quantities only; 1 = also G* and the mean gradient; 2 = G* only -- the fused acquisition-gradient path
+//       (api.cu) folds the mean-gradient contraction into the second contraction's epilogue, which saves the d + 2
+//       fp64 operations per (candidate, training point) the mean gradient costs here.
+template <int KIND, int DP, int GRAD, int SPL>
 __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restrict__ Xc, int64_t Nvalid, int64_t Nc, int d,
                                                     int n, int n16, int n_pad, int m, int h,
                                                     const OutHyp* __restrict__ hyp, const double* __restrict__ XsAll,
@@ -153,12 +156,12 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
             r2 = -2.0 * (dot0 + dot1) + (xsq_i + sxsq[bb]);
             r2 = fmax(r2, 0.0);
           }
-          kern_eval<KIND, GRAD, (KV_EXPTAB != 0)>(r2, variance, kv, gv, sexp);
+          kern_eval<KIND, (GRAD != 0), (KV_EXPTAB != 0)>(r2, variance, kv, gv, sexp);
           // padded points b >= n need no mask: their alpha, column scale and factor rows / columns are zero, so whatever
           // finite K*, G* they produce is multiplied by an exact zero downstream (mean, both contractions, epilogues)
           const double a = salpha[bb];
           mu += kv * a;
-          if (GRAD) {
+          if (GRAD == 1) {
             const double w = gv * a;
             wsum += w;
 #pragma unroll
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
   }
   const int64_t slab = (int64_t)kz * m * Nc;                   // 0 without the K-split
   mean[slab + (int64_t)j * Nc + i] = (ks == 1) ? mu + hp.ybar : mu;
-  if (GRAD) {
+  if (GRAD == 1) {
 #pragma unroll
     for (int q = 0; q < DP; ++q)
       if (q < d) dmean[(slab + (int64_t)j * Nc + i) * d + q] = (xs[q] * wsum - gm[q]) / hp.ls[q];
@@ -472,7 +475,7 @@ void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBu
 }
 
 template <int KIND, int DP>
-static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, const ChunkBuffers& cb,
+static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid, int grad, const ChunkBuffers& cb,
                           cudaStream_t st) {
   SplitOut so;
   so.A1 = cb.A1;
@@ -490,25 +493,27 @@ static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid
 #define BOCF_KSTAR(G, SP)                                                                                               \
   kstar_kernel<KIND, DP, G, SP><<<kgrid, 128, 0, st>>>(Xc, Nvalid, cb.Nc, M->d, M->n, M->n16, M->n_pad, M->m, h, M->hyp, \
                                                        M->Xs, M->xsq, M->alpha, cb.KsT, cb.GsT, mean_out, dmean_out, so)
-  if (grad && spl == 5) BOCF_KSTAR(true, 5);
-  else if (grad && spl == 6) BOCF_KSTAR(true, 6);
-  else if (grad) BOCF_KSTAR(true, 0);
-  else if (spl == 5) BOCF_KSTAR(false, 5);
-  else if (spl == 6) BOCF_KSTAR(false, 6);
-  else BOCF_KSTAR(false, 0);
+  if (grad == 2 && spl == 5) BOCF_KSTAR(2, 5);
+  else if (grad == 2 && spl == 6) BOCF_KSTAR(2, 6);
+  else if (grad && spl == 5) BOCF_KSTAR(1, 5);
+  else if (grad && spl == 6) BOCF_KSTAR(1, 6);
+  else if (grad) BOCF_KSTAR(1, 0);
+  else if (spl == 5) BOCF_KSTAR(0, 5);
+  else if (spl == 6) BOCF_KSTAR(0, 6);
+  else BOCF_KSTAR(0, 0);
 #undef BOCF_KSTAR
   BOCF_LAUNCH_OK("kstar_kernel");
   if (ks > 1) {
-    dim3 rgrid((unsigned)ceil_div(grad ? cb.Nc * M->d : cb.Nc, 256), (unsigned)M->m);
-    kstar_reduce_kernel<<<rgrid, 256, 0, st>>>(mean_out, dmean_out, ks, cb.Nc, M->m, M->d, h, M->hyp, grad ? 1 : 0, cb.mean,
-                                               cb.dmean);
+    dim3 rgrid((unsigned)ceil_div(grad == 1 ? cb.Nc * M->d : cb.Nc, 256), (unsigned)M->m);
+    kstar_reduce_kernel<<<rgrid, 256, 0, st>>>(mean_out, dmean_out, ks, cb.Nc, M->m, M->d, h, M->hyp, grad == 1 ? 1 : 0,
+                                               cb.mean, cb.dmean);
     BOCF_LAUNCH_OK("kstar_reduce_kernel");
   }
   return 0;
 }
 
 template <int KIND>
-static int launch_kstar_k(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, const ChunkBuffers& cb,
+static int launch_kstar_k(bocf_model* M, int h, const double* Xc, int64_t Nvalid, int grad, const ChunkBuffers& cb,
                           cudaStream_t st) {
   const int d = M->d;
   if (d <= 4) return launch_kstar_t<KIND, 4>(M, h, Xc, Nvalid, grad, cb, st);
@@ -517,6 +522,73 @@ static int launch_kstar_k(bocf_model* M, int h, const double* Xc, int64_t Nvalid
   if (d <= 10) return launch_kstar_t<KIND, 10>(M, h, Xc, Nvalid, grad, cb, st);
   if (d <= 12) return launch_kstar_t<KIND, 12>(M, h, Xc, Nvalid, grad, cb, st);
   return launch_kstar_t<KIND, MAXD>(M, h, Xc, Nvalid, grad, cb, st);
+}
+
+static int launch_kstar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, int grad, const ChunkBuffers& cb,
+                        cudaStream_t st) {
+  ProfScope ps("kstar_kernel", st);
+  switch (M->kernel) {
+    case BOCF_KERN_SE: return launch_kstar_k<BOCF_KERN_SE>(M, h, Xc, Nvalid, grad, cb, st);
+    case BOCF_KERN_RBF: return launch_kstar_k<BOCF_KERN_RBF>(M, h, Xc, Nvalid, grad, cb, st);
+    case BOCF_KERN_MATERN52: return launch_kstar_k<BOCF_KERN_MATERN52>(M, h, Xc, Nvalid, grad, cb, st);
+    case BOCF_KERN_MATERN32: return launch_kstar_k<BOCF_KERN_MATERN32>(M, h, Xc, Nvalid, grad, cb, st);
+  }
+  set_error("unknown kernel kind");
+  return -1;
+}
+
+// sum over outputs and partials of the fused gradient:  dacq[i][q] (+)= sum_j (xs_jq S0_j - ACC_jq) / l_jq
+// (S0 / ACC: the weighted sums the EPI_DACQ epilogue leaves per output, split_gemm.cu)
+__global__ void finalize_grad_kernel(const double* __restrict__ part_dvar, const double* __restrict__ part_s0,
+                                     const OutHyp* __restrict__ hyp, int64_t Nc, int64_t Nvalid, int nparts, int m, int d,
+                                     int h, const double* __restrict__ Xc, int accumulate, double* __restrict__ dacq) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Nvalid * d) return;
+  const int64_t i = idx / d;
+  const int q = (int)(idx - i * d);
+  const double x = Xc[i * d + q];
+  double g = 0.0;
+  for (int j = 0; j < m; ++j) {
+    const OutHyp& hp = hyp[h * m + j];
+    double acc = 0.0, s0 = 0.0;
+    for (int t = 0; t < nparts; ++t) {
+      acc += part_dvar[(((int64_t)j * nparts + t) * Nc + i) * d + q];
+      s0 += part_s0[((int64_t)j * nparts + t) * Nc + i];
+    }
+    g += ((x / hp.ls[q]) * s0 - acc) / hp.ls[q];
+  }
+  dacq[idx] = accumulate ? dacq[idx] + g : g;
+}
+
+// Fused acquisition-gradient sweep of one chunk and one hyper-sample (EI-CF / mean-utility with gradients, tensor-core
+// contraction mode): K* (mean, digit planes, G*; no mean gradient) -> first contraction -> variance -> MC forward pass
+// leaving the value and the per-(candidate, output) gradient weights WA, WB -> second contraction whose epilogue
+// contracts G* (WA alpha - 2 WB Wt) against the training inputs -> sum over outputs.  The per-output mean / variance
+// gradients (2 m d doubles per candidate) are never formed.
+int launch_fused_grad_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, int noiseless, const ChunkBuffers& cb,
+                            AcqParams P, double* acq, double* dacq, cudaStream_t st) {
+  if (int rc = launch_kstar(M, h, Xc, Nvalid, 2, cb, st)) return rc;
+  if (int rc = launch_split_var(M, h, cb, true, st)) return rc;
+  {
+    const int nct = split_partials_var(M, cb.Nc);
+    dim3 fgrid((unsigned)ceil_div(cb.Nc, 256), (unsigned)M->m);
+    ProfScope ps("finalize_kernel", st);
+    finalize_kernel<<<fgrid, 256, 0, st>>>(cb.part_var, cb.part_dvar, M->hyp, cb.Nc, nct, 0, M->m, M->d, h, 0, noiseless,
+                                           cb.var, cb.dvar, nullptr, Xc, Nvalid);
+    BOCF_LAUNCH_OK("finalize_kernel");
+  }
+  P.wa = cb.wa;
+  P.wb = cb.wb;
+  if (int rc = launch_acq_chunk(P, cb, Nvalid, acq, nullptr, st)) return rc;
+  if (int rc = launch_split_dacq(M, h, Xc, Nvalid, cb, st)) return rc;
+  {
+    ProfScope ps("finalize_kernel", st);
+    finalize_grad_kernel<<<(unsigned)ceil_div(Nvalid * M->d, 256), 256, 0, st>>>(cb.part_dvar, cb.part_s0, M->hyp, cb.Nc, Nvalid,
+                                                                               split_partials_dvar(M, cb.Nc), M->m, M->d, h,
+                                                                               Xc, P.accumulate, dacq);
+    BOCF_LAUNCH_OK("finalize_grad_kernel");
+  }
+  return 0;
 }
 
 int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, bool grad, int noiseless,
@@ -529,18 +601,7 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
   }
   need_dvar = need_dvar && grad;
   need_var = need_var || need_dvar;
-  int rc;
-  {
-    ProfScope ps("kstar_kernel", st);
-    switch (M->kernel) {
-      case BOCF_KERN_SE: rc = launch_kstar_k<BOCF_KERN_SE>(M, h, Xc, Nvalid, grad, cb, st); break;
-      case BOCF_KERN_RBF: rc = launch_kstar_k<BOCF_KERN_RBF>(M, h, Xc, Nvalid, grad, cb, st); break;
-      case BOCF_KERN_MATERN52: rc = launch_kstar_k<BOCF_KERN_MATERN52>(M, h, Xc, Nvalid, grad, cb, st); break;
-      case BOCF_KERN_MATERN32: rc = launch_kstar_k<BOCF_KERN_MATERN32>(M, h, Xc, Nvalid, grad, cb, st); break;
-      default: set_error("unknown kernel kind"); return -1;
-    }
-  }
-  if (rc) return rc;
+  if (int rc = launch_kstar(M, h, Xc, Nvalid, grad ? 1 : 0, cb, st)) return rc;
   if (!need_var) return 0;      // mean (and mean gradient) only: no contraction against the factor
   const bool split = (cb.A1 != nullptr);
   const int nct = split ? split_partials_var(M, cb.Nc) : M->n_pad / NT;       // partial sums per candidate: variance

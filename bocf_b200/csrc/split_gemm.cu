@@ -129,7 +129,10 @@ struct Cfg {
 #define BOCF_KO(x) false
 #endif
 
-enum { EPI_RAW = 0, EPI_VAR = 1, EPI_DVAR = 2 };
+// EPI_DACQ: the second contraction with the fused acquisition-gradient epilogue -- instead of T = Wt G* it contracts
+//   u_b = G*_b (WA_j alpha_b - 2 WB_j Wt_b)      (WA, WB: per-candidate weights from the MC pass, acq.cu)
+// so that sum_j (xs_j sum_b u_b - sum_b u_b Xs_b) / l_j = sum_j WA_j dmu_j + WB_j dvar_j = grad acq  (uEI_noiseless.py:163-166).
+enum { EPI_RAW = 0, EPI_VAR = 1, EPI_DVAR = 2, EPI_DACQ = 3 };
 enum { TRI_FULL = 0, TRI_K_LE_N = 1, TRI_K_GE_N = 2 };
 
 struct GemmParams {
@@ -152,6 +155,9 @@ struct GemmParams {
   const double* GsT;       // [m][n16][Nc]
   const double* Xc;        // [Nvalid][d]
   const double* Xs;        // [Hm][n_pad][d]
+  const double* alpha;     // DACQ: [Hm][n_pad]
+  const double* wa;        // DACQ: [m][Nc] weight of the mean gradient
+  const double* wb;        // DACQ: [m][Nc] weight of the variance gradient
   const OutHyp* hyp;
   int d, n16, n_pad;
   int np;                  // parts per candidate tile
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
       while (walk.next(P, ti)) {
         const uint8_t* gA = P.A + ((size_t)(ti.j * P.RT + ti.rt) * P.KCH) * C::A_STAGE;
         const uint8_t* gB = P.B + ((size_t)((P.h * P.m + ti.j) * P.nct + ti.ct) * P.KCH) * C::B_STAGE;
-        if (EPI == EPI_DVAR) {
+        if (EPI == EPI_DVAR || EPI == EPI_DACQ) {
           // the epilogue of this tile (one tile later in time) reads 128 G* values of each of its NT columns:
           // pull those 1 KB rows into L2 now so its loads do not pay HBM latency
           const double* g0 = P.GsT + (size_t)ti.j * P.n16 * P.Nc + (size_t)ti.rt * TM;
@@ -477,11 +483,17 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
     // per-tile constants (column scales, scaled training inputs of the column tile) are fetched one tile AHEAD into
     // registers and parked in shared memory at the top of the tile, so their global-load latency is never exposed
     constexpr int DPA0 = DP > 0 ? DP : 1;
-    constexpr int XPT = (EPI == EPI_DVAR) ? (NT * DPA0 + EPI_THREADS - 1) / EPI_THREADS : 1;
+    constexpr bool GRADEPI = (EPI == EPI_DVAR || EPI == EPI_DACQ);
+    constexpr int XPT = GRADEPI ? (NT * DPA0 + EPI_THREADS - 1) / EPI_THREADS : 1;
     double pre_cs = 0.0, pre_vq = 0.0, pre_xb[XPT];
     auto prefetch_tile_consts = [&](const TileInfo& tn) {
       const int hjn = P.h * P.m + tn.j;
-      if (EPI != EPI_DVAR) {
+      if (EPI == EPI_DACQ && et < NT) {
+        // alpha_b / (256 cs2_b): the mean-gradient weight in the units of the merged, unscaled accumulator
+        const int b = tn.ct * NT + et;
+        pre_cs = (b < P.n) ? __ldg(P.alpha + (size_t)hjn * P.n_pad + b) / (256.0 * __ldg(P.cs + (size_t)hjn * P.nct * NT + b)) : 0.0;
+      }
+      if (!GRADEPI) {
         if (et < NT) pre_cs = __ldg(P.cs + (size_t)hjn * P.nct * NT + tn.ct * NT + et);
         if (EPI == EPI_VAR) pre_vq = __ldg(P.vq + hjn);
       } else {
@@ -519,9 +531,10 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
       // it & 1), so ONE barrier per tile suffices: a warp can be at most one tile ahead of the slowest one.
       // DVAR: the training-input tile is single buffered (it would cost a pipeline stage): two barriers.
       const double2* cs_t = s_cs + (it & 1) * NT;
-      if (EPI != EPI_DVAR) {
+      if (!GRADEPI) {
         if (et < NT) s_cs[(it & 1) * NT + et] = make_double2(pre_cs * (EPI == EPI_RAW ? 1.0 : 256.0), pre_cs * 256.0 * pre_vq);
       } else {
+        if (EPI == EPI_DACQ && et < NT) s_cs[(it & 1) * NT + et] = make_double2(pre_cs, 0.0);    // double buffered
         tc::named_bar_sync(1, EPI_THREADS);                     // previous tile's readers of s_xb are done
 #pragma unroll
         for (int x = 0; x < XPT; ++x) {
@@ -548,7 +561,12 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
       const double* Gcol = nullptr;
       const int64_t gstride = P.Nc;
       const bool tile_full = (col0 + NT <= P.n);
-      if (EPI == EPI_DVAR) {
+      double wa_i = 0.0, wb2_i = 0.0;
+      if (EPI == EPI_DACQ) {                                     // this candidate's gradient weights for output j
+        wa_i = __ldg(P.wa + (size_t)ti.j * P.Nc + i);
+        wb2_i = -2.0 * __ldg(P.wb + (size_t)ti.j * P.Nc + i);
+      }
+      if (GRADEPI) {
         Gcol = P.GsT + (size_t)ti.j * P.n16 * P.Nc + i;
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {                      // first column group: in flight while the MMAs finish
@@ -564,7 +582,7 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
       // VAR / RAW: the levels of the NEXT column group are requested from tensor memory before the current group is
       // processed (two register buffers), so the TMEM round trip overlaps the fp64 work.  DVAR keeps one buffer: its
       // 2 d + 2 accumulators leave no registers for a second one.
-      constexpr bool PREF = (EPI != EPI_DVAR);
+      constexpr bool PREF = !GRADEPI;
       uint32_t c[PREF ? 2 : 1][NL][CGW];
       if (PREF) {
 #pragma unroll
@@ -611,7 +629,8 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
             dgv[e] = balanced_digits<S2>(__double_as_longlong(fma(y, sc.y, 6755399441055744.0)));
           } else {
             // the column scale (and the factor 256 of the merged Horner) is folded into G* by the K* kernel
-            const double w = levels_to_f64_merged<NL, CGW>(cc, e) * gv[e];
+            const double y = levels_to_f64_merged<NL, CGW>(cc, e);
+            const double w = (EPI == EPI_DACQ) ? fma(wb2_i, y, wa_i * cs_t[cg * CGW + e].x) * gv[e] : y * gv[e];
             if (gi + 1 < NGW) {                                // refill the slot with this warp's next column group's G*
               const int bn = col0 + (cg + PART_SPLIT) * CGW + e;
               gv[e] = __ldg(Gcol + (size_t)(tile_full ? bn : min(bn, P.n - 1)) * gstride);
@@ -664,7 +683,7 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
       // one partial per (unit part, warp of the lane group): summed in fixed order by finalize_kernel
       const size_t pidx = ((size_t)ti.j * P.np + ti.p) * PART_SPLIT + hw;
       if (EPI == EPI_VAR && ti.last) P.part_var[pidx * P.Nc + i] = sumsq;
-      if (EPI == EPI_DVAR && ti.last) {
+      if (GRADEPI && ti.last) {
         // xs_iq * S0 - ACC_q is formed by finalize_kernel (one division per candidate instead of one per tile)
         P.part_s0[pidx * P.Nc + i] = s0;
         double* out = P.part_dvar + (pidx * P.Nc + i) * P.d;
@@ -837,6 +856,24 @@ static int launch_dvar_d(int sch, const GemmParams& P, cudaStream_t st) {
   }
   return bad_scheme();
 }
+template <int DP>
+static int launch_dacq_d(int sch, const GemmParams& P, cudaStream_t st) {
+  switch (sch) {
+    case 331: return launch_k<P331, EPI_DACQ, DP, 3>(P, st);
+    case 442: return launch_k<P442, EPI_DACQ, DP, 4>(P, st);
+    case 554: return launch_k<P554, EPI_DACQ, DP, 5>(P, st);
+    case 665: return launch_k<P665, EPI_DACQ, DP, 6>(P, st);
+  }
+  return bad_scheme();
+}
+static int launch_dacq(int sch, int d, const GemmParams& P, cudaStream_t st) {
+  if (d <= 4) return launch_dacq_d<4>(sch, P, st);
+  if (d <= 6) return launch_dacq_d<6>(sch, P, st);
+  if (d <= 8) return launch_dacq_d<8>(sch, P, st);
+  if (d <= 10) return launch_dacq_d<10>(sch, P, st);
+  if (d <= 12) return launch_dacq_d<12>(sch, P, st);
+  return launch_dacq_d<16>(sch, P, st);
+}
 static int launch_dvar(int sch, int d, const GemmParams& P, cudaStream_t st) {
   if (d <= 4) return launch_dvar_d<4>(sch, P, st);
   if (d <= 6) return launch_dvar_d<6>(sch, P, st);
@@ -977,6 +1014,7 @@ uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
     per += (uint64_t)M->m * M->KCH * sg::KC * M->S2;    // A2 digit planes of V
     per += (uint64_t)M->m * split_partials_dvar(M, 0) * (M->d + 1) * 8;   // part_dvar, part_s0
     per += 2ull * M->m * M->d * 8;                      // dmean, dvar
+    per += 2ull * M->m * 8;                             // wa, wb (fused gradient path)
   }
   return per;
 }
@@ -1002,6 +1040,8 @@ void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, C
     cb->part_s0 = reinterpret_cast<double*>(take((uint64_t)M->m * split_partials_dvar(M, 0) * Nc * 8));
     cb->dmean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
     cb->dvar = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
+    cb->wa = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
+    cb->wb = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
   } else {
     cb->GsT = cb->part_dvar = cb->dmean = cb->dvar = nullptr;
     cb->A2 = nullptr;
@@ -1068,6 +1108,30 @@ int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, co
   }
   ProfScope ps("split_dvar_kernel", st);
   return sg::launch_dvar(M->sch2, M->d, P, st);
+}
+
+int launch_split_dacq(bocf_model* M, int h, const double* Xc, int64_t Nvalid, const ChunkBuffers& cb, cudaStream_t st) {
+  sg::GemmParams P = base_params(M, h, cb);
+  P.A = cb.A2;
+  P.B = M->B2;
+  P.cs = M->cs2;
+  P.nct = M->nct2;
+  P.tri = sg::TRI_K_GE_N;
+  P.part_dvar = cb.part_dvar;
+  P.part_s0 = cb.part_s0;
+  P.GsT = cb.GsT;
+  P.Xc = Xc;
+  P.Nvalid = Nvalid;
+  P.Xs = M->Xs;
+  P.alpha = M->alpha;
+  P.wa = cb.wa;
+  P.wb = cb.wb;
+  if (M->nct2 < P.np) {
+    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_dvar, 0, sizeof(double) * M->m * split_partials_dvar(M, cb.Nc) * cb.Nc * M->d, st));
+    BOCF_CUDA_OK(cudaMemsetAsync(cb.part_s0, 0, sizeof(double) * M->m * split_partials_dvar(M, cb.Nc) * cb.Nc, st));
+  }
+  ProfScope ps("split_dvar_kernel", st);
+  return sg::launch_dacq(M->sch2, M->d, P, st);
 }
 
 // Test entry: out (R x N) = A (R x K) * B (N x K)^T through the digit-plane machinery.  All pointers [dev] fp64 row-major.
