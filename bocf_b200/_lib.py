@@ -16,7 +16,7 @@ VARIANTS = {"ei_cf": 0, "pi_cf": 1, "ma_ei": 2, "ma_pi": 3, "mean_utility": 4, "
 
 EXPORTS = [
     "bocf_last_error", "bocf_version", "bocf_launch_count",
-    "bocf_model_create", "bocf_model_destroy", "bocf_model_set_data", "bocf_model_set_hypers",
+    "bocf_model_create", "bocf_model_set_kernels", "bocf_model_destroy", "bocf_model_set_data", "bocf_model_set_hypers",
     "bocf_model_factorize", "bocf_model_get_factor", "bocf_model_n", "bocf_model_H",
     "bocf_model_set_scratch_limit", "bocf_posterior", "bocf_posterior_cov_point", "bocf_acq_eval", "bocf_acq_eval_host",
     "bocf_utility_eval", "bocf_topk", "bocf_profile_enable", "bocf_profile_report",
@@ -64,6 +64,7 @@ def load_library():
     lib.bocf_version.restype = ctypes.c_char_p
     lib.bocf_launch_count.restype = u64
     lib.bocf_model_create.argtypes = [ctypes.POINTER(c_vp), i32, i32, i32, i32]
+    lib.bocf_model_set_kernels.argtypes = [c_vp, ctypes.POINTER(i32), i32]
     lib.bocf_model_destroy.argtypes = [c_vp]
     lib.bocf_model_set_data.argtypes = [c_vp, i32, c_dp, c_dp, c_vp]
     lib.bocf_model_set_hypers.argtypes = [c_vp, i32, c_dp, c_dp, c_dp]

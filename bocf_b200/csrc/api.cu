@@ -267,6 +267,7 @@ int bocf_model_create(bocf_model** out, int m, int d, int kernel, int device) {
   M->m = m;
   M->d = d;
   M->kernel = kernel;
+  M->kinds.assign((size_t)m, kernel);
   M->device = device;
   M->precision = BOCF_PREC_AUTO;                                // library default
   if (const char* env = std::getenv("BOCF_PRECISION")) {      // fp64 | auto | mixed | split3 .. split6 | split<s1><s2>
@@ -281,6 +282,24 @@ int bocf_model_create(bocf_model** out, int m, int d, int kernel, int device) {
     }
   }
   *out = M;
+  return 0;
+}
+
+int bocf_model_set_kernels(bocf_model* M, const int* kinds, int m) {
+  if (!M || !kinds || m != M->m) {
+    set_error("bocf_model_set_kernels: need one kernel family per output (m entries)");
+    return BOCF_ERR_INVALID;
+  }
+  for (int j = 0; j < m; ++j)
+    if (kinds[j] < 0 || kinds[j] > BOCF_KERN_MATERN32) {
+      set_error("bocf_model_set_kernels: unknown kernel family");
+      return BOCF_ERR_INVALID;
+    }
+  M->kinds.assign(kinds, kinds + m);
+  M->kernel = kinds[0];
+  M->factorized = false;                                        // Gram, factor, alpha and the digit planes are stale
+  M->split_ready = false;
+  M->precision_resolved = false;
   return 0;
 }
 

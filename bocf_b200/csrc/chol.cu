@@ -61,8 +61,9 @@ __global__ void scale_inputs_kernel(const double* __restrict__ X, int n, int n_p
 // SE: exact squared differences, diagonal = variance (se.py:56-58).
 template <int KIND>
 __global__ void gram_kernel(const double* __restrict__ Xs, const double* __restrict__ xsq,
-                            const OutHyp* __restrict__ hyp, int n, int n_pad, int d, double* __restrict__ A) {
-  const int hj = blockIdx.z;
+                            const OutHyp* __restrict__ hyp, int n, int n_pad, int d, double* __restrict__ A, OutRun run,
+                            int m) {
+  const int hj = run_hj(blockIdx.z, run, m);
   const int a = blockIdx.y * 16 + threadIdx.y;
   const int b = blockIdx.x * 16 + threadIdx.x;
   __shared__ double sa[16][MAXD + 1], sb[16][MAXD + 1];
@@ -448,10 +449,11 @@ __global__ void __launch_bounds__(256) append_factor_kernel(double* __restrict__
                                                             const double* __restrict__ XsAll,
                                                             const double* __restrict__ xsqAll,
                                                             const OutHyp* __restrict__ hyp, int n, int n_pad, int d,
-                                                            int* __restrict__ info, double* __restrict__ work) {
+                                                            int* __restrict__ info, double* __restrict__ work,
+                                                            OutRun run, int m) {
   __shared__ double red[8];
   __shared__ double s_lnn;
-  const int hj = blockIdx.x, tid = threadIdx.x;
+  const int hj = run_hj(blockIdx.x, run, m), tid = threadIdx.x;
   const OutHyp& hp = hyp[hj];
   double* L = LmatAll + (int64_t)hj * n_pad * n_pad;
   double* Li = LinvAll + (int64_t)hj * n_pad * n_pad;
@@ -533,17 +535,21 @@ int launch_prepare(bocf_model* M, cudaStream_t st) {
 }
 
 int launch_gram(bocf_model* M, cudaStream_t st) {
-  const int Hm = M->H * M->m;
-  dim3 grid((unsigned)(M->n_pad / 16), (unsigned)(M->n_pad / 16), (unsigned)Hm), block(16, 16);
-  switch (M->kernel) {
-    case BOCF_KERN_SE: gram_kernel<BOCF_KERN_SE><<<grid, block, 0, st>>>(M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, M->Lmat); break;
-    case BOCF_KERN_RBF: gram_kernel<BOCF_KERN_RBF><<<grid, block, 0, st>>>(M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, M->Lmat); break;
-    case BOCF_KERN_MATERN52: gram_kernel<BOCF_KERN_MATERN52><<<grid, block, 0, st>>>(M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, M->Lmat); break;
-    case BOCF_KERN_MATERN32: gram_kernel<BOCF_KERN_MATERN32><<<grid, block, 0, st>>>(M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, M->Lmat); break;
-    default: set_error("unknown kernel kind"); return -1;
-  }
-  BOCF_LAUNCH_OK("gram_kernel");
-  return 0;
+  const dim3 block(16, 16);
+  return for_each_kind_run(M, [&](int kind, OutRun run) -> int {
+    const dim3 grid((unsigned)(M->n_pad / 16), (unsigned)(M->n_pad / 16), (unsigned)(M->H * run.cnt));
+#define BOCF_GRAM(K) gram_kernel<K><<<grid, block, 0, st>>>(M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, M->Lmat, run, M->m)
+    switch (kind) {
+      case BOCF_KERN_SE: BOCF_GRAM(BOCF_KERN_SE); break;
+      case BOCF_KERN_RBF: BOCF_GRAM(BOCF_KERN_RBF); break;
+      case BOCF_KERN_MATERN52: BOCF_GRAM(BOCF_KERN_MATERN52); break;
+      case BOCF_KERN_MATERN32: BOCF_GRAM(BOCF_KERN_MATERN32); break;
+      default: set_error("unknown kernel kind"); return -1;
+    }
+#undef BOCF_GRAM
+    BOCF_LAUNCH_OK("gram_kernel");
+    return 0;
+  });
 }
 
 static int set_smem_attrs() {
@@ -613,13 +619,21 @@ int launch_append(bocf_model* M, int n_old, double* work, cudaStream_t st) {
   const int Hm = M->H * M->m;
   BOCF_CUDA_OK(cudaMemsetAsync(M->info, 0, sizeof(int) * Hm, st));
   if (int rc = launch_prepare(M, st)) return rc;             // ybar, centred y, scaled inputs incl. the new row
-  switch (M->kernel) {
-    case BOCF_KERN_SE: append_factor_kernel<BOCF_KERN_SE><<<Hm, 256, 0, st>>>(M->Lmat, M->Linv, M->Xs, M->xsq, M->hyp, n_old, M->n_pad, M->d, M->info, work); break;
-    case BOCF_KERN_RBF: append_factor_kernel<BOCF_KERN_RBF><<<Hm, 256, 0, st>>>(M->Lmat, M->Linv, M->Xs, M->xsq, M->hyp, n_old, M->n_pad, M->d, M->info, work); break;
-    case BOCF_KERN_MATERN52: append_factor_kernel<BOCF_KERN_MATERN52><<<Hm, 256, 0, st>>>(M->Lmat, M->Linv, M->Xs, M->xsq, M->hyp, n_old, M->n_pad, M->d, M->info, work); break;
-    default: append_factor_kernel<BOCF_KERN_MATERN32><<<Hm, 256, 0, st>>>(M->Lmat, M->Linv, M->Xs, M->xsq, M->hyp, n_old, M->n_pad, M->d, M->info, work); break;
-  }
-  BOCF_LAUNCH_OK("append_factor_kernel");
+  const int rc_runs = for_each_kind_run(M, [&](int kind, OutRun run) -> int {
+    const int blocks = M->H * run.cnt;
+#define BOCF_APPEND(K) \
+  append_factor_kernel<K><<<blocks, 256, 0, st>>>(M->Lmat, M->Linv, M->Xs, M->xsq, M->hyp, n_old, M->n_pad, M->d, M->info, work, run, M->m)
+    switch (kind) {
+      case BOCF_KERN_SE: BOCF_APPEND(BOCF_KERN_SE); break;
+      case BOCF_KERN_RBF: BOCF_APPEND(BOCF_KERN_RBF); break;
+      case BOCF_KERN_MATERN52: BOCF_APPEND(BOCF_KERN_MATERN52); break;
+      default: BOCF_APPEND(BOCF_KERN_MATERN32); break;
+    }
+#undef BOCF_APPEND
+    BOCF_LAUNCH_OK("append_factor_kernel");
+    return 0;
+  });
+  if (rc_runs) return rc_runs;
   return launch_alpha(M, st);
 }
 

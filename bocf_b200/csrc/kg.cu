@@ -38,8 +38,8 @@ __device__ __forceinline__ double sq_dist(const double* __restrict__ a, const do
 // k2[hj][b] = k_j(X_b, x2), zero beyond n
 template <int KIND>
 __global__ void kvec_kernel(const double* __restrict__ XsAll, const OutHyp* __restrict__ hyp, const double* __restrict__ x2,
-                            int n, int n_pad, int d, int m, int h, double* __restrict__ k2) {
-  const int j = blockIdx.y, hj = h * m + j;
+                            int n, int n_pad, int d, int m, int h, double* __restrict__ k2, int j0) {
+  const int j = j0 + blockIdx.y, hj = h * m + j;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_pad) return;
   const OutHyp& hp = hyp[hj];
@@ -81,10 +81,10 @@ template <int KIND, bool GRAD>
 __global__ void __launch_bounds__(128) cov_point_kernel(const double* __restrict__ Xc, int64_t N, const double* __restrict__ x2,
                                                         const double* __restrict__ XsAll, const OutHyp* __restrict__ hyp,
                                                         const double* __restrict__ beta, int n, int n_pad, int d, int m, int h,
-                                                        double* __restrict__ cov, double* __restrict__ dcov) {
+                                                        double* __restrict__ cov, double* __restrict__ dcov, int j0) {
   __shared__ double sX[64][MAXD];
   __shared__ double sb[64];
-  const int j = blockIdx.y, hj = h * m + j;
+  const int j = j0 + blockIdx.y, hj = h * m + j;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const OutHyp& hp = hyp[hj];
   double xs[MAXD], xs2[MAXD];
@@ -127,38 +127,56 @@ __global__ void __launch_bounds__(128) cov_point_kernel(const double* __restrict
     }
 }
 
+// the two launches that evaluate the kernel family, for one run of outputs
 template <int KIND>
-static int cov_point_t(bocf_model* M, int h, const double* Xc, int64_t N, const double* x2, double* cov, double* dcov,
-                       double* work, cudaStream_t st) {
-  double* k2 = work;
-  double* tv = work + (size_t)M->m * M->n_pad;
-  double* beta = work + 2 * (size_t)M->m * M->n_pad;
-  kvec_kernel<KIND><<<dim3((unsigned)ceil_div(M->n_pad, 128), (unsigned)M->m), 128, 0, st>>>(M->Xs, M->hyp, x2, M->n, M->n_pad,
-                                                                                              M->d, M->m, h, k2);
+static int kvec_t(bocf_model* M, int h, const double* x2, double* k2, OutRun run, cudaStream_t st) {
+  kvec_kernel<KIND><<<dim3((unsigned)ceil_div(M->n_pad, 128), (unsigned)run.cnt), 128, 0, st>>>(M->Xs, M->hyp, x2, M->n, M->n_pad,
+                                                                                                 M->d, M->m, h, k2, run.j0);
   BOCF_LAUNCH_OK("kvec_kernel");
-  kg_linv_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 8), (unsigned)M->m), 256, 0, st>>>(M->Linv, k2, M->m, h, M->n_pad, tv);
-  BOCF_LAUNCH_OK("kg_linv_matvec_kernel");
-  kg_linv_t_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 128), (unsigned)M->m), 128, 0, st>>>(M->Linv, tv, M->m, h, M->n_pad, beta);
-  BOCF_LAUNCH_OK("kg_linv_t_matvec_kernel");
-  dim3 grid((unsigned)ceil_div(N, 128), (unsigned)M->m);
+  return 0;
+}
+template <int KIND>
+static int cov_point_t(bocf_model* M, int h, const double* Xc, int64_t N, const double* x2, const double* beta, double* cov,
+                       double* dcov, OutRun run, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(N, 128), (unsigned)run.cnt);
   if (dcov)
-    cov_point_kernel<KIND, true><<<grid, 128, 0, st>>>(Xc, N, x2, M->Xs, M->hyp, beta, M->n, M->n_pad, M->d, M->m, h, cov, dcov);
+    cov_point_kernel<KIND, true><<<grid, 128, 0, st>>>(Xc, N, x2, M->Xs, M->hyp, beta, M->n, M->n_pad, M->d, M->m, h, cov, dcov, run.j0);
   else
-    cov_point_kernel<KIND, false><<<grid, 128, 0, st>>>(Xc, N, x2, M->Xs, M->hyp, beta, M->n, M->n_pad, M->d, M->m, h, cov, dcov);
+    cov_point_kernel<KIND, false><<<grid, 128, 0, st>>>(Xc, N, x2, M->Xs, M->hyp, beta, M->n, M->n_pad, M->d, M->m, h, cov, dcov, run.j0);
   BOCF_LAUNCH_OK("cov_point_kernel");
   return 0;
 }
 
 int launch_cov_point(bocf_model* M, int h, const double* Xc, int64_t N, const double* x2, double* cov, double* dcov,
                      double* work, cudaStream_t st) {
-  switch (M->kernel) {
-    case BOCF_KERN_SE: return cov_point_t<BOCF_KERN_SE>(M, h, Xc, N, x2, cov, dcov, work, st);
-    case BOCF_KERN_RBF: return cov_point_t<BOCF_KERN_RBF>(M, h, Xc, N, x2, cov, dcov, work, st);
-    case BOCF_KERN_MATERN52: return cov_point_t<BOCF_KERN_MATERN52>(M, h, Xc, N, x2, cov, dcov, work, st);
-    case BOCF_KERN_MATERN32: return cov_point_t<BOCF_KERN_MATERN32>(M, h, Xc, N, x2, cov, dcov, work, st);
-  }
-  set_error("unknown kernel kind");
-  return BOCF_ERR_INVALID;
+  double* k2 = work;
+  double* tv = work + (size_t)M->m * M->n_pad;
+  double* beta = work + 2 * (size_t)M->m * M->n_pad;
+  int rc = for_each_kind_run(M, [&](int kind, OutRun run) -> int {
+    switch (kind) {
+      case BOCF_KERN_SE: return kvec_t<BOCF_KERN_SE>(M, h, x2, k2, run, st);
+      case BOCF_KERN_RBF: return kvec_t<BOCF_KERN_RBF>(M, h, x2, k2, run, st);
+      case BOCF_KERN_MATERN52: return kvec_t<BOCF_KERN_MATERN52>(M, h, x2, k2, run, st);
+      case BOCF_KERN_MATERN32: return kvec_t<BOCF_KERN_MATERN32>(M, h, x2, k2, run, st);
+    }
+    set_error("unknown kernel kind");
+    return BOCF_ERR_INVALID;
+  });
+  if (rc) return rc;
+  kg_linv_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 8), (unsigned)M->m), 256, 0, st>>>(M->Linv, k2, M->m, h, M->n_pad, tv);
+  BOCF_LAUNCH_OK("kg_linv_matvec_kernel");
+  kg_linv_t_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 128), (unsigned)M->m), 128, 0, st>>>(M->Linv, tv, M->m, h, M->n_pad, beta);
+  BOCF_LAUNCH_OK("kg_linv_t_matvec_kernel");
+  return for_each_kind_run(M, [&](int kind, OutRun run) -> int {
+    switch (kind) {
+      case BOCF_KERN_SE: return cov_point_t<BOCF_KERN_SE>(M, h, Xc, N, x2, beta, cov, dcov, run, st);
+      case BOCF_KERN_RBF: return cov_point_t<BOCF_KERN_RBF>(M, h, Xc, N, x2, beta, cov, dcov, run, st);
+      case BOCF_KERN_MATERN52: return cov_point_t<BOCF_KERN_MATERN52>(M, h, Xc, N, x2, beta, cov, dcov, run, st);
+      case BOCF_KERN_MATERN32: return cov_point_t<BOCF_KERN_MATERN32>(M, h, Xc, N, x2, beta, cov, dcov, run, st);
+    }
+    set_error("unknown kernel kind");
+    return BOCF_ERR_INVALID;
+  });
 }
 
 }  // namespace bocf

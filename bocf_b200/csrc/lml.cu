@@ -27,9 +27,10 @@ __global__ void __launch_bounds__(LT::NTHREADS, 1) lml_tile_kernel(const double*
                                                                     const double* __restrict__ XsAll,
                                                                     const double* __restrict__ xsqAll,
                                                                     const OutHyp* __restrict__ hyp, int n, int n_pad, int d,
-                                                                    int ntiles, double* __restrict__ part) {
+                                                                    int ntiles, double* __restrict__ part, OutRun run,
+                                                                    int m) {
   extern __shared__ __align__(16) double smem[];
-  const int hj = blockIdx.y;
+  const int hj = run_hj(blockIdx.y, run, m);
   int p = blockIdx.x;                                   // lower-triangular tile pair (I >= J)
   int I = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
   while ((I + 1) * (I + 2) / 2 <= p) ++I;
@@ -162,14 +163,14 @@ __global__ void lml_finish_kernel(const double* __restrict__ part, const double*
 }
 
 template <int KIND>
-static int launch_tiles(bocf_model* M, int ntiles, double* part, cudaStream_t st) {
+static int launch_tiles(bocf_model* M, int ntiles, double* part, OutRun run, cudaStream_t st) {
   static bool done[64] = {false};              // per device: function attributes belong to the device's context
   if (M->device >= 0 && M->device < 64 && !done[M->device]) {
     BOCF_CUDA_OK(cudaFuncSetAttribute(lml_tile_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::SMEM_BYTES));
     done[M->device] = true;
   }
-  lml_tile_kernel<KIND><<<dim3((unsigned)ntiles, (unsigned)(M->H * M->m)), LT::NTHREADS, LT::SMEM_BYTES, st>>>(
-      M->Linv, M->alpha, M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, ntiles, part);
+  lml_tile_kernel<KIND><<<dim3((unsigned)ntiles, (unsigned)(M->H * run.cnt)), LT::NTHREADS, LT::SMEM_BYTES, st>>>(
+      M->Linv, M->alpha, M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, ntiles, part, run, M->m);
   BOCF_LAUNCH_OK("lml_tile_kernel");
   return 0;
 }
@@ -192,13 +193,14 @@ int launch_log_likelihood(bocf_model* M, double* out_host, cudaStream_t st) {
   }
   double* part = M->lml_ws;
   double* out = M->lml_ws + n_part;
-  int rc = 0;
-  switch (M->kernel) {
-    case BOCF_KERN_SE: rc = launch_tiles<BOCF_KERN_SE>(M, ntiles, part, st); break;
-    case BOCF_KERN_RBF: rc = launch_tiles<BOCF_KERN_RBF>(M, ntiles, part, st); break;
-    case BOCF_KERN_MATERN52: rc = launch_tiles<BOCF_KERN_MATERN52>(M, ntiles, part, st); break;
-    default: rc = launch_tiles<BOCF_KERN_MATERN32>(M, ntiles, part, st); break;
-  }
+  int rc = for_each_kind_run(M, [&](int kind, OutRun run) -> int {
+    switch (kind) {
+      case BOCF_KERN_SE: return launch_tiles<BOCF_KERN_SE>(M, ntiles, part, run, st);
+      case BOCF_KERN_RBF: return launch_tiles<BOCF_KERN_RBF>(M, ntiles, part, run, st);
+      case BOCF_KERN_MATERN52: return launch_tiles<BOCF_KERN_MATERN52>(M, ntiles, part, run, st);
+      default: return launch_tiles<BOCF_KERN_MATERN32>(M, ntiles, part, run, st);
+    }
+  });
   if (!rc) {
     lml_finish_kernel<<<Hm, 256, 0, st>>>(part, M->Lmat, M->alpha, M->yc, M->hyp, M->n, M->n_pad, M->d, M->m, ntiles, out);
     count_launch();

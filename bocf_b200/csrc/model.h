@@ -22,10 +22,19 @@ struct OutHyp {
   double ls[MAXD];            // lengthscale per input dimension
 };
 
+// A run of consecutive outputs j0 .. j0 + cnt - 1 that share one kernel family (multi_outputGP.py:23,38-44 takes a kernel
+// LIST: the family may differ per output).  The family is a template parameter of every kernel that evaluates k(.,.), so
+// the launchers issue one launch per run; kernels whose grid walks (hyper-sample, output) pairs decode through run_hj.
+struct OutRun {
+  int j0, cnt;
+};
+__host__ __device__ __forceinline__ int run_hj(int idx, OutRun r, int m) { return (idx / r.cnt) * m + r.j0 + idx % r.cnt; }
+
 }  // namespace bocf
 
 struct bocf_model {
   int m = 0, d = 0, kernel = 0, device = 0;
+  std::vector<int> kinds;     // kernel family per output (bocf_model_set_kernels; all = `kernel` by default)
   int n = 0, n_pad = 0, n16 = 0, nb = 0, H = 0;
   bool has_data = false, has_hyp = false, factorized = false;
 
@@ -81,6 +90,20 @@ struct bocf_model {
 };
 
 namespace bocf {
+
+// f(kind, OutRun) for every maximal run of consecutive outputs with the same kernel family; stops at the first non-zero rc
+template <class F>
+inline int for_each_kind_run(const bocf_model* M, F f) {
+  int j0 = 0;
+  while (j0 < M->m) {
+    const int kind = M->kinds.empty() ? M->kernel : M->kinds[j0];
+    int j1 = j0 + 1;
+    while (j1 < M->m && (M->kinds.empty() ? M->kernel : M->kinds[j1]) == kind) ++j1;
+    if (int rc = f(kind, OutRun{j0, j1 - j0})) return rc;
+    j0 = j1;
+  }
+  return 0;
+}
 
 // ---- chol.cu ------------------------------------------------------------------------------------
 int launch_prepare(bocf_model* M, cudaStream_t st);                       // ybar, yc, Xs, xsq

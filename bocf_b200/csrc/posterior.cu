@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
                                                     const double* __restrict__ xsqAll,
                                                     const double* __restrict__ alphaAll, double* __restrict__ KsT,
                                                     double* __restrict__ GsT, double* __restrict__ mean,
-                                                    double* __restrict__ dmean, const SplitOut so) {
+                                                    double* __restrict__ dmean, const SplitOut so, int j0) {
   // gridDim.z > 1: K-SPLIT for small batches.  One thread walks its candidate's training points serially -- ~120 us of
   // pure latency at n = 1000 however few candidates there are (the L-BFGS rounds of the acquisition optimiser evaluate
   // tens).  Block z then takes the 128-point blocks z, z + gridDim.z, ... and writes ADDITIVE partial sums of the mean
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
   __shared__ double sexp[32];
   const int tid = threadIdx.x;
   if (KV_EXPTAB) exp_table_fill(sexp, tid);     // visible after the first __syncthreads of the tile loop
-  const int j = blockIdx.y;
+  const int j = j0 + blockIdx.y;                 // this launch covers one run of outputs that share the kernel family
   const int hj = h * m + j;
   const int64_t i = (int64_t)blockIdx.x * 128 + tid;
   const OutHyp& hp = hyp[hj];
@@ -476,7 +476,7 @@ void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBu
 
 template <int KIND, int DP>
 static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid, int grad, const ChunkBuffers& cb,
-                          cudaStream_t st) {
+                          OutRun run, cudaStream_t st) {
   SplitOut so;
   so.A1 = cb.A1;
   so.aq = M->aq;
@@ -487,12 +487,13 @@ static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid
   const int spl = (cb.A1 == nullptr) ? 0 : (M->S == 5 ? 5 : 6);
   // small batches: split the training points over gridDim.z blocks (latency), partial sums into cb.kpart
   const int ks = kstar_ksplit(M, cb.Nc);
-  dim3 kgrid((unsigned)(cb.Nc / 128), (unsigned)M->m, (unsigned)ks);
+  dim3 kgrid((unsigned)(cb.Nc / 128), (unsigned)run.cnt, (unsigned)ks);
   double* mean_out = (ks > 1) ? cb.kpart : cb.mean;
   double* dmean_out = (ks > 1) ? cb.kpart + (size_t)ks * M->m * cb.Nc : cb.dmean;
 #define BOCF_KSTAR(G, SP)                                                                                               \
   kstar_kernel<KIND, DP, G, SP><<<kgrid, 128, 0, st>>>(Xc, Nvalid, cb.Nc, M->d, M->n, M->n16, M->n_pad, M->m, h, M->hyp, \
-                                                       M->Xs, M->xsq, M->alpha, cb.KsT, cb.GsT, mean_out, dmean_out, so)
+                                                       M->Xs, M->xsq, M->alpha, cb.KsT, cb.GsT, mean_out, dmean_out, so,     \
+                                                       run.j0)
   if (grad == 2 && spl == 5) BOCF_KSTAR(2, 5);
   else if (grad == 2 && spl == 6) BOCF_KSTAR(2, 6);
   else if (grad && spl == 5) BOCF_KSTAR(1, 5);
@@ -503,38 +504,46 @@ static int launch_kstar_t(bocf_model* M, int h, const double* Xc, int64_t Nvalid
   else BOCF_KSTAR(0, 0);
 #undef BOCF_KSTAR
   BOCF_LAUNCH_OK("kstar_kernel");
-  if (ks > 1) {
-    dim3 rgrid((unsigned)ceil_div(grad == 1 ? cb.Nc * M->d : cb.Nc, 256), (unsigned)M->m);
-    kstar_reduce_kernel<<<rgrid, 256, 0, st>>>(mean_out, dmean_out, ks, cb.Nc, M->m, M->d, h, M->hyp, grad == 1 ? 1 : 0,
-                                               cb.mean, cb.dmean);
-    BOCF_LAUNCH_OK("kstar_reduce_kernel");
-  }
   return 0;
 }
 
 template <int KIND>
 static int launch_kstar_k(bocf_model* M, int h, const double* Xc, int64_t Nvalid, int grad, const ChunkBuffers& cb,
-                          cudaStream_t st) {
+                          OutRun run, cudaStream_t st) {
   const int d = M->d;
-  if (d <= 4) return launch_kstar_t<KIND, 4>(M, h, Xc, Nvalid, grad, cb, st);
-  if (d <= 6) return launch_kstar_t<KIND, 6>(M, h, Xc, Nvalid, grad, cb, st);
-  if (d <= 8) return launch_kstar_t<KIND, 8>(M, h, Xc, Nvalid, grad, cb, st);
-  if (d <= 10) return launch_kstar_t<KIND, 10>(M, h, Xc, Nvalid, grad, cb, st);
-  if (d <= 12) return launch_kstar_t<KIND, 12>(M, h, Xc, Nvalid, grad, cb, st);
-  return launch_kstar_t<KIND, MAXD>(M, h, Xc, Nvalid, grad, cb, st);
+  if (d <= 4) return launch_kstar_t<KIND, 4>(M, h, Xc, Nvalid, grad, cb, run, st);
+  if (d <= 6) return launch_kstar_t<KIND, 6>(M, h, Xc, Nvalid, grad, cb, run, st);
+  if (d <= 8) return launch_kstar_t<KIND, 8>(M, h, Xc, Nvalid, grad, cb, run, st);
+  if (d <= 10) return launch_kstar_t<KIND, 10>(M, h, Xc, Nvalid, grad, cb, run, st);
+  if (d <= 12) return launch_kstar_t<KIND, 12>(M, h, Xc, Nvalid, grad, cb, run, st);
+  return launch_kstar_t<KIND, MAXD>(M, h, Xc, Nvalid, grad, cb, run, st);
 }
 
 static int launch_kstar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, int grad, const ChunkBuffers& cb,
                         cudaStream_t st) {
   ProfScope ps("kstar_kernel", st);
-  switch (M->kernel) {
-    case BOCF_KERN_SE: return launch_kstar_k<BOCF_KERN_SE>(M, h, Xc, Nvalid, grad, cb, st);
-    case BOCF_KERN_RBF: return launch_kstar_k<BOCF_KERN_RBF>(M, h, Xc, Nvalid, grad, cb, st);
-    case BOCF_KERN_MATERN52: return launch_kstar_k<BOCF_KERN_MATERN52>(M, h, Xc, Nvalid, grad, cb, st);
-    case BOCF_KERN_MATERN32: return launch_kstar_k<BOCF_KERN_MATERN32>(M, h, Xc, Nvalid, grad, cb, st);
+  // one launch per run of outputs that share a kernel family (one launch when they all do)
+  const int rc = for_each_kind_run(M, [&](int kind, OutRun run) -> int {
+    switch (kind) {
+      case BOCF_KERN_SE: return launch_kstar_k<BOCF_KERN_SE>(M, h, Xc, Nvalid, grad, cb, run, st);
+      case BOCF_KERN_RBF: return launch_kstar_k<BOCF_KERN_RBF>(M, h, Xc, Nvalid, grad, cb, run, st);
+      case BOCF_KERN_MATERN52: return launch_kstar_k<BOCF_KERN_MATERN52>(M, h, Xc, Nvalid, grad, cb, run, st);
+      case BOCF_KERN_MATERN32: return launch_kstar_k<BOCF_KERN_MATERN32>(M, h, Xc, Nvalid, grad, cb, run, st);
+    }
+    set_error("unknown kernel kind");
+    return -1;
+  });
+  if (rc) return rc;
+  const int ks = kstar_ksplit(M, cb.Nc);
+  if (ks > 1) {                                  // K-split partial sums of every output, added in fixed order
+    double* mean_part = cb.kpart;
+    double* dmean_part = cb.kpart + (size_t)ks * M->m * cb.Nc;
+    dim3 rgrid((unsigned)ceil_div(grad == 1 ? cb.Nc * M->d : cb.Nc, 256), (unsigned)M->m);
+    kstar_reduce_kernel<<<rgrid, 256, 0, st>>>(mean_part, dmean_part, ks, cb.Nc, M->m, M->d, h, M->hyp, grad == 1 ? 1 : 0,
+                                               cb.mean, cb.dmean);
+    BOCF_LAUNCH_OK("kstar_reduce_kernel");
   }
-  set_error("unknown kernel kind");
-  return -1;
+  return 0;
 }
 
 // sum over outputs and partials of the fused gradient:  dacq[i][q] (+)= sum_j (xs_jq S0_j - ACC_jq) / l_jq

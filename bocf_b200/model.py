@@ -73,7 +73,8 @@ class multi_outputGP(object):
         """Load H hyper-samples: variance (H,m), lengthscale (H,m,d), noise (H,m).
 
         Stands in for the per-sample GPRegression instances GPModel.updateModel fills from HMC
-        (gpmodel.py:121-126).  ``kind`` in {'se','rbf','matern52','matern32'}.
+        (gpmodel.py:121-126).  ``kind`` in {'se','rbf','matern52','matern32'}, or a sequence with one such name per
+        output.
         """
         variance = np.ascontiguousarray(variance, dtype=np.float64)
         lengthscale = np.ascontiguousarray(lengthscale, dtype=np.float64)
@@ -82,16 +83,22 @@ class multi_outputGP(object):
         assert m == self.output_dim and lengthscale.shape[:2] == (H, m) and noise.shape == (H, m)
         if kind is None:
             kind = self._kernel_kind()
+        elif not isinstance(kind, str):
+            kind = tuple(kind)
+            assert len(kind) == m, "one kernel family per output"
+            if len(set(kind)) == 1:
+                kind = kind[0]
         self._hyp = (kind, variance, lengthscale, noise)
         self._explicit_hyp = True
         if self.X is not None:
             self._upload_and_factorize()
 
     def _kernel_kind(self):
-        kinds = set(k.kind for k in self.kernel if k is not None)
-        if len(kinds) > 1:
-            raise NotImplementedError("all outputs must share one kernel family (one enum per device model)")
-        return kinds.pop() if kinds else "se"
+        """Kernel family of the model: one name when every output uses the same family, else a tuple with one name per
+        output (multi_outputGP.py:23,38-44 builds output j from kernel[j]; an output without a kernel gets the
+        reference's default SE, gpmodel.py:57-58)."""
+        kinds = tuple("se" if k is None else k.kind for k in self.kernel)
+        return kinds[0] if len(set(kinds)) == 1 else kinds
 
     def _default_hypers(self, d, Y_all):
         """Initial hyper-parameters of the reference's model constructors, as one hyper-sample (H = 1)."""
@@ -211,10 +218,14 @@ class multi_outputGP(object):
         if self._handle is None or self._handle_sig != (kind, d):
             self._destroy()
             h = ctypes.c_void_p()
-            _lib.check(lib.bocf_model_create(ctypes.byref(h), self.output_dim, d, _lib.KERNELS[kind],
+            kinds = [kind] * self.output_dim if isinstance(kind, str) else list(kind)
+            _lib.check(lib.bocf_model_create(ctypes.byref(h), self.output_dim, d, _lib.KERNELS[kinds[0]],
                                              self.device.index or 0))
             self._handle = h
             self._handle_sig = (kind, d)
+            if len(set(kinds)) > 1:             # a kernel family per output
+                codes = (ctypes.c_int * self.output_dim)(*[_lib.KERNELS[k] for k in kinds])
+                _lib.check(lib.bocf_model_set_kernels(self._handle, codes, self.output_dim))
             upload_data = True
             if self.precision is not None:
                 mode, slices = _lib.parse_precision(self.precision)

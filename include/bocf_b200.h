@@ -89,8 +89,13 @@ const char* bocf_version(void);
 /* ---- model: replaces multi_outputGP (multi_outputGP.py:9-348) + GPModel/GPModelFixedHyps prediction
  *      state (GPyOpt/models/gpmodel.py:136-175,259-271) -------------------------------------------- */
 
-/* m independent outputs over d inputs, all with the same kernel family. */
+/* m independent outputs over d inputs, all with the kernel family `kernel` (see bocf_model_set_kernels). */
 int bocf_model_create(bocf_model** out, int m, int d, int kernel, int device);
+/* One kernel family per output: kinds[0..m) of enum bocf_kernel.  Replaces the `kernel` LIST multi_outputGP takes
+ * (multi_outputGP.py:23,38-44: output j is built from kernel[j]).  Takes effect at the next bocf_model_factorize (the
+ * factorised state is invalidated); the family is a compile-time parameter of every kernel that evaluates k(.,.), so
+ * runs of consecutive outputs with the same family share one launch. */
+int bocf_model_set_kernels(bocf_model* model, const int* kinds, int m);
 int bocf_model_destroy(bocf_model* mdl);
 
 /* Training data.  X [dev] n x d, Y [dev] m x n (row j = observations of output j).

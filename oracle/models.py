@@ -157,7 +157,8 @@ class multi_outputGP(object):
 
     @classmethod
     def from_hyper_samples(cls, kind, variance, lengthscale, noise, ARD=True, n_samples=None):
-        """variance (H,m), lengthscale (H,m,d) [or (H,m,1) if not ARD], noise (H,m)."""
+        """variance (H,m), lengthscale (H,m,d) [or (H,m,1) if not ARD], noise (H,m); kind: one kernel family or one per
+        output (multi_outputGP.py:38-44 builds output j from kernel[j])."""
         variance = np.asarray(variance, dtype=float)
         lengthscale = np.asarray(lengthscale, dtype=float)
         noise = np.asarray(noise, dtype=float)
@@ -165,7 +166,8 @@ class multi_outputGP(object):
         d = lengthscale.shape[2]
         outs = []
         for j in range(m):
-            kerns = [Kern(kind, d, variance[h, j], lengthscale[h, j], ARD=ARD) for h in range(H)]
+            kj = kind if isinstance(kind, str) else kind[j]
+            kerns = [Kern(kj, d, variance[h, j], lengthscale[h, j], ARD=ARD) for h in range(H)]
             outs.append(GPModel(kerns, [noise[h, j] for h in range(H)]))
         return cls(m, outs, H if n_samples is None else n_samples)
 

@@ -40,7 +40,8 @@ def _gen_score(composite, theta, Y):
 def make_problem(m=4, d=6, n=200, H=1, kind="rbf", composite="sumsq_target", N=1024, S=256, L=1, seed=0,
                  noise=1e-2, prior_draw=True, focus=0.75, focus_scale=0.08):
     """Synthetic inputs of SURVEY.md 8(d): X ~ U[0,1]^{n x d}, Y_j a prior-GP draw + noise, lengthscales
-    U[0.2,1]*sqrt(d)/2, sigma_f^2 = 1, sigma_n^2 = 1e-2, candidates U[0,1]^{N x d} (seed 7), Z ~ N(0,1) (seed 11)."""
+    U[0.2,1]*sqrt(d)/2, sigma_f^2 = 1, sigma_n^2 = 1e-2, candidates U[0,1]^{N x d} (seed 7), Z ~ N(0,1) (seed 11).
+    ``kind``: one kernel family, or a sequence with one family per output (multi_outputGP.py:23,38-44)."""
     P = Problem()
     rng = np.random.default_rng(seed)
     P.m, P.d, P.n, P.H, P.kind, P.composite, P.N, P.S, P.L = m, d, n, H, kind, composite, N, S, L
@@ -52,7 +53,7 @@ def make_problem(m=4, d=6, n=200, H=1, kind="rbf", composite="sumsq_target", N=1
     for j in range(m):
         r = np.random.default_rng(1000 + j + 17 * seed)
         if prior_draw and n <= 2500:
-            K = _gen_kernel(kind, P.variance[0, j], P.lengthscale[0, j], P.X)
+            K = _gen_kernel(kind if isinstance(kind, str) else kind[j], P.variance[0, j], P.lengthscale[0, j], P.X)
             K[np.diag_indices_from(K)] += 1e-8
             Lc = np.linalg.cholesky(K)
             y = Lc @ r.standard_normal(n) + np.sqrt(noise) * r.standard_normal(n)
