@@ -458,6 +458,8 @@ int bocf_model_factorize(bocf_model* M, double* jitter_out, void* stream) {
     if (int rc = dev_alloc(&M->xsq, (size_t)Hm * M->n_pad)) return rc;
     if (int rc = dev_alloc(&M->Lmat, (size_t)Hm * nn)) return rc;
     if (int rc = dev_alloc(&M->Linv, (size_t)Hm * nn)) return rc;
+    // blocks above the block diagonal are never written afterwards and must read as zero (contractions, matvecs)
+    BOCF_CUDA_OK(cudaMemsetAsync(M->Linv, 0, sizeof(double) * (size_t)Hm * nn, st));
     if (int rc = dev_alloc(&M->Dinv, (size_t)Hm * M->nb * TILE * TILE)) return rc;
     if (int rc = dev_alloc(&M->alpha, (size_t)Hm * M->n_pad)) return rc;
     if (int rc = dev_alloc(&M->tvec, (size_t)Hm * M->n_pad)) return rc;
@@ -474,6 +476,10 @@ int bocf_model_factorize(bocf_model* M, double* jitter_out, void* stream) {
     if (int rc = launch_gram(M, st)) return rc;
     if (int rc = launch_cholesky(M, st)) return rc;
     BOCF_CUDA_OK(cudaMemcpyAsync(info.data(), M->info, sizeof(int) * Hm, cudaMemcpyDeviceToHost, st));
+    // optimistic: the inverse and alpha are queued behind the factor without waiting for the pivot flags (a failed
+    // factor carries unit pivots, so the work is finite and simply redone after the jitter retry): one host
+    // synchronisation per factorisation instead of two -- the fit loops factorise thousands of times
+    if (int rc = launch_inverse_and_alpha(M, st)) return rc;
     BOCF_CUDA_OK(cudaStreamSynchronize(st));
     bool any_fail = false;
     for (int hj = 0; hj < Hm; ++hj) {
@@ -494,8 +500,6 @@ int bocf_model_factorize(bocf_model* M, double* jitter_out, void* stream) {
     }
     if (!any_fail) break;
   }
-  if (int rc = launch_inverse_and_alpha(M, st)) return rc;
-  BOCF_CUDA_OK(cudaStreamSynchronize(st));
   if (jitter_out)
     for (int hj = 0; hj < Hm; ++hj) jitter_out[hj] = M->hyp_host[hj].jitter;
   // the digit planes belong to the previous factor: rebuilt lazily by the first posterior / acquisition call, so

@@ -63,6 +63,7 @@ template <int KIND>
 __global__ void gram_kernel(const double* __restrict__ Xs, const double* __restrict__ xsq,
                             const OutHyp* __restrict__ hyp, int n, int n_pad, int d, double* __restrict__ A, OutRun run,
                             int m) {
+  if (blockIdx.x > blockIdx.y) return;             // only the lower triangle is ever read (potrf / trsm / syrk)
   const int hj = run_hj(blockIdx.z, run, m);
   const int a = blockIdx.y * 16 + threadIdx.y;
   const int b = blockIdx.x * 16 + threadIdx.x;
@@ -99,194 +100,210 @@ __global__ void gram_kernel(const double* __restrict__ Xs, const double* __restr
 
 // ---------------------------------------------------------------------------------------------------
 // Diagonal block: Cholesky + in-place triangular inverse of one 128 x 128 block in shared memory (one CTA / matrix).
-// Both halves are blocked with 8-wide panels so the 128-step dependency chain of the unblocked algorithms (3 barriers
-// and a divide per column, a 8128-long serial dot-product chain in the inverse) shrinks to 16 panel steps:
-//   Cholesky (right-looking):  8 x 8 diagonal sub-block by one warp (lane = row, shuffles), rows below by forward
-//                              substitution (thread per row), rank-8 trailing update in 4 x 4 register tiles;
-//   inverse (dtrtri, lower):   from the last panel up,  A21 <- -X22 . A21 . D^-1  with X22 the already inverted trailing
-//                              block (two threads per row, eight accumulators each), D^-1 by one warp (lane = column).
+// This kernel sits nb times on the critical path of every factorisation (only H*m CTAs run, everything else waits), so
+// it is organised around its dependency chain, in 32-wide sub-blocks:
+//   factor    the 32 x 32 diagonal sub-block by ONE warp, register resident (lane = row, column k broadcast by shuffles,
+//             reciprocal square root instead of sqrt + divide on the chain);
+//   solve     the rows below it by forward substitution, thread per row, L broadcast from shared memory;
+//   update    the trailing lower triangle on the fp64 tensor cores (DMMA 8x8x4, K = 32);
+//   invert    afterwards the four 32 x 32 diagonal sub-blocks in parallel (warp each, lane = column) and assemble the
+//             128 x 128 inverse recursively,  X21 = -X22 (L21 X11),  at 32 then 64 wide, again on DMMA.
 // The dpotrf failure convention is kept: the first non-positive pivot is reported in info[] (1-based), replaced by 1.
-constexpr int DLD = TILE + 1;
-constexpr int PW = 8;
-constexpr int POTRF_SMEM = (TILE * DLD + TILE * PW + PW * PW) * (int)sizeof(double);
+constexpr int PSB = 32;                       // sub-block
+constexpr int DLD = TILE + 4;                 // row stride == 4 mod 16 doubles: conflict-free 64-bit fragment loads
+constexpr int WLD = 64 + 4;
+constexpr int POTRF_SMEM = (TILE * DLD + 64 * WLD + TILE) * (int)sizeof(double);
+
+// C[i0.., j0..] (8 x 8) = sum_k A[i0 + g][k] B(k, j0 + g), K a multiple of 4.  BT: B(k, n) = Bm[n * ldb + k] (rows of Bm
+// are columns of B), else B(k, n) = Bm[k * ldb + n].  lane = 4 g + t.
+template <bool BT>
+__device__ __forceinline__ void dmma_tile(double& c0, double& c1, const double* __restrict__ A, int lda,
+                                          const double* __restrict__ Bm, int ldb, int K, int g, int t) {
+#pragma unroll 8
+  for (int k = 0; k < K; k += 4) {
+    const double a = A[g * lda + k + t];
+    const double b = BT ? Bm[g * ldb + k + t] : Bm[(k + t) * ldb + g];
+    dmma884(c0, c1, a, b);
+  }
+}
+
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lmat, double* __restrict__ Dinv,
                                                          int* __restrict__ info, int n, int n_pad, int nb, int kb) {
-  extern __shared__ __align__(16) double T[];   // TILE x DLD | Bt[TILE][PW] | Di[PW][PW]
-  double* Bt = T + TILE * DLD;
-  double* Di = Bt + TILE * PW;
+  extern __shared__ __align__(16) double T[];   // T[TILE][DLD] | W[64][WLD] | dinv[TILE]
+  double* W = T + TILE * DLD;
+  double* dinv = W + 64 * WLD;
   const int hj = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int k0 = kb * TILE;
   const int nrem = min(TILE, n - k0);
   double* Ablk = Lmat + (int64_t)hj * n_pad * n_pad + (int64_t)k0 * n_pad + k0;
   for (int idx = tid; idx < TILE * TILE; idx += 256) {
-    int r = idx >> 7, c = idx & 127;
-    double v = (r < nrem && c < nrem) ? Ablk[(int64_t)r * n_pad + c] : (r == c ? 1.0 : 0.0);
-    T[r * DLD + c] = v;
+    const int r = idx >> 7, c = idx & 127;
+    // lower triangle of the valid part, identity on the padding, zero above the diagonal
+    T[r * DLD + c] = (c > r) ? 0.0 : (r < nrem) ? Ablk[(int64_t)r * n_pad + c] : (r == c ? 1.0 : 0.0);
   }
   __syncthreads();
 
   // ---------------- Cholesky ----------------
-  for (int c0 = 0; c0 < TILE; c0 += PW) {
+  for (int c0 = 0; c0 < TILE; c0 += PSB) {
     if (warp == 0) {
-      // lane k (< PW) owns row c0 + k of the diagonal sub-block
-      double a[PW];
+      double a[PSB];                              // row c0 + lane of the diagonal sub-block
 #pragma unroll
-      for (int q = 0; q < PW; ++q) a[q] = (lane < PW) ? T[(c0 + lane) * DLD + c0 + q] : 0.0;
+      for (int q = 0; q < PSB; ++q) a[q] = T[(c0 + lane) * DLD + c0 + q];
 #pragma unroll
-      for (int k = 0; k < PW; ++k) {
+      for (int k = 0; k < PSB; ++k) {
         double piv = __shfl_sync(0xffffffffu, a[k], k);
         if (!(piv > 0.0)) {                      // dpotrf info != 0  -> jitchol retry on the host side
           if (lane == 0 && info[hj] == 0) info[hj] = k0 + c0 + k + 1;
           piv = 1.0;
         }
-        const double sq = sqrt(piv);
-        a[k] = (lane == k) ? sq : a[k] / sq;     // column k of L (meaningful for lanes >= k)
+        double rs = rsqrt(piv);
+        double sq = piv * rs;
+        sq = fma(fma(-sq, sq, piv), 0.5 * rs, sq);          // sqrt(piv) to the last bit or so
+        rs = fma(fma(-sq, rs, 1.0), rs, rs);                // 1 / sqrt(piv)
+        a[k] = (lane == k) ? sq : a[k] * rs;                // column k of L (meaningful for lanes >= k)
+        if (lane == k) dinv[c0 + k] = rs;
 #pragma unroll
-        for (int c2 = k + 1; c2 < PW; ++c2) {
+        for (int c2 = k + 1; c2 < PSB; ++c2) {
           const double lc2 = __shfl_sync(0xffffffffu, a[k], c2);
-          if (lane >= c2) a[c2] -= a[k] * lc2;
+          a[c2] = fma(-a[k], lc2, a[c2]);                   // lanes < c2 carry don't-care values, masked at the store
         }
       }
-      if (lane < PW) {
 #pragma unroll
-        for (int q = 0; q < PW; ++q)
-          if (q <= lane) T[(c0 + lane) * DLD + c0 + q] = a[q];
+      for (int q = 0; q < PSB; ++q) T[(c0 + lane) * DLD + c0 + q] = (q <= lane) ? a[q] : 0.0;
+    }
+    __syncthreads();
+    const int w0 = c0 + PSB;
+    if (w0 >= TILE) break;
+    {
+      // rows below:  P[r][k] = (A[r][k] - sum_{t<k} P[r][t] L[k][t]) / L[k][k], in update form so the multiply-adds of a
+      // step are independent; threads 32.. take one row each (warp 0 has just finished the factor)
+      const int r = w0 + tid - 32;
+      if (tid >= 32 && r < TILE) {
+        double a[PSB];
+        const double* Ld = T + c0 * DLD + c0;
+#pragma unroll
+        for (int q = 0; q < PSB; ++q) a[q] = T[r * DLD + c0 + q];
+#pragma unroll
+        for (int k = 0; k < PSB; ++k) {
+          a[k] *= dinv[c0 + k];
+#pragma unroll
+          for (int k2 = k + 1; k2 < PSB; ++k2) a[k2] = fma(-a[k], Ld[k2 * DLD + k], a[k2]);
+        }
+#pragma unroll
+        for (int q = 0; q < PSB; ++q) T[r * DLD + c0 + q] = a[q];
       }
     }
     __syncthreads();
     {
-      // rows below the sub-block:  L[r][c0+k] = (A[r][c0+k] - sum_{t<k} L[r][c0+t] L[c0+k][c0+t]) / L[c0+k][c0+k]
-      const int r = c0 + PW + tid;
-      if (r < TILE) {
-        double a[PW];
-#pragma unroll
-        for (int q = 0; q < PW; ++q) a[q] = T[r * DLD + c0 + q];
-#pragma unroll
-        for (int k = 0; k < PW; ++k) {
-          double acc = a[k];
-#pragma unroll
-          for (int t = 0; t < k; ++t) acc -= a[t] * T[(c0 + k) * DLD + c0 + t];
-          a[k] = acc / T[(c0 + k) * DLD + c0 + k];
-        }
-#pragma unroll
-        for (int q = 0; q < PW; ++q) T[r * DLD + c0 + q] = a[q];
-      }
-    }
-    __syncthreads();
-    {
-      // trailing update  A[r][c] -= sum_k L[r][c0+k] L[c][c0+k]  on the lower triangle of [w0, TILE)^2, 4 x 4 tiles
-      const int w0 = c0 + PW;
-      const int nt = (TILE - w0) >> 2;
-      const int nblk = nt * (nt + 1) / 2;
-      for (int b = tid; b < nblk; b += 256) {
-        int bi = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
-        while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
-        while (bi * (bi + 1) / 2 > b) --bi;
-        const int bj = b - bi * (bi + 1) / 2;
-        const double* Lr = T + (w0 + 4 * bi) * DLD + c0;
-        const double* Lc = T + (w0 + 4 * bj) * DLD + c0;
-        double acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-#pragma unroll
-        for (int k = 0; k < PW; ++k) {
-          double lr[4], lc[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            lr[i] = Lr[i * DLD + k];
-            lc[i] = Lc[i * DLD + k];
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fma(lr[i], lc[j], acc[i][j]);
-        }
-        double* Tt = T + (w0 + 4 * bi) * DLD + w0 + 4 * bj;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (bi != bj || j <= i) Tt[i * DLD + j] -= acc[i][j];
+      // trailing update  A[r][c] -= sum_k P[r][k] P[c][k]  on the lower triangle of [w0, TILE)^2: 8 x 8 DMMA tiles
+      const int nt = (TILE - w0) >> 3;
+      const int ntile = nt * (nt + 1) / 2;
+      int bi = 0, bj = 0;
+      for (int b = 0; b < warp; ++b)
+        if (++bj > bi) { ++bi; bj = 0; }
+      for (int b = warp; b < ntile; b += 8) {
+        double x0 = 0.0, x1 = 0.0;
+        dmma_tile<true>(x0, x1, T + (w0 + 8 * bi) * DLD + c0, DLD, T + (w0 + 8 * bj) * DLD + c0, DLD, PSB, g, t);
+        double* Tt = T + (w0 + 8 * bi + g) * DLD + w0 + 8 * bj + 2 * t;
+        Tt[0] -= x0;
+        Tt[1] -= x1;
+        for (int q = 0; q < 8; ++q)
+          if (++bj > bi) { ++bi; bj = 0; }
       }
     }
     __syncthreads();
   }
   // write the factor back (lower triangle of the valid part; strict upper and padding -> 0)
   for (int idx = tid; idx < TILE * TILE; idx += 256) {
-    int r = idx >> 7, c = idx & 127;
+    const int r = idx >> 7, c = idx & 127;
     Ablk[(int64_t)r * n_pad + c] = (r < nrem && c <= r) ? T[r * DLD + c] : 0.0;
   }
   __syncthreads();
 
-  // ---------------- in-place inverse of the lower-triangular block, last panel first ----------------
-  for (int jb = TILE - PW; jb >= 0; jb -= PW) {
-    const int w0 = jb + PW;                      // first row / column of the already inverted trailing block X22
-    // copy the panel below the diagonal sub-block (rows >= w0, columns jb .. jb+PW-1)
-    for (int idx = tid; idx < (TILE - w0) * PW; idx += 256) {
-      const int rr = idx / PW, q = idx - rr * PW;
-      Bt[rr * PW + q] = T[(w0 + rr) * DLD + jb + q];
+  // ---------------- inverse of the four diagonal sub-blocks: lane = column, x[r] -= L[r][k] x[k] ----------------
+  if (warp < TILE / PSB) {
+    const int c0 = warp * PSB;
+    const double* Ld = T + c0 * DLD + c0;
+    double x[PSB];
+#pragma unroll
+    for (int r = 0; r < PSB; ++r) x[r] = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < PSB; ++k) {
+      x[k] *= dinv[c0 + k];
+#pragma unroll
+      for (int r = k + 1; r < PSB; ++r) x[r] = fma(-Ld[r * DLD + k], x[k], x[r]);
     }
-    if (warp == 0) {
-      // D^-1 of the PW x PW sub-block: lane k (< PW) owns column k of the inverse (forward substitution)
-      double x[PW];
+    __syncwarp();                                 // every lane has read the factor before anyone overwrites it
 #pragma unroll
-      for (int r = 0; r < PW; ++r) {
-        double acc = 0.0;
-#pragma unroll
-        for (int t = 0; t < r; ++t) acc += (t >= lane) ? T[(jb + r) * DLD + jb + t] * x[t] : 0.0;
-        const double drr = T[(jb + r) * DLD + jb + r];
-        x[r] = (r == lane) ? 1.0 / drr : ((r > lane) ? -acc / drr : 0.0);
-      }
-      __syncwarp();
-      if (lane < PW) {
-#pragma unroll
-        for (int r = 0; r < PW; ++r) {
-          Di[r * PW + lane] = x[r];
-          if (r >= lane) T[(jb + r) * DLD + jb + lane] = x[r];
-        }
-      }
-    }
-    __syncthreads();
-    {
-      // row r of the panel:  tmp[k] = sum_{t = w0..r} X22[r][t] Bt[t][k] ;  out[k] = -sum_{q >= k} tmp[q] Di[q][k]
-      const int r = w0 + (tid >> 1), half = tid & 1;
-      double tmp[PW];
-#pragma unroll
-      for (int q = 0; q < PW; ++q) tmp[q] = 0.0;
-      if (r < TILE) {
-        const double* Xr = T + r * DLD;
-        for (int t = w0 + half; t <= r; t += 2) {
-          const double xv = Xr[t];
-          const double2* b2 = reinterpret_cast<const double2*>(Bt + (t - w0) * PW);
-#pragma unroll
-          for (int q2 = 0; q2 < PW / 2; ++q2) {
-            const double2 bv = b2[q2];
-            tmp[2 * q2] = fma(xv, bv.x, tmp[2 * q2]);
-            tmp[2 * q2 + 1] = fma(xv, bv.y, tmp[2 * q2 + 1]);
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < PW; ++q) tmp[q] += __shfl_xor_sync(0xffffffffu, tmp[q], 1);
-      if (r < TILE) {
-#pragma unroll
-        for (int kk = 0; kk < PW / 2; ++kk) {
-          const int k = half * (PW / 2) + kk;
-          double o = 0.0;
-#pragma unroll
-          for (int q = 0; q < PW; ++q) o += (q >= k) ? tmp[q] * Di[q * PW + k] : 0.0;
-          T[r * DLD + jb + k] = -o;
-        }
-      }
-    }
-    __syncthreads();
+    for (int r = 0; r < PSB; ++r) T[(c0 + r) * DLD + c0 + lane] = x[r];      // exactly 0 above the diagonal
   }
+  __syncthreads();
+  // ---------------- 64 x 64 inverses:  X21 = -X22 (L21 X11)  for the sub-block pairs (1,0) and (3,2) ----------------
+  {
+    const int p = warp >> 2, w4 = warp & 3;       // pair, warp within the pair: output tiles w4, w4 + 4, ... of 16
+    const int o = 2 * PSB * p;
+    double* Wp = W + p * PSB * WLD;
+    double x0[4], x1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int tt = w4 + 4 * q, ti = tt >> 2, tj = tt & 3;
+      x0[q] = x1[q] = 0.0;
+      dmma_tile<false>(x0[q], x1[q], T + (o + PSB + 8 * ti) * DLD + o, DLD, T + o * DLD + o + 8 * tj, DLD, PSB, g, t);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int tt = w4 + 4 * q, ti = tt >> 2, tj = tt & 3;
+      Wp[(8 * ti + g) * WLD + 8 * tj + 2 * t] = x0[q];
+      Wp[(8 * ti + g) * WLD + 8 * tj + 2 * t + 1] = x1[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int tt = w4 + 4 * q, ti = tt >> 2, tj = tt & 3;
+      x0[q] = x1[q] = 0.0;
+      dmma_tile<false>(x0[q], x1[q], T + (o + PSB + 8 * ti) * DLD + o + PSB, DLD, Wp + 8 * tj, WLD, PSB, g, t);
+    }
+    __syncthreads();                              // L21 has been consumed by everyone (first product) before it is replaced
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int tt = w4 + 4 * q, ti = tt >> 2, tj = tt & 3;
+      T[(o + PSB + 8 * ti + g) * DLD + o + 8 * tj + 2 * t] = -x0[q];
+      T[(o + PSB + 8 * ti + g) * DLD + o + 8 * tj + 2 * t + 1] = -x1[q];
+    }
+  }
+  __syncthreads();
+  // ---------------- 128 x 128 inverse:  X21 = -X22 (L21 X11)  with 64 x 64 blocks; warp w owns row tile w ----------
+  {
+    double x0[8], x1[8];
+#pragma unroll
+    for (int tj = 0; tj < 8; ++tj) {
+      x0[tj] = x1[tj] = 0.0;
+      dmma_tile<false>(x0[tj], x1[tj], T + (64 + 8 * warp) * DLD, DLD, T + 8 * tj, DLD, 64, g, t);
+    }
+#pragma unroll
+    for (int tj = 0; tj < 8; ++tj) {
+      W[(8 * warp + g) * WLD + 8 * tj + 2 * t] = x0[tj];
+      W[(8 * warp + g) * WLD + 8 * tj + 2 * t + 1] = x1[tj];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tj = 0; tj < 8; ++tj) {
+      x0[tj] = x1[tj] = 0.0;
+      dmma_tile<false>(x0[tj], x1[tj], T + (64 + 8 * warp) * DLD + 64, DLD, W + 8 * tj, WLD, 64, g, t);
+    }
+    // rows 64 + 8 warp .. of the (1,0) block are read only by this warp's own first product, which is complete
+#pragma unroll
+    for (int tj = 0; tj < 8; ++tj) {
+      T[(64 + 8 * warp + g) * DLD + 8 * tj + 2 * t] = -x0[tj];
+      T[(64 + 8 * warp + g) * DLD + 8 * tj + 2 * t + 1] = -x1[tj];
+    }
+  }
+  __syncthreads();
   double* Dblk = Dinv + ((int64_t)hj * nb + kb) * TILE * TILE;
   for (int idx = tid; idx < TILE * TILE; idx += 256) {
-    int r = idx >> 7, c = idx & 127;
+    const int r = idx >> 7, c = idx & 127;
     Dblk[idx] = (r < nrem && c <= r) ? T[r * DLD + c] : 0.0;
   }
 }
@@ -364,38 +381,63 @@ __global__ void linv_init_kernel(double* __restrict__ Linv, const double* __rest
   }
 }
 
+// Merge step of the recursive inverse.  With L = [[L11, 0], [L21, L22]] and X11 = L11^-1, X22 = L22^-1 known,
+//   X21 = -X22 (L21 X11).
+// Level b (= 1, 2, 4, ... blocks of 128): the groups [o, o + 2b) of block rows, o = 0, 2b, ..., merge their halves, all
+// groups and all matrices in one launch per product -- 2 ceil(log2 nb) launches whose tiles are all independent, instead
+// of the 2 (nb - 1) launches of a row-by-row recursion whose longest tile grows with the row.
+//   STEP 1:  Tm[I][J] = sum_{T = J}^{o+b-1} L[I][T] X[T][J]        (I in the lower half, J in the upper half)
+//            kept TRANSPOSED in the unused mirror block (J, I) of Lmat (nothing reads Lmat above the diagonal)
+//   STEP 2:  X[I][J]  = -sum_{T = o+b}^{I} X[I][T] Tm[T][J]
+// grid.x = tile rank * Hm + hj, heaviest tiles (longest K) first.
 template <int STEP>
-__global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) linv_row_kernel(const double* __restrict__ Lmat,
-                                                                    double* __restrict__ Linv,
-                                                                    const double* __restrict__ Dinv, int n_pad, int nb,
-                                                                    int I) {
+__global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) linv_merge_kernel(double* __restrict__ Lmat,
+                                                                      double* __restrict__ Linv, int n_pad, int nb, int b,
+                                                                      int Hm) {
   extern __shared__ __align__(16) double smem[];
-  const int hj = blockIdx.y, J = blockIdx.x;   // J < I
-  const double* Lb = Lmat + (int64_t)hj * n_pad * n_pad;
+  const int hj = blockIdx.x % Hm;
+  const int rank = blockIdx.x / Hm;
+  const int ngroups = (nb - b + 2 * b - 1) / (2 * b);
+  // rank -> (heavy index, group, light index): K depends on j for STEP 1 (small j heavy), on i for STEP 2 (large i heavy)
+  const int hv = rank / (ngroups * b), rem = rank - hv * (ngroups * b);
+  const int grp = rem / b, lt = rem - grp * b;
+  const int o = grp * 2 * b;
+  const int i = (STEP == 1) ? lt : b - 1 - hv;
+  const int j = (STEP == 1) ? hv : lt;
+  const int I = o + b + i, J = o + j;
+  if (I >= nb) return;                             // the last group may have a short lower half
+  double* Lb = Lmat + (int64_t)hj * n_pad * n_pad;
   double* Li = Linv + (int64_t)hj * n_pad * n_pad;
-  double* C = Li + (int64_t)I * TILE * n_pad + (int64_t)J * TILE;
   double acc[8][4][2];
   gemm::zero_acc(acc);
-  if (STEP == 1) {
-    // A(m,k) = L[I*128+m][k] (m-major) ; B(k,n) = Linv[k][J*128+n] (k-major) ; k in [J*128, I*128)
-    gemm::mainloop<gemm::Tile128, false, true>(acc, Lb + (int64_t)I * TILE * n_pad, n_pad, Li + (int64_t)J * TILE, n_pad, J * TILE,
-                                I * TILE, smem);
-  } else {
-    // A = Dinv_I (m-major, ld 128) ; B(k,n) = S[k][n] at C[k*n_pad + n] (k-major)
-    const double* D = Dinv + ((int64_t)hj * nb + I) * TILE * TILE;
-    gemm::mainloop<gemm::Tile128, false, true>(acc, D, TILE, C, n_pad, 0, TILE, smem);
-  }
-  const double sgn = (STEP == 1) ? 1.0 : -1.0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int mbase = (warp >> 2) * 64, nbase = (warp & 3) * 32;
+  if (STEP == 1) {
+    // A(m,k) = L[I*128+m][k] (m-major) ; B(k,n) = X[k][J*128+n] (k-major) ; k in [J*128, (o+b)*128)
+    gemm::mainloop<gemm::Tile128, false, true>(acc, Lb + (int64_t)I * TILE * n_pad, n_pad, Li + (int64_t)J * TILE, n_pad,
+                                               J * TILE, (o + b) * TILE, smem);
+    double* C = Lb + (int64_t)J * TILE * n_pad + (int64_t)I * TILE;      // Tm^T: element (r, c) at C[c * n_pad + r]
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+    for (int ii = 0; ii < 8; ++ii)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int r = mbase + 8 * i + g, c = nbase + 8 * j + 2 * t;
-      *reinterpret_cast<double2*>(C + (int64_t)r * n_pad + c) =
-          make_double2(sgn * acc[i][j][0], sgn * acc[i][j][1]);
-    }
+      for (int jj = 0; jj < 4; ++jj) {
+        const int r = mbase + 8 * ii + g, c = nbase + 8 * jj + 2 * t;
+        C[(int64_t)c * n_pad + r] = acc[ii][jj][0];
+        C[(int64_t)(c + 1) * n_pad + r] = acc[ii][jj][1];
+      }
+  } else {
+    // A(m,k) = X[I*128+m][k] (m-major) ; B(k,n) = Tm[k][J*128+n] = Lmat[(J*128+n)*n_pad + k] (n-major) ; k in [(o+b)*128, (I+1)*128)
+    gemm::mainloop<gemm::Tile128, false, false>(acc, Li + (int64_t)I * TILE * n_pad, n_pad, Lb + (int64_t)J * TILE * n_pad, n_pad,
+                                                (o + b) * TILE, (I + 1) * TILE, smem);
+    double* C = Li + (int64_t)I * TILE * n_pad + (int64_t)J * TILE;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int r = mbase + 8 * ii + g, c = nbase + 8 * jj + 2 * t;
+        *reinterpret_cast<double2*>(C + (int64_t)r * n_pad + c) = make_double2(-acc[ii][jj][0], -acc[ii][jj][1]);
+      }
+  }
 }
 
 // t = Linv . yc   (warp per row)
@@ -413,17 +455,31 @@ __global__ void linv_matvec_kernel(const double* __restrict__ Linv, const double
   if (lane == 0) tvec[(int64_t)hj * n_pad + a] = s;
 }
 
-// alpha = Linv^T . t   (thread per column, coalesced over b)
-__global__ void linv_t_matvec_kernel(const double* __restrict__ Linv, const double* __restrict__ tvec, int n_pad,
-                                     double* __restrict__ alpha) {
+// alpha = Linv^T . t : CTA = 32 columns x 8 row groups (rows a = b0 + q, b0 + q + 8, ...: each row read is 256
+// contiguous bytes), partial sums reduced through shared memory in fixed order
+__global__ void __launch_bounds__(256) linv_t_matvec_kernel(const double* __restrict__ Linv, const double* __restrict__ tvec,
+                                                            int n_pad, double* __restrict__ alpha) {
+  __shared__ double red[8][33];
   const int hj = blockIdx.y;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n_pad) return;
+  const int cl = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const int b0 = blockIdx.x * 32, b = b0 + cl;
   const double* Li = Linv + (int64_t)hj * n_pad * n_pad;
   const double* tv = tvec + (int64_t)hj * n_pad;
-  double s = 0.0;
-  for (int a = b; a < n_pad; ++a) s += Li[(int64_t)a * n_pad + b] * tv[a];
-  alpha[(int64_t)hj * n_pad + b] = s;
+  double s0 = 0.0, s1 = 0.0;
+  int a = b0 + q;                                   // rows a < b hold exact zeros above the diagonal
+  for (; a + 8 < n_pad; a += 16) {
+    s0 = fma(Li[(int64_t)a * n_pad + b], tv[a], s0);
+    s1 = fma(Li[(int64_t)(a + 8) * n_pad + b], tv[a + 8], s1);
+  }
+  if (a < n_pad) s0 = fma(Li[(int64_t)a * n_pad + b], tv[a], s0);
+  red[q][cl] = s0 + s1;
+  __syncthreads();
+  if (q == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][cl];
+    alpha[(int64_t)hj * n_pad + b] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -566,8 +622,8 @@ static int set_smem_attrs() {
   BOCF_CUDA_OK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
   BOCF_CUDA_OK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
   BOCF_CUDA_OK(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
-  BOCF_CUDA_OK(cudaFuncSetAttribute(linv_row_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
-  BOCF_CUDA_OK(cudaFuncSetAttribute(linv_row_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(linv_merge_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(linv_merge_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
   done = true;
   return 0;
 }
@@ -593,14 +649,17 @@ int launch_cholesky(bocf_model* M, cudaStream_t st) {
 int launch_inverse_and_alpha(bocf_model* M, cudaStream_t st) {
   if (int rc = set_smem_attrs()) return rc;
   const int Hm = M->H * M->m, nb = M->nb;
-  BOCF_CUDA_OK(cudaMemsetAsync(M->Linv, 0, sizeof(double) * (size_t)Hm * M->n_pad * M->n_pad, st));
+  // Linv above the block diagonal stays zero from its allocation (bocf_model_factorize); every block on or below it is
+  // rewritten here
   linv_init_kernel<<<dim3(nb, Hm), 256, 0, st>>>(M->Linv, M->Dinv, M->n_pad, nb);
   BOCF_LAUNCH_OK("linv_init_kernel");
-  for (int I = 1; I < nb; ++I) {
-    linv_row_kernel<1><<<dim3(I, Hm), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
-    BOCF_LAUNCH_OK("linv_row_kernel<1>");
-    linv_row_kernel<2><<<dim3(I, Hm), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->Dinv, M->n_pad, nb, I);
-    BOCF_LAUNCH_OK("linv_row_kernel<2>");
+  for (int b = 1; b < nb; b *= 2) {
+    const int ngroups = (nb - b + 2 * b - 1) / (2 * b);
+    const unsigned grid = (unsigned)(ngroups * b * b * Hm);
+    linv_merge_kernel<1><<<grid, gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->n_pad, nb, b, Hm);
+    BOCF_LAUNCH_OK("linv_merge_kernel<1>");
+    linv_merge_kernel<2><<<grid, gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->n_pad, nb, b, Hm);
+    BOCF_LAUNCH_OK("linv_merge_kernel<2>");
   }
   return launch_alpha(M, st);
 }
@@ -609,7 +668,7 @@ int launch_alpha(bocf_model* M, cudaStream_t st) {
   const int Hm = M->H * M->m;
   linv_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 8), Hm), 256, 0, st>>>(M->Linv, M->yc, M->m, M->n_pad, M->tvec);
   BOCF_LAUNCH_OK("linv_matvec_kernel");
-  linv_t_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 128), Hm), 128, 0, st>>>(M->Linv, M->tvec, M->n_pad, M->alpha);
+  linv_t_matvec_kernel<<<dim3((unsigned)(M->n_pad / 32), Hm), 256, 0, st>>>(M->Linv, M->tvec, M->n_pad, M->alpha);
   BOCF_LAUNCH_OK("linv_t_matvec_kernel");
   return 0;
 }
