@@ -138,22 +138,46 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
   const int k0 = kb * TILE;
   const int nrem = min(TILE, n - k0);
   double* Ablk = Lmat + (int64_t)hj * n_pad * n_pad + (int64_t)k0 * n_pad + k0;
-  for (int idx = tid; idx < TILE * TILE; idx += 256) {
-    const int r = idx >> 7, c = idx & 127;
-    // lower triangle of the valid part, identity on the padding, zero above the diagonal
-    T[r * DLD + c] = (c > r) ? 0.0 : (r < nrem) ? Ablk[(int64_t)r * n_pad + c] : (r == c ? 1.0 : 0.0);
+  // lower triangle of the valid part, identity on the padding, zero above the diagonal; 16-byte async copies so the whole
+  // 128 KB block is in flight at once (a scalar load loop cost ~19 us of exposed latency per launch)
+  for (int idx = tid; idx < TILE * (TILE / 2); idx += 256) {
+    const int r = idx >> 6, c = (idx & 63) * 2;
+    double* dst = T + r * DLD + c;
+    if (c > r) {
+      dst[0] = 0.0;
+      dst[1] = 0.0;
+    } else if (r < nrem) {
+      cp_async16(dst, Ablk + (int64_t)r * n_pad + c);
+    } else {
+      dst[0] = (r == c) ? 1.0 : 0.0;
+      dst[1] = (r == c + 1) ? 1.0 : 0.0;
+    }
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
+  if (tid < TILE / 2) T[(2 * tid) * DLD + 2 * tid + 1] = 0.0;      // the pair that straddles the diagonal
+  __syncthreads();
+  double* Lt = W;                                 // [4][32][32]: column k of sub-block s at Lt[s*1024 + k*32 + row]
 
   // ---------------- Cholesky ----------------
   for (int c0 = 0; c0 < TILE; c0 += PSB) {
+    double* Ls = Lt + (c0 / PSB) * (PSB * PSB);
     if (warp == 0) {
-      double a[PSB];                              // row c0 + lane of the diagonal sub-block
+      // lane = row of the diagonal sub-block, held in registers.  Right-looking: column k is finished (scaled by
+      // 1 / sqrt(pivot)), parked in shared memory (Ls, column-major: the panel solve and the inverse below read it
+      // again), and every lane subtracts its multiple from the columns to the right -- independent multiply-adds fed by
+      // broadcast 16-byte loads.  Column k + 1 goes first so the next pivot's reciprocal square root overlaps the rest.
+      double a[PSB];
 #pragma unroll
-      for (int q = 0; q < PSB; ++q) a[q] = T[(c0 + lane) * DLD + c0 + q];
+      for (int q = 0; q < PSB; q += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(T + (c0 + lane) * DLD + c0 + q);
+        a[q] = v.x;
+        a[q + 1] = v.y;
+      }
+      double piv = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
       for (int k = 0; k < PSB; ++k) {
-        double piv = __shfl_sync(0xffffffffu, a[k], k);
         if (!(piv > 0.0)) {                      // dpotrf info != 0  -> jitchol retry on the host side
           if (lane == 0 && info[hj] == 0) info[hj] = k0 + c0 + k + 1;
           piv = 1.0;
@@ -164,14 +188,23 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
         rs = fma(fma(-sq, rs, 1.0), rs, rs);                // 1 / sqrt(piv)
         a[k] = (lane == k) ? sq : a[k] * rs;                // column k of L (meaningful for lanes >= k)
         if (lane == k) dinv[c0 + k] = rs;
+        Ls[k * PSB + lane] = a[k];
+        __syncwarp();
+        if (k + 1 < PSB) {
+          a[k + 1] = fma(-a[k], Ls[k * PSB + k + 1], a[k + 1]);
+          piv = __shfl_sync(0xffffffffu, a[k + 1], k + 1);
 #pragma unroll
-        for (int c2 = k + 1; c2 < PSB; ++c2) {
-          const double lc2 = __shfl_sync(0xffffffffu, a[k], c2);
-          a[c2] = fma(-a[k], lc2, a[c2]);                   // lanes < c2 carry don't-care values, masked at the store
+          for (int c2 = (k + 2) & ~1; c2 < PSB; c2 += 2) {  // lanes < c2 carry don't-care values, masked at the store
+            const double2 l2 = *reinterpret_cast<const double2*>(Ls + k * PSB + c2);
+            if (c2 >= k + 2) a[c2] = fma(-a[k], l2.x, a[c2]);
+            a[c2 + 1] = fma(-a[k], l2.y, a[c2 + 1]);
+          }
         }
       }
 #pragma unroll
-      for (int q = 0; q < PSB; ++q) T[(c0 + lane) * DLD + c0 + q] = (q <= lane) ? a[q] : 0.0;
+      for (int q = 0; q < PSB; q += 2)
+        *reinterpret_cast<double2*>(T + (c0 + lane) * DLD + c0 + q) =
+            make_double2((q <= lane) ? a[q] : 0.0, (q + 1 <= lane) ? a[q + 1] : 0.0);
     }
     __syncthreads();
     const int w0 = c0 + PSB;
@@ -182,17 +215,24 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
       const int r = w0 + tid - 32;
       if (tid >= 32 && r < TILE) {
         double a[PSB];
-        const double* Ld = T + c0 * DLD + c0;
 #pragma unroll
-        for (int q = 0; q < PSB; ++q) a[q] = T[r * DLD + c0 + q];
+        for (int q = 0; q < PSB; q += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(T + r * DLD + c0 + q);
+          a[q] = v.x;
+          a[q + 1] = v.y;
+        }
 #pragma unroll
         for (int k = 0; k < PSB; ++k) {
           a[k] *= dinv[c0 + k];
 #pragma unroll
-          for (int k2 = k + 1; k2 < PSB; ++k2) a[k2] = fma(-a[k], Ld[k2 * DLD + k], a[k2]);
+          for (int k2 = (k + 1) & ~1; k2 < PSB; k2 += 2) {
+            const double2 l2 = *reinterpret_cast<const double2*>(Ls + k * PSB + k2);
+            if (k2 >= k + 1) a[k2] = fma(-a[k], l2.x, a[k2]);
+            a[k2 + 1] = fma(-a[k], l2.y, a[k2 + 1]);
+          }
         }
 #pragma unroll
-        for (int q = 0; q < PSB; ++q) T[r * DLD + c0 + q] = a[q];
+        for (int q = 0; q < PSB; q += 2) *reinterpret_cast<double2*>(T + r * DLD + c0 + q) = make_double2(a[q], a[q + 1]);
       }
     }
     __syncthreads();
@@ -225,7 +265,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
   // ---------------- inverse of the four diagonal sub-blocks: lane = column, x[r] -= L[r][k] x[k] ----------------
   if (warp < TILE / PSB) {
     const int c0 = warp * PSB;
-    const double* Ld = T + c0 * DLD + c0;
+    const double* Ls = Lt + warp * (PSB * PSB);
     double x[PSB];
 #pragma unroll
     for (int r = 0; r < PSB; ++r) x[r] = (r == lane) ? 1.0 : 0.0;
@@ -233,13 +273,17 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
     for (int k = 0; k < PSB; ++k) {
       x[k] *= dinv[c0 + k];
 #pragma unroll
-      for (int r = k + 1; r < PSB; ++r) x[r] = fma(-Ld[r * DLD + k], x[k], x[r]);
+      for (int r = (k + 1) & ~1; r < PSB; r += 2) {
+        const double2 l2 = *reinterpret_cast<const double2*>(Ls + k * PSB + r);
+        if (r >= k + 1) x[r] = fma(-l2.x, x[k], x[r]);
+        x[r + 1] = fma(-l2.y, x[k], x[r + 1]);
+      }
     }
     __syncwarp();                                 // every lane has read the factor before anyone overwrites it
 #pragma unroll
     for (int r = 0; r < PSB; ++r) T[(c0 + r) * DLD + c0 + lane] = x[r];      // exactly 0 above the diagonal
   }
-  __syncthreads();
+  __syncthreads();                                // Lt (in W) is dead from here on: W becomes the product scratch
   // ---------------- 64 x 64 inverses:  X21 = -X22 (L21 X11)  for the sub-block pairs (1,0) and (3,2) ----------------
   {
     const int p = warp >> 2, w4 = warp & 3;       // pair, warp within the pair: output tiles w4, w4 + 4, ... of 16

@@ -21,7 +21,10 @@ namespace bocf {
 
 using LT = gemm::Tile128;
 
-template <int KIND>
+// DP: input dimension rounded up (compile time), so the per-thread lengthscale-gradient sums stay in registers and the
+// loops over the dimensions unroll; the staged inputs use an ODD row stride (DP + 1): rows 8 apart in a warp otherwise hit
+// one bank (stride 16 doubles: 8-way conflicts on every read of the epilogue -- it cost more than the contraction).
+template <int KIND, int DP>
 __global__ void __launch_bounds__(LT::NTHREADS, 1) lml_tile_kernel(const double* __restrict__ LinvAll,
                                                                     const double* __restrict__ alphaAll,
                                                                     const double* __restrict__ XsAll,
@@ -43,17 +46,18 @@ __global__ void __launch_bounds__(LT::NTHREADS, 1) lml_tile_kernel(const double*
   gemm::mainloop<LT, true, true>(acc, Linv + I * TILE, n_pad, Linv + J * TILE, n_pad, I * TILE, n_pad, smem);
 
   // stage the scaled inputs / alpha of both blocks (the pipeline buffers are free now)
-  double* sxa = smem;                         // TILE x d
-  double* sxb = sxa + TILE * MAXD;            // TILE x d
-  double* sal = sxb + TILE * MAXD;            // 2 x TILE alpha
+  constexpr int SXL = DP + 1;
+  double* sxa = smem;                         // TILE x SXL, zero beyond d
+  double* sxb = sxa + TILE * SXL;             // TILE x SXL
+  double* sal = sxb + TILE * SXL;             // 2 x TILE alpha
   double* ssq = sal + 2 * TILE;               // 2 x TILE |xs|^2
   double* red = ssq + 2 * TILE;               // warps x (MAXD + 2)
   const int tid = threadIdx.x;
   const double* Xs = XsAll + (int64_t)hj * n_pad * d;
-  for (int idx = tid; idx < TILE * d; idx += LT::NTHREADS) {
-    const int r = idx / d, q = idx - r * d;
-    sxa[r * MAXD + q] = Xs[(int64_t)(I * TILE + r) * d + q];
-    sxb[r * MAXD + q] = Xs[(int64_t)(J * TILE + r) * d + q];
+  for (int idx = tid; idx < TILE * DP; idx += LT::NTHREADS) {
+    const int r = idx / DP, q = idx - r * DP;
+    sxa[r * SXL + q] = (q < d) ? Xs[(int64_t)(I * TILE + r) * d + q] : 0.0;
+    sxb[r * SXL + q] = (q < d) ? Xs[(int64_t)(J * TILE + r) * d + q] : 0.0;
   }
   for (int r = tid; r < TILE; r += LT::NTHREADS) {
     sal[r] = alphaAll[(int64_t)hj * n_pad + I * TILE + r];
@@ -66,9 +70,9 @@ __global__ void __launch_bounds__(LT::NTHREADS, 1) lml_tile_kernel(const double*
   const OutHyp& hp = hyp[hj];
   const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int mbase = (warp >> 2) * 64, nbase = (warp & 3) * 32;
-  double gvar = 0.0, gnoise = 0.0, gl[MAXD];
+  double gvar = 0.0, gnoise = 0.0, gl[DP];
 #pragma unroll
-  for (int q = 0; q < MAXD; ++q) gl[q] = 0.0;
+  for (int q = 0; q < DP; ++q) gl[q] = 0.0;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -80,16 +84,20 @@ __global__ void __launch_bounds__(LT::NTHREADS, 1) lml_tile_kernel(const double*
         if (a >= n || b >= n || b > a) continue;                 // lower triangle of the n x n problem only
         const double w = (a == b) ? 1.0 : 2.0;                   // symmetric: count (a,b) and (b,a)
         const double dLdK = 0.5 * (sal[r] * sal[TILE + c] - acc[i][jn][e]);
+        const double* xa = sxa + r * SXL;
+        const double* xb = sxb + c * SXL;
         double r2;
         if (KIND == BOCF_KERN_SE) {
           r2 = 0.0;
-          for (int q = 0; q < d; ++q) {
-            const double df = sxa[r * MAXD + q] - sxb[c * MAXD + q];
+#pragma unroll
+          for (int q = 0; q < DP; ++q) {
+            const double df = xa[q] - xb[q];
             r2 += df * df;
           }
         } else {
           double dot = 0.0;
-          for (int q = 0; q < d; ++q) dot += sxa[r * MAXD + q] * sxb[c * MAXD + q];
+#pragma unroll
+          for (int q = 0; q < DP; ++q) dot += xa[q] * xb[q];
           r2 = -2.0 * dot + (ssq[r] + ssq[TILE + c]);
           r2 = fmax(r2, 0.0);
         }
@@ -99,20 +107,23 @@ __global__ void __launch_bounds__(LT::NTHREADS, 1) lml_tile_kernel(const double*
         gvar += w * dLdK * kv;
         if (a == b) gnoise += dLdK;
         const double wg = w * dLdK * gv;
-        for (int q = 0; q < d; ++q) {
-          const double df = sxa[r * MAXD + q] - sxb[c * MAXD + q];
+#pragma unroll
+        for (int q = 0; q < DP; ++q) {
+          const double df = xa[q] - xb[q];
           gl[q] += wg * df * df;
         }
       }
   // block reduction of d + 2 values
   gvar = warp_sum(gvar);
   gnoise = warp_sum(gnoise);
-  for (int q = 0; q < d; ++q) gl[q] = warp_sum(gl[q]);
+#pragma unroll
+  for (int q = 0; q < DP; ++q) gl[q] = warp_sum(gl[q]);
   __syncthreads();
   if (lane == 0) {
     red[warp * (MAXD + 2) + 0] = gvar;
     red[warp * (MAXD + 2) + 1] = gnoise;
-    for (int q = 0; q < d; ++q) red[warp * (MAXD + 2) + 2 + q] = gl[q];
+#pragma unroll
+    for (int q = 0; q < DP; ++q) red[warp * (MAXD + 2) + 2 + q] = gl[q];
   }
   __syncthreads();
   if (tid < d + 2) {
@@ -162,22 +173,30 @@ __global__ void lml_finish_kernel(const double* __restrict__ part, const double*
   }
 }
 
-template <int KIND>
-static int launch_tiles(bocf_model* M, int ntiles, double* part, OutRun run, cudaStream_t st) {
+template <int KIND, int DP>
+static int launch_tiles_d(bocf_model* M, int ntiles, double* part, OutRun run, cudaStream_t st) {
   static bool done[64] = {false};              // per device: function attributes belong to the device's context
   if (M->device >= 0 && M->device < 64 && !done[M->device]) {
-    BOCF_CUDA_OK(cudaFuncSetAttribute(lml_tile_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::SMEM_BYTES));
+    BOCF_CUDA_OK(cudaFuncSetAttribute(lml_tile_kernel<KIND, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT::SMEM_BYTES));
     done[M->device] = true;
   }
-  lml_tile_kernel<KIND><<<dim3((unsigned)ntiles, (unsigned)(M->H * run.cnt)), LT::NTHREADS, LT::SMEM_BYTES, st>>>(
+  lml_tile_kernel<KIND, DP><<<dim3((unsigned)ntiles, (unsigned)(M->H * run.cnt)), LT::NTHREADS, LT::SMEM_BYTES, st>>>(
       M->Linv, M->alpha, M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, ntiles, part, run, M->m);
   BOCF_LAUNCH_OK("lml_tile_kernel");
   return 0;
 }
+template <int KIND>
+static int launch_tiles(bocf_model* M, int ntiles, double* part, OutRun run, cudaStream_t st) {
+  const int d = M->d;
+  if (d <= 4) return launch_tiles_d<KIND, 4>(M, ntiles, part, run, st);
+  if (d <= 6) return launch_tiles_d<KIND, 6>(M, ntiles, part, run, st);
+  if (d <= 10) return launch_tiles_d<KIND, 10>(M, ntiles, part, run, st);
+  return launch_tiles_d<KIND, MAXD>(M, ntiles, part, run, st);
+}
 
 // out_host: H*m x (MAXD + 3) doubles [lml, d/dvariance, d/dnoise, d/dlengthscale[0..d)]
 int launch_log_likelihood(bocf_model* M, double* out_host, cudaStream_t st) {
-  static_assert(2 * TILE * MAXD + 4 * TILE + 8 * (MAXD + 2) <= LT::SMEM_BYTES / (int)sizeof(double), "epilogue staging fits");
+  static_assert(2 * TILE * (MAXD + 1) + 4 * TILE + 8 * (MAXD + 2) <= LT::SMEM_BYTES / (int)sizeof(double), "epilogue staging fits");
   const int Hm = M->H * M->m;
   const int ntiles = M->nb * (M->nb + 1) / 2;
   const size_t n_part = (size_t)Hm * ntiles * (MAXD + 2), n_out = (size_t)Hm * (MAXD + 3);
