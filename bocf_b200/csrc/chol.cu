@@ -112,7 +112,7 @@ __global__ void gram_kernel(const double* __restrict__ Xs, const double* __restr
 constexpr int PSB = 32;                       // sub-block
 constexpr int DLD = TILE + 4;                 // row stride == 4 mod 16 doubles: conflict-free 64-bit fragment loads
 constexpr int WLD = 64 + 4;
-constexpr int POTRF_SMEM = (TILE * DLD + 64 * WLD + TILE) * (int)sizeof(double);
+constexpr int POTRF_SMEM = (TILE * DLD + 64 * WLD + TILE + (TILE / PSB) * PSB * PSB) * (int)sizeof(double);
 
 // C[i0.., j0..] (8 x 8) = sum_k A[i0 + g][k] B(k, j0 + g), K a multiple of 4.  BT: B(k, n) = Bm[n * ldb + k] (rows of Bm
 // are columns of B), else B(k, n) = Bm[k * ldb + n].  lane = 4 g + t.
@@ -129,9 +129,10 @@ __device__ __forceinline__ void dmma_tile(double& c0, double& c1, const double* 
 
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lmat, double* __restrict__ Dinv,
                                                          int* __restrict__ info, int n, int n_pad, int nb, int kb) {
-  extern __shared__ __align__(16) double T[];   // T[TILE][DLD] | W[64][WLD] | dinv[TILE]
+  extern __shared__ __align__(16) double T[];   // T[TILE][DLD] | W[64][WLD] | dinv[TILE] | Xb[4][32][32]
   double* W = T + TILE * DLD;
   double* dinv = W + 64 * WLD;
+  double* Xb = dinv + TILE;                     // inverses of the four diagonal sub-blocks (row-major 32 x 32 each)
   const int hj = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -178,26 +179,32 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
       double piv = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
       for (int k = 0; k < PSB; ++k) {
-        if (!(piv > 0.0)) {                      // dpotrf info != 0  -> jitchol retry on the host side
+        double pk = piv;
+        if (!(pk > 0.0)) {                       // dpotrf info != 0  -> jitchol retry on the host side
           if (lane == 0 && info[hj] == 0) info[hj] = k0 + c0 + k + 1;
-          piv = 1.0;
+          pk = 1.0;
         }
-        double rs = rsqrt(piv);
-        double sq = piv * rs;
-        sq = fma(fma(-sq, sq, piv), 0.5 * rs, sq);          // sqrt(piv) to the last bit or so
-        rs = fma(fma(-sq, rs, 1.0), rs, rs);                // 1 / sqrt(piv)
-        a[k] = (lane == k) ? sq : a[k] * rs;                // column k of L (meaningful for lanes >= k)
-        if (lane == k) dinv[c0 + k] = rs;
+        // the dependency chain of the whole block runs through here, 128 times: pivot -> 1/sqrt -> scaled column ->
+        // next pivot.  Only rsqrt and one multiply sit on it; the square root itself and the refined reciprocal are
+        // needed by lane k's stores alone.
+        const double rs = rsqrt(pk);
+        const double ak = a[k] * rs;              // column k of L (meaningful for lanes > k)
+        if (k + 1 < PSB) {
+          // lane k + 1 owns both L[k+1][k] (its ak) and A[k+1][k+1]: the next pivot needs no other lane
+          piv = __shfl_sync(0xffffffffu, fma(-ak, ak, a[k + 1]), k + 1);
+        }
+        double sq = pk * rs;
+        sq = fma(fma(-sq, sq, pk), 0.5 * rs, sq);            // sqrt(pivot) to the last bit or so
+        if (lane == k) dinv[c0 + k] = fma(fma(-sq, rs, 1.0), rs, rs);
+        a[k] = (lane == k) ? sq : ak;
         Ls[k * PSB + lane] = a[k];
         __syncwarp();
         if (k + 1 < PSB) {
-          a[k + 1] = fma(-a[k], Ls[k * PSB + k + 1], a[k + 1]);
-          piv = __shfl_sync(0xffffffffu, a[k + 1], k + 1);
 #pragma unroll
-          for (int c2 = (k + 2) & ~1; c2 < PSB; c2 += 2) {  // lanes < c2 carry don't-care values, masked at the store
+          for (int c2 = (k + 1) & ~1; c2 < PSB; c2 += 2) {  // lanes < c2 carry don't-care values, masked at the store
             const double2 l2 = *reinterpret_cast<const double2*>(Ls + k * PSB + c2);
-            if (c2 >= k + 2) a[c2] = fma(-a[k], l2.x, a[c2]);
-            a[c2 + 1] = fma(-a[k], l2.y, a[c2 + 1]);
+            if (c2 >= k + 1) a[c2] = fma(-ak, l2.x, a[c2]);
+            a[c2 + 1] = fma(-ak, l2.y, a[c2 + 1]);
           }
         }
       }
@@ -208,16 +215,21 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
     }
     __syncthreads();
     const int w0 = c0 + PSB;
-    if (w0 >= TILE) break;
     {
-      // rows below:  P[r][k] = (A[r][k] - sum_{t<k} P[r][t] L[k][t]) / L[k][k], in update form so the multiply-adds of a
-      // step are independent; threads 32.. take one row each (warp 0 has just finished the factor)
-      const int r = w0 + tid - 32;
-      if (tid >= 32 && r < TILE) {
+      // forward substitution  y L^T = b,  thread per right-hand side, in update form (the multiply-adds of a step are
+      // independent), L broadcast from shared memory.  Warps 1 .. take the rows of the panel below the sub-block
+      // (P = A L^-T); the next warp takes the rows of the identity, which gives the sub-block's INVERSE one column per
+      // thread -- the same instruction stream, so it costs no extra phase (and no cold code) on the critical path.
+      const int idx = tid - 32, nrows = TILE - w0;
+      const bool is_row = tid >= 32 && idx < nrows;
+      const bool is_inv = tid >= 32 && idx >= nrows && idx < nrows + PSB;
+      if (is_row || is_inv) {
+        const int r = w0 + idx;
         double a[PSB];
 #pragma unroll
         for (int q = 0; q < PSB; q += 2) {
-          const double2 v = *reinterpret_cast<const double2*>(T + r * DLD + c0 + q);
+          double2 v = make_double2((q == idx - nrows) ? 1.0 : 0.0, (q + 1 == idx - nrows) ? 1.0 : 0.0);
+          if (is_row) v = *reinterpret_cast<const double2*>(T + r * DLD + c0 + q);
           a[q] = v.x;
           a[q + 1] = v.y;
         }
@@ -231,10 +243,17 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
             a[k2 + 1] = fma(-a[k], l2.y, a[k2 + 1]);
           }
         }
+        if (is_row) {
 #pragma unroll
-        for (int q = 0; q < PSB; q += 2) *reinterpret_cast<double2*>(T + r * DLD + c0 + q) = make_double2(a[q], a[q + 1]);
+          for (int q = 0; q < PSB; q += 2) *reinterpret_cast<double2*>(T + r * DLD + c0 + q) = make_double2(a[q], a[q + 1]);
+        } else {
+          double* Xs = Xb + (c0 / PSB) * (PSB * PSB) + (idx - nrows);      // X[q][c]: exactly 0 above the diagonal
+#pragma unroll
+          for (int q = 0; q < PSB; ++q) Xs[q * PSB] = a[q];
+        }
       }
     }
+    if (w0 >= TILE) break;
     __syncthreads();
     {
       // trailing update  A[r][c] -= sum_k P[r][k] P[c][k]  on the lower triangle of [w0, TILE)^2: 8 x 8 DMMA tiles
@@ -262,26 +281,10 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
   }
   __syncthreads();
 
-  // ---------------- inverse of the four diagonal sub-blocks: lane = column, x[r] -= L[r][k] x[k] ----------------
-  if (warp < TILE / PSB) {
-    const int c0 = warp * PSB;
-    const double* Ls = Lt + warp * (PSB * PSB);
-    double x[PSB];
-#pragma unroll
-    for (int r = 0; r < PSB; ++r) x[r] = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < PSB; ++k) {
-      x[k] *= dinv[c0 + k];
-#pragma unroll
-      for (int r = (k + 1) & ~1; r < PSB; r += 2) {
-        const double2 l2 = *reinterpret_cast<const double2*>(Ls + k * PSB + r);
-        if (r >= k + 1) x[r] = fma(-l2.x, x[k], x[r]);
-        x[r + 1] = fma(-l2.y, x[k], x[r + 1]);
-      }
-    }
-    __syncwarp();                                 // every lane has read the factor before anyone overwrites it
-#pragma unroll
-    for (int r = 0; r < PSB; ++r) T[(c0 + r) * DLD + c0 + lane] = x[r];      // exactly 0 above the diagonal
+  // ---------------- the four sub-block inverses (Xb, from the solve phases) replace the factor's diagonal sub-blocks ----
+  for (int idx = tid; idx < (TILE / PSB) * PSB * PSB; idx += 256) {
+    const int sblk = idx >> 10, q = (idx >> 5) & 31, c = idx & 31;
+    T[(sblk * PSB + q) * DLD + sblk * PSB + c] = Xb[idx];
   }
   __syncthreads();                                // Lt (in W) is dead from here on: W becomes the product scratch
   // ---------------- 64 x 64 inverses:  X21 = -X22 (L21 X11)  for the sub-block pairs (1,0) and (3,2) ----------------
@@ -393,21 +396,28 @@ __global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) syrk_update_kernel
   const double* PI = base + (int64_t)I * TILE * n_pad + (int64_t)kb * TILE;
   const double* PJ = base + (int64_t)J * TILE * n_pad + (int64_t)kb * TILE;
   double* C = base + (int64_t)I * TILE * n_pad + (int64_t)J * TILE;
-  double acc[8][4][2];
-  gemm::zero_acc(acc);
-  gemm::mainloop<gemm::Tile128, false, false>(acc, PI, n_pad, PJ, n_pad, 0, TILE, smem);
+  // acc starts as -C and the product is added, so the tile is read BEFORE the contraction (its latency hides behind the
+  // operand pipeline's own prologue) and the epilogue only stores: with K = 128 the read-modify-write after the loop was
+  // a quarter of the kernel
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int mbase = (warp >> 2) * 64, nbase = (warp & 3) * 32;
+  double acc[8][4][2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int r = mbase + 8 * i + g, c = nbase + 8 * j + 2 * t;
-      double2* ptr = reinterpret_cast<double2*>(C + (int64_t)r * n_pad + c);
-      double2 old = *ptr;
-      old.x -= acc[i][j][0];
-      old.y -= acc[i][j][1];
-      *ptr = old;
+      const int r = mbase + 8 * i + g, c = nbase + 8 * j + 2 * t;
+      const double2 old = *reinterpret_cast<const double2*>(C + (int64_t)r * n_pad + c);
+      acc[i][j][0] = -old.x;
+      acc[i][j][1] = -old.y;
+    }
+  gemm::mainloop<gemm::Tile128, false, false>(acc, PI, n_pad, PJ, n_pad, 0, TILE, smem);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = mbase + 8 * i + g, c = nbase + 8 * j + 2 * t;
+      *reinterpret_cast<double2*>(C + (int64_t)r * n_pad + c) = make_double2(-acc[i][j][0], -acc[i][j][1]);
     }
 }
 

@@ -73,46 +73,54 @@ __global__ void __launch_bounds__(LT::NTHREADS, 1) lml_tile_kernel(const double*
   double gvar = 0.0, gnoise = 0.0, gl[DP];
 #pragma unroll
   for (int q = 0; q < DP; ++q) gl[q] = 0.0;
+  // the two adjacent columns a thread owns in each 8 x 8 accumulator tile are evaluated together, branch-free inside the
+  // pair (two independent dependency chains through the kernel evaluation); pairs are separated by a real branch, which
+  // also keeps the scheduler from hoisting all 64 elements' loads at once (that version spilled 3 KB per thread)
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
+    for (int jn = 0; jn < 4; ++jn) {
+      const int r = mbase + 8 * i + g, c0 = nbase + 8 * jn + 2 * t;
+      const int a = I * TILE + r, b0 = J * TILE + c0;
+      if (a >= n || b0 >= n || b0 > a) continue;               // lower triangle of the n x n problem only
+      const double* xa = sxa + r * SXL;
+      double r2[2], wd[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int r = mbase + 8 * i + g, c = nbase + 8 * jn + 2 * t + e;
-        const int a = I * TILE + r, b = J * TILE + c;
-        if (a >= n || b >= n || b > a) continue;                 // lower triangle of the n x n problem only
-        const double w = (a == b) ? 1.0 : 2.0;                   // symmetric: count (a,b) and (b,a)
-        const double dLdK = 0.5 * (sal[r] * sal[TILE + c] - acc[i][jn][e]);
-        const double* xa = sxa + r * SXL;
+        const int c = c0 + e, b = b0 + e;
         const double* xb = sxb + c * SXL;
-        double r2;
+        const double w = (b >= n || b > a) ? 0.0 : (a == b) ? 1.0 : 2.0;      // symmetric: count (a,b) and (b,a)
+        wd[e] = w * 0.5 * (sal[r] * sal[TILE + c] - acc[i][jn][e]);            // w dL/dK
         if (KIND == BOCF_KERN_SE) {
-          r2 = 0.0;
+          double x = 0.0;
 #pragma unroll
           for (int q = 0; q < DP; ++q) {
             const double df = xa[q] - xb[q];
-            r2 += df * df;
+            x += df * df;
           }
+          r2[e] = x;
         } else {
           double dot = 0.0;
 #pragma unroll
           for (int q = 0; q < DP; ++q) dot += xa[q] * xb[q];
-          r2 = -2.0 * dot + (ssq[r] + ssq[TILE + c]);
-          r2 = fmax(r2, 0.0);
+          r2[e] = fmax(-2.0 * dot + (ssq[r] + ssq[TILE + c]), 0.0);
         }
-        if (a == b) r2 = 0.0;                                    // stationary.py:136, se.py:58
-        double kv, gv;
-        kern_eval<KIND, true>(r2, hp.variance, kv, gv);
-        gvar += w * dLdK * kv;
-        if (a == b) gnoise += dLdK;
-        const double wg = w * dLdK * gv;
-#pragma unroll
-        for (int q = 0; q < DP; ++q) {
-          const double df = xa[q] - xb[q];
-          gl[q] += wg * df * df;
-        }
+        if (a == b) r2[e] = 0.0;                                 // stationary.py:136, se.py:58
       }
+      double kv[2], gv[2];
+      kern_eval<KIND, true>(r2[0], hp.variance, kv[0], gv[0]);
+      kern_eval<KIND, true>(r2[1], hp.variance, kv[1], gv[1]);
+      gvar += wd[0] * kv[0] + wd[1] * kv[1];
+      if (a == b0) gnoise += wd[0];                              // w == 1 on the diagonal
+      if (a == b0 + 1) gnoise += wd[1];
+      const double wg0 = wd[0] * gv[0], wg1 = wd[1] * gv[1];
+      const double* xb0 = sxb + c0 * SXL;
+#pragma unroll
+      for (int q = 0; q < DP; ++q) {
+        const double d0 = xa[q] - xb0[q], d1 = xa[q] - xb0[SXL + q];
+        gl[q] += wg0 * d0 * d0 + wg1 * d1 * d1;
+      }
+    }
   // block reduction of d + 2 values
   gvar = warp_sum(gvar);
   gnoise = warp_sum(gnoise);

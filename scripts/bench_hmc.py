@@ -26,6 +26,12 @@ inf = mod._inference
 num = inf.n_burnin + inf.n_samples * inf.subsample_interval
 moves = [int(np.sum(np.any(np.diff(c, axis=0) != 0, axis=1))) for c in inf.chain]
 
+if cpu_samples == 0:                               # HCPU_SAMPLES=0: device side only
+    print(json.dumps({"what": "ML-II + HMC hyper-parameter inference, all outputs (GPModel.updateModel defaults)", "m": m,
+                      "d": d, "n": n, "kind": kind, "gpu_s": gpu_s, "device_passes": inf.device_passes,
+                      "ms_per_pass": 1e3 * gpu_s / inf.device_passes, "samples": num, "accepted_moves_per_output": moves}))
+    sys.exit(0)
+
 from oracle.hmc import GPModelHMC, HMC  # noqa: E402
 np.random.seed(0)
 t_opt = t_smp = 0.0
