@@ -345,12 +345,18 @@ class HyperInference(object):
     # ---- GPModel.updateModel ---------------------------------------------------------------------------------------------
     def update(self):
         """Returns (variance (H,m), lengthscale (H,m,d), noise (H,m)) of the n_samples hyper-sample instances."""
+        import time
+        t0, p0 = time.perf_counter(), self.device_passes
         self.optimize()
+        t1, p1 = time.perf_counter(), self.device_passes
         num = self.n_burnin + self.n_samples * self.subsample_interval
         perturb, momenta, uniforms = self.draw_randomness(num)
         for j, e in enumerate(perturb):
             self.PA[j, self.valid[j]] = self.param_array(j) * (1. + e * 0.01)
         self.chain = self.sample(momenta, uniforms)
+        t2 = time.perf_counter()
+        # where the wall time of this update went (scripts/bench_hmc.py reports it)
+        self.timing = {"mlii_s": t1 - t0, "mlii_passes": p1 - p0, "hmc_s": t2 - t1, "hmc_passes": self.device_passes - p1}
         H, d = self.n_samples, self.d
         var = np.empty((H, self.m))
         ls = np.empty((H, self.m, d))
