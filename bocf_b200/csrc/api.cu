@@ -357,6 +357,9 @@ int bocf_model_destroy(bocf_model* M) {
   if (M->par_host) cudaFreeHost(M->par_host);
   if (M->par_dev) cudaFree(M->par_dev);
   if (M->io_buf) cudaFree(M->io_buf);
+  if (M->gs.side) cudaStreamDestroy(M->gs.side);
+  if (M->gs.fork) cudaEventDestroy(M->gs.fork);
+  if (M->gs.join) cudaEventDestroy(M->gs.join);
   delete M;
   return 0;
 }
@@ -473,13 +476,20 @@ int bocf_model_factorize(bocf_model* M, double* jitter_out, void* stream) {
   for (int attempt = 0; attempt <= 5; ++attempt) {
     BOCF_CUDA_OK(cudaMemcpyAsync(M->hyp, M->hyp_host.data(), sizeof(OutHyp) * Hm, cudaMemcpyHostToDevice, st));
     if (int rc = launch_prepare(M, st)) return rc;
-    if (int rc = launch_gram(M, st)) return rc;
-    if (int rc = launch_cholesky(M, st)) return rc;
-    BOCF_CUDA_OK(cudaMemcpyAsync(info.data(), M->info, sizeof(int) * Hm, cudaMemcpyDeviceToHost, st));
+    BOCF_CUDA_OK(cudaMemsetAsync(M->info, 0, sizeof(int) * Hm, st));
     // optimistic: the inverse and alpha are queued behind the factor without waiting for the pivot flags (a failed
     // factor carries unit pivots, so the work is finite and simply redone after the jitter retry): one host
     // synchronisation per factorisation instead of two -- the fit loops factorise thousands of times
-    if (int rc = launch_inverse_and_alpha(M, st)) return rc;
+    if (int rc = for_each_output_group(
+            M, st,
+            [](bocf_model* Mm, OutRun grp, cudaStream_t s, void*) -> int {
+              if (int r = launch_gram(Mm, grp, s)) return r;
+              if (int r = launch_cholesky(Mm, grp, s)) return r;
+              return launch_inverse_and_alpha(Mm, grp, s);
+            },
+            nullptr))
+      return rc;
+    BOCF_CUDA_OK(cudaMemcpyAsync(info.data(), M->info, sizeof(int) * Hm, cudaMemcpyDeviceToHost, st));
     BOCF_CUDA_OK(cudaStreamSynchronize(st));
     bool any_fail = false;
     for (int hj = 0; hj < Hm; ++hj) {

@@ -128,12 +128,13 @@ __device__ __forceinline__ void dmma_tile(double& c0, double& c1, const double* 
 }
 
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lmat, double* __restrict__ Dinv,
-                                                         int* __restrict__ info, int n, int n_pad, int nb, int kb) {
+                                                         int* __restrict__ info, int n, int n_pad, int nb, int kb,
+                                                         OutRun grp, int m) {
   extern __shared__ __align__(16) double T[];   // T[TILE][DLD] | W[64][WLD] | dinv[TILE] | Xb[4][32][32]
   double* W = T + TILE * DLD;
   double* dinv = W + 64 * WLD;
   double* Xb = dinv + TILE;                     // inverses of the four diagonal sub-blocks (row-major 32 x 32 each)
-  const int hj = blockIdx.x;
+  const int hj = run_hj(blockIdx.x, grp, m);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int k0 = kb * TILE;
@@ -359,9 +360,9 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
 // Panel solve: A[I][K] <- A[I][K] . L_KK^-T  (= A . Dinv^T), I > K.   grid (nb-1-K, H*m)
 __global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) trsm_panel_kernel(double* __restrict__ Lmat,
                                                                       const double* __restrict__ Dinv, int n_pad,
-                                                                      int nb, int kb) {
+                                                                      int nb, int kb, OutRun grp, int m) {
   extern __shared__ __align__(16) double smem[];
-  const int hj = blockIdx.y;
+  const int hj = run_hj(blockIdx.y, grp, m);
   const int I = kb + 1 + blockIdx.x;
   double* Ablk = Lmat + (int64_t)hj * n_pad * n_pad + (int64_t)I * TILE * n_pad + (int64_t)kb * TILE;
   const double* D = Dinv + ((int64_t)hj * nb + kb) * TILE * TILE;
@@ -382,9 +383,9 @@ __global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) trsm_panel_kernel(
 
 // Trailing update: A[I][J] -= P_I . P_J^T for K < J <= I.   grid (#pairs, H*m)
 __global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) syrk_update_kernel(double* __restrict__ Lmat, int n_pad, int nb,
-                                                                       int kb) {
+                                                                       int kb, OutRun grp, int m) {
   extern __shared__ __align__(16) double smem[];
-  const int hj = blockIdx.y;
+  const int hj = run_hj(blockIdx.y, grp, m);
   // decode the lower-triangular pair index
   int p = blockIdx.x;
   int rr = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
@@ -425,8 +426,9 @@ __global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) syrk_update_kernel
 // Blocked inverse of L.  Diagonal blocks come from Dinv; block row I is built from rows < I:
 //   S[I][J]    = sum_{T=J}^{I-1} L[I][T] . Linv[T][J]          (step 1, stored in place of Linv[I][J])
 //   Linv[I][J] = -Dinv_I . S[I][J]                              (step 2)
-__global__ void linv_init_kernel(double* __restrict__ Linv, const double* __restrict__ Dinv, int n_pad, int nb) {
-  const int hj = blockIdx.y, kb = blockIdx.x;
+__global__ void linv_init_kernel(double* __restrict__ Linv, const double* __restrict__ Dinv, int n_pad, int nb, OutRun grp,
+                                 int m) {
+  const int hj = run_hj(blockIdx.y, grp, m), kb = blockIdx.x;
   const double* D = Dinv + ((int64_t)hj * nb + kb) * TILE * TILE;
   double* dst = Linv + (int64_t)hj * n_pad * n_pad + (int64_t)kb * TILE * n_pad + (int64_t)kb * TILE;
   for (int idx = threadIdx.x; idx < TILE * TILE; idx += blockDim.x) {
@@ -447,15 +449,15 @@ __global__ void linv_init_kernel(double* __restrict__ Linv, const double* __rest
 template <int STEP>
 __global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) linv_merge_kernel(double* __restrict__ Lmat,
                                                                       double* __restrict__ Linv, int n_pad, int nb, int b,
-                                                                      int Hm) {
+                                                                      int Hm, OutRun grp, int m) {
   extern __shared__ __align__(16) double smem[];
-  const int hj = blockIdx.x % Hm;
+  const int hj = run_hj(blockIdx.x % Hm, grp, m);              // Hm = matrices of this launch (H * grp.cnt)
   const int rank = blockIdx.x / Hm;
   const int ngroups = (nb - b + 2 * b - 1) / (2 * b);
   // rank -> (heavy index, group, light index): K depends on j for STEP 1 (small j heavy), on i for STEP 2 (large i heavy)
   const int hv = rank / (ngroups * b), rem = rank - hv * (ngroups * b);
-  const int grp = rem / b, lt = rem - grp * b;
-  const int o = grp * 2 * b;
+  const int bg = rem / b, lt = rem - bg * b;      // block-row group of this level
+  const int o = bg * 2 * b;
   const int i = (STEP == 1) ? lt : b - 1 - hv;
   const int j = (STEP == 1) ? hv : lt;
   const int I = o + b + i, J = o + j;
@@ -496,8 +498,8 @@ __global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) linv_merge_kernel(
 
 // t = Linv . yc   (warp per row)
 __global__ void linv_matvec_kernel(const double* __restrict__ Linv, const double* __restrict__ yc, int m, int n_pad,
-                                   double* __restrict__ tvec) {
-  const int hj = blockIdx.y, j = hj % m;
+                                   double* __restrict__ tvec, OutRun grp) {
+  const int hj = run_hj(blockIdx.y, grp, m), j = hj % m;
   const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (a >= n_pad) return;
   const int lane = threadIdx.x & 31;
@@ -512,9 +514,9 @@ __global__ void linv_matvec_kernel(const double* __restrict__ Linv, const double
 // alpha = Linv^T . t : CTA = 32 columns x 8 row groups (rows a = b0 + q, b0 + q + 8, ...: each row read is 256
 // contiguous bytes), partial sums reduced through shared memory in fixed order
 __global__ void __launch_bounds__(256) linv_t_matvec_kernel(const double* __restrict__ Linv, const double* __restrict__ tvec,
-                                                            int n_pad, double* __restrict__ alpha) {
+                                                            int n_pad, double* __restrict__ alpha, OutRun grp, int m) {
   __shared__ double red[8][33];
-  const int hj = blockIdx.y;
+  const int hj = run_hj(blockIdx.y, grp, m);
   const int cl = threadIdx.x & 31, q = threadIdx.x >> 5;
   const int b0 = blockIdx.x * 32, b = b0 + cl;
   const double* Li = Linv + (int64_t)hj * n_pad * n_pad;
@@ -644,9 +646,9 @@ int launch_prepare(bocf_model* M, cudaStream_t st) {
   return 0;
 }
 
-int launch_gram(bocf_model* M, cudaStream_t st) {
+int launch_gram(bocf_model* M, OutRun grp, cudaStream_t st) {
   const dim3 block(16, 16);
-  return for_each_kind_run(M, [&](int kind, OutRun run) -> int {
+  return for_each_kind_run(M, grp, [&](int kind, OutRun run) -> int {
     const dim3 grid((unsigned)(M->n_pad / 16), (unsigned)(M->n_pad / 16), (unsigned)(M->H * run.cnt));
 #define BOCF_GRAM(K) gram_kernel<K><<<grid, block, 0, st>>>(M->Xs, M->xsq, M->hyp, M->n, M->n_pad, M->d, M->Lmat, run, M->m)
     switch (kind) {
@@ -660,6 +662,26 @@ int launch_gram(bocf_model* M, cudaStream_t st) {
     BOCF_LAUNCH_OK("gram_kernel");
     return 0;
   });
+}
+
+// Two output groups on two streams when there are enough matrices for it to pay (see GroupStreams, model.h).
+int for_each_output_group(bocf_model* M, cudaStream_t st, int (*f)(bocf_model*, OutRun, cudaStream_t, void*), void* ctx) {
+  static const bool off = std::getenv("BOCF_NO_GROUPS") != nullptr;
+  if (M->m < 4 || M->H * M->m < 8 || M->nb < 3 || off) return f(M, OutRun{0, M->m}, st, ctx);
+  GroupStreams& gs = M->gs;
+  if (!gs.side) {
+    BOCF_CUDA_OK(cudaStreamCreateWithFlags(&gs.side, cudaStreamNonBlocking));
+    BOCF_CUDA_OK(cudaEventCreateWithFlags(&gs.fork, cudaEventDisableTiming));
+    BOCF_CUDA_OK(cudaEventCreateWithFlags(&gs.join, cudaEventDisableTiming));
+  }
+  const int half = M->m / 2;
+  BOCF_CUDA_OK(cudaEventRecord(gs.fork, st));
+  BOCF_CUDA_OK(cudaStreamWaitEvent(gs.side, gs.fork, 0));
+  int rc = f(M, OutRun{0, half}, st, ctx);
+  const int rc2 = f(M, OutRun{half, M->m - half}, gs.side, ctx);
+  BOCF_CUDA_OK(cudaEventRecord(gs.join, gs.side));             // always rejoin, also after a failed launch
+  BOCF_CUDA_OK(cudaStreamWaitEvent(st, gs.join, 0));
+  return rc ? rc : rc2;
 }
 
 static int set_smem_attrs() {
@@ -682,47 +704,46 @@ static int set_smem_attrs() {
   return 0;
 }
 
-int launch_cholesky(bocf_model* M, cudaStream_t st) {
+int launch_cholesky(bocf_model* M, OutRun grp, cudaStream_t st) {
   if (int rc = set_smem_attrs()) return rc;
-  const int Hm = M->H * M->m, nb = M->nb;
-  BOCF_CUDA_OK(cudaMemsetAsync(M->info, 0, sizeof(int) * Hm, st));
+  const int Hg = M->H * grp.cnt, nb = M->nb;
   for (int kb = 0; kb < nb; ++kb) {
-    potrf_diag_kernel<<<Hm, 256, POTRF_SMEM, st>>>(M->Lmat, M->Dinv, M->info, M->n, M->n_pad, nb, kb);
+    potrf_diag_kernel<<<Hg, 256, POTRF_SMEM, st>>>(M->Lmat, M->Dinv, M->info, M->n, M->n_pad, nb, kb, grp, M->m);
     BOCF_LAUNCH_OK("potrf_diag_kernel");
     const int rem = nb - 1 - kb;
     if (rem > 0) {
-      trsm_panel_kernel<<<dim3(rem, Hm), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Dinv, M->n_pad, nb, kb);
+      trsm_panel_kernel<<<dim3(rem, Hg), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Dinv, M->n_pad, nb, kb, grp, M->m);
       BOCF_LAUNCH_OK("trsm_panel_kernel");
-      syrk_update_kernel<<<dim3(rem * (rem + 1) / 2, Hm), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->n_pad, nb, kb);
+      syrk_update_kernel<<<dim3(rem * (rem + 1) / 2, Hg), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->n_pad, nb, kb, grp, M->m);
       BOCF_LAUNCH_OK("syrk_update_kernel");
     }
   }
   return 0;
 }
 
-int launch_inverse_and_alpha(bocf_model* M, cudaStream_t st) {
+int launch_inverse_and_alpha(bocf_model* M, OutRun grp, cudaStream_t st) {
   if (int rc = set_smem_attrs()) return rc;
-  const int Hm = M->H * M->m, nb = M->nb;
+  const int Hg = M->H * grp.cnt, nb = M->nb;
   // Linv above the block diagonal stays zero from its allocation (bocf_model_factorize); every block on or below it is
   // rewritten here
-  linv_init_kernel<<<dim3(nb, Hm), 256, 0, st>>>(M->Linv, M->Dinv, M->n_pad, nb);
+  linv_init_kernel<<<dim3(nb, Hg), 256, 0, st>>>(M->Linv, M->Dinv, M->n_pad, nb, grp, M->m);
   BOCF_LAUNCH_OK("linv_init_kernel");
   for (int b = 1; b < nb; b *= 2) {
     const int ngroups = (nb - b + 2 * b - 1) / (2 * b);
-    const unsigned grid = (unsigned)(ngroups * b * b * Hm);
-    linv_merge_kernel<1><<<grid, gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->n_pad, nb, b, Hm);
+    const unsigned grid = (unsigned)(ngroups * b * b * Hg);
+    linv_merge_kernel<1><<<grid, gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->n_pad, nb, b, Hg, grp, M->m);
     BOCF_LAUNCH_OK("linv_merge_kernel<1>");
-    linv_merge_kernel<2><<<grid, gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->n_pad, nb, b, Hm);
+    linv_merge_kernel<2><<<grid, gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Linv, M->n_pad, nb, b, Hg, grp, M->m);
     BOCF_LAUNCH_OK("linv_merge_kernel<2>");
   }
-  return launch_alpha(M, st);
+  return launch_alpha(M, grp, st);
 }
 
-int launch_alpha(bocf_model* M, cudaStream_t st) {
-  const int Hm = M->H * M->m;
-  linv_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 8), Hm), 256, 0, st>>>(M->Linv, M->yc, M->m, M->n_pad, M->tvec);
+int launch_alpha(bocf_model* M, OutRun grp, cudaStream_t st) {
+  const int Hg = M->H * grp.cnt;
+  linv_matvec_kernel<<<dim3((unsigned)ceil_div(M->n_pad, 8), Hg), 256, 0, st>>>(M->Linv, M->yc, M->m, M->n_pad, M->tvec, grp);
   BOCF_LAUNCH_OK("linv_matvec_kernel");
-  linv_t_matvec_kernel<<<dim3((unsigned)(M->n_pad / 32), Hm), 256, 0, st>>>(M->Linv, M->tvec, M->n_pad, M->alpha);
+  linv_t_matvec_kernel<<<dim3((unsigned)(M->n_pad / 32), Hg), 256, 0, st>>>(M->Linv, M->tvec, M->n_pad, M->alpha, grp, M->m);
   BOCF_LAUNCH_OK("linv_t_matvec_kernel");
   return 0;
 }
@@ -747,7 +768,7 @@ int launch_append(bocf_model* M, int n_old, double* work, cudaStream_t st) {
     return 0;
   });
   if (rc_runs) return rc_runs;
-  return launch_alpha(M, st);
+  return launch_alpha(M, OutRun{0, M->m}, st);
 }
 
 int launch_append_xy(const double* Xold, const double* Yold, const double* xnew, const double* ynew, int n, int d, int m,

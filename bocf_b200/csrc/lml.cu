@@ -145,9 +145,9 @@ __global__ void __launch_bounds__(LT::NTHREADS, 1) lml_tile_kernel(const double*
 __global__ void lml_finish_kernel(const double* __restrict__ part, const double* __restrict__ Lmat,
                                   const double* __restrict__ alphaAll, const double* __restrict__ yc,
                                   const OutHyp* __restrict__ hyp, int n, int n_pad, int d, int m, int ntiles,
-                                  double* __restrict__ out) {
+                                  double* __restrict__ out, OutRun grp) {
   __shared__ double s_ld[32], s_fit[32];
-  const int hj = blockIdx.x, j = hj % m;
+  const int hj = run_hj(blockIdx.x, grp, m), j = hj % m;
   const int tid = threadIdx.x;
   double ld = 0.0, fit = 0.0;
   const double* L = Lmat + (int64_t)hj * n_pad * n_pad;
@@ -220,19 +220,31 @@ int launch_log_likelihood(bocf_model* M, double* out_host, cudaStream_t st) {
   }
   double* part = M->lml_ws;
   double* out = M->lml_ws + n_part;
-  int rc = for_each_kind_run(M, [&](int kind, OutRun run) -> int {
-    switch (kind) {
-      case BOCF_KERN_SE: return launch_tiles<BOCF_KERN_SE>(M, ntiles, part, run, st);
-      case BOCF_KERN_RBF: return launch_tiles<BOCF_KERN_RBF>(M, ntiles, part, run, st);
-      case BOCF_KERN_MATERN52: return launch_tiles<BOCF_KERN_MATERN52>(M, ntiles, part, run, st);
-      default: return launch_tiles<BOCF_KERN_MATERN32>(M, ntiles, part, run, st);
-    }
-  });
+  struct Ctx {
+    int ntiles;
+    double *part, *out;
+  } ctx{ntiles, part, out};
+  int rc = for_each_output_group(
+      M, st,
+      [](bocf_model* Mm, OutRun grp, cudaStream_t s, void* vc) -> int {
+        const Ctx& c = *static_cast<const Ctx*>(vc);
+        int r = for_each_kind_run(Mm, grp, [&](int kind, OutRun run) -> int {
+          switch (kind) {
+            case BOCF_KERN_SE: return launch_tiles<BOCF_KERN_SE>(Mm, c.ntiles, c.part, run, s);
+            case BOCF_KERN_RBF: return launch_tiles<BOCF_KERN_RBF>(Mm, c.ntiles, c.part, run, s);
+            case BOCF_KERN_MATERN52: return launch_tiles<BOCF_KERN_MATERN52>(Mm, c.ntiles, c.part, run, s);
+            default: return launch_tiles<BOCF_KERN_MATERN32>(Mm, c.ntiles, c.part, run, s);
+          }
+        });
+        if (r) return r;
+        lml_finish_kernel<<<Mm->H * grp.cnt, 256, 0, s>>>(c.part, Mm->Lmat, Mm->alpha, Mm->yc, Mm->hyp, Mm->n, Mm->n_pad, Mm->d,
+                                                        Mm->m, c.ntiles, c.out, grp);
+        BOCF_LAUNCH_OK("lml_finish_kernel");
+        return 0;
+      },
+      &ctx);
   if (!rc) {
-    lml_finish_kernel<<<Hm, 256, 0, st>>>(part, M->Lmat, M->alpha, M->yc, M->hyp, M->n, M->n_pad, M->d, M->m, ntiles, out);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, out, sizeof(double) * Hm * (MAXD + 3), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaMemcpyAsync(out_host, out, sizeof(double) * Hm * (MAXD + 3), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
       set_error(std::string("bocf_model_log_likelihood: ") + cudaGetErrorString(e));

@@ -30,6 +30,14 @@ struct OutRun {
 };
 __host__ __device__ __forceinline__ int run_hj(int idx, OutRun r, int m) { return (idx / r.cnt) * m + r.j0 + idx % r.cnt; }
 
+// The factorisation and the likelihood pass are chains of small, dependent launches (a 128-block Cholesky step keeps
+// H*m of the 148 SMs busy): with enough outputs they are issued as TWO output groups on two streams, so one group's
+// latency-bound steps run under the other's wide ones (fork / join around the groups with events; api.cu, lml.cu).
+struct GroupStreams {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+
 }  // namespace bocf
 
 struct bocf_model {
@@ -85,33 +93,43 @@ struct bocf_model {
   double* vq = nullptr;       // H*m   2^(8 S2 - 2 - eV): quantiser of V    (|V| <= sigma_f)
   double* lml_ws = nullptr;   // workspace of the likelihood pass (per-tile partials + results), kept across calls: the
   size_t lml_ws_count = 0;    // fit loops call it thousands of times and cudaMalloc / cudaFree cost milliseconds each
+  bocf::GroupStreams gs;      // second stream + events of the two-group factorisation / likelihood pass
   bool split_ready = false;
   bool precision_resolved = false;   // M->S and the digit planes match the current factor and requested mode
 };
 
 namespace bocf {
 
-// f(kind, OutRun) for every maximal run of consecutive outputs with the same kernel family; stops at the first non-zero rc
+// f(kind, OutRun) for every maximal run of consecutive outputs with the same kernel family inside the output group
+// `grp` (default: all outputs); stops at the first non-zero rc
 template <class F>
-inline int for_each_kind_run(const bocf_model* M, F f) {
-  int j0 = 0;
-  while (j0 < M->m) {
+inline int for_each_kind_run(const bocf_model* M, OutRun grp, F f) {
+  int j0 = grp.j0;
+  const int jend = grp.j0 + grp.cnt;
+  while (j0 < jend) {
     const int kind = M->kinds.empty() ? M->kernel : M->kinds[j0];
     int j1 = j0 + 1;
-    while (j1 < M->m && (M->kinds.empty() ? M->kernel : M->kinds[j1]) == kind) ++j1;
+    while (j1 < jend && (M->kinds.empty() ? M->kernel : M->kinds[j1]) == kind) ++j1;
     if (int rc = f(kind, OutRun{j0, j1 - j0})) return rc;
     j0 = j1;
   }
   return 0;
 }
+template <class F>
+inline int for_each_kind_run(const bocf_model* M, F f) {
+  return for_each_kind_run(M, OutRun{0, M->m}, f);
+}
 
 // ---- chol.cu ------------------------------------------------------------------------------------
 int launch_prepare(bocf_model* M, cudaStream_t st);                       // ybar, yc, Xs, xsq
-int launch_gram(bocf_model* M, cudaStream_t st);                          // K + (noise+1e-8+jitter) I
-int launch_cholesky(bocf_model* M, cudaStream_t st);                      // blocked potrf, info flags
-int launch_inverse_and_alpha(bocf_model* M, cudaStream_t st);             // Linv, alpha
+// `grp`: the outputs the launches cover (all hyper-samples of them)
+int launch_gram(bocf_model* M, OutRun grp, cudaStream_t st);              // K + (noise+1e-8+jitter) I
+int launch_cholesky(bocf_model* M, OutRun grp, cudaStream_t st);          // blocked potrf, info flags (info zeroed by the caller)
+int launch_inverse_and_alpha(bocf_model* M, OutRun grp, cudaStream_t st); // Linv, alpha
+// f(group, stream) for one group on `st`, or for two halves of the outputs on `st` and the model's side stream
+int for_each_output_group(bocf_model* M, cudaStream_t st, int (*f)(bocf_model*, OutRun, cudaStream_t, void*), void* ctx);
 int launch_copy_factor(bocf_model* M, int hj, double* L, double* Linv, double* alpha, cudaStream_t st);
-int launch_alpha(bocf_model* M, cudaStream_t st);                          // alpha = Linv^T (Linv yc)
+int launch_alpha(bocf_model* M, OutRun grp, cudaStream_t st);              // alpha = Linv^T (Linv yc)
 int launch_append_xy(const double* Xold, const double* Yold, const double* xnew, const double* ynew, int n, int d, int m,
                      double* Xn, double* Yn, cudaStream_t st);
 int launch_append(bocf_model* M, int n_old, double* work, cudaStream_t st);   // bordered Cholesky / inverse update
