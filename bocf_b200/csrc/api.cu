@@ -270,6 +270,10 @@ int bocf_model_create(bocf_model** out, int m, int d, int kernel, int device) {
   M->kinds.assign((size_t)m, kernel);
   M->device = device;
   M->precision = BOCF_PREC_AUTO;                                // library default
+  if (const char* env = std::getenv("BOCF_SCRATCH_GIB")) {     // per-chunk scratch limit (bocf_model_set_scratch_limit)
+    const double gib = std::atof(env);
+    if (gib >= 0.0625 && gib <= 160.0) M->scratch_limit = (uint64_t)(gib * 1073741824.0);
+  }
   if (const char* env = std::getenv("BOCF_PRECISION")) {      // fp64 | auto | mixed | split3 .. split6 | split<s1><s2>
     const std::string v(env);
     if (v == "auto") M->precision = BOCF_PREC_AUTO;

@@ -171,25 +171,32 @@ struct GemmParams {
 // instead of one per column tile.  NP = 1 (a CTA owns the whole row of column tiles of its candidate tile) measured
 // best on B200: 354 vs 371 (NP = 2) vs 390 ms (NP = 4) per 1M-candidate step at cfg 3 -- fewer partial sums, and the
 // tile's digit planes are re-read by one SM back to back.  More parts only pay when there are fewer units than SMs.
-constexpr int NP_DEFAULT = 1;   // parts per candidate tile (BOCF_SPLIT_NP overrides: 1, 2 or 4)
-inline int parts_per_tile() {
-  static int np = 0;
-  if (np == 0) {
-    np = NP_DEFAULT;
+constexpr int NP_DEFAULT = 1;   // parts per candidate tile (BOCF_SPLIT_NP overrides: 1, 2, 4 or 8)
+inline int parts_env() {        // 0: no override
+  static int np = -1;
+  if (np < 0) {
+    np = 0;
     if (const char* env = std::getenv("BOCF_SPLIT_NP")) {
       const int v = std::atoi(env);
-      if (v == 1 || v == 2 || v == 4) np = v;
+      if (v == 1 || v == 2 || v == 4 || v == 8) np = v;
     }
   }
   return np;
 }
-// small batches (the L-BFGS rounds of the acquisition optimiser: tens of candidates = one candidate tile per output)
-// have fewer units than SMs: split the column tiles of a candidate tile over up to 4 CTAs then
-inline int parts_for(int units_at_np1, int sms) {
-  const int np = parts_per_tile();
-  if (std::getenv("BOCF_SPLIT_NP")) return np;
-  if (units_at_np1 * 4 <= sms) return 4;
-  if (units_at_np1 * 2 <= sms) return 2;
+// Two reasons to give a candidate tile to more than one CTA:
+//  * small batches (the L-BFGS rounds of the acquisition optimiser: tens of candidates = one candidate tile per output)
+//    have fewer units than SMs;
+//  * LARGE n: a unit's A tile (SA planes x 128 candidates x n) is re-streamed once per column tile, and the tiles of all
+//    resident units must stay in L2 for that to be cheap: 655 KB x 148 CTAs = 97 MB at n = 1000 (fits the 126 MB), 2.6 MB x
+//    148 = 382 MB at n = 4000 -- there the re-streaming went to HBM and both contractions ran HBM-bound (cfg 5: 0.99 /
+//    0.81 s per 200k candidates with one part, 0.59 / 0.54 s with four CTAs sharing each tile).
+inline int parts_for(int units_at_np1, int sms, int64_t a_tile_bytes, int64_t l2_bytes) {
+  if (parts_env()) return parts_env();
+  int np = NP_DEFAULT;
+  if (units_at_np1 * 4 <= sms) np = 4;
+  else if (units_at_np1 * 2 <= sms) np = 2;
+  const int64_t budget = l2_bytes * 4 / 5;
+  while (np < 8 && (int64_t)(sms / np) * a_tile_bytes > budget) np *= 2;
   return np;
 }
 
@@ -891,13 +898,16 @@ int split_scheme_pairs(int sch) {
   sg::SchemeInfo si;
   return sg::scheme_info(sch, &si) ? si.pairs : 0;
 }
-// parts per candidate tile for a chunk of Nc candidates (Nc <= 0: the upper bound, for sizing the scratch)
+// parts per candidate tile for a chunk of Nc candidates (Nc <= 0: the upper bound over chunk sizes, for sizing the scratch)
 int split_parts(const bocf_model* M, int64_t Nc) {
-  if (Nc <= 0) return 4;
-  int dev = 0, sms = 148;
+  int dev = 0, sms = 148, l2 = 126 << 20;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sg::parts_for((int)(M->m * (Nc / sg::TM)), sms);
+  cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+  const int64_t a_tile = (int64_t)(M->S > M->S2 ? M->S : M->S2) * sg::TM * sg::KC * M->KCH;
+  const int np_large = sg::parts_for(sms, sms, a_tile, l2);              // what many units would get
+  if (Nc <= 0) return np_large > 4 ? np_large : 4;
+  return sg::parts_for((int)(M->m * (Nc / sg::TM)), sms, a_tile, l2);
 }
 int split_partials_var(const bocf_model* M, int64_t Nc) {      // partial sums per candidate and output written by the epilogues
   sg::SchemeInfo si;
@@ -1172,7 +1182,7 @@ int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int 
     P.cs = cs;
     P.m = 1;
     P.h = 0;
-    P.np = sg::parts_per_tile();
+    P.np = sg::parts_env() ? sg::parts_env() : sg::NP_DEFAULT;
     P.RT = RT;
     P.nct = nct;
     P.KCH = KCH;
