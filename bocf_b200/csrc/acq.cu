@@ -96,7 +96,11 @@ constexpr int MCU = 4;         // sample groups per trip (independent base-sampl
 //       4 = mean utility value + gradient, 5 / 6 = as 1 / 4 but the gradient is left as per-(candidate, output) WEIGHTS
 //       WA_j = scale sum_l w_l sum_s 1 dphi_j,  WB_j = scale sum_l w_l sum_s 1 dphi_j Z_sj / (2 sigma_j)
 //       for the fused gradient path (the second contraction's epilogue applies them, split_gemm.cu EPI_DACQ)
-template <int COMP, int MODE, int MCB>
+// NW: warps per candidate.  1 for everything but tiny batches (the L-BFGS rounds of the acquisition optimiser: <= 128
+// candidates), where a block of MC_WARPS warps shares ONE candidate: each warp takes a slice of every 1024-sample block
+// and the per-warp partial sums -- every output of the kernel is linear in them -- are added through shared memory in
+// fixed order at the end (93 -> ~25 us at 17 candidates, S = 1024: the warp's serial walk over the samples was latency).
+template <int COMP, int MODE, int MCB, int NW = 1>
 __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
     const double* __restrict__ mean, const double* __restrict__ var, const double* __restrict__ dmean,
     const double* __restrict__ dvar, int64_t Nc, int64_t Nvalid, int m, int d, const double* __restrict__ Zt, int S,
@@ -105,9 +109,10 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
     double* __restrict__ dacq, double* __restrict__ wa_out, double* __restrict__ wb_out) {
   constexpr bool WITH_GRAD = (MODE == 1 || MODE == 4), WEIGHTS = (MODE == 5 || MODE == 6);
   constexpr bool PLAIN_U = (MODE == 3 || MODE == 4 || MODE == 6);
+  static_assert(NW == 1 || (NW == MC_WARPS && MCB == 1 && 32 % (NW * MCU) == 0), "a block shares one candidate or none");
   __shared__ double2 s_ms[MC_WARPS][MAXM][MCB];            // (mu, sigma) of the warp's MCB candidates, output-major
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i0 = ((int64_t)blockIdx.x * MC_WARPS + warp) * MCB;
+  const int64_t i0 = (NW == 1) ? ((int64_t)blockIdx.x * MC_WARPS + warp) * MCB : (int64_t)blockIdx.x;
   if (i0 >= Nvalid) return;
   const int nc = (int)min((int64_t)MCB, Nvalid - i0);       // valid candidates of this warp
   for (int idx = lane; idx < m * MCB; idx += 32) {
@@ -137,8 +142,10 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
       unsigned mask[MCB];
 #pragma unroll
       for (int c = 0; c < MCB; ++c) mask[c] = 0u;
+      // the 32 sample groups of this block of 1024: all of them (NW == 1) or this warp's slice
+      const int kbeg = (NW == 1) ? 0 : warp * (32 / NW), kend = (NW == 1) ? 32 : kbeg + 32 / NW;
 #pragma unroll 1
-      for (int k0 = 0; k0 < 32; k0 += MCU) {
+      for (int k0 = kbeg; k0 < kend; k0 += MCU) {
         double U[MCB][MCU];
 #pragma unroll
         for (int c = 0; c < MCB; ++c)
@@ -218,6 +225,36 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
     }
 #pragma unroll
     for (int c = 0; c < MCB; ++c) val_total[c] += wl * warp_sum(val_l[c]);
+  }
+  if (NW > 1) {
+    // add the warps' partial sums in fixed order; warp 0 then writes like the single-warp path
+    __shared__ double r_val[MC_WARPS], r_grad[MC_WARPS][MAXD], r_wa[MC_WARPS][MAXM], r_wb[MC_WARPS][MAXM];
+    if (lane == 0) r_val[warp] = val_total[0];
+    if (WITH_GRAD && lane < MAXD) r_grad[warp][lane] = grad_q[0];
+    if (WEIGHTS) {
+#pragma unroll
+      for (int w = 0; w < MAXM / 32; ++w) {
+        r_wa[warp][w * 32 + lane] = wa[0][w];
+        r_wb[warp][w * 32 + lane] = wb[0][w];
+      }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    val_total[0] = 0.0;
+    grad_q[0] = 0.0;
+#pragma unroll
+    for (int w = 0; w < MAXM / 32; ++w) wa[0][w] = wb[0][w] = 0.0;
+    for (int k = 0; k < MC_WARPS; ++k) {
+      val_total[0] += r_val[k];
+      if (WITH_GRAD && lane < MAXD) grad_q[0] += r_grad[k][lane];
+      if (WEIGHTS) {
+#pragma unroll
+        for (int w = 0; w < MAXM / 32; ++w) {
+          wa[0][w] += r_wa[k][w * 32 + lane];
+          wb[0][w] += r_wb[k][w * 32 + lane];
+        }
+      }
+    }
   }
 #pragma unroll
   for (int c = 0; c < MCB; ++c) {
@@ -527,8 +564,8 @@ __global__ void topk_gather_kernel(const double* __restrict__ val, const int64_t
 template <int COMP>
 static int launch_mc_t(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvalid, double* acq, double* dacq,
                        cudaStream_t st) {
-  const bool small = (Nvalid <= 1024);
-  const unsigned grid = (unsigned)ceil_div(Nvalid, (int64_t)MC_WARPS * (small ? 1 : 4));
+  const bool small = (Nvalid <= 1024), tiny = (Nvalid <= 128);
+  const unsigned grid = tiny ? (unsigned)Nvalid : (unsigned)ceil_div(Nvalid, (int64_t)MC_WARPS * (small ? 1 : 4));
   const bool weights = (P.wa != nullptr);
   const int mode = (P.variant == BOCF_ACQ_MEAN_UTILITY) ? (weights ? 6 : dacq ? 4 : 3)
                    : (P.variant == BOCF_ACQ_PI_CF)      ? 2
@@ -540,7 +577,8 @@ static int launch_mc_t(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvali
   ProfScope ps("mc_acq_kernel", st);
 #define BOCF_MC_LAUNCH(MD)                                                                       \
   do {                                                                                           \
-    if (small) mc_acq_kernel<COMP, MD, 1><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);         \
+    if (tiny) mc_acq_kernel<COMP, MD, 1, MC_WARPS><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);     \
+    else if (small) mc_acq_kernel<COMP, MD, 1><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);    \
     else mc_acq_kernel<COMP, MD, 4><<<grid, MC_WARPS * 32, 0, st>>>(BOCF_MC_ARGS);               \
   } while (0)
   if (mode == 0) BOCF_MC_LAUNCH(0);
