@@ -639,7 +639,7 @@ int bocf_posterior(bocf_model* M, int h, const double* Xc, int64_t N, int noisel
   if (int rc = resolve_precision(M, st)) return rc;
   const bool grad = (dvar != nullptr) || (dmean != nullptr);
   const int64_t Nc = pick_chunk(M, N, grad, 0);
-  if (int rc = ensure_scratch(M, chunk_bytes_per_candidate(M, grad) * Nc + kstar_part_bytes(M, Nc) + (1 << 16))) return rc;
+  if (int rc = ensure_scratch(M, chunk_bytes_per_candidate(M, grad, Nc) * Nc + kstar_part_bytes(M, Nc) + (1 << 16))) return rc;
   ChunkBuffers cb;
   carve_chunk(M, M->scratch, Nc, grad, &cb);
   for (int64_t off = 0; off < N; off += Nc) {
@@ -712,7 +712,7 @@ int bocf_acq_eval(bocf_model* M, int variant, int composite, const double* Xc, i
   const size_t n_theta = (size_t)L * (p > 0 ? p : 1);
   const size_t par_doubles = n_theta + (size_t)L + (size_t)H_use * L;
   const int64_t Nc = pick_chunk(M, N, grad, 0);
-  const uint64_t chunk_bytes = chunk_bytes_per_candidate(M, grad) * Nc + kstar_part_bytes(M, Nc) + (1 << 16);
+  const uint64_t chunk_bytes = chunk_bytes_per_candidate(M, grad, Nc) * Nc + kstar_part_bytes(M, Nc) + (1 << 16);
   if (int rc = ensure_scratch(M, chunk_bytes + 256)) return rc;
   ChunkBuffers cb;
   carve_chunk(M, M->scratch, Nc, grad, &cb);

@@ -159,7 +159,8 @@ struct ChunkBuffers {          // scratch views for one candidate chunk (Nc rows
 };
 int kstar_ksplit(const bocf_model* M, int64_t Nc);
 uint64_t kstar_part_bytes(const bocf_model* M, int64_t Nc);
-uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad);
+// Nc > 0: exact for a chunk of Nc candidates; Nc <= 0: the sizing figure of a LARGE chunk (pick_chunk divides the limit by it)
+uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad, int64_t Nc = 0);
 void carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* out);
 // Posterior of hyper-sample h for candidates Xc[0..Nvalid) into the chunk buffers.
 // grad: also K*-side gradient quantities (dmean, G*); need_var / need_dvar select the two contractions.
@@ -170,13 +171,13 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
 // ---- split_gemm.cu ------------------------------------------------------------------------------
 int split_scheme_for_slices(int S);                 // 3..6 digit planes -> scheme code (331, 442, 554, 665)
 int split_scheme_pairs(int sch);                     // int8 GEMM passes of a scheme
-int split_parts(const bocf_model* M, int64_t Nc);    // parts per candidate tile for a chunk of Nc candidates (<= 0: upper bound)
+int split_parts(const bocf_model* M, int64_t Nc);    // parts per candidate tile for a chunk of Nc candidates (<= 0: a large chunk)
 int split_partials_var(const bocf_model* M, int64_t Nc);    // partial sums per candidate the VAR / DVAR epilogues write
 int split_partials_dvar(const bocf_model* M, int64_t Nc);
 int split_prepare(bocf_model* M, int sch1, int sch2, cudaStream_t st);   // digit planes of Linv + scales
 void split_release(bocf_model* M);
 int split_linv_absmax(bocf_model* M, double* out_host, cudaStream_t st);
-uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad);
+uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad, int64_t Nc = 0);
 void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, ChunkBuffers* out);
 int launch_split_var(bocf_model* M, int h, const ChunkBuffers& cb, bool need_dvar, cudaStream_t st);
 int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, const ChunkBuffers& cb, cudaStream_t st);

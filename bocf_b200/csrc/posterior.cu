@@ -428,8 +428,8 @@ uint64_t kstar_part_bytes(const bocf_model* M, int64_t Nc) {
   return ks > 1 ? (uint64_t)ks * M->m * Nc * (1 + M->d) * sizeof(double) + 1024 : 0;
 }
 
-uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
-  if (M->S > 0) return split_chunk_bytes_per_candidate(M, grad);
+uint64_t chunk_bytes_per_candidate(const bocf_model* M, bool grad, int64_t Nc) {
+  if (M->S > 0) return split_chunk_bytes_per_candidate(M, grad, Nc);
   const uint64_t nct = M->n_pad / NT;
   uint64_t per = 0;
   per += (uint64_t)M->m * M->n16;                       // KsT

@@ -193,8 +193,8 @@ inline int parts_env() {        // 0: no override
 inline int parts_for(int units_at_np1, int sms, int64_t a_tile_bytes, int64_t l2_bytes) {
   if (parts_env()) return parts_env();
   int np = NP_DEFAULT;
-  if (units_at_np1 * 4 <= sms) np = 4;
-  else if (units_at_np1 * 2 <= sms) np = 2;
+  if (units_at_np1 * 4 <= sms) np = 4;            // 8 parts measured no faster at 17 candidates: a small batch still
+  else if (units_at_np1 * 2 <= sms) np = 2;       // streams every factor plane (148 MB at cfg 3), that is its floor
   const int64_t budget = l2_bytes * 4 / 5;
   while (np < 8 && (int64_t)(sms / np) * a_tile_bytes > budget) np *= 2;
   return np;
@@ -898,15 +898,15 @@ int split_scheme_pairs(int sch) {
   sg::SchemeInfo si;
   return sg::scheme_info(sch, &si) ? si.pairs : 0;
 }
-// parts per candidate tile for a chunk of Nc candidates (Nc <= 0: the upper bound over chunk sizes, for sizing the scratch)
+// parts per candidate tile for a chunk of Nc candidates (Nc <= 0: what a large chunk gets -- the sizing figure; small
+// chunks may use more parts, their scratch is sized exactly: chunk_bytes_per_candidate(M, grad, Nc))
 int split_parts(const bocf_model* M, int64_t Nc) {
   int dev = 0, sms = 148, l2 = 126 << 20;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
   const int64_t a_tile = (int64_t)(M->S > M->S2 ? M->S : M->S2) * sg::TM * sg::KC * M->KCH;
-  const int np_large = sg::parts_for(sms, sms, a_tile, l2);              // what many units would get
-  if (Nc <= 0) return np_large > 4 ? np_large : 4;
+  if (Nc <= 0) return sg::parts_for(sms, sms, a_tile, l2);               // what many units get
   return sg::parts_for((int)(M->m * (Nc / sg::TM)), sms, a_tile, l2);
 }
 int split_partials_var(const bocf_model* M, int64_t Nc) {      // partial sums per candidate and output written by the epilogues
@@ -1014,15 +1014,15 @@ int split_prepare(bocf_model* M, int sch1, int sch2, cudaStream_t st) {
   return 0;
 }
 
-uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad) {
+uint64_t split_chunk_bytes_per_candidate(const bocf_model* M, bool grad, int64_t Nc) {
   uint64_t per = 0;
   per += (uint64_t)M->m * M->KCH * sg::KC * M->S;       // A1 digit planes of K*
-  per += (uint64_t)M->m * split_partials_var(M, 0) * 8; // part_var (upper bound on the parts)
+  per += (uint64_t)M->m * split_partials_var(M, Nc) * 8; // part_var
   per += 2ull * M->m * 8;                               // mean, var
   if (grad) {
     per += (uint64_t)M->m * M->n16 * 8;                 // GsT
     per += (uint64_t)M->m * M->KCH * sg::KC * M->S2;    // A2 digit planes of V
-    per += (uint64_t)M->m * split_partials_dvar(M, 0) * (M->d + 1) * 8;   // part_dvar, part_s0
+    per += (uint64_t)M->m * split_partials_dvar(M, Nc) * (M->d + 1) * 8;  // part_dvar, part_s0
     per += 2ull * M->m * M->d * 8;                      // dmean, dvar
     per += 2ull * M->m * 8;                             // wa, wb (fused gradient path)
   }
@@ -1040,14 +1040,14 @@ void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, C
   cb->Nc = Nc;
   cb->KsT = cb->V = nullptr;
   cb->A1 = take(plane * M->S);
-  cb->part_var = reinterpret_cast<double*>(take((uint64_t)M->m * split_partials_var(M, 0) * Nc * 8));
+  cb->part_var = reinterpret_cast<double*>(take((uint64_t)M->m * split_partials_var(M, Nc) * Nc * 8));
   cb->mean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
   cb->var = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
   if (grad) {
     cb->GsT = reinterpret_cast<double*>(take((uint64_t)M->m * M->n16 * Nc * 8));
     cb->A2 = take(plane * M->S2);
-    cb->part_dvar = reinterpret_cast<double*>(take((uint64_t)M->m * split_partials_dvar(M, 0) * Nc * M->d * 8));
-    cb->part_s0 = reinterpret_cast<double*>(take((uint64_t)M->m * split_partials_dvar(M, 0) * Nc * 8));
+    cb->part_dvar = reinterpret_cast<double*>(take((uint64_t)M->m * split_partials_dvar(M, Nc) * Nc * M->d * 8));
+    cb->part_s0 = reinterpret_cast<double*>(take((uint64_t)M->m * split_partials_dvar(M, Nc) * Nc * 8));
     cb->dmean = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
     cb->dvar = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * M->d * 8));
     cb->wa = reinterpret_cast<double*>(take((uint64_t)M->m * Nc * 8));
