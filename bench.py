@@ -616,8 +616,9 @@ def run_ours(args, cfg):
         rate_v, done_v, el_v = cpu_vectorised_rate(P, args.cpu_budget / 2)
         cpu = {"value": rate_l, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
                "sample": "%d candidates x %d MC samples in %.1f s; oracle port with the reference's loop structure "
-                         "(Python loops over theta x Z x candidates; LAPACK/BLAS posterior on all host threads)"
-                         % (done_l, c["S"], el_l),
+                         "(Python loops over theta x Z x candidates; LAPACK/BLAS posterior on all host threads); the same "
+                         "oracle with the MC loops vectorised in numpy reaches %.0f evals/s on the same cores "
+                         "(vectorised_numpy_value)" % (done_l, c["S"], el_l, rate_v),
                "vectorised_numpy_value": rate_v,
                "vectorised_sample": "%d candidates in %.1f s, chunks of 2048" % (done_v, el_v)}
 
