@@ -127,14 +127,13 @@ __device__ __forceinline__ void dmma_tile(double& c0, double& c1, const double* 
   }
 }
 
-__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lmat, double* __restrict__ Dinv,
-                                                         int* __restrict__ info, int n, int n_pad, int nb, int kb,
-                                                         OutRun grp, int m) {
-  extern __shared__ __align__(16) double T[];   // T[TILE][DLD] | W[64][WLD] | dinv[TILE] | Xb[4][32][32]
-  double* W = T + TILE * DLD;
+// The whole CTA (256 threads) factors and inverts block kb of matrix hj; T = POTRF_SMEM bytes of shared memory.  Called by
+// potrf_diag_kernel (first block) and, as a look-ahead, by the CTA of the trailing update that owns the next diagonal tile.
+__device__ __forceinline__ void potrf_block(double* __restrict__ T, double* __restrict__ Lmat, double* __restrict__ Dinv,
+                                            int* __restrict__ info, int n, int n_pad, int nb, int kb, int hj) {
+  double* W = T + TILE * DLD;                   // T[TILE][DLD] | W[64][WLD] | dinv[TILE] | Xb[4][32][32]
   double* dinv = W + 64 * WLD;
   double* Xb = dinv + TILE;                     // inverses of the four diagonal sub-blocks (row-major 32 x 32 each)
-  const int hj = run_hj(blockIdx.x, grp, m);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int k0 = kb * TILE;
@@ -356,6 +355,13 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lm
   }
 }
 
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lmat, double* __restrict__ Dinv,
+                                                         int* __restrict__ info, int n, int n_pad, int nb, int kb,
+                                                         OutRun grp, int m) {
+  extern __shared__ __align__(16) double T[];
+  potrf_block(T, Lmat, Dinv, info, n, n_pad, nb, kb, run_hj(blockIdx.x, grp, m));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Panel solve: A[I][K] <- A[I][K] . L_KK^-T  (= A . Dinv^T), I > K.   grid (nb-1-K, H*m)
 __global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) trsm_panel_kernel(double* __restrict__ Lmat,
@@ -383,7 +389,9 @@ __global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) trsm_panel_kernel(
 
 // Trailing update: A[I][J] -= P_I . P_J^T for K < J <= I.   grid (#pairs, H*m)
 __global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) syrk_update_kernel(double* __restrict__ Lmat, int n_pad, int nb,
-                                                                       int kb, OutRun grp, int m) {
+                                                                       int kb, OutRun grp, int m,
+                                                                       double* __restrict__ Dinv, int* __restrict__ info,
+                                                                       int n) {
   extern __shared__ __align__(16) double smem[];
   const int hj = run_hj(blockIdx.y, grp, m);
   // decode the lower-triangular pair index
@@ -420,6 +428,13 @@ __global__ void __launch_bounds__(gemm::Tile128::NTHREADS, 1) syrk_update_kernel
       const int r = mbase + 8 * i + g, c = nbase + 8 * j + 2 * t;
       *reinterpret_cast<double2*>(C + (int64_t)r * n_pad + c) = make_double2(-acc[i][j][0], -acc[i][j][1]);
     }
+  // LOOK-AHEAD: tile 0 is the next diagonal block (kb+1, kb+1), now final.  Its owner factors and inverts it right here,
+  // while the other CTAs of this launch are still updating the rest of the trailing matrix, so the diagonal-block step
+  // (H*m CTAs, ~46 us, nb times on the chain of every factorisation) no longer has a launch of its own after the first.
+  if (blockIdx.x == 0) {
+    __syncthreads();                             // the tile's stores are visible to the whole CTA; smem is free (mainloop)
+    potrf_block(smem, Lmat, Dinv, info, n, n_pad, nb, kb + 1, hj);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -684,6 +699,7 @@ int for_each_output_group(bocf_model* M, cudaStream_t st, int (*f)(bocf_model*, 
   return rc ? rc : rc2;
 }
 
+constexpr int SYRK_SMEM = POTRF_SMEM > gemm::Tile128::SMEM_BYTES ? POTRF_SMEM : gemm::Tile128::SMEM_BYTES;
 static int set_smem_attrs() {
   // per device: function attributes belong to the device's context (one process may drive several GPUs)
   static bool done_dev[64] = {false};
@@ -697,7 +713,7 @@ static int set_smem_attrs() {
   if (done) return 0;
   BOCF_CUDA_OK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
   BOCF_CUDA_OK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
-  BOCF_CUDA_OK(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
+  BOCF_CUDA_OK(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM));
   BOCF_CUDA_OK(cudaFuncSetAttribute(linv_merge_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
   BOCF_CUDA_OK(cudaFuncSetAttribute(linv_merge_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::Tile128::SMEM_BYTES));
   done = true;
@@ -707,16 +723,16 @@ static int set_smem_attrs() {
 int launch_cholesky(bocf_model* M, OutRun grp, cudaStream_t st) {
   if (int rc = set_smem_attrs()) return rc;
   const int Hg = M->H * grp.cnt, nb = M->nb;
-  for (int kb = 0; kb < nb; ++kb) {
-    potrf_diag_kernel<<<Hg, 256, POTRF_SMEM, st>>>(M->Lmat, M->Dinv, M->info, M->n, M->n_pad, nb, kb, grp, M->m);
-    BOCF_LAUNCH_OK("potrf_diag_kernel");
+  // block 0 has its own launch; every later diagonal block is factored by the trailing update that completes it
+  potrf_diag_kernel<<<Hg, 256, POTRF_SMEM, st>>>(M->Lmat, M->Dinv, M->info, M->n, M->n_pad, nb, 0, grp, M->m);
+  BOCF_LAUNCH_OK("potrf_diag_kernel");
+  for (int kb = 0; kb + 1 < nb; ++kb) {
     const int rem = nb - 1 - kb;
-    if (rem > 0) {
-      trsm_panel_kernel<<<dim3(rem, Hg), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Dinv, M->n_pad, nb, kb, grp, M->m);
-      BOCF_LAUNCH_OK("trsm_panel_kernel");
-      syrk_update_kernel<<<dim3(rem * (rem + 1) / 2, Hg), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->n_pad, nb, kb, grp, M->m);
-      BOCF_LAUNCH_OK("syrk_update_kernel");
-    }
+    trsm_panel_kernel<<<dim3(rem, Hg), gemm::Tile128::NTHREADS, gemm::Tile128::SMEM_BYTES, st>>>(M->Lmat, M->Dinv, M->n_pad, nb, kb, grp, M->m);
+    BOCF_LAUNCH_OK("trsm_panel_kernel");
+    syrk_update_kernel<<<dim3(rem * (rem + 1) / 2, Hg), gemm::Tile128::NTHREADS, SYRK_SMEM, st>>>(M->Lmat, M->n_pad, nb, kb, grp, M->m,
+                                                                                                 M->Dinv, M->info, M->n);
+    BOCF_LAUNCH_OK("syrk_update_kernel");
   }
   return 0;
 }
