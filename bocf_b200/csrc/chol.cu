@@ -100,14 +100,17 @@ __global__ void gram_kernel(const double* __restrict__ Xs, const double* __restr
 
 // ---------------------------------------------------------------------------------------------------
 // Diagonal block: Cholesky + in-place triangular inverse of one 128 x 128 block in shared memory (one CTA / matrix).
-// This kernel sits nb times on the critical path of every factorisation (only H*m CTAs run, everything else waits), so
-// it is organised around its dependency chain, in 32-wide sub-blocks:
-//   factor    the 32 x 32 diagonal sub-block by ONE warp, register resident (lane = row, column k broadcast by shuffles,
-//             reciprocal square root instead of sqrt + divide on the chain);
-//   solve     the rows below it by forward substitution, thread per row, L broadcast from shared memory;
+// This step sits nb times on the critical path of every factorisation (only H*m CTAs can work on it), so it is organised
+// around its dependency chain, in 32-wide sub-blocks (profiles/r2_fit_pass.md has the ncu history, 143 -> 46 us):
+//   factor    the 32 x 32 diagonal sub-block by ONE warp, register resident (lane = row).  Per column the chain is
+//             pivot shuffle -> rsqrt -> multiply -> multiply-add: the next pivot needs only lane k+1's own two values;
+//             the finished column is parked in shared memory (column-major) and subtracted from the columns to its
+//             right with independent multiply-adds fed by 16-byte broadcast loads;
+//   solve     the rows below it by forward substitution, thread per row, from the parked columns -- and in the same
+//             phase, by the same instructions, the rows of the IDENTITY, which gives the sub-block's inverse;
 //   update    the trailing lower triangle on the fp64 tensor cores (DMMA 8x8x4, K = 32);
-//   invert    afterwards the four 32 x 32 diagonal sub-blocks in parallel (warp each, lane = column) and assemble the
-//             128 x 128 inverse recursively,  X21 = -X22 (L21 X11),  at 32 then 64 wide, again on DMMA.
+//   assemble  the 128 x 128 inverse from the four sub-block inverses recursively,  X21 = -X22 (L21 X11),  at 32 then 64
+//             wide, again on DMMA.
 // The dpotrf failure convention is kept: the first non-positive pivot is reported in info[] (1-based), replaced by 1.
 constexpr int PSB = 32;                       // sub-block
 constexpr int DLD = TILE + 4;                 // row stride == 4 mod 16 doubles: conflict-free 64-bit fragment loads
