@@ -3,6 +3,7 @@ around the ORACLE model and acquisition on a test_1a-shaped problem (test_1a.py:
 grid, objective = their posterior means, utility -sum_j (y_j - theta_j)^2 with theta taken at a reference point), with a
 fixed seed.  No GPU: this covers the host plumbing the GPU loop tests share (tests/test_gpu_cbo.py)."""
 import numpy as np
+import pytest
 
 
 def _build(seed, fixed_hyps=True, sampler=None):
@@ -121,3 +122,22 @@ def test_theta_matrix_and_utility_consistency():
     B.Utility(func=lambda th, y: -np.sum(np.square((y.T - th).T), axis=0), parameter_dist=pd, composite="sumsq_target")
     with pytest.raises(ValueError):
         B.Utility(func=lambda th, y: np.sum(y, axis=0), parameter_dist=pd, composite="sumsq_target")
+
+
+def test_kernel_list_is_resolved_per_output():
+    # multi_outputGP.py:23,38-44: output j is built from kernel[j]; the product keeps one family name when they all agree
+    # and one name per output otherwise (host logic only: no device call before updateModel)
+    import bocf_b200 as B
+    from bocf_b200 import kern
+    d = 3
+    mod = B.multi_outputGP(3, kernel=[kern.Matern52(d), None, kern.RBF(d)], fixed_hyps=True)
+    assert mod._kernel_kind() == ("matern52", "se", "rbf")
+    assert B.multi_outputGP(2, kernel=[kern.RBF(d), kern.RBF(d)], fixed_hyps=True)._kernel_kind() == "rbf"
+    assert B.multi_outputGP(2, fixed_hyps=True)._kernel_kind() == "se"
+    var, ls, nz = np.ones((1, 3)), np.ones((1, 3, d)), np.full((1, 3), 1e-2)
+    mod.set_hyperparameter_samples(var, ls, nz, kind=["se", "se", "se"])
+    assert mod._hyp[0] == "se"
+    mod.set_hyperparameter_samples(var, ls, nz, kind=("se", "matern32", "se"))
+    assert mod._hyp[0] == ("se", "matern32", "se")
+    with pytest.raises(AssertionError):
+        mod.set_hyperparameter_samples(var, ls, nz, kind=["se", "rbf"])
