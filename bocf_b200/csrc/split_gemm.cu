@@ -522,6 +522,7 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
     // reductions over the column tiles of a unit live in registers
     constexpr int DPA = DP > 0 ? DP : 2;
     double sumsq = 0.0, s0 = 0.0, acc[DPA];
+    double wa_i = 0.0, wb2_i = 0.0;                             // DACQ: this candidate's gradient weights for the unit's output
     while (have) {
       ti = tnext;
       have = walk.next(P, tnext);
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
       // columns per TMEM load group.  VAR: 16, so a thread's digits of one plane are ONE 16-byte piece of the swizzled
       // 64-byte row -- half as many L2 write requests as 8-byte stores (knock-out: the V-digit stores cost 22 of the
       // first contraction's 121 ms per 1M-candidate step as 8-byte pieces, profiles/r2_knockouts.md)
-      constexpr int CGW = (EPI == EPI_VAR) ? 16 : 8;
+      constexpr int CGW = (EPI == EPI_VAR) ? 16 : (GRADEPI ? 4 : 8);
       static_assert(NT % (CGW * PART_SPLIT) == 0, "column groups must divide evenly over the warps");
       constexpr int NCG = NT / CGW;
       constexpr int NGW = NCG / PART_SPLIT;                     // column groups per warp
@@ -568,10 +569,9 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
       const double* Gcol = nullptr;
       const int64_t gstride = P.Nc;
       const bool tile_full = (col0 + NT <= P.n);
-      double wa_i = 0.0, wb2_i = 0.0;
-      if (EPI == EPI_DACQ) {                                     // this candidate's gradient weights for output j
-        wa_i = __ldg(P.wa + (size_t)ti.j * P.Nc + i);
-        wb2_i = -2.0 * __ldg(P.wb + (size_t)ti.j * P.Nc + i);
+      if (EPI == EPI_DACQ && ti.first) {                         // once per unit, not per column tile: the loads' latency
+        wa_i = __ldg(P.wa + (size_t)ti.j * P.Nc + i);            // sat exposed at the top of every tile (13 % of the
+        wb2_i = -2.0 * __ldg(P.wb + (size_t)ti.j * P.Nc + i);    // epilogue warps' samples in ncu)
       }
       if (GRADEPI) {
         Gcol = P.GsT + (size_t)ti.j * P.n16 * P.Nc + i;
@@ -586,10 +586,11 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
       tc::fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
 
-      // VAR / RAW: the levels of the NEXT column group are requested from tensor memory before the current group is
-      // processed (two register buffers), so the TMEM round trip overlaps the fp64 work.  DVAR keeps one buffer: its
-      // 2 d + 2 accumulators leave no registers for a second one.
-      constexpr bool PREF = !GRADEPI;
+      // The levels of the NEXT column group are requested from tensor memory before the current group is processed (two
+      // register buffers), so the TMEM round trip overlaps the fp64 work.  The gradient epilogues, whose 2 d + 2
+      // accumulators leave fewer registers, do the same with 4-column groups (two buffers of NL x 4 words = the one
+      // buffer of NL x 8 they had: the exposed TMEM latency was 12 % of their samples in ncu).
+      constexpr bool PREF = true;
       uint32_t c[PREF ? 2 : 1][NL][CGW];
       if (PREF) {
 #pragma unroll

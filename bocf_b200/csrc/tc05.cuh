@@ -117,8 +117,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
 template <int W>
 __device__ __forceinline__ void tmem_ldw(uint32_t taddr, uint32_t (&v)[W]);
+template <>
+__device__ __forceinline__ void tmem_ldw<4>(uint32_t taddr, uint32_t (&v)[4]) { tmem_ld4(taddr, v); }
 template <>
 __device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 template <>
