@@ -122,3 +122,26 @@ def test_append_and_kg_helper_with_a_kernel_list(cuda_device):
     for j in range(P.m):
         assert_close(np.asarray(vc)[j], np.asarray(vc_o)[j], tol(1e-6), "varcond[%d]" % j)
         assert_close(np.asarray(dvc)[j], np.asarray(dvc_o)[j], tol(1e-6), "dvarcond[%d]" % j)
+
+
+def test_kernel_list_across_output_groups(cuda_device):
+    # n = 300 (three 128-blocks), H m = 12: the factorisation and the likelihood pass run as two output groups on two
+    # streams (for_each_output_group, chol.cu), each group cutting the family runs at its own border
+    P = _problem(n=300, N=64)
+    om, pm = oracle_model(P), product_model(P, cuda_device)
+    lml, gv, gl, gn = pm.log_likelihood_and_gradients()
+    for h in range(P.H):
+        om.set_hyperparameters(h)
+        pm.set_hyperparameters(h)
+        for j in range(P.m):
+            gp = om.output[j].model_instances[h]
+            L, Linv, alpha = pm.get_factor(h, j)
+            assert rel_err(L, gp.woodbury_chol) < 1e-10, (h, j, KINDS[j])
+            assert rel_err(Linv @ gp.woodbury_chol, np.eye(P.n)) < 1e-9
+            assert rel_err(alpha, gp.woodbury_vector[:, 0]) < 1e-8
+            o_gv, o_gl, o_gn = gp.likelihood_gradients()
+            assert abs(lml[h, j] - gp.log_likelihood()) < 1e-10 * max(1.0, abs(gp.log_likelihood()))
+            assert rel_err(gl[h, j], o_gl) < 1e-8 and abs(gv[h, j] - o_gv) < 1e-8 * max(1.0, abs(o_gv))
+        assert_close(pm.posterior_mean(P.Xc), om.posterior_mean(P.Xc), tol(1e-8), "mean")
+        v, v_o = pm.posterior_variance(P.Xc), om.posterior_variance(P.Xc)
+        assert np.max(np.abs(v - v_o) / np.abs(v_o)) < tol(1e-7)
