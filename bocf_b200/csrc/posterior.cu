@@ -569,6 +569,31 @@ __global__ void finalize_grad_kernel(const double* __restrict__ part_dvar, const
   dacq[idx] = accumulate ? dacq[idx] + g : g;
 }
 
+// The same sum for tiny batches (the L-BFGS rounds: <= 128 candidates), where one thread per (candidate, dimension)
+// walking m x nparts partials serially is pure latency (~50 us at m = 16, 12 partials): a WARP per (candidate, dimension),
+// lanes striding over the (output, partial) pairs -- the sum is linear in them -- then one shuffle reduction.
+__global__ void __launch_bounds__(256) finalize_grad_small_kernel(const double* __restrict__ part_dvar,
+                                                                  const double* __restrict__ part_s0,
+                                                                  const OutHyp* __restrict__ hyp, int64_t Nc, int64_t Nvalid,
+                                                                  int nparts, int m, int d, int h,
+                                                                  const double* __restrict__ Xc, int accumulate,
+                                                                  double* __restrict__ dacq) {
+  const int64_t idx = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (idx >= Nvalid * d) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = idx / d;
+  const int q = (int)(idx - i * d);
+  const double x = Xc[i * d + q];
+  double g = 0.0;
+  for (int p = lane; p < m * nparts; p += 32) {
+    const int j = p / nparts;                                  // p = j * nparts + t
+    const double il = 1.0 / hyp[h * m + j].ls[q];
+    g += (x * il * part_s0[(int64_t)p * Nc + i] - part_dvar[((int64_t)p * Nc + i) * d + q]) * il;
+  }
+  g = warp_sum(g);
+  if (lane == 0) dacq[idx] = accumulate ? dacq[idx] + g : g;
+}
+
 // Fused acquisition-gradient sweep of one chunk and one hyper-sample (EI-CF / mean-utility with gradients, tensor-core
 // contraction mode): K* (mean, digit planes, G*; no mean gradient) -> first contraction -> variance -> MC forward pass
 // leaving the value and the per-(candidate, output) gradient weights WA, WB -> second contraction whose epilogue
@@ -592,9 +617,14 @@ int launch_fused_grad_chunk(bocf_model* M, int h, const double* Xc, int64_t Nval
   if (int rc = launch_split_dacq(M, h, Xc, Nvalid, cb, st)) return rc;
   {
     ProfScope ps("finalize_kernel", st);
-    finalize_grad_kernel<<<(unsigned)ceil_div(Nvalid * M->d, 256), 256, 0, st>>>(cb.part_dvar, cb.part_s0, M->hyp, cb.Nc, Nvalid,
-                                                                               split_partials_dvar(M, cb.Nc), M->m, M->d, h,
-                                                                               Xc, P.accumulate, dacq);
+    if (Nvalid <= 128)
+      finalize_grad_small_kernel<<<(unsigned)ceil_div(Nvalid * M->d, 8), 256, 0, st>>>(cb.part_dvar, cb.part_s0, M->hyp, cb.Nc,
+                                                                                     Nvalid, split_partials_dvar(M, cb.Nc),
+                                                                                     M->m, M->d, h, Xc, P.accumulate, dacq);
+    else
+      finalize_grad_kernel<<<(unsigned)ceil_div(Nvalid * M->d, 256), 256, 0, st>>>(cb.part_dvar, cb.part_s0, M->hyp, cb.Nc, Nvalid,
+                                                                                 split_partials_dvar(M, cb.Nc), M->m, M->d, h,
+                                                                                 Xc, P.accumulate, dacq);
     BOCF_LAUNCH_OK("finalize_grad_kernel");
   }
   return 0;
