@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
   // tens).  Block z then takes the 128-point blocks z, z + gridDim.z, ... and writes ADDITIVE partial sums of the mean
   // and its gradient (slab z of mean / dmean); kstar_reduce_kernel adds the slabs in fixed order.
   const int ks = (int)gridDim.z, kz = (int)blockIdx.z;
+  if ((int64_t)blockIdx.x * 128 >= Nvalid) return;          // a tile of pure padding: nothing downstream reads it
   __shared__ double sX[128][DP];
   __shared__ double sxsq[128];
   __shared__ double salpha[128];
@@ -398,14 +399,15 @@ __global__ void finalize_kernel(const double* __restrict__ part_var, const doubl
   const int j = blockIdx.y;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const OutHyp& hp = hyp[h * m + j];
-  if (idx < Nc) {
+  const int64_t Nv = min(Nc, (Nvalid + 127) / 128 * 128);     // candidate tiles beyond the valid ones were skipped upstream
+  if (idx < Nv) {
     double s = 0.0;
     for (int tI = 0; tI < nct; ++tI) s += part_var[((int64_t)j * nct + tI) * Nc + idx];
     double v = hp.variance - s;
     if (!noiseless) v = hp.noise + v;
     var[(int64_t)j * Nc + idx] = (noiseless == 2) ? v : fmax(v, 1e-10);     // 2: the KG helpers' unclipped form (gp.py:543)
   }
-  if (grad && idx < Nc * d) {
+  if (grad && idx < Nv * d) {
     const int q = (int)(idx % d);
     double gsum = 0.0;
     for (int tI = 0; tI < nct_g; ++tI) gsum += part_dvar[((int64_t)j * nct_g + tI) * Nc * d + idx];
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(256) finalize_grad_small_kernel(const double* 
 int launch_fused_grad_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvalid, int noiseless, const ChunkBuffers& cb,
                             AcqParams P, double* acq, double* dacq, cudaStream_t st) {
   if (int rc = launch_kstar(M, h, Xc, Nvalid, 2, cb, st)) return rc;
-  if (int rc = launch_split_var(M, h, cb, true, st)) return rc;
+  if (int rc = launch_split_var(M, h, Nvalid, cb, true, st)) return rc;
   {
     const int nct = split_partials_var(M, cb.Nc);
     dim3 fgrid((unsigned)ceil_div(cb.Nc, 256), (unsigned)M->m);
@@ -648,7 +650,7 @@ int launch_posterior_chunk(bocf_model* M, int h, const double* Xc, int64_t Nvali
   const unsigned tiles = (unsigned)((cb.Nc / CT) * nct * M->m);
   if (split) {
     // tcgen05 kind::i8 digit-plane contractions (split_gemm.cu); same partial-sum layout, same finalize
-    if (int rc2 = launch_split_var(M, h, cb, need_dvar, st)) return rc2;
+    if (int rc2 = launch_split_var(M, h, Nvalid, cb, need_dvar, st)) return rc2;
     if (need_dvar)
       if (int rc2 = launch_split_dvar(M, h, Xc, Nvalid, cb, st)) return rc2;
   } else {

@@ -140,6 +140,8 @@ struct GemmParams {
   const uint8_t* B;        // [Hm][nct][KCH][SB][NT][64] packed digit planes of the factor-side operand
   const double* cs;        // [Hm][nct*NT]               column scale (power of two)
   int m, h, RT, nct, KCH, n, tri;
+  int RTv;                 // candidate tiles that hold at least one valid candidate (<= RT): the others are skipped -- the
+                           // ragged last chunk of a sweep and the tiny batches of the optimiser are mostly padding
   int64_t Nc, Nvalid;
   // RAW
   double* raw_out;         // [m*RT*128][ldo]
@@ -213,7 +215,7 @@ template <int NT>
 struct TileWalk {
   int u, units, j, rt, p, ct;
   __device__ __forceinline__ void start(const GemmParams& P) {
-    units = P.m * P.RT * P.np;
+    units = P.m * P.RTv * P.np;
     u = (int)blockIdx.x - (int)gridDim.x;
     ct = P.nct;                                            // forces the first next() to open a unit
     j = rt = p = 0;
@@ -224,8 +226,8 @@ struct TileWalk {
     while (ct >= P.nct) {                                  // open the next unit that has at least one column tile
       u += (int)gridDim.x;
       if (u >= units) return false;
-      j = u / (P.RT * P.np);
-      const int r = u - j * (P.RT * P.np);
+      j = u / (P.RTv * P.np);
+      const int r = u - j * (P.RTv * P.np);
       rt = r / P.np;
       p = r - rt * P.np;
       ct = p;
@@ -821,7 +823,7 @@ static int launch_k(const GemmParams& P, cudaStream_t st) {
     attr_done[dev] = true;
   }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int units = P.m * P.RT * P.np;            // scheduling entities
+  const int units = P.m * P.RTv * P.np;           // scheduling entities
   const int grid = units < sms ? units : sms;
   split_gemm_kernel<SCH, EPI, DP, S2><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(P);
   BOCF_LAUNCH_OK("split_gemm_kernel");
@@ -1060,12 +1062,14 @@ void split_carve_chunk(const bocf_model* M, void* base, int64_t Nc, bool grad, C
   cb->kpart = (kstar_ksplit(M, Nc) > 1) ? reinterpret_cast<double*>(take(kstar_part_bytes(M, Nc))) : nullptr;
 }
 
-static sg::GemmParams base_params(const bocf_model* M, int h, const ChunkBuffers& cb) {
+static sg::GemmParams base_params(const bocf_model* M, int h, const ChunkBuffers& cb, int64_t Nvalid) {
   sg::GemmParams P;
   std::memset(&P, 0, sizeof(P));
   P.m = M->m;
   P.h = h;
   P.RT = (int)(cb.Nc / sg::TM);
+  P.RTv = (Nvalid > 0 && Nvalid < cb.Nc) ? (int)ceil_div(Nvalid, sg::TM) : P.RT;
+  P.Nvalid = Nvalid;
   P.KCH = M->KCH;
   P.n = M->n;
   P.Nc = cb.Nc;
@@ -1084,8 +1088,8 @@ static sg::GemmParams base_params(const bocf_model* M, int h, const ChunkBuffers
   return P;
 }
 
-int launch_split_var(bocf_model* M, int h, const ChunkBuffers& cb, bool need_dvar, cudaStream_t st) {
-  sg::GemmParams P = base_params(M, h, cb);
+int launch_split_var(bocf_model* M, int h, int64_t Nvalid, const ChunkBuffers& cb, bool need_dvar, cudaStream_t st) {
+  sg::GemmParams P = base_params(M, h, cb, Nvalid);
   P.A = cb.A1;
   P.B = M->B1;
   P.cs = M->cs1;
@@ -1101,7 +1105,7 @@ int launch_split_var(bocf_model* M, int h, const ChunkBuffers& cb, bool need_dva
 }
 
 int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, const ChunkBuffers& cb, cudaStream_t st) {
-  sg::GemmParams P = base_params(M, h, cb);
+  sg::GemmParams P = base_params(M, h, cb, Nvalid);
   P.A = cb.A2;
   P.B = M->B2;
   P.cs = M->cs2;
@@ -1122,7 +1126,7 @@ int launch_split_dvar(bocf_model* M, int h, const double* Xc, int64_t Nvalid, co
 }
 
 int launch_split_dacq(bocf_model* M, int h, const double* Xc, int64_t Nvalid, const ChunkBuffers& cb, cudaStream_t st) {
-  sg::GemmParams P = base_params(M, h, cb);
+  sg::GemmParams P = base_params(M, h, cb, Nvalid);
   P.A = cb.A2;
   P.B = M->B2;
   P.cs = M->cs2;
@@ -1185,6 +1189,7 @@ int split_debug_gemm(const double* A, const double* B, int R, int N, int K, int 
     P.h = 0;
     P.np = sg::parts_env() ? sg::parts_env() : sg::NP_DEFAULT;
     P.RT = RT;
+    P.RTv = RT;
     P.nct = nct;
     P.KCH = KCH;
     P.n = K;
