@@ -283,14 +283,17 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_acq_kernel(
 
 // ---------------------------------------------------------------------------------------------------
 // analytic EI / PI of the linear scalarisation.  One thread per candidate.
-// PI: 0 = maEI, 1 = maPI.   GRAD: with gradient.  FORM (EI only): 1 = (mu-best)Phi + sigma phi (maEI.py:117-119,
+// PI: 0 = maEI, 1 = maPI.   GRAD: 1 = with gradient; 2 = the gradient is left as per-(candidate, output) WEIGHTS of the
+// posterior mean / variance gradients (wa_out, wb_out) for the fused gradient path, like the MC kernel's modes 5 / 6 (the
+// second contraction's epilogue applies them, split_gemm.cu EPI_DACQ; needs m <= 16).  FORM (EI only): 1 = (mu-best)Phi + sigma phi (maEI.py:117-119,
 // norm.cdf/pdf, sigma not clipped), 0 = sigma (u Phi + phi) with sigma clipped inside _get_quantiles (:95-96,147-163).
 template <int PI, int GRAD>
 __global__ void ma_acq_kernel(const double* __restrict__ mean, const double* __restrict__ var,
                               const double* __restrict__ dmean, const double* __restrict__ dvar, int64_t Nc,
                               int64_t Nvalid, int m, int d, const double* __restrict__ theta, int L, int p,
                               const double* __restrict__ weight, const double* __restrict__ best, int form,
-                              double scale, int accumulate, double* __restrict__ acq, double* __restrict__ dacq) {
+                              double scale, int accumulate, double* __restrict__ acq, double* __restrict__ dacq,
+                              double* __restrict__ wa_out, double* __restrict__ wb_out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Nvalid) return;
   double val = 0.0;
@@ -348,7 +351,14 @@ __global__ void ma_acq_kernel(const double* __restrict__ mean, const double* __r
         }
       }
     }
-    if (GRAD) {
+    if (GRAD == 2) {
+#pragma unroll
+      for (int j = 0; j < MREG; ++j)
+        if (j < m) {
+          wa_out[(int64_t)j * Nc + i] = A[j] * scale;
+          wb_out[(int64_t)j * Nc + i] = B[j] * scale;
+        }
+    } else if (GRAD) {
 #pragma unroll
       for (int j = 0; j < MREG; ++j) {
         if (j < m) {
@@ -386,7 +396,7 @@ __global__ void ma_acq_kernel(const double* __restrict__ mean, const double* __r
     else v = sigma * (u * Phi + phi);                                        // maEI.py:96
     const double wl = weight[l];
     val += wl * v;
-    if (GRAD) {
+    if (GRAD == 1) {
 #pragma unroll
       for (int q = 0; q < MAXD; ++q) {
         if (q < d) {
@@ -406,7 +416,7 @@ __global__ void ma_acq_kernel(const double* __restrict__ mean, const double* __r
   }
   const double v = val * scale;
   acq[i] = accumulate ? acq[i] + v : v;
-  if (GRAD) {
+  if (GRAD == 1) {
 #pragma unroll
     for (int q = 0; q < MAXD; ++q)
       if (q < d) {
@@ -491,7 +501,7 @@ __global__ void psi_acq_kernel(const double* __restrict__ mean, const double* __
   }
   const double v = val * scale;
   acq[i] = accumulate ? acq[i] + v : v;
-  if (GRAD) {
+  if (GRAD == 1) {
 #pragma unroll
     for (int q = 0; q < MAXD; ++q)
       if (q < d) {
@@ -692,12 +702,18 @@ int launch_acq_chunk(const AcqParams& P, const ChunkBuffers& cb, int64_t Nvalid,
   const int pi = (P.variant == BOCF_ACQ_MA_PI) ? 1 : 0;
 #define BOCF_MA_ARGS                                                                                         \
   cb.mean, cb.var, cb.dmean, cb.dvar, cb.Nc, Nvalid, P.m, P.d, P.theta, P.L, P.p, P.weight, P.fstar,        \
-      P.with_grad_formula, P.scale, P.accumulate, acq, dacq
+      P.with_grad_formula, P.scale, P.accumulate, acq, dacq, P.wa, P.wb
+  if (P.wa != nullptr && P.m > 16) {
+    set_error("analytic acquisition: the fused gradient path needs m <= 16");
+    return BOCF_ERR_UNSUPPORTED;
+  }
   if (pi) {
-    if (dacq) ma_acq_kernel<1, 1><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
+    if (P.wa) ma_acq_kernel<1, 2><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
+    else if (dacq) ma_acq_kernel<1, 1><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
     else ma_acq_kernel<1, 0><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
   } else {
-    if (dacq) ma_acq_kernel<0, 1><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
+    if (P.wa) ma_acq_kernel<0, 2><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
+    else if (dacq) ma_acq_kernel<0, 1><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
     else ma_acq_kernel<0, 0><<<grid, 128, 0, st>>>(BOCF_MA_ARGS);
   }
 #undef BOCF_MA_ARGS

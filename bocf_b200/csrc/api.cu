@@ -741,14 +741,17 @@ int bocf_acq_eval(bocf_model* M, int variant, int composite, const double* Xc, i
   P.scale = marginal ? 1.0 : (mc ? 1.0 / ((double)H_use * (double)S) : 1.0 / (double)H_use);
   const bool mean_only = (variant == BOCF_ACQ_PSI && composite == BOCF_U_LINEAR);   // posterior-mean branch: no contraction
 
-  // MC variants with gradients on the tensor-core contraction path: the fused gradient sweep (posterior.cu) -- the
-  // per-output mean / variance gradients are never materialised.  BOCF_FUSED_GRAD=0 keeps the unfused sequence.
+  // Variants with gradients on the tensor-core contraction path: the fused gradient sweep (posterior.cu) -- the
+  // per-output mean / variance gradients are never materialised (MC variants; the analytic ones up to 16 outputs, whose
+  // weights live in registers).  BOCF_FUSED_GRAD=0 keeps the unfused sequence.
   static int fused_on = -1;
   if (fused_on < 0) {
     const char* env = std::getenv("BOCF_FUSED_GRAD");
     fused_on = (env && std::atoi(env) == 0) ? 0 : 1;
   }
-  const bool fused = fused_on && grad && M->S > 0 && (variant == BOCF_ACQ_EI_CF || variant == BOCF_ACQ_MEAN_UTILITY);
+  const bool fused = fused_on && grad && M->S > 0 &&
+                     (variant == BOCF_ACQ_EI_CF || variant == BOCF_ACQ_MEAN_UTILITY ||
+                      ((variant == BOCF_ACQ_MA_EI || variant == BOCF_ACQ_MA_PI) && M->m <= 16));
   for (int64_t off = 0; off < N; off += Nc) {
     const int64_t cnt = (N - off < Nc) ? N - off : Nc;
     for (int h = 0; h < H_use; ++h) {
