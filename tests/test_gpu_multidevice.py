@@ -9,12 +9,15 @@ from tests.helpers import make_problem, oracle_model, product_model, rel_err
 pytestmark = pytest.mark.gpu
 
 
+# m = 3: one output group; m = 8: the factorisation / likelihood pass fork onto the handle's own side stream (two output
+# groups, chol.cu: for_each_output_group), which must live on the handle's device
+@pytest.mark.parametrize("m", [3, 8])
 @pytest.mark.parametrize("precision", ["fp64", "auto"])
-def test_two_handles_on_two_devices(built_library, precision):
+def test_two_handles_on_two_devices(built_library, precision, m):
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs two CUDA devices")
-    P = make_problem(m=3, d=5, n=300, H=1, kind="matern52", N=700, S=8, seed=21)
+    P = make_problem(m=m, d=5, n=300, H=1, kind="matern52", N=700, S=8, seed=21)
     om = oracle_model(P)
     v_o, dv_o = om.posterior_variance(P.Xc), om.posterior_variance_gradient(P.Xc)
     models = [product_model(P, "cuda:%d" % k, precision=precision) for k in (0, 1)]     # factorise on both first
