@@ -106,8 +106,11 @@ static __constant__ double EXPT[8] = {
     4.1666666666666664e-02,      // [5] 1/24
     1.6666666666666666e-01,      // [6] 1/6
     0.0};
+// CLAMP = false: the caller guarantees -708 < x <= 0 (clamp_r2 below bounds the distance instead), and `tab` may carry
+// a common factor (the kernel variance) folded into its 32 entries.
+template <bool CLAMP = true>
 __device__ __forceinline__ double exp_nonpos_tab(double x, const double* __restrict__ tab) {
-  const double xc = fmax(x, EXPC[15]);
+  const double xc = CLAMP ? fmax(x, EXPC[15]) : x;
   const double sh = fma(xc, EXPT[0], EXPC[12]);
   const double kf = sh - EXPC[12];
   double r = fma(-kf, EXPT[1], xc);
@@ -123,8 +126,26 @@ __device__ __forceinline__ double exp_nonpos_tab(double x, const double* __restr
   p *= t;
   return __hiloint2double(__double2hiint(p) + ((n >> 5) << 20), __double2loint(p));
 }
-__device__ __forceinline__ void exp_table_fill(double* tab, int tid) {   // 2^(j/32) to < 1 ulp via the Horner exp
-  if (tid < 32) tab[tid] = exp2((double)tid * 0.03125);
+__device__ __forceinline__ void exp_table_fill(double* tab, int tid, double factor = 1.0) {   // factor * 2^(j/32)
+  if (tid < 32) tab[tid] = factor * exp2((double)tid * 0.03125);
+}
+
+// max(r2, 0) and min(., R2MAX) of a finite squared distance on the INTEGER pipe.  sm_100 has no fp64 min / max
+// instruction: each fmax(double) is DSETP + 2 moves + 2 selects + a NaN fix-up (6 issue slots, one on the fp64 pipe), and
+// the K* kernel paid that twice per (candidate, training point): the clip of the expanded distance at 0
+// (stationary.py:153) and exp's clamp at -700.  Here: a negative value (sign bit, -0 included) becomes +0 exactly, and
+// the high word is capped so that the exponent the kernel family forms from r2 stays above -700.01 (RBF / SE: r2/2,
+// Matern: sqrt5 r, sqrt3 r) -- beyond that the covariance is < 1e-304 either way.  4 integer instructions.
+template <int KIND>
+__device__ __forceinline__ double clamp_r2(double r2) {
+  constexpr int HIMAX = (KIND == BOCF_KERN_MATERN52) ? 0x40F7ED00      // 98000   = 700^2 / 5
+                      : (KIND == BOCF_KERN_MATERN32) ? 0x4103F000      // 163328  < 700^2 / 3
+                                                     : 0x4095E000;     // 1400    = 2 * 700
+  int hi = __double2hiint(r2), lo = __double2loint(r2);
+  const int keep = ~(hi >> 31);
+  hi = min(hi & keep, HIMAX);
+  lo &= keep;
+  return __hiloint2double(hi, lo);
 }
 
 // sqrt(a) for a >= 0 (finite).  libdevice's rsqrt(double) wraps the hardware seed (MUFU.RSQ64H, ~22 bits) in a range check
@@ -162,29 +183,30 @@ __device__ __forceinline__ double sqrt_nonneg(double a0) {
 #endif
 }
 
-#define BOCF_EXP(x) (TAB ? exp_nonpos_tab((x), tab) : exp_nonpos(x))
-template <int KIND, bool GRAD, bool TAB = false>
+// FAST (K* kernel only): r2 went through clamp_r2 (no clamp inside exp) and `tab` carries the variance (no multiply).
+#define BOCF_EXP(x) (FAST ? exp_nonpos_tab<false>((x), tab) : variance * (TAB ? exp_nonpos_tab((x), tab) : exp_nonpos(x)))
+template <int KIND, bool GRAD, bool TAB = false, bool FAST = false>
 __device__ __forceinline__ void kern_eval(double r2, double variance, double& k, double& g, const double* tab = nullptr) {
   if (KIND == BOCF_KERN_SE) {
     // se.py:60  variance * exp(-0.5 * sqdist)
-    k = variance * BOCF_EXP(-0.5 * r2);
+    k = BOCF_EXP(-0.5 * r2);
     if (GRAD) g = -k;
   } else if (KIND == BOCF_KERN_RBF) {
     // rbf.py:42-46 (r*r of the rounded sqrt differs from r2 by <= 1 ulp)
-    k = variance * BOCF_EXP(-0.5 * r2);
+    k = BOCF_EXP(-0.5 * r2);
     if (GRAD) g = (r2 != 0.0) ? -k : 0.0;
   } else if (KIND == BOCF_KERN_MATERN52) {
     // stationary.py:529-533
     const double r = sqrt_nonneg(r2);
 #if KV_CONST
     const double t = KERC[0] * r;               // sqrt(5) r
-    const double e = variance * BOCF_EXP(-t);
+    const double e = BOCF_EXP(-t);
     const double lin = 1.0 + t;
     k = fma(KERC[1], r2, lin) * e;
     if (GRAD) g = (r2 != 0.0) ? KERC[2] * (lin * e) : 0.0;
 #else
     const double s5 = 2.23606797749978969641;   // sqrt(5)
-    const double e = variance * BOCF_EXP(-s5 * r);
+    const double e = BOCF_EXP(-s5 * r);
     const double lin = 1.0 + s5 * r;
     k = (lin + 5.0 / 3.0 * r2) * e;
     if (GRAD) g = (r2 != 0.0) ? (-5.0 / 3.0) * (lin * e) : 0.0;
@@ -193,7 +215,7 @@ __device__ __forceinline__ void kern_eval(double r2, double variance, double& k,
     // Matern32, stationary.py:440-444
     const double r = sqrt_nonneg(r2);
     const double t = KERC[3] * r;               // sqrt(3) r
-    const double e = variance * BOCF_EXP(-t);
+    const double e = BOCF_EXP(-t);
     k = (1.0 + t) * e;
     if (GRAD) g = (r2 != 0.0) ? -3.0 * e : 0.0;
   }

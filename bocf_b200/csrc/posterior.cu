@@ -72,20 +72,22 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
   __shared__ double sgcs[128];
   __shared__ double sexp[32];
   const int tid = threadIdx.x;
-  if (KV_EXPTAB) exp_table_fill(sexp, tid);     // visible after the first __syncthreads of the tile loop
+  // visible after the first __syncthreads of the tile loop; the output's signal variance rides in the table entries
+  if (KV_EXPTAB) exp_table_fill(sexp, tid, hyp[h * m + j0 + blockIdx.y].variance);
   const int j = j0 + blockIdx.y;                 // this launch covers one run of outputs that share the kernel family
   const int hj = h * m + j;
   const int64_t i = (int64_t)blockIdx.x * 128 + tid;
   const OutHyp& hp = hyp[hj];
   const double variance = hp.variance;
 
-  double xs[DP];
+  double xs[DP], xm2[DP];   // scaled candidate and -2 x it (exact): r2 = (|x|^2 + |X_b|^2) + sum_q (-2 x_q) X_bq
   double xsq_i = 0.0;
 #pragma unroll
   for (int q = 0; q < DP; ++q) {
     double v = 0.0;
     if (q < d && i < Nvalid) v = Xc[i * d + q] / hp.ls[q];
     xs[q] = v;
+    xm2[q] = -2.0 * v;
     xsq_i += v * v;
   }
   double mu = 0.0, wsum = 0.0;
@@ -148,16 +150,19 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
             }
             r2 = r2a + r2b;
           } else {
-            double dot0 = 0.0, dot1 = 0.0;               // two chains: half the dependent-DFMA depth
+            // two chains (half the dependent-DFMA depth), the first seeded with the squared norms: d DFMA + 2 DADD
+            double dot0 = xsq_i + sxsq[bb], dot1 = 0.0;
 #pragma unroll
             for (int q = 0; q < DP; q += 2) {
-              dot0 = fma(xs[q], sX[bb][q], dot0);
-              if (q + 1 < DP) dot1 = fma(xs[q + 1], sX[bb][q + 1], dot1);
+              dot0 = fma(xm2[q], sX[bb][q], dot0);
+              if (q + 1 < DP) dot1 = fma(xm2[q + 1], sX[bb][q + 1], dot1);
             }
-            r2 = -2.0 * (dot0 + dot1) + (xsq_i + sxsq[bb]);
-            r2 = fmax(r2, 0.0);
+            r2 = dot0 + dot1;
           }
-          kern_eval<KIND, (GRAD != 0), (KV_EXPTAB != 0)>(r2, variance, kv, gv, sexp);
+          // clip at 0 (stationary.py:153) and the cap that replaces exp's clamp, on the integer pipe (kernfn.cuh)
+          if (KV_EXPTAB) r2 = clamp_r2<KIND>(r2);
+          else if (KIND != BOCF_KERN_SE) r2 = fmax(r2, 0.0);
+          kern_eval<KIND, (GRAD != 0), (KV_EXPTAB != 0), (KV_EXPTAB != 0)>(r2, variance, kv, gv, sexp);
           // padded points b >= n need no mask: their alpha, column scale and factor rows / columns are zero, so whatever
           // finite K*, G* they produce is multiplied by an exact zero downstream (mean, both contractions, epilogues)
           const double a = salpha[bb];
