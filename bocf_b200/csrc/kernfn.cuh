@@ -70,7 +70,8 @@ static __constant__ double KERC[8] = {
     -5.0 / 3.0,                  // [2]
     1.73205080756887729353,      // [3] sqrt(3)
     1e-300,                      // [4] keeps sqrt's seed finite at r2 == 0
-    0.0, 0.0, 0.0};
+    1.0 / 3.0,                   // [5]
+    0.0, 0.0};
 __device__ __forceinline__ double exp_nonpos(double x) {
   const double xc = fmax(x, EXPC[15]);
   // round-to-nearest integer of xc * log2(e) through the 1.5 * 2^52 shift: no FRND / F2I conversion instructions,
@@ -130,22 +131,31 @@ __device__ __forceinline__ void exp_table_fill(double* tab, int tid, double fact
   if (tid < 32) tab[tid] = factor * exp2((double)tid * 0.03125);
 }
 
-// max(r2, 0) and min(., R2MAX) of a finite squared distance on the INTEGER pipe.  sm_100 has no fp64 min / max
+// ---- the K* kernel's arithmetic (kern_eval_fast below) works on q = KFast<KIND>::SCALE * r2 ----
+// SCALE is what the family multiplies r2 (or r) by before exp / sqrt -- Matern-5/2: sqrt5 r = sqrt(5 r2), Matern-3/2:
+// sqrt(3 r2), RBF / SE: r2 / 2 -- folded into the scaled candidate and the squared norms once per thread / staged point,
+// and GFAC is the constant factor of (dK/dr)/r, folded into the column scale G* is multiplied by anyway.
+template <int KIND>
+struct KFast {
+  static constexpr double SCALE = (KIND == BOCF_KERN_MATERN52) ? 5.0 : (KIND == BOCF_KERN_MATERN32) ? 3.0 : 0.5;
+  static constexpr double GFAC = (KIND == BOCF_KERN_MATERN52) ? -5.0 / 3.0 : (KIND == BOCF_KERN_MATERN32) ? -3.0 : -1.0;
+  // high word of the largest q whose exponent argument stays above -700.01: Matern t = sqrt(q) <= 700, RBF / SE q <= 700
+  static constexpr int HIMAX = (KIND == BOCF_KERN_MATERN52 || KIND == BOCF_KERN_MATERN32) ? 0x411DE840 : 0x4085E000;
+};
+
+// Clip of a finite scaled squared distance to [QMIN, QMAX] on the INTEGER pipe.  sm_100 has no fp64 min / max
 // instruction: each fmax(double) is DSETP + 2 moves + 2 selects + a NaN fix-up (6 issue slots, one on the fp64 pipe), and
 // the K* kernel paid that twice per (candidate, training point): the clip of the expanded distance at 0
-// (stationary.py:153) and exp's clamp at -700.  Here: a negative value (sign bit, -0 included) becomes +0 exactly, and
-// the high word is capped so that the exponent the kernel family forms from r2 stays above -700.01 (RBF / SE: r2/2,
-// Matern: sqrt5 r, sqrt3 r) -- beyond that the covariance is < 1e-304 either way.  4 integer instructions.
+// (stationary.py:153) and exp's clamp at -700.  For doubles >= 0 the order of the values is the order of their high
+// words, so one signed min / max pair on the high word does both: anything negative (or below the smallest normal
+// number, 2.2e-308) becomes ~2.2e-308 -- which stands for "r == 0": 1 + sqrt(2e-308) == 1, the rsqrt seed stays finite
+// without sqrt_nonneg's 1e-300 bias, and `nz` tells the caller to zero the gradient weight like the reference's
+// inv_dist -- and the cap keeps exp's argument above -700.01 (beyond it the covariance is < 1e-304 either way).
 template <int KIND>
-__device__ __forceinline__ double clamp_r2(double r2) {
-  constexpr int HIMAX = (KIND == BOCF_KERN_MATERN52) ? 0x40F7ED00      // 98000   = 700^2 / 5
-                      : (KIND == BOCF_KERN_MATERN32) ? 0x4103F000      // 163328  < 700^2 / 3
-                                                     : 0x4095E000;     // 1400    = 2 * 700
-  int hi = __double2hiint(r2), lo = __double2loint(r2);
-  const int keep = ~(hi >> 31);
-  hi = min(hi & keep, HIMAX);
-  lo &= keep;
-  return __hiloint2double(hi, lo);
+__device__ __forceinline__ double clamp_q(double q, bool& nz) {
+  const int hi = __double2hiint(q);
+  nz = hi >= 0x00100000;
+  return __hiloint2double(min(max(hi, 0x00100000), KFast<KIND>::HIMAX), __double2loint(q));
 }
 
 // sqrt(a) for a >= 0 (finite).  libdevice's rsqrt(double) wraps the hardware seed (MUFU.RSQ64H, ~22 bits) in a range check
@@ -183,9 +193,8 @@ __device__ __forceinline__ double sqrt_nonneg(double a0) {
 #endif
 }
 
-// FAST (K* kernel only): r2 went through clamp_r2 (no clamp inside exp) and `tab` carries the variance (no multiply).
-#define BOCF_EXP(x) (FAST ? exp_nonpos_tab<false>((x), tab) : variance * (TAB ? exp_nonpos_tab((x), tab) : exp_nonpos(x)))
-template <int KIND, bool GRAD, bool TAB = false, bool FAST = false>
+#define BOCF_EXP(x) (variance * (TAB ? exp_nonpos_tab((x), tab) : exp_nonpos(x)))
+template <int KIND, bool GRAD, bool TAB = false>
 __device__ __forceinline__ void kern_eval(double r2, double variance, double& k, double& g, const double* tab = nullptr) {
   if (KIND == BOCF_KERN_SE) {
     // se.py:60  variance * exp(-0.5 * sqdist)
@@ -218,6 +227,39 @@ __device__ __forceinline__ void kern_eval(double r2, double variance, double& k,
     const double e = BOCF_EXP(-t);
     k = (1.0 + t) * e;
     if (GRAD) g = (r2 != 0.0) ? -3.0 * e : 0.0;
+  }
+}
+
+// sqrt(a) for a >= 0 as a * rsqrt: only the root is refined (s0 = a y0, e = 1 - s0 y0, s = s0 (1 + e/2 + 3 e^2/8); the
+// neglected 5 e^3 / 16 is ~3e-21), one fp64 instruction less than refining y first.  a >= 2.2e-308 (clamp_q): no bias.
+__device__ __forceinline__ double sqrt_nonneg_root(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double s0 = a * y;
+  const double e = fma(-s0, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(s0 * e, p, s0);
+}
+
+// K* kernel only.  q, nz from clamp_q(SCALE * r2); `tab` = variance * 2^(j/32) (exp_table_fill with the output's
+// variance).  Returns k and gp = (dK/dr)/r / GFAC (exactly 0 where the clipped distance is 0, the reference's inv_dist
+// convention) -- same formulas as kern_eval with the constant factors moved to where they are free.
+template <int KIND, bool GRAD>
+__device__ __forceinline__ void kern_eval_fast(double q, bool nz, double& k, double& gp, const double* __restrict__ tab) {
+  if (KIND == BOCF_KERN_SE || KIND == BOCF_KERN_RBF) {
+    k = exp_nonpos_tab<false>(-q, tab);
+    if (GRAD) gp = (KIND == BOCF_KERN_SE || nz) ? k : 0.0;
+  } else if (KIND == BOCF_KERN_MATERN52) {
+    const double t = sqrt_nonneg_root(q);        // sqrt(5) r
+    const double e = exp_nonpos_tab<false>(-t, tab);
+    const double lin = 1.0 + t;
+    k = fma(KERC[5], q, lin) * e;                // 1 + sqrt5 r + (5 r2) / 3
+    if (GRAD) gp = nz ? lin * e : 0.0;
+  } else {
+    const double t = sqrt_nonneg_root(q);        // sqrt(3) r
+    const double e = exp_nonpos_tab<false>(-t, tab);
+    k = (1.0 + t) * e;
+    if (GRAD) gp = nz ? e : 0.0;
   }
 }
 

@@ -80,16 +80,21 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
   const OutHyp& hp = hyp[hj];
   const double variance = hp.variance;
 
-  double xs[DP], xm2[DP];   // scaled candidate and -2 x it (exact): r2 = (|x|^2 + |X_b|^2) + sum_q (-2 x_q) X_bq
+  // FAST arithmetic (kernfn.cuh): everything the kernel family multiplies the squared distance by is folded into the
+  // operands of the distance itself:  q = SCALE r2 = SCALE (|x|^2 + |X_b|^2) + sum_q (-2 SCALE x_q) X_bq
+  constexpr bool FAST = (KV_EXPTAB != 0);
+  constexpr double QS = FAST ? KFast<KIND>::SCALE : 1.0;
+  double xs[DP], xm2[DP];
   double xsq_i = 0.0;
 #pragma unroll
   for (int q = 0; q < DP; ++q) {
     double v = 0.0;
     if (q < d && i < Nvalid) v = Xc[i * d + q] / hp.ls[q];
     xs[q] = v;
-    xm2[q] = -2.0 * v;
+    xm2[q] = (-2.0 * QS) * v;
     xsq_i += v * v;
   }
+  xsq_i *= QS;
   double mu = 0.0, wsum = 0.0;
   double gm[DP];       // sum_b w_b Xs_bq ;  dmean_q = (xs_q * sum_b w_b - gm_q) / l_q
 #pragma unroll
@@ -99,6 +104,7 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
   const double* xsq = xsqAll + (int64_t)hj * n_pad;
   const double* alpha = alphaAll + (int64_t)hj * n_pad;
   constexpr bool SPLIT = SPL > 0;
+  constexpr bool GFOLD = FAST && SPLIT && GRAD == 2;
   double* Kout = SPLIT ? nullptr : KsT + (int64_t)j * n16 * Nc;
   double* Gout = GRAD ? GsT + (int64_t)j * n16 * Nc : nullptr;
   // split mode: digit planes of this block's 128 candidates (row = tid) for output j
@@ -118,10 +124,11 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
     }
     {
       int b = b0 + tid;
-      sxsq[tid] = (b < n) ? xsq[b] : 0.0;
+      sxsq[tid] = (b < n) ? QS * xsq[b] : 0.0;
       salpha[tid] = (b < n) ? alpha[b] : 0.0;
       // column scale of the second contraction times the 256 its epilogue's merged Horner leaves out (split_gemm.cu)
-      if (SPL > 0) sgcs[tid] = (b < n) ? 256.0 * so.gcs[(size_t)hj * so.gcs_ld + b] : 0.0;
+      // (and, on the FAST path, the constant factor of (dK/dr)/r that kern_eval_fast leaves out)
+      if (SPL > 0) sgcs[tid] = (b < n) ? (GFOLD ? 256.0 * KFast<KIND>::GFAC : 256.0) * so.gcs[(size_t)hj * so.gcs_ld + b] : 0.0;
     }
     __syncthreads();
     const int bmax = min(128, n16 - b0);
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
                 r2b = fma(d1, d1, r2b);
               }
             }
-            r2 = r2a + r2b;
+            r2 = QS * (r2a + r2b);
           } else {
             // two chains (half the dependent-DFMA depth), the first seeded with the squared norms: d DFMA + 2 DADD
             double dot0 = xsq_i + sxsq[bb], dot1 = 0.0;
@@ -159,10 +166,16 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
             }
             r2 = dot0 + dot1;
           }
-          // clip at 0 (stationary.py:153) and the cap that replaces exp's clamp, on the integer pipe (kernfn.cuh)
-          if (KV_EXPTAB) r2 = clamp_r2<KIND>(r2);
-          else if (KIND != BOCF_KERN_SE) r2 = fmax(r2, 0.0);
-          kern_eval<KIND, (GRAD != 0), (KV_EXPTAB != 0), (KV_EXPTAB != 0)>(r2, variance, kv, gv, sexp);
+          if (FAST) {
+            // clip at 0 (stationary.py:153) and the cap that replaces exp's clamp, on the integer pipe
+            bool nz;
+            const double qc = clamp_q<KIND>(r2, nz);
+            kern_eval_fast<KIND, (GRAD != 0)>(qc, nz, kv, gv, sexp);
+            if (GRAD && !GFOLD) gv *= KFast<KIND>::GFAC;
+          } else {
+            if (KIND != BOCF_KERN_SE) r2 = fmax(r2, 0.0);
+            kern_eval<KIND, (GRAD != 0), false>(r2, variance, kv, gv, sexp);
+          }
           // padded points b >= n need no mask: their alpha, column scale and factor rows / columns are zero, so whatever
           // finite K*, G* they produce is multiplied by an exact zero downstream (mean, both contractions, epilogues)
           const double a = salpha[bb];
