@@ -95,20 +95,20 @@ __device__ __forceinline__ double exp_nonpos(double x) {
 #endif
 }
 
-// Table variant for the K* kernel: x = (32 k + j) ln2/32 + r, |r| <= ln2/64, exp(x) = 2^k * 2^(j/32) * p(r) with a degree-6
-// polynomial (remainder r^7/5040 < 4e-18) -- 11 fp64 instructions instead of 17; `tab` = 2^(j/32), j = 0..31, in SHARED
-// memory (lanes index it independently).  Same clamp at -700.
+// Table variant for the K* kernel: x = (128 k + j) ln2/128 + r, |r| <= ln2/256, exp(x) = 2^k * 2^(j/128) * p(r) with a
+// degree-5 polynomial (remainder r^6/720 < 6e-19) -- 10 fp64 instructions instead of the Horner version's 17; `tab` =
+// factor * 2^(j/128), j = 0..127, in SHARED memory (lanes index it independently; the factor is the kernel variance).
+// (Round 2 started with 32 entries and degree 6: one DFMA more per evaluation.)
+constexpr int EXP_TAB_N = 128;
 static __constant__ double EXPT[8] = {
-    46.166241308446828384,       // [0] 32 log2(e)
-    0.021660849392446835,  // [1] ln2/32 high (low 17 mantissa bits zero: n*hi is exact for |n| < 2^17)
-    5.145609244655338e-14,     // [2] ln2/32 low
-    1.3888888888888889e-03,      // [3] 1/720
-    8.333333333333333e-03,       // [4] 1/120
-    4.1666666666666664e-02,      // [5] 1/24
-    1.6666666666666666e-01,      // [6] 1/6
-    0.0};
-// CLAMP = false: the caller guarantees -708 < x <= 0 (clamp_r2 below bounds the distance instead), and `tab` may carry
-// a common factor (the kernel variance) folded into its 32 entries.
+    184.6649652337873,           // [0] 128 log2(e)
+    0.005415212348111709,        // [1] ln2/128 high (low 17 mantissa bits zero: n*hi is exact for |n| < 2^17; n >= -129272)
+    1.2864023111638346e-14,      // [2] ln2/128 low
+    8.333333333333333e-03,       // [3] 1/120
+    4.1666666666666664e-02,      // [4] 1/24
+    1.6666666666666666e-01,      // [5] 1/6
+    0.0, 0.0};
+// CLAMP = false: the caller guarantees -700.01 < x <= 0 (clamp_q below bounds the distance instead).
 template <bool CLAMP = true>
 __device__ __forceinline__ double exp_nonpos_tab(double x, const double* __restrict__ tab) {
   const double xc = CLAMP ? fmax(x, EXPC[15]) : x;
@@ -117,18 +117,17 @@ __device__ __forceinline__ double exp_nonpos_tab(double x, const double* __restr
   double r = fma(-kf, EXPT[1], xc);
   r = fma(-kf, EXPT[2], r);
   const int n = __double2loint(sh);
-  const double t = tab[n & 31];
+  const double t = tab[n & (EXP_TAB_N - 1)];
   double p = fma(EXPT[3], r, EXPT[4]);
   p = fma(p, r, EXPT[5]);
-  p = fma(p, r, EXPT[6]);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   p *= t;
-  return __hiloint2double(__double2hiint(p) + ((n >> 5) << 20), __double2loint(p));
+  return __hiloint2double(__double2hiint(p) + ((n >> 7) << 20), __double2loint(p));
 }
-__device__ __forceinline__ void exp_table_fill(double* tab, int tid, double factor = 1.0) {   // factor * 2^(j/32)
-  if (tid < 32) tab[tid] = factor * exp2((double)tid * 0.03125);
+__device__ __forceinline__ void exp_table_fill(double* tab, int tid, double factor = 1.0) {   // factor * 2^(j/128)
+  if (tid < EXP_TAB_N) tab[tid] = factor * exp2((double)tid * (1.0 / EXP_TAB_N));
 }
 
 // ---- the K* kernel's arithmetic (kern_eval_fast below) works on q = KFast<KIND>::SCALE * r2 ----
@@ -193,9 +192,9 @@ __device__ __forceinline__ double sqrt_nonneg(double a0) {
 #endif
 }
 
-#define BOCF_EXP(x) (variance * (TAB ? exp_nonpos_tab((x), tab) : exp_nonpos(x)))
-template <int KIND, bool GRAD, bool TAB = false>
-__device__ __forceinline__ void kern_eval(double r2, double variance, double& k, double& g, const double* tab = nullptr) {
+#define BOCF_EXP(x) (variance * exp_nonpos(x))
+template <int KIND, bool GRAD>
+__device__ __forceinline__ void kern_eval(double r2, double variance, double& k, double& g) {
   if (KIND == BOCF_KERN_SE) {
     // se.py:60  variance * exp(-0.5 * sqdist)
     k = BOCF_EXP(-0.5 * r2);

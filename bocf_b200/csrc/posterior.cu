@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
   __shared__ double sxsq[128];
   __shared__ double salpha[128];
   __shared__ double sgcs[128];
-  __shared__ double sexp[32];
+  __shared__ double sexp[EXP_TAB_N];
   const int tid = threadIdx.x;
   // visible after the first __syncthreads of the tile loop; the output's signal variance rides in the table entries
   if (KV_EXPTAB) exp_table_fill(sexp, tid, hyp[h * m + j0 + blockIdx.y].variance);
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
             }
             r2 = QS * (r2a + r2b);
           } else {
-            // two chains (half the dependent-DFMA depth), the first seeded with the squared norms: d DFMA + 2 DADD
-            double dot0 = xsq_i + sxsq[bb], dot1 = 0.0;
+            // two chains (half the dependent-DFMA depth), seeded with the two squared norms: d DFMA + 1 DADD
+            double dot0 = xsq_i, dot1 = sxsq[bb];
 #pragma unroll
             for (int q = 0; q < DP; q += 2) {
               dot0 = fma(xm2[q], sX[bb][q], dot0);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
             if (GRAD && !GFOLD) gv *= KFast<KIND>::GFAC;
           } else {
             if (KIND != BOCF_KERN_SE) r2 = fmax(r2, 0.0);
-            kern_eval<KIND, (GRAD != 0), false>(r2, variance, kv, gv, sexp);
+            kern_eval<KIND, (GRAD != 0)>(r2, variance, kv, gv);
           }
           // padded points b >= n need no mask: their alpha, column scale and factor rows / columns are zero, so whatever
           // finite K*, G* they produce is multiplied by an exact zero downstream (mean, both contractions, epilogues)

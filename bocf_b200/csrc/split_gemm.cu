@@ -568,8 +568,10 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
       double gv[CGW];
       // G* of this warp's column groups: rows b of GsT, one candidate per lane (coalesced).  Columns b >= n of the last
       // tile carry an exactly zero Wt (zero factor planes), so their G* is read from row n-1 instead of being masked.
+      // (row index and stride are 32-bit: one widening multiply per address instead of a 64 x 64 one -- the address
+      // arithmetic was 9 of the gradient epilogue's 48 instructions per element)
       const double* Gcol = nullptr;
-      const int64_t gstride = P.Nc;
+      const uint32_t gstride = (uint32_t)P.Nc;                  // candidates per chunk: < 2^31
       const bool tile_full = (col0 + NT <= P.n);
       if (EPI == EPI_DACQ && ti.first) {                         // once per unit, not per column tile: the loads' latency
         wa_i = __ldg(P.wa + (size_t)ti.j * P.Nc + i);            // sat exposed at the top of every tile (13 % of the
@@ -580,7 +582,7 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
 #pragma unroll
         for (int e = 0; e < CGW; ++e) {                      // first column group: in flight while the MMAs finish
           const int b = col0 + hw * CGW + e;
-          gv[e] = __ldg(Gcol + (size_t)(tile_full ? b : min(b, P.n - 1)) * gstride);
+          gv[e] = __ldg(Gcol + (uint64_t)(uint32_t)(tile_full ? b : min(b, P.n - 1)) * gstride);
         }
       }
 
@@ -643,7 +645,7 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
             const double w = (EPI == EPI_DACQ) ? fma(wb2_i, y, wa_i * cs_t[cg * CGW + e].x) * gv[e] : y * gv[e];
             if (gi + 1 < NGW) {                                // refill the slot with this warp's next column group's G*
               const int bn = col0 + (cg + PART_SPLIT) * CGW + e;
-              gv[e] = __ldg(Gcol + (size_t)(tile_full ? bn : min(bn, P.n - 1)) * gstride);
+              gv[e] = __ldg(Gcol + (uint64_t)(uint32_t)(tile_full ? bn : min(bn, P.n - 1)) * gstride);
             }
             s0 += w;
             const double2* xb2 = reinterpret_cast<const double2*>(s_xb + (cg * CGW + e) * DPA);
