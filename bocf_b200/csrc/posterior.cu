@@ -111,7 +111,10 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
   constexpr int MAXS = SPLIT ? SPL : 1;
   uint32_t dv[MAXS][4];
   const double aq = SPLIT ? so.aq[hj] : 0.0;
-  const unsigned long long dbias = SPLIT ? (0x808080808080ull >> (8 * (6 - so.S))) : 0ull;
+  // rounding constant 1.5 * 2^52 plus the balanced-digit bias 0x80..80 (so.S bytes): both integers below 2^53, so the sum
+  // is exact and the low bytes of the fused multiply-add's mantissa are digit + 128; the bias comes off with one XOR per
+  // transposed word (a 64-bit add and a 64-bit XOR per training point before)
+  const double magicb = SPLIT ? 6755399441055744.0 + (double)(0x808080808080ull >> (8 * (6 - so.S))) : 0.0;
   uint8_t* Aout = SPLIT ? so.A1 + ((size_t)((size_t)j * gridDim.x + blockIdx.x) * so.KCH) * so.S * (128 * 64) : nullptr;
   const uint32_t swz = (uint32_t)((tid >> 1) & 3);
 
@@ -191,12 +194,12 @@ __global__ void __launch_bounds__(128, KV_LB) kstar_kernel(const double* __restr
         if (!SPLIT) {
           Kout[(int64_t)b * Nc + i] = kv;
         } else {
-          dg4[e & 3] = ((unsigned long long)__double_as_longlong(fma(kv, aq, 6755399441055744.0)) + dbias) ^ dbias;
+          dg4[e & 3] = (unsigned long long)__double_as_longlong(fma(kv, aq, magicb));
           if ((e & 3) == 3) {                                     // byte transpose of four points' digits
             uint32_t o[MAXS];
             digits_transpose4<MAXS>(dg4, o);
 #pragma unroll
-            for (int t = 0; t < MAXS; ++t) dv[t][e >> 2] = o[t];
+            for (int t = 0; t < MAXS; ++t) dv[t][e >> 2] = o[t] ^ 0x80808080u;
           }
         }
       }

@@ -264,12 +264,12 @@ struct TileWalk {
 
 // digits of a 64-bit integer |Y| < 2^(8S-2): byte t of the result is the balanced base-256 digit of weight 256^t
 template <int S>
+__host__ __device__ constexpr unsigned long long digit_bias() {
+  return (S == 6) ? 0x808080808080ull : (S == 5) ? 0x8080808080ull : (S == 4) ? 0x80808080ull : (S == 3) ? 0x808080ull : 0x8080ull;
+}
+template <int S>
 __device__ __forceinline__ unsigned long long balanced_digits(long long Y) {
-  constexpr unsigned long long BIAS = (S == 6)   ? 0x808080808080ull
-                                      : (S == 5) ? 0x8080808080ull
-                                      : (S == 4) ? 0x80808080ull
-                                      : (S == 3) ? 0x808080ull
-                                                 : 0x8080ull;
+  constexpr unsigned long long BIAS = digit_bias<S>();
   return ((unsigned long long)Y + BIAS) ^ BIAS;
 }
 
@@ -638,7 +638,9 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
             const double v = y * sc.x;
             sumsq = fma(v, v, sumsq);
             // digits of rint(V vq): one fused multiply-add onto the 1.5 * 2^52 rounding constant
-            dgv[e] = balanced_digits<S2>(__double_as_longlong(fma(y, sc.y, 6755399441055744.0)));
+            // (the digit bias rides in the rounding constant -- exact, both are integers below 2^53 -- and the bias is
+            // removed by one XOR per transposed word below: balanced_digits' 64-bit add + XOR per element are gone)
+            dgv[e] = (unsigned long long)__double_as_longlong(fma(y, sc.y, 6755399441055744.0 + (double)digit_bias<S2>()));
           } else {
             // the column scale (and the factor 256 of the merged Horner) is folded into G* by the K* kernel
             const double y = levels_to_f64_merged<NL, CGW>(cc, e);
@@ -673,7 +675,7 @@ __global__ void __launch_bounds__(Cfg<SCH, DP>::NTHREADS, 1) split_gemm_kernel(c
             uint32_t o[S2];
             digits_transpose4<S2>(four, o);
 #pragma unroll
-            for (int tt = 0; tt < S2; ++tt) vec[tt][w] = o[tt];
+            for (int tt = 0; tt < S2; ++tt) vec[tt][w] = o[tt] ^ 0x80808080u;
           }
           const int k = col0 + cg * CGW;
           if (k < P.KCH * KC) {
