@@ -1,5 +1,6 @@
 // api.cu -- the C ABI of libbocf_b200 (include/bocf_b200.h): handle management, the jitchol retry
 // loop, candidate chunking and the fused sweep  posterior -> acquisition  over all hyper-samples.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
@@ -111,12 +112,20 @@ static int64_t pick_chunk(const bocf_model* M, int64_t N, bool grad, uint64_t ex
 }
 
 // Resolve the requested contraction precision into the active digit-pair schemes (M->sch1 / M->sch2; M->S = 0 means
-// fp64 DMMA) and build the split operands.  Error model (tests/test_split_numerics.py, tests/test_gpu_split.py): the
-// relative error of the variance stays below ~2000 * a^2 * 256^-5 for scheme 554 (15 digit pairs), ~2000 * a^2 * 256^-6
-// for 665 and ~150 * a^2 * 256^-4 for 442 (13 pairs), a = max|Linv|.  AUTO accepts a scheme when a fifth of that bound
-// is <= 1e-7 (bound <= 5e-7, half the north-star fp64 bar); the variance gradient runs one scheme below the variance
-// (442 under 554: ~1e-7 relative, norm-wise).  MIXED targets the 1e-4 bar on acq / grad acq instead: variance bound
-// <= 2e-5, gradient two schemes down to 331 (8 pairs, ~1e-5).  Models too ill-conditioned for 665 stay on fp64.
+// fp64 DMMA) and build the split operands.  Error model (tests/test_split_numerics.py, tests/test_gpu_split.py):
+//  (i)  for candidates away from the data the relative error of the variance stays below ~2000 * a^2 * 256^-5 for scheme
+//       554 (15 digit pairs), ~2000 * a^2 * 256^-6 for 665 and ~150 * a^2 * 256^-4 for 442 (13 pairs), a = max|Linv|;
+//  (ii) the ABSOLUTE error of sum V^2 is K_S * 256^-S * sigma_f^2 whatever the conditioning (K_4 < 60, K_5 < 1000,
+//       K_6 < 1200 across kernels, sizes and noise levels 1e-1 ... 1e-6), while the variance itself drops to the noise
+//       variance at candidates next to a training input -- the points the acquisition optimiser converges to, where
+//       sigma enters the pathwise gradient as 0.5 / sigma.  The element-wise relative error of `posterior_variance`
+//       there is K_S 256^-S sigma_f^2 / noise; the rule asks a quarter of the bar of it, so that the NOISELESS variance
+//       of uEI_noiseless (which has no floor: it falls below the noise where many neighbours average) holds the bar
+//       too wherever it is >= noise / 4.
+// AUTO accepts a scheme when bound (i) is <= 5e-7 and bound (ii) <= 2.5e-7 for every output (the north-star fp64 bar of
+// 1e-6, element-wise, at every candidate); the variance gradient runs one scheme below the variance (442 under 554: ~1e-7
+// relative, norm-wise).  MIXED targets the 1e-4 bar on acq / grad acq instead: bounds 2e-5 / 1e-5, gradient two
+// schemes down to 331 (8 pairs, ~1e-5).  Models too ill-conditioned or too noise-free for 665 stay on fp64.
 static int apply_precision(bocf_model* M, cudaStream_t st) {
   int s1 = 0, s2 = 0;
   if (M->precision == BOCF_PREC_SPLIT_I8) {
@@ -128,8 +137,12 @@ static int apply_precision(bocf_model* M, cudaStream_t st) {
     const double bound[7] = {0, 0, 0, 0, 150.0 * a2 * std::pow(256.0, -4), 2000.0 * a2 * std::pow(256.0, -5),
                              2000.0 * a2 * std::pow(256.0, -6)};
     const double target = (M->precision == BOCF_PREC_MIXED) ? 2e-5 : 5e-7;
+    double vmin = 1e300;                                          // smallest noise-to-signal ratio over (hyper-sample, output)
+    for (const auto& o : M->hyp_host) vmin = std::min(vmin, (o.noise + 1e-8 + o.jitter) / o.variance);
+    const double near_data[7] = {0, 0, 0, 0, 60.0 * std::pow(256.0, -4) / (0.25 * vmin), 1000.0 * std::pow(256.0, -5) / (0.25 * vmin),
+                                 1200.0 * std::pow(256.0, -6) / (0.25 * vmin)};
     for (int s = 4; s <= 6 && s1 == 0; ++s)
-      if (bound[s] <= target) s1 = s;
+      if (bound[s] <= target && near_data[s] <= 2.0 * target) s1 = s;
     if (s1 > 0) s2 = (M->precision == BOCF_PREC_MIXED) ? (s1 == 4 ? 3 : s1 - 1) : (s1 > 4 ? s1 - 1 : 4);
   }
   if (s1 == 0) {

@@ -74,9 +74,12 @@ enum bocf_precision {
                                accumulation in tensor memory.  `slices` = s (3..6): both contractions use the scheme of
                                s planes (3: 8 digit pairs, 4: 13, 5: 15, 6: 21);  `slices` = 10 s1 + s2: the first
                                contraction (variance) uses s1, the second (variance gradient) s2 <= s1               */
-  BOCF_PREC_AUTO = 2,       /* default: variance scheme from max|L^-1| so its predicted relative error stays below
-                               1e-7 (5 planes / 15 pairs for well-conditioned models), variance gradient one scheme
-                               below (4 planes / 13 pairs: ~1e-7 on the gradient); fp64 DMMA for ill-conditioned factors */
+  BOCF_PREC_AUTO = 2,       /* default: smallest variance scheme whose predicted relative error stays inside the fp64
+                               bar (1e-6, element-wise) both away from the data (bound from max|L^-1|) and next to a
+                               training input, where the variance drops to the noise level (bound from the smallest
+                               noise / signal-variance ratio): 5 planes / 15 pairs for noise >= 3.6e-3 sigma_f^2, 6
+                               planes below; variance gradient one scheme below (4 planes / 13 pairs: ~1e-7 on the
+                               gradient); fp64 DMMA for ill-conditioned factors or noise < 1.7e-5 sigma_f^2        */
   BOCF_PREC_MIXED = 3       /* the north star's mixed mode (1e-4 on acq / grad acq): variance 4 planes / 13 pairs
                                (~1e-6), variance gradient 3 planes / 8 pairs (~1e-5); falls back towards AUTO when
                                max|L^-1| is large                                                                   */

@@ -14,7 +14,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from tests.helpers import make_problem, oracle_model, oracle_acq, product_model, product_acq, rel_err
+from tests.helpers import make_problem, oracle_model, oracle_acq, product_model, product_acq, rel_err, assert_close
 
 pytestmark = pytest.mark.gpu
 
@@ -171,3 +171,28 @@ def test_auto_precision_holds_the_fp64_bar_across_conditioning(cuda_device, kind
     assert rel_err(dv, dv_o) < 1e-6, (pm.active_slices(), noise)
     if noise >= 1e-2:
         assert pm.active_slices() in (4, 5)          # well conditioned: the tensor-core path is the one that runs
+
+
+@pytest.mark.parametrize("noise", [1e-2, 1e-3, 1e-4])
+def test_auto_holds_the_bar_next_to_training_inputs(cuda_device, noise):
+    # Candidates next to (and exactly at) training inputs: the variance collapses to the noise level there, so an
+    # absolute error that is harmless elsewhere becomes a large RELATIVE one -- and these are the points the acquisition
+    # optimiser converges to, where sigma enters the pathwise gradient as 0.5 / sigma.  AUTO sizes the digit planes for
+    # it (api.cu apply_precision, bound (ii); CPU model: tests/test_split_numerics.py).
+    P = make_problem(m=2, d=4, n=220, H=1, kind="matern52", composite="sumsq_target", N=128, S=64, noise=noise, seed=3)
+    rng = np.random.default_rng(1)
+    Xc = np.ascontiguousarray(np.concatenate([P.X[:96] + 1e-4 * rng.standard_normal((96, P.d)), P.X[:32]]))
+    om, pm = oracle_model(P), product_model(P, cuda_device, precision="auto")
+    v, v_o = pm.posterior_variance(Xc), om.posterior_variance(Xc)
+    assert v_o.min() < 3.0 * noise                                             # the variance does collapse here
+    assert np.max(np.abs(v - v_o) / v_o) < 1e-6, (pm.active_slices(), noise, np.max(np.abs(v - v_o) / v_o))
+    vn, vn_o = pm.posterior_variance_noiseless(Xc), om.posterior_variance_noiseless(Xc)
+    big = vn_o >= 0.25 * noise                                                 # the noiseless variance has no floor
+    assert np.max(np.abs(vn - vn_o)[big] / vn_o[big]) < 1e-6, (pm.active_slices(), noise)
+    assert np.max(np.abs(vn - vn_o)) < 2.5e-7 * noise, (pm.active_slices(), noise)
+    if noise <= 1e-4:
+        assert pm.active_slices() in (0, 6)                                   # five planes would miss the bar here
+    a_o, g_o = oracle_acq(P, grad=True, Xc=Xc)
+    a, g = product_acq(P, grad=True, device=cuda_device, Xc=Xc, model=pm)
+    assert_close(a, a_o, 1e-6, "acq next to the data")
+    assert_close(g, g_o, 1e-5, "grad acq next to the data")

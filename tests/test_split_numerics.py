@@ -119,3 +119,54 @@ def test_variance_gradient_error_model(kind, noise, n, d):
     assert err["332"] > 20 * err["331"], err
 
 
+
+
+# ---- candidates next to a training input (the points the acquisition optimiser converges to) -------------------------
+# Absolute error of sum V^2 over sigma_f^2 is K_S * 256^-S whatever the conditioning, while `posterior_variance` (noise
+# included, the quantity the north-star bar names) drops to the noise variance there: api.cu's AUTO rule asks
+# K_S 256^-S sigma_f^2 / noise <= 2.5e-7, a quarter of the bar, so that the NOISELESS variance uEI_noiseless samples with
+# (which has no floor: it falls below the noise where many neighbours average) also holds 1e-6 wherever it is >= noise / 4.
+# Constants restated from apply_precision.
+NEAR_K = {4: 60.0, 5: 1000.0, 6: 1200.0}
+
+
+def auto_planes(amax, noise_to_signal, target=5e-7):
+    """api.cu apply_precision (AUTO): first S in 4..6 with both bounds inside the target; 0 = stay on the fp64 engine."""
+    a2 = amax * amax
+    away = {4: 150.0 * a2 * 256.0 ** -4, 5: 2000.0 * a2 * 256.0 ** -5, 6: 2000.0 * a2 * 256.0 ** -6}
+    for S in (4, 5, 6):
+        if away[S] <= target and NEAR_K[S] * 256.0 ** -S / (0.25 * noise_to_signal) <= 2.0 * target:
+            return S
+    return 0
+
+
+@pytest.mark.parametrize("kind,n,d", [("matern52", 400, 10), ("rbf", 200, 6), ("matern52", 220, 4)])
+@pytest.mark.parametrize("noise", [1e-1, 1e-2, 1e-3, 1e-4, 1e-5, 1e-6])
+def test_variance_error_next_to_training_inputs(kind, n, d, noise):
+    P, var_f, ls, Linv, _, _, _ = _posterior_pieces(kind, noise, n=n, d=d)
+    rng = np.random.default_rng(0)
+    Xc = np.concatenate([P.X[:96] + 1e-4 * rng.standard_normal((96, d)), P.X[:32]])      # next to, and exactly at, the data
+    r2 = (((Xc / ls)[:, None, :] - (P.X / ls)[None, :, :]) ** 2).sum(-1)
+    r = np.sqrt(r2)
+    Ks = var_f * np.exp(-0.5 * r2) if kind == "rbf" else var_f * (1 + np.sqrt(5) * r + 5 / 3 * r2) * np.exp(-np.sqrt(5) * r)
+    V = Ks @ Linv.T
+    ssq = (V ** 2).sum(1)
+    var_noiseless = var_f - ssq                                   # what uEI_noiseless samples with (clipped at 1e-10)
+    assert var_noiseless.min() < 1.2 * noise * var_f + 1e-6       # the candidates ARE where the variance collapses
+    eA = np.full(len(Xc), np.frexp(var_f * 1.02)[1], dtype=np.int64)
+    for S in (4, 5, 6):
+        ssq_S = (split_matmul(Ks, eA, Linv, row_exp(Linv), S) ** 2).sum(1)
+        assert np.max(np.abs(ssq_S - ssq)) / var_f < NEAR_K[S] * 256.0 ** -S, S      # the constant of the rule
+    S = auto_planes(np.abs(Linv).max(), (noise + 1e-8) / var_f)
+    if noise >= 1e-2:
+        assert S in (4, 5)                                        # well conditioned: tensor-core path, 13 or 15 pairs
+    if noise == 1e-2 and n >= 400:
+        assert S == 5                                             # the benchmark configurations keep 554
+    if noise <= 1e-6:
+        assert S == 0                                             # nothing on int8 planes holds 1e-6 next to the data
+    if S:
+        ssq_S = (split_matmul(Ks, eA, Linv, row_exp(Linv), S) ** 2).sum(1)
+        v_ref, v_S = var_noiseless + noise, var_f + noise - ssq_S
+        assert np.max(np.abs(v_S - v_ref) / v_ref) < 2.5e-7, (S, noise)             # posterior_variance, element-wise
+        big = var_noiseless >= 0.25 * noise * var_f
+        assert np.max(np.abs(ssq_S - ssq)[big] / var_noiseless[big]) < 1e-6, (S, noise)    # noiseless, where it has a floor
