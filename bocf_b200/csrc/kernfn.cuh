@@ -101,7 +101,7 @@ __device__ __forceinline__ double exp_nonpos(double x) {
 // (Round 2 started with 32 entries and degree 6: one DFMA more per evaluation.)
 constexpr int EXP_TAB_N = 128;
 // (16 interleaved copies, one per lane of a half-warp, make the lookup bank-conflict free: measured, no change --
-// 69.8 vs 69.1 ms per step, profiles/r2_experiments.md section 9 -- so there is one copy)
+// 69.8 vs 69.1 ms per step, profiles/r2_experiments.md section 8 -- so there is one copy)
 static __constant__ double EXPT[8] = {
     184.6649652337873,           // [0] 128 log2(e)
     0.005415212348111709,        // [1] ln2/128 high (low 17 mantissa bits zero: n*hi is exact for |n| < 2^17; n >= -129272)
